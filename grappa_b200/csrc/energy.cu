@@ -1,0 +1,432 @@
+// K13 / K14: MM bonded energy, analytic forces and parameter gradients over conformations.
+//
+// Replaces reference src/grappa/models/internal_coordinates.py:15-125 (gathered geometry),
+// models/energy.py:8-71 (harmonic / torsion energies, per-molecule pooling) and the autograd call at
+// models/energy.py:139 (forces) -- plus the double-backward through it that training on forces needs
+// (training/loss.py:64-68).  Math lives in energy_math.cuh.
+//
+// Forward, two kernels:
+//   energy_tiled_kernel   one CTA per (molecule, tile of W conformations).  The molecule's xyz tile
+//                         is staged once in shared memory as [atom][xyz][conf] (coalesced 12*W-byte
+//                         rows in, bank-conflict-free columns out), W*G threads = W conformations x
+//                         G tuple groups; every thread keeps its conformation for the whole kernel
+//                         so per-level energies accumulate in registers, forces accumulate in a
+//                         shared-memory tile and are written back once, coalesced.  No global atomics.
+//   energy_global_kernel  fallback for molecules whose tile does not fit in shared memory
+//                         (> ~250 atoms): threads over (tuple, conformation), global RED atomics.
+// Backward: one warp per tuple, lanes stride over conformations, warp-shuffle reduction, one
+// deterministic store per parameter (no atomics, no workspace).
+#include "common.cuh"
+#include "energy_math.cuh"
+
+namespace gb {
+
+static __device__ __forceinline__ V3 ld3(const float* p) { return v3(p[0], p[1], p[2]); }
+
+// molecule that owns tuple t (off has n_mols+1 monotone entries)
+static __device__ __forceinline__ int find_segment(const int32_t* __restrict__ off, int n, int t) {
+  int lo = 0, hi = n;  // invariant: off[lo] <= t < off[hi]
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(off + mid) <= t) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tiled forward
+// ---------------------------------------------------------------------------------------------
+template <bool ATOMIC>
+static __device__ __forceinline__ void sm_add(float* p, float v) {
+  if (ATOMIC) atomicAdd(p, v); else *p += v;
+}
+
+template <bool ATOMIC>
+__global__ void __launch_bounds__(512) energy_tiled_kernel(gb_energy_args a, int W, int G, int n_tiles) {
+  extern __shared__ float smem[];
+  const int b = blockIdx.x / n_tiles;
+  const int tile = blockIdx.x % n_tiles;
+  const int a0 = a.atom_off[b];
+  const int n_at = a.atom_off[b + 1] - a0;
+  const int C = a.n_confs;
+  const int c0 = tile * W;
+  const int wc = min(W, C - c0);           // valid conformations in this tile
+  float* xs = smem;                        // [n_at][3][W]
+  float* gs = smem + (size_t)n_at * 3 * W; // [n_at][3][W]
+  const int tid = threadIdx.x;
+  const int nthr = blockDim.x;
+
+  // stage xyz: global row of atom = 3*C floats, tile slice = 3*wc contiguous floats
+  for (int i = tid; i < n_at * 3 * W; i += nthr) {
+    int at = i / (3 * W), rem = i - at * 3 * W;
+    int cl = rem / 3, comp = rem - cl * 3;
+    float v = 0.f;
+    if (cl < wc) v = __ldg(a.xyz + ((size_t)(a0 + at) * C + c0) * 3 + rem);
+    xs[(at * 3 + comp) * W + cl] = v;
+    gs[(at * 3 + comp) * W + cl] = 0.f;
+  }
+  __syncthreads();
+
+  const int cl = tid % W;
+  const int grp = tid / W;
+  const bool active = (grp < G) && (cl < wc);
+  const int c = c0 + cl;
+  float e_lvl[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool want_grad = a.grad != nullptr;
+
+  if (active) {
+#define XS(at) v3(xs[((at) * 3 + 0) * W + cl], xs[((at) * 3 + 1) * W + cl], xs[((at) * 3 + 2) * W + cl])
+#define GADD(at, vec)                                       \
+  do {                                                      \
+    sm_add<ATOMIC>(&gs[((at) * 3 + 0) * W + cl], (vec).x);  \
+    sm_add<ATOMIC>(&gs[((at) * 3 + 1) * W + cl], (vec).y);  \
+    sm_add<ATOMIC>(&gs[((at) * 3 + 2) * W + cl], (vec).z);  \
+  } while (0)
+    // ---- bonds
+    if ((a.level_mask & 1) && a.n_tuples[0] > 0) {
+      const int t1 = a.tup_off[0][b + 1];
+      for (int t = a.tup_off[0][b] + grp; t < t1; t += G) {
+        int i0 = __ldg(a.idx[0] + 2 * t) - a0, i1 = __ldg(a.idx[0] + 2 * t + 1) - a0;
+        float k = __ldg(a.k[0] + t), eq = __ldg(a.eq[0] + t);
+        BondGeom g = bond_geom(XS(i0), XS(i1));
+        float d = g.r - eq;
+        float e = 0.5f * k * d * d;
+        e_lvl[0] += e;
+        if (a.x[0]) a.x[0][(size_t)t * C + c] = g.r;
+        if (a.tuple_energy[0]) a.tuple_energy[0][(size_t)t * C + c] = e;
+        if (want_grad) {
+          V3 f = (k * d) * g.d0;
+          GADD(i0, f);
+          GADD(i1, v3(-f.x, -f.y, -f.z));
+        }
+      }
+    }
+    // ---- angles
+    if ((a.level_mask & 2) && a.n_tuples[1] > 0) {
+      const int t1 = a.tup_off[1][b + 1];
+      for (int t = a.tup_off[1][b] + grp; t < t1; t += G) {
+        int i0 = __ldg(a.idx[1] + 3 * t) - a0, i1 = __ldg(a.idx[1] + 3 * t + 1) - a0,
+            i2 = __ldg(a.idx[1] + 3 * t + 2) - a0;
+        float k = __ldg(a.k[1] + t), eq = __ldg(a.eq[1] + t);
+        AngleGeom g = angle_geom(XS(i0), XS(i1), XS(i2));
+        float d = g.theta - eq;
+        float e = 0.5f * k * d * d;
+        e_lvl[1] += e;
+        if (a.x[1]) a.x[1][(size_t)t * C + c] = g.theta;
+        if (a.tuple_energy[1]) a.tuple_energy[1][(size_t)t * C + c] = e;
+        if (want_grad) {
+          float s = k * d;
+          V3 f0 = s * g.d0, f2 = s * g.d2;
+          GADD(i0, f0);
+          GADD(i2, f2);
+          GADD(i1, v3(-f0.x - f2.x, -f0.y - f2.y, -f0.z - f2.z));
+        }
+      }
+    }
+    // ---- torsions (propers, impropers)
+#pragma unroll
+    for (int lv = 2; lv < 4; ++lv) {
+      if (!((a.level_mask >> lv) & 1) || a.n_tuples[lv] == 0) continue;
+      const int nper = a.n_per[lv - 2];
+      const int t1 = a.tup_off[lv][b + 1];
+      for (int t = a.tup_off[lv][b] + grp; t < t1; t += G) {
+        const int32_t* ip = a.idx[lv] + 4 * t;
+        int i0 = __ldg(ip) - a0, i1 = __ldg(ip + 1) - a0, i2 = __ldg(ip + 2) - a0, i3 = __ldg(ip + 3) - a0;
+        float kk[GB_MAX_PERIODICITY];
+#pragma unroll
+        for (int n = 0; n < GB_MAX_PERIODICITY; ++n) kk[n] = n < nper ? __ldg(a.k[lv] + (size_t)t * nper + n) : 0.f;
+        TorsionGeom g = torsion_geom(XS(i0), XS(i1), XS(i2), XS(i3));
+        float e, dedphi;
+        if (nper == 3) torsion_series<3>(kk, g.cphi, g.sphi, e, dedphi, nullptr, nullptr);
+        else torsion_series_dyn(nper, kk, g.cphi, g.sphi, e, dedphi, nullptr, nullptr);
+        e_lvl[lv] += e;
+        if (a.x[lv]) a.x[lv][(size_t)t * C + c] = atan2f(g.sphi, g.cphi);
+        if (a.tuple_energy[lv]) a.tuple_energy[lv][(size_t)t * C + c] = e;
+        if (want_grad) {
+          GADD(i0, dedphi * g.d0);
+          GADD(i1, dedphi * g.d1);
+          GADD(i2, dedphi * g.d2);
+          GADD(i3, dedphi * g.d3);
+        }
+      }
+    }
+#undef XS
+#undef GADD
+  }
+  __syncthreads();
+
+  // forces back to global, coalesced
+  if (want_grad) {
+    for (int i = tid; i < n_at * 3 * W; i += nthr) {
+      int at = i / (3 * W), rem = i - at * 3 * W;
+      int cl2 = rem / 3, comp = rem - cl2 * 3;
+      if (cl2 < wc) a.grad[((size_t)(a0 + at) * C + c0) * 3 + rem] = gs[(at * 3 + comp) * W + cl2];
+    }
+  }
+  __syncthreads();
+  // per-level energies: reduce the G groups of each conformation through shared memory (reuse xs)
+  float* red = xs;  // [4][G][W]  (fits: 4*G*W <= 4*512 floats, checked on the host)
+  if (grp < G) {
+#pragma unroll
+    for (int lv = 0; lv < 4; ++lv) red[(lv * G + grp) * W + cl] = active ? e_lvl[lv] : 0.f;
+  }
+  __syncthreads();
+  if (tid < wc) {
+    float tot = 0.f;
+#pragma unroll
+    for (int lv = 0; lv < 4; ++lv) {
+      float s = 0.f;
+      for (int g2 = 0; g2 < G; ++g2) s += red[(lv * G + g2) * W + tid];
+      if (a.term_energy[lv]) a.term_energy[lv][(size_t)b * C + c0 + tid] = s;
+      tot += s;
+    }
+    if (a.energy) a.energy[(size_t)b * C + c0 + tid] = tot;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// global-atomics forward (any molecule size)
+// ---------------------------------------------------------------------------------------------
+template <int LV>
+__global__ void __launch_bounds__(256) energy_global_kernel(gb_energy_args a) {
+  const int C = a.n_confs;
+  const long long n_items = (long long)a.n_tuples[LV] * C;
+  const bool want_grad = a.grad != nullptr;
+  constexpr int L = LV == 0 ? 2 : (LV == 1 ? 3 : 4);
+  for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < n_items;
+       it += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(it / C);
+    const int c = (int)(it - (long long)t * C);
+    int id[L];
+#pragma unroll
+    for (int j = 0; j < L; ++j) id[j] = __ldg(a.idx[LV] + (size_t)L * t + j);
+    V3 p[L];
+#pragma unroll
+    for (int j = 0; j < L; ++j) p[j] = ld3(a.xyz + ((size_t)id[j] * C + c) * 3);
+    float e, xval;
+    V3 f[L];
+    if (LV == 0) {
+      float k = __ldg(a.k[0] + t), eq = __ldg(a.eq[0] + t);
+      BondGeom g = bond_geom(p[0], p[1]);
+      float d = g.r - eq;
+      e = 0.5f * k * d * d;
+      xval = g.r;
+      f[0] = (k * d) * g.d0;
+      f[1] = v3(-f[0].x, -f[0].y, -f[0].z);
+    } else if (LV == 1) {
+      float k = __ldg(a.k[1] + t), eq = __ldg(a.eq[1] + t);
+      AngleGeom g = angle_geom(p[0], p[1], p[2]);
+      float d = g.theta - eq;
+      e = 0.5f * k * d * d;
+      xval = g.theta;
+      f[0] = (k * d) * g.d0;
+      f[2] = (k * d) * g.d2;
+      f[1] = v3(-f[0].x - f[2].x, -f[0].y - f[2].y, -f[0].z - f[2].z);
+    } else {
+      const int nper = a.n_per[LV - 2];
+      float kk[GB_MAX_PERIODICITY];
+#pragma unroll
+      for (int n = 0; n < GB_MAX_PERIODICITY; ++n) kk[n] = n < nper ? __ldg(a.k[LV] + (size_t)t * nper + n) : 0.f;
+      TorsionGeom g = torsion_geom(p[0], p[1], p[2], p[L - 1]);
+      float dedphi;
+      torsion_series_dyn(nper, kk, g.cphi, g.sphi, e, dedphi, nullptr, nullptr);
+      xval = (a.x[LV] != nullptr) ? atan2f(g.sphi, g.cphi) : 0.f;
+      f[0] = dedphi * g.d0;
+      f[1] = dedphi * g.d1;
+      f[2] = dedphi * g.d2;
+      f[L - 1] = dedphi * g.d3;
+    }
+    if (a.x[LV]) a.x[LV][(size_t)t * C + c] = xval;
+    if (a.tuple_energy[LV]) a.tuple_energy[LV][(size_t)t * C + c] = e;
+    const int b = find_segment(a.tup_off[LV], a.n_mols, t);
+    if (a.energy) atomicAdd(a.energy + (size_t)b * C + c, e);
+    if (a.term_energy[LV]) atomicAdd(a.term_energy[LV] + (size_t)b * C + c, e);
+    if (want_grad) {
+#pragma unroll
+      for (int j = 0; j < L; ++j) {
+        float* gp = a.grad + ((size_t)id[j] * C + c) * 3;
+        atomicAdd(gp, f[j].x);
+        atomicAdd(gp + 1, f[j].y);
+        atomicAdd(gp + 2, f[j].z);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward: one warp per tuple
+// ---------------------------------------------------------------------------------------------
+template <int LV>
+__global__ void __launch_bounds__(256) energy_bwd_kernel(gb_energy_bwd_args ba) {
+  const gb_energy_args& a = ba.fwd;
+  const int C = a.n_confs;
+  constexpr int L = LV == 0 ? 2 : (LV == 1 ? 3 : 4);
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  for (int t = blockIdx.x * warps_per_block + (threadIdx.x >> 5); t < a.n_tuples[LV];
+       t += gridDim.x * warps_per_block) {
+    int id[L];
+#pragma unroll
+    for (int j = 0; j < L; ++j) id[j] = __ldg(a.idx[LV] + (size_t)L * t + j);
+    const int b = find_segment(a.tup_off[LV], a.n_mols, t);
+    const bool on = (a.level_mask >> LV) & 1;
+    if (LV < 2) {
+      const float k = __ldg(a.k[LV] + t), eq = __ldg(a.eq[LV] + t);
+      float acc_k = 0.f, acc_eq = 0.f;
+      for (int c = lane; c < C && on; c += 32) {
+        V3 p[L], gf[L];
+#pragma unroll
+        for (int j = 0; j < L; ++j) {
+          p[j] = ld3(a.xyz + ((size_t)id[j] * C + c) * 3);
+          gf[j] = ba.g_grad ? ld3(ba.g_grad + ((size_t)id[j] * C + c) * 3) : v3(0.f, 0.f, 0.f);
+        }
+        float q, s;
+        if (LV == 0) {
+          BondGeom g = bond_geom(p[0], p[1]);
+          q = g.r;
+          s = dot(gf[0] - gf[1], g.d0);
+        } else {
+          AngleGeom g = angle_geom(p[0], p[1], p[2]);
+          q = g.theta;
+          s = dot(gf[0] - gf[1], g.d0) + dot(gf[2] - gf[1], g.d2);
+        }
+        const float ge = ba.g_energy ? __ldg(ba.g_energy + (size_t)b * C + c) : 0.f;
+        const float d = q - eq;
+        acc_k += ge * 0.5f * d * d + d * s;
+        acc_eq += -ge * k * d - k * s;
+      }
+      acc_k = warp_sum(acc_k);
+      acc_eq = warp_sum(acc_eq);
+      if (lane == 0) {
+        if (ba.dk[LV]) ba.dk[LV][t] = acc_k;
+        if (ba.deq[LV < 2 ? LV : 0]) ba.deq[LV < 2 ? LV : 0][t] = acc_eq;
+      }
+    } else {
+      const int nper = a.n_per[LV - 2];
+      float acc[GB_MAX_PERIODICITY];
+#pragma unroll
+      for (int n = 0; n < GB_MAX_PERIODICITY; ++n) acc[n] = 0.f;
+      float zero_k[GB_MAX_PERIODICITY] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int c = lane; c < C && on; c += 32) {
+        V3 p[4], gf[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          p[j] = ld3(a.xyz + ((size_t)id[j] * C + c) * 3);
+          gf[j] = ba.g_grad ? ld3(ba.g_grad + ((size_t)id[j] * C + c) * 3) : v3(0.f, 0.f, 0.f);
+        }
+        TorsionGeom g = torsion_geom(p[0], p[1], p[2], p[3]);
+        const float s = dot(gf[0], g.d0) + dot(gf[1], g.d1) + dot(gf[2], g.d2) + dot(gf[3], g.d3);
+        const float ge = ba.g_energy ? __ldg(ba.g_energy + (size_t)b * C + c) : 0.f;
+        float cn[GB_MAX_PERIODICITY], sn[GB_MAX_PERIODICITY], e, de;
+        torsion_series<GB_MAX_PERIODICITY>(zero_k, g.cphi, g.sphi, e, de, cn, sn);
+#pragma unroll
+        for (int n = 0; n < GB_MAX_PERIODICITY; ++n) acc[n] += ge * cn[n] - float(n + 1) * sn[n] * s;
+      }
+#pragma unroll
+      for (int n = 0; n < GB_MAX_PERIODICITY; ++n) acc[n] = warp_sum(acc[n]);
+      if (lane == 0 && ba.dk[LV]) {
+#pragma unroll
+        for (int n = 0; n < GB_MAX_PERIODICITY; ++n)
+          if (n < nper) ba.dk[LV][(size_t)t * nper + n] = acc[n];
+      }
+    }
+  }
+}
+
+static int validate(const gb_energy_args* a) {
+  GB_REQUIRE(a != nullptr, "energy: args is NULL");
+  GB_REQUIRE(a->xyz != nullptr, "energy: xyz is NULL (xyz coordinates must be stored in g.nodes['n1'].data['xyz'])");
+  GB_REQUIRE(a->n_atoms >= 0 && a->n_confs >= 0 && a->n_mols >= 0, "energy: negative size");
+  GB_REQUIRE(a->atom_off != nullptr || a->n_mols == 0, "energy: atom_off is NULL");
+  for (int l = 0; l < 4; ++l) {
+    GB_REQUIRE(a->n_tuples[l] >= 0, "energy: negative tuple count at level %d", l);
+    if (a->n_tuples[l] > 0 && ((a->level_mask >> l) & 1)) {
+      GB_REQUIRE(a->idx[l] && a->tup_off[l], "energy: level %d has tuples but idx/tup_off is NULL", l);
+      GB_REQUIRE(a->k[l] != nullptr, "energy: level %d has no k attribute", l);
+      if (l < 2) GB_REQUIRE(a->eq[l] != nullptr, "energy: level %d has no eq attribute", l);
+    }
+  }
+  for (int l = 0; l < 2; ++l)
+    GB_REQUIRE(a->n_per[l] >= 0 && a->n_per[l] <= GB_MAX_PERIODICITY, "energy: n_periodicity %d > %d", a->n_per[l],
+               GB_MAX_PERIODICITY);
+  return GB_OK;
+}
+
+}  // namespace gb
+
+using namespace gb;
+
+extern "C" int grappa_b200_energy_fwd(const gb_energy_args* a, int variant, void* stream_) {
+  int rc = validate(a);
+  if (rc) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int C = a->n_confs, B = a->n_mols;
+  if (C == 0 || B == 0) return GB_OK;
+  const size_t bc = (size_t)B * C * sizeof(float);
+  const int mode = variant;
+  const int max_atoms = a->max_atoms_per_mol;
+  int W = (C + ((C + 31) / 32) - 1) / ((C + 31) / 32);  // ceil(C / ceil(C/32)) <= 32
+  int n_tiles = (C + W - 1) / W;
+  int G = 256 / W;
+  if (G < 1) G = 1;
+  if (G > 16) G = 16;
+  size_t smem_floats = (size_t)max_atoms * 3 * W * 2;
+  if (smem_floats < (size_t)4 * G * W) smem_floats = (size_t)4 * G * W;
+  const size_t smem = smem_floats * sizeof(float);
+  const bool tile_ok = max_atoms > 0 && smem <= 200 * 1024;
+  GB_REQUIRE(mode != 2 || tile_ok, "energy: tiled variant requested but max_atoms=%d does not fit", max_atoms);
+  const bool tiled = (mode == 2) || (mode == 0 && tile_ok);
+  if (tiled) {
+    auto kern = G > 1 ? energy_tiled_kernel<true> : energy_tiled_kernel<false>;
+    if (smem > 48 * 1024) GB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int threads = ((W * G + 31) / 32) * 32;
+    kern<<<B * n_tiles, threads, smem, stream>>>(*a, W, G, n_tiles);
+    GB_CHECK_LAUNCH();
+    return GB_OK;
+  }
+  if (a->energy) GB_CHECK_CUDA(cudaMemsetAsync(a->energy, 0, bc, stream));
+  for (int l = 0; l < 4; ++l)
+    if (a->term_energy[l]) GB_CHECK_CUDA(cudaMemsetAsync(a->term_energy[l], 0, bc, stream));
+  if (a->grad) GB_CHECK_CUDA(cudaMemsetAsync(a->grad, 0, (size_t)a->n_atoms * C * 3 * sizeof(float), stream));
+  const int sms = sm_count();
+  for (int l = 0; l < 4; ++l) {
+    if (!((a->level_mask >> l) & 1) || a->n_tuples[l] == 0) continue;
+    long long items = (long long)a->n_tuples[l] * C;
+    int blocks = (int)((items + 255) / 256);
+    if (blocks > sms * 16) blocks = sms * 16;
+    switch (l) {
+      case 0: energy_global_kernel<0><<<blocks, 256, 0, stream>>>(*a); break;
+      case 1: energy_global_kernel<1><<<blocks, 256, 0, stream>>>(*a); break;
+      case 2: energy_global_kernel<2><<<blocks, 256, 0, stream>>>(*a); break;
+      default: energy_global_kernel<3><<<blocks, 256, 0, stream>>>(*a); break;
+    }
+    GB_CHECK_LAUNCH();
+  }
+  return GB_OK;
+}
+
+extern "C" int64_t grappa_b200_energy_bwd_workspace(const gb_energy_args*) { return 0; }
+
+extern "C" int grappa_b200_energy_bwd(const gb_energy_bwd_args* ba, void* stream_) {
+  GB_REQUIRE(ba != nullptr, "energy_bwd: args is NULL");
+  int rc = validate(&ba->fwd);
+  if (rc) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const gb_energy_args* a = &ba->fwd;
+  if (a->n_mols == 0) return GB_OK;
+  const int sms = sm_count();
+  for (int l = 0; l < 4; ++l) {
+    if (a->n_tuples[l] == 0 || ba->dk[l] == nullptr) continue;
+    GB_REQUIRE(a->idx[l] && a->tup_off[l] && a->k[l], "energy_bwd: level %d inputs missing", l);
+    int blocks = (a->n_tuples[l] + 7) / 8;
+    if (blocks > sms * 8) blocks = sms * 8;
+    switch (l) {
+      case 0: energy_bwd_kernel<0><<<blocks, 256, 0, stream>>>(*ba); break;
+      case 1: energy_bwd_kernel<1><<<blocks, 256, 0, stream>>>(*ba); break;
+      case 2: energy_bwd_kernel<2><<<blocks, 256, 0, stream>>>(*ba); break;
+      default: energy_bwd_kernel<3><<<blocks, 256, 0, stream>>>(*ba); break;
+    }
+    GB_CHECK_LAUNCH();
+  }
+  return GB_OK;
+}

@@ -1,0 +1,192 @@
+// Host-side tuple index construction (angles, propers, impropers) from a bond list.
+//
+// Reproduces the ORDER of the reference's pure-Python routines bit-exactly
+// (reference src/grappa/utils/tuple_indices.py:7-63 get_idx_tuples, :66-83 get_neighbor_dict,
+//  :87-140 is_improper / is_proper, :144-216 get_torsions) with a different mechanism: a CSR
+// adjacency with sorted rows plus a "first appearance" atom order instead of Python dicts.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <array>
+#include <set>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/grappa_b200.h"
+
+namespace gb {
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace gb
+
+extern "C" const char* grappa_b200_last_error(void) { return gb::g_err; }
+extern "C" int grappa_b200_abi_version(void) { return GB_ABI_VERSION; }
+
+namespace {
+
+struct Adjacency {
+  std::vector<int64_t> order;                       // atoms in order of first appearance in `bonds`
+  std::unordered_map<int64_t, int64_t> slot;        // atom id -> row
+  std::vector<std::vector<int64_t>> nbr;            // sorted neighbour lists (duplicates kept)
+
+  const std::vector<int64_t>& of(int64_t atom) const { return nbr[slot.at(atom)]; }
+  bool has(int64_t atom) const { return slot.find(atom) != slot.end(); }
+  bool bonded(int64_t a, int64_t b) const {
+    const auto& r = of(a);
+    return std::binary_search(r.begin(), r.end(), b);
+  }
+};
+
+int build_adjacency(const int64_t* bonds, int64_t n_bonds, Adjacency& adj) {
+  for (int64_t b = 0; b < n_bonds; ++b) {
+    for (int i = 0; i < 2; ++i) {
+      int64_t a = bonds[2 * b + i], o = bonds[2 * b + 1 - i];
+      if (a == o) {
+        gb::set_error("Encountered self-bond: (%lld, %lld)", (long long)a, (long long)o);
+        return GB_ERR_INVALID;
+      }
+      auto it = adj.slot.find(a);
+      if (it == adj.slot.end()) {
+        adj.slot.emplace(a, (int64_t)adj.order.size());
+        adj.order.push_back(a);
+        adj.nbr.emplace_back();
+        adj.nbr.back().push_back(o);
+      } else {
+        adj.nbr[it->second].push_back(o);
+      }
+    }
+  }
+  for (auto& r : adj.nbr) std::sort(r.begin(), r.end());
+  return GB_OK;
+}
+
+// Visits angles and propers in the reference's emission order.
+template <class FA, class FP>
+void walk(const Adjacency& adj, FA&& on_angle, FP&& on_proper) {
+  for (int64_t a1 : adj.order) {
+    for (int64_t a2 : adj.of(a1)) {
+      for (int64_t a3 : adj.of(a2)) {
+        if (a3 == a1) continue;
+        if (a1 < a3) on_angle(a1, a2, a3);
+        for (int64_t a4 : adj.of(a3)) {
+          if (a4 >= a1) break;      // rows are sorted: enforces proper[0] < proper[3]
+          if (a4 == a2) continue;
+          on_proper(a4, a3, a2, a1);
+        }
+      }
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int grappa_b200_tuples_count(const int64_t* bonds, int64_t n_bonds, int64_t* n_angles,
+                                        int64_t* n_propers) {
+  Adjacency adj;
+  int rc = build_adjacency(bonds, n_bonds, adj);
+  if (rc) return rc;
+  int64_t na = 0, np = 0;
+  walk(adj, [&](int64_t, int64_t, int64_t) { ++na; }, [&](int64_t, int64_t, int64_t, int64_t) { ++np; });
+  *n_angles = na;
+  *n_propers = np;
+  return GB_OK;
+}
+
+extern "C" int grappa_b200_tuples_build(const int64_t* bonds, int64_t n_bonds, int64_t* bonds_sorted,
+                                        int64_t* angles, int64_t* propers) {
+  Adjacency adj;
+  int rc = build_adjacency(bonds, n_bonds, adj);
+  if (rc) return rc;
+  for (int64_t b = 0; b < n_bonds; ++b) {
+    int64_t u = bonds[2 * b], v = bonds[2 * b + 1];
+    bonds_sorted[2 * b] = std::min(u, v);
+    bonds_sorted[2 * b + 1] = std::max(u, v);
+  }
+  int64_t na = 0, np = 0;
+  walk(
+      adj,
+      [&](int64_t a, int64_t b, int64_t c) {
+        angles[3 * na] = a; angles[3 * na + 1] = b; angles[3 * na + 2] = c; ++na;
+      },
+      [&](int64_t a, int64_t b, int64_t c, int64_t d) {
+        propers[4 * np] = a; propers[4 * np + 1] = b; propers[4 * np + 2] = c; propers[4 * np + 3] = d; ++np;
+      });
+  return GB_OK;
+}
+
+extern "C" int grappa_b200_torsions_classify(const int64_t* bonds, int64_t n_bonds, const int64_t* torsions,
+                                             int64_t n_torsions, int central_pos, int64_t* propers_out,
+                                             int64_t* n_propers_out, int64_t* impropers_out,
+                                             int64_t* n_impropers_out) {
+  if (central_pos < 0 || central_pos > 3) {
+    gb::set_error("central_pos must be in [0,3], got %d", central_pos);
+    return GB_ERR_INVALID;
+  }
+  Adjacency adj;
+  int rc = build_adjacency(bonds, n_bonds, adj);
+  if (rc) return rc;
+  std::set<std::array<int64_t, 4>> seen;   // sorted atom sets already emitted (proper or improper)
+  int64_t np = 0, ni = 0;
+  static const int probe[4] = {2, 1, 0, 3};  // central-atom candidates in the reference's order
+  for (int64_t t = 0; t < n_torsions; ++t) {
+    std::array<int64_t, 4> ids = {torsions[4 * t], torsions[4 * t + 1], torsions[4 * t + 2], torsions[4 * t + 3]};
+    std::array<int64_t, 4> key = ids;
+    std::sort(key.begin(), key.end());
+    if (seen.count(key)) continue;
+    for (int i = 0; i < 4; ++i) {
+      if (!adj.has(ids[i])) {
+        gb::set_error("torsion %lld references atom %lld that has no bond", (long long)t, (long long)ids[i]);
+        return GB_ERR_INVALID;
+      }
+    }
+    int central = -1;
+    for (int p : probe) {
+      int64_t c = ids[p];
+      bool all = true;
+      for (int i = 0; i < 4; ++i)
+        if (ids[i] != c && !adj.bonded(c, ids[i])) { all = false; break; }
+      if (all) {
+        // position of the first occurrence of the central atom (python tuple.index)
+        for (int i = 0; i < 4; ++i)
+          if (ids[i] == c) { central = i; break; }
+        break;
+      }
+    }
+    bool is_proper = adj.bonded(ids[1], ids[0]) && adj.bonded(ids[2], ids[1]) && adj.bonded(ids[3], ids[2]);
+    bool is_improper = central >= 0 && !is_proper;   // both -> proper (tuple_indices.py:168-171)
+    if (!is_proper && !is_improper) {
+      gb::set_error("Encountered torsion that is neither proper nor improper: (%lld, %lld, %lld, %lld)",
+                    (long long)ids[0], (long long)ids[1], (long long)ids[2], (long long)ids[3]);
+      return GB_ERR_INVALID;
+    }
+    if (!is_improper) {
+      for (int i = 0; i < 4; ++i) propers_out[4 * np + i] = ids[i];
+      ++np;
+      seen.insert(key);
+    } else {
+      int64_t others[3];
+      int j = 0;
+      for (int i = 0; i < 4; ++i)
+        if (i != central) others[j++] = ids[i];
+      static const int rot[3][3] = {{0, 1, 2}, {1, 2, 0}, {2, 0, 1}};
+      for (int v = 0; v < 3; ++v) {
+        int o = 0;
+        for (int pos = 0; pos < 4; ++pos) {
+          impropers_out[4 * ni + pos] = (pos == central_pos) ? ids[central] : others[rot[v][o++]];
+        }
+        ++ni;
+      }
+      seen.insert(key);
+    }
+  }
+  *n_propers_out = np;
+  *n_impropers_out = ni;
+  return GB_OK;
+}
