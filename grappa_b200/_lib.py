@@ -33,6 +33,7 @@ class EnergyArgs(C.Structure):
         ("eq", c_f32p * 2),
         ("n_per", C.c_int32 * 2),
         ("level_mask", C.c_int32),
+        ("offset_torsion", C.c_int32),
         ("energy", c_f32p),
         ("term_energy", c_f32p * 4),
         ("grad", c_f32p),

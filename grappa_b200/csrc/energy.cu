@@ -139,6 +139,10 @@ __global__ void __launch_bounds__(512) energy_tiled_kernel(gb_energy_args a, int
         float e, dedphi;
         if (nper == 3) torsion_series<3>(kk, g.cphi, g.sphi, e, dedphi, nullptr, nullptr);
         else torsion_series_dyn(nper, kk, g.cphi, g.sphi, e, dedphi, nullptr, nullptr);
+        if (a.offset_torsion) {
+#pragma unroll
+          for (int n = 0; n < GB_MAX_PERIODICITY; ++n) e += fabsf(kk[n]);
+        }
         e_lvl[lv] += e;
         if (a.x[lv]) a.x[lv][(size_t)t * C + c] = atan2f(g.sphi, g.cphi);
         if (a.tuple_energy[lv]) a.tuple_energy[lv][(size_t)t * C + c] = e;
@@ -230,6 +234,10 @@ __global__ void __launch_bounds__(256) energy_global_kernel(gb_energy_args a) {
       TorsionGeom g = torsion_geom(p[0], p[1], p[2], p[L - 1]);
       float dedphi;
       torsion_series_dyn(nper, kk, g.cphi, g.sphi, e, dedphi, nullptr, nullptr);
+      if (a.offset_torsion) {
+#pragma unroll
+        for (int n = 0; n < GB_MAX_PERIODICITY; ++n) e += fabsf(kk[n]);
+      }
       xval = (a.x[LV] != nullptr) ? atan2f(g.sphi, g.cphi) : 0.f;
       f[0] = dedphi * g.d0;
       f[1] = dedphi * g.d1;
@@ -321,6 +329,15 @@ __global__ void __launch_bounds__(256) energy_bwd_kernel(gb_energy_bwd_args ba) 
         torsion_series<GB_MAX_PERIODICITY>(zero_k, g.cphi, g.sphi, e, de, cn, sn);
 #pragma unroll
         for (int n = 0; n < GB_MAX_PERIODICITY; ++n) acc[n] += ge * cn[n] - float(n + 1) * sn[n] * s;
+        if (a.offset_torsion) {
+#pragma unroll
+          for (int n = 0; n < GB_MAX_PERIODICITY; ++n) {
+            if (n < nper) {
+              float kv = __ldg(a.k[LV] + (size_t)t * nper + n);
+              acc[n] += ge * (kv > 0.f ? 1.f : (kv < 0.f ? -1.f : 0.f));
+            }
+          }
+        }
       }
 #pragma unroll
       for (int n = 0; n < GB_MAX_PERIODICITY; ++n) acc[n] = warp_sum(acc[n]);

@@ -1,0 +1,134 @@
+"""Packed, kernel-ready view of a batched molecular graph.
+
+The kernels want int32 indices and flat segment tables rather than a graph object:
+
+  atom_off[B+1]            first atom of every molecule
+  idx[l]  (T_l, L_l) int32 tuple atom indices per level (n2, n3, n4, n4_improper), already batched
+  tup_off[l][B+1]          first tuple of every molecule per level
+  edge CSR by destination  indptr[N+1], src[E]  -- the bonded graph is symmetric, so the CSR of
+                           in-edges doubles as the CSR of out-edges; `rev[e]` is the position of the
+                           reverse edge, which makes the attention backward a pure gather
+  inv CSR per level        atom -> (tuple, slot) incidence lists, so the backward of the tuple gather
+                           is a deterministic segmented sum instead of atomics
+
+A pack is built once per batch on the HOST (numpy, in the data loader / collate step) and moved to
+the device with the graph; it is cached on the graph object.  Index range is validated here, on the
+host, instead of by the device->host syncs of reference models/grappa.py:122-128.
+"""
+from __future__ import annotations
+
+from typing import Dict, List
+
+import numpy as np
+import torch
+
+LEVELS = ("n2", "n3", "n4", "n4_improper")
+TUPLE_LEN = (2, 3, 4, 4)
+
+
+def _offsets(counts) -> np.ndarray:
+    out = np.zeros(len(counts) + 1, dtype=np.int32)
+    np.cumsum(np.asarray(counts, dtype=np.int64), out=out[1:])
+    return out
+
+
+class PackedBatch:
+    """Device-resident int32 index tables of one batch (see module docstring)."""
+
+    def __init__(self, g, device=None):
+        n_atoms = g.num_nodes("n1")
+        dev = device if device is not None else g.nodes["n1"].data[next(iter(g.nodes["n1"].data))].device
+        self.device = torch.device(dev)
+        self.n_atoms = n_atoms
+        atom_counts = np.asarray(g.batch_num_nodes("n1").cpu().numpy(), dtype=np.int64)
+        self.n_mols = len(atom_counts)
+        self.max_atoms_per_mol = int(atom_counts.max()) if len(atom_counts) else 0
+        host: Dict[str, np.ndarray] = {"atom_off": _offsets(atom_counts)}
+        self.n_tuples: List[int] = []
+        for l, (lvl, L) in enumerate(zip(LEVELS, TUPLE_LEN)):
+            if lvl in g.ntypes:
+                idx_t = g.nodes[lvl].data["idxs"]
+                if idx_t.dtype not in (torch.int64, torch.int32):
+                    raise IndexError(f"g.nodes['{lvl}'].data['idxs'] has the wrong datatype. It should be a long "
+                                     f"but is {idx_t.dtype}")
+                idx = idx_t.detach().cpu().numpy().reshape(-1, L)
+                counts = g.batch_num_nodes(lvl).cpu().numpy()
+            else:
+                idx = np.zeros((0, L), dtype=np.int64)
+                counts = np.zeros(self.n_mols, dtype=np.int64)
+            if idx.size and (idx.max() >= n_atoms or idx.min() < 0):
+                # reference models/grappa.py:128 (its '<=' tolerates idx == n_atoms, which would then fail in the gather)
+                raise AssertionError(f"Encountered idxs up to {idx.max()} at the level g.nodes[{lvl}].data[\"idxs\"], "
+                                     f"but there are only {n_atoms} atom-level-nodes in the graph")
+            self.n_tuples.append(int(idx.shape[0]))
+            host[f"idx{l}"] = np.ascontiguousarray(idx.astype(np.int32))
+            host[f"tup_off{l}"] = _offsets(counts)
+            # inverse incidence: for every atom the flat (tuple*L + slot) entries that reference it
+            flat = idx.reshape(-1)
+            order = np.argsort(flat, kind="stable").astype(np.int32)
+            host[f"inv_ptr{l}"] = _offsets(np.bincount(flat, minlength=n_atoms)) if n_atoms else np.zeros(1, np.int32)
+            host[f"inv_ent{l}"] = order
+        # bonded graph CSR by destination
+        src, dst = g.edges(etype="n1_edge")
+        src = src.detach().cpu().numpy().astype(np.int64)
+        dst = dst.detach().cpu().numpy().astype(np.int64)
+        self.n_edges = len(src)
+        order = np.lexsort((src, dst))               # sort by dst, then src
+        s_src, s_dst = src[order], dst[order]
+        host["indptr"] = _offsets(np.bincount(s_dst, minlength=n_atoms)) if n_atoms else np.zeros(1, np.int32)
+        host["esrc"] = s_src.astype(np.int32)
+        # reverse edge position: edge (u -> v) at position e; reverse (v -> u) found by key lookup
+        key = s_dst * max(n_atoms, 1) + s_src        # sorted ascending by construction
+        rkey = s_src * max(n_atoms, 1) + s_dst
+        pos = np.searchsorted(key, rkey)
+        if len(key) and (pos.max() >= len(key) or not np.array_equal(key[np.minimum(pos, len(key) - 1)], rkey)):
+            raise ValueError("bonded edges must be symmetric (both directions of every bond; reference "
+                             "data/Molecule.py:465-472)")
+        host["erev"] = pos.astype(np.int32)
+        deg = np.diff(host["indptr"])
+        if n_atoms and deg.min() == 0:
+            raise ValueError("every atom must be part of a bond (zero in-degree atom; reference data/Molecule.py:470)")
+        self.max_degree = int(deg.max()) if n_atoms else 0
+        self.host = host
+        self._dev: Dict[str, torch.Tensor] = {}
+        names = list(host.keys())
+        # one pinned staging buffer + one H2D copy for all tables
+        sizes = [host[k].size for k in names]
+        total = int(sum(sizes))
+        stage = torch.empty(total, dtype=torch.int32)
+        if self.device.type == "cuda":
+            stage = stage.pin_memory()
+        off = 0
+        for k, s in zip(names, sizes):
+            stage[off:off + s] = torch.from_numpy(host[k].reshape(-1))
+            off += s
+        flat = stage.to(self.device, non_blocking=True)
+        self.bytes = total * 4
+        off = 0
+        for k, s in zip(names, sizes):
+            self._dev[k] = flat[off:off + s].view(host[k].shape)
+            off += s
+
+    def __getitem__(self, k) -> torch.Tensor:
+        return self._dev[k]
+
+    def ptr(self, k) -> int:
+        t = self._dev[k]
+        return t.data_ptr() if t.numel() else 0
+
+
+def get_pack(g) -> PackedBatch:
+    """Cached PackedBatch of a graph (built on first use)."""
+    dev = None
+    for d in (g.nodes["n1"].data,):
+        for v in d.values():
+            dev = v.device
+            break
+    p = getattr(g, "_pack_cache", None)
+    if p is None or p.device != dev:
+        p = PackedBatch(g, device=dev)
+        try:
+            g._pack_cache = p
+        except Exception:  # pragma: no cover (foreign graph objects that forbid attributes)
+            pass
+    return p

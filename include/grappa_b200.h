@@ -71,6 +71,7 @@ typedef struct {
   const float* eq[2];
   int32_t n_per[2];          /* periodicities of propers / impropers (<= 6)                          */
   int32_t level_mask;        /* bit l set = level l contributes (Energy(terms=...))                  */
+  int32_t offset_torsion;    /* 1: add sum_n |k_n| to every torsion energy (Energy(offset_torsion=True)) */
   /* outputs (any may be NULL) */
   float* energy;             /* [n_mols, n_confs] total bonded energy                                */
   float* term_energy[4];     /* [n_mols, n_confs] per level                                          */

@@ -58,3 +58,36 @@ def import_reference():
     import dgl
     ns.dgl = dgl
     return ns
+
+
+def to_reference_graph(ns, g):
+    """MolGraph (grappa_b200.graph) -> shim DGL heterograph with the layout of data/Molecule.py:429-520."""
+    import torch
+    src, dst = g.edges(etype="n1_edge")
+    data = {("n1", "n1_edge", "n1"): (src.long(), dst.long())}
+    num = {"n1": g.num_nodes("n1")}
+    for nt in ("n2", "n3", "n4", "n4_improper", "g"):
+        n = g.num_nodes(nt)
+        data[(nt, f"{nt}_edge", nt)] = (torch.arange(n), torch.arange(n))
+        num[nt] = n
+    dg = ns.dgl.heterograph(data, num)
+    for nt in g.ntypes:
+        for k, v in g.nodes[nt].data.items():
+            dg.nodes[nt].data[k] = v.clone()
+        dg._batch_num_nodes[nt] = g.batch_num_nodes(nt).clone()
+    return dg
+
+
+class no_dihedral_noise:
+    """Context manager: torch.randn_like -> zeros, neutralising internal_coordinates.py:194-196."""
+
+    def __enter__(self):
+        import torch
+        self._orig = torch.randn_like
+        torch.randn_like = lambda x, *a, **k: torch.zeros_like(x)
+        return self
+
+    def __exit__(self, *exc):
+        import torch
+        torch.randn_like = self._orig
+        return False

@@ -1,0 +1,179 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (run in the build container only).
+
+    python tests/golden/make_golden.py
+
+Imports /root/reference's grappa.models through oracle/ref_import.py (dgl shim), gives the
+reference model weights from grappa_b200.synthetic.deterministic_state_dict (a pure function of key,
+shape and seed, so no checkpoint is shipped), runs Sequential(GrappaModel, Energy) in eval mode with
+the dihedral noise patched out, and stores inputs + outputs.  The GPU box has no /root/reference;
+tests there only read the .npz files.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+from grappa_b200 import graph as gbgraph, synthetic  # noqa: E402
+import grappa_oracle as orc  # noqa: E402
+from ref_import import import_reference, no_dihedral_noise, to_reference_graph  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+LEVELS = ("n2", "n3", "n4", "n4_improper")
+
+
+def graph_inputs(g, prefix="in."):
+    d = {}
+    src, dst = g.edges()
+    d[prefix + "src"] = src.numpy()
+    d[prefix + "dst"] = dst.numpy()
+    for nt in g.ntypes:
+        d[prefix + f"count.{nt}"] = g.batch_num_nodes(nt).numpy()
+        for k, v in g.nodes[nt].data.items():
+            d[prefix + f"{nt}.{k}"] = v.numpy()
+    return d
+
+
+def run_reference(ns, cfg, g, seed, with_loss):
+    torch.manual_seed(1234)
+    model = ns.deploy.model_from_config(dict(cfg), param_statistics=ns.graph_utils.get_default_statistics())
+    sd = synthetic.deterministic_state_dict(model.state_dict(), seed=seed)
+    model.load_state_dict(sd)
+    model.eval()
+    full = torch.nn.Sequential(model, ns.energy.Energy())
+    dg = to_reference_graph(ns, g)
+    with no_dihedral_noise():
+        dg = full(dg)
+    out = {"out.h": dg.nodes["n1"].data["h"].detach().numpy()}
+    for lvl in LEVELS:
+        out[f"out.{lvl}.k"] = dg.nodes[lvl].data["k"].detach().numpy()
+        if lvl in ("n2", "n3"):
+            out[f"out.{lvl}.eq"] = dg.nodes[lvl].data["eq"].detach().numpy()
+        out[f"out.{lvl}.x"] = dg.nodes[lvl].data["x"].detach().numpy()
+        out[f"out.{lvl}.energy"] = dg.nodes[lvl].data["energy"].detach().numpy()
+        out[f"out.g.energy_{lvl}"] = dg.nodes["g"].data[f"energy_{lvl}"].detach().numpy()
+    out["out.g.energy"] = dg.nodes["g"].data["energy"].detach().numpy()
+    out["out.n1.gradient"] = dg.nodes["n1"].data["gradient"].detach().numpy()
+    keys = sorted(model.state_dict().keys())
+    out["meta.state_dict_keys"] = np.array(keys)
+    out["meta.state_dict_shapes"] = np.array([",".join(map(str, model.state_dict()[k].shape)) for k in keys])
+    if with_loss:
+        loss_fn = ns.loss.MolwiseLoss(gradient_weight=0.8, energy_weight=1.0, param_weight=1e-3,
+                                      proper_regularisation=1e-3, improper_regularisation=1e-3)
+        loss = loss_fn(dg)
+        model.zero_grad()
+        loss.backward()
+        out["out.loss"] = np.array(loss.item(), dtype=np.float64)
+        named = dict(model.named_parameters())
+        picks = [k for k in named if any(s in k for s in (
+            "gnn.pre_dense.0.weight", "gnn.att_blocks.0.graph_module.fc.weight", "gnn.att_blocks.1.layer_norm.weight",
+            "gnn.att_blocks.1.self_interaction.2.bias", "gnn.post_dense.0.weight",
+            "bond_writer.rep_projector.mlp.0.weight", "angle_writer.angle_model.grappa_transformer.transformer.0.attn.in_proj_weight",
+            "proper_writer.torsion_model.symmetriser.mlp.0.linear1.weight", "improper_writer.torsion_model.symmetriser.mlp.2.linear2.weight",
+            "proper_writer.torsion_model.grappa_transformer.transformer.1.ff.norm1.bias"))]
+        for k in picks:
+            out[f"grad.{k}"] = named[k].grad.detach().numpy()
+        out["meta.grad_norms_keys"] = np.array(sorted(named.keys()))
+        out["meta.grad_norms"] = np.array([float(named[k].grad.norm()) if named[k].grad is not None else 0.0
+                                           for k in sorted(named.keys())])
+    return out, sd
+
+
+def main():
+    ns = import_reference()
+    torch.set_num_threads(8)
+
+    # ---- case 1: BASELINE config 1 -- grappa-1.2 architecture, capped dipeptide, 50 conformations
+    g = synthetic.dipeptide(seed=11, n_confs=50)
+    cfg = orc.grappa_1_2_model_config()
+    out, sd = run_reference(ns, cfg, g, seed=3, with_loss=False)
+    # the restatement must agree with the reference before the fixture is written
+    h, params, en = orc.path_forward(sd, g, cfg)
+    assert np.allclose(h.detach().numpy(), out["out.h"], rtol=1e-4, atol=1e-5), "oracle h != reference"
+    assert np.allclose(en["energy"].detach().numpy(), out["out.g.energy"], rtol=1e-5, atol=1e-3)
+    np.savez_compressed(os.path.join(OUT, "dipeptide_grappa12.npz"), **graph_inputs(g), **out)
+    print("dipeptide_grappa12: energy[0,:3] =", out["out.g.energy"][0, :3])
+
+    # ---- case 2: narrow architecture, mixed batch (peptide + small molecules + ring systems), with loss + grads
+    rng = np.random.default_rng(5)
+    mols = [synthetic.make_molecule(rng, "peptide", n_confs=7, n_res=1),
+            synthetic.make_molecule(rng, "small", n_confs=7, n_atoms=9),
+            synthetic.make_molecule(rng, "small", n_confs=7, n_atoms=31),
+            synthetic.make_molecule(rng, "peptide", n_confs=7, n_res=2)]
+    # the reference loss NaNs on molecules without impropers (training/loss.py:130-132): keep only those with >= 1
+    mols = [m for m in mols if m.num_nodes("n4_improper") > 0]
+    g = gbgraph.batch(mols)
+    cfg = orc.small_model_config()
+    out, sd = run_reference(ns, cfg, g, seed=7, with_loss=True)
+    np.savez_compressed(os.path.join(OUT, "mixed_batch_small_model.npz"), **graph_inputs(g), **out)
+    print("mixed_batch_small_model: loss =", out["out.loss"], "mols =", len(mols))
+
+    # ---- case 3: Energy alone with given parameters on a larger mixed batch (incl. rna-like rings),
+    #      plus the double backward (dL/dk, dL/deq for random upstream gE, gF) that K14 replaces
+    rng = np.random.default_rng(9)
+    mols = [synthetic.make_molecule(rng, "rna", n_confs=13), synthetic.make_molecule(rng, "peptide", n_confs=13, n_res=3),
+            synthetic.make_molecule(rng, "small", n_confs=13, n_atoms=3), synthetic.make_molecule(rng, "small", n_confs=13, n_atoms=44)]
+    g = gbgraph.batch(mols)
+    dg = to_reference_graph(ns, g)
+    prm = {}
+    gen = torch.Generator().manual_seed(21)
+    for lvl in LEVELS:
+        T = g.num_nodes(lvl)
+        if lvl == "n2":
+            prm[lvl] = {"k": 500 + 300 * torch.rand(T, generator=gen), "eq": 1.0 + 0.5 * torch.rand(T, generator=gen)}
+        elif lvl == "n3":
+            prm[lvl] = {"k": 60 + 80 * torch.rand(T, generator=gen), "eq": 1.7 + 0.5 * torch.rand(T, generator=gen)}
+        else:
+            prm[lvl] = {"k": torch.randn(T, 3 if lvl == "n4" else 2, generator=gen)}
+        for name, v in prm[lvl].items():
+            v.requires_grad_(True)
+            dg.nodes[lvl].data[name] = v
+    with no_dihedral_noise():
+        dg = ns.energy.Energy()(dg)
+    E = dg.nodes["g"].data["energy"]
+    Gd = dg.nodes["n1"].data["gradient"]
+    gE = torch.randn(E.shape, generator=gen)
+    gF = torch.randn(Gd.shape, generator=gen)
+    leaves = [prm[l][n] for l in LEVELS for n in sorted(prm[l])]
+    grads = torch.autograd.grad((E * gE).sum() + (Gd * gF).sum(), leaves)
+    out = {"out.g.energy": E.detach().numpy(), "out.n1.gradient": Gd.detach().numpy(), "in.gE": gE.numpy(), "in.gF": gF.numpy()}
+    i = 0
+    for l in LEVELS:
+        out[f"out.{l}.x"] = dg.nodes[l].data["x"].detach().numpy()
+        out[f"out.g.energy_{l}"] = dg.nodes["g"].data[f"energy_{l}"].detach().numpy()
+        for n in sorted(prm[l]):
+            out[f"in.{l}.{n}"] = prm[l][n].detach().numpy()
+            out[f"grad.{l}.{n}"] = grads[i].numpy()
+            i += 1
+    np.savez_compressed(os.path.join(OUT, "energy_mixed_batch.npz"), **graph_inputs(g), **out)
+    print("energy_mixed_batch: atoms", g.num_nodes("n1"), "E[0,:2]", out["out.g.energy"][0, :2])
+
+    # ---- case 4: tuple indices of shuffled bond lists (bit-exact contract)
+    rng = np.random.default_rng(13)
+    tup = {}
+    for name, (el, b, imp) in {
+        "dipeptide": synthetic.polyalanine_topology(1), "peptide4": synthetic.polyalanine_topology(4),
+        "tree": synthetic.random_tree_topology(rng, 27, 2), "rna": synthetic.rna_like_topology(rng, 93),
+        "protein30": synthetic.polyalanine_topology(30)}.items():
+        b = b[rng.permutation(len(b))]
+        flip = rng.random(len(b)) < 0.5
+        b[flip] = b[flip][:, ::-1]
+        ref = ns.tuple_indices.get_idx_tuples([tuple(x) for x in b.tolist()])
+        nd = ns.tuple_indices.get_neighbor_dict([tuple(x) for x in b.tolist()])
+        _, ri = ns.tuple_indices.get_torsions([tuple(x) for x in imp], nd)
+        tup[f"{name}.in_bonds"] = b
+        tup[f"{name}.in_improper_candidates"] = np.array(imp, dtype=np.int64).reshape(-1, 4)
+        tup[f"{name}.bonds"] = np.array(ref["bonds"], dtype=np.int64).reshape(-1, 2)
+        tup[f"{name}.angles"] = np.array(ref["angles"], dtype=np.int64).reshape(-1, 3)
+        tup[f"{name}.propers"] = np.array(ref["propers"], dtype=np.int64).reshape(-1, 4)
+        tup[f"{name}.impropers"] = np.array(ri, dtype=np.int64).reshape(-1, 4)
+    np.savez_compressed(os.path.join(OUT, "tuple_indices.npz"), **tup)
+    print("tuple_indices:", sorted({k.split('.')[0] for k in tup}))
+
+
+if __name__ == "__main__":
+    main()
