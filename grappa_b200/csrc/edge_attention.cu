@@ -1,0 +1,162 @@
+// K4: graph attention over bonded neighbours, CSR-segmented by destination atom.
+//
+// Replaces the three DGL kernels behind DotGatConv (SDDMM u_dot_v, edge_softmax, SpMM u_mul_e + sum;
+// call site reference models/graph_attention.py:283) and their autograd with
+//   fwd : one warp per destination atom, neighbour rows gathered with 16-byte loads, online softmax in
+//         registers, fp32 accumulation; saves the attention weights alpha[E,H]
+//   bwd : pass 1 (per destination) softmax backward -> ds[E,H]; pass 2 (per atom) pure gather over the
+//         symmetric CSR using the reverse-edge table -- deterministic, no atomics.
+// Row layout: ft[n, H*D]; a lane owns float4 chunks c = lane + 32*it; the D/4 lanes of one head reduce
+// their partial dot products with segmented shuffles.
+#include "common.cuh"
+
+namespace gb {
+
+__device__ __forceinline__ float seg_sum(float v, int gs) {
+  for (int o = gs >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+
+__global__ void __launch_bounds__(256) edge_attn_fwd_kernel(const float* __restrict__ ft, const int* __restrict__ indptr,
+                                                            const int* __restrict__ esrc, float* __restrict__ out,
+                                                            float* __restrict__ alpha, int n_nodes, int H, int D) {
+  const int lane = threadIdx.x & 31;
+  const int v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (v >= n_nodes) return;
+  const int nchunks = (H * D) >> 2, gs = D >> 2;
+  const float scale = rsqrtf((float)D);
+  const int e0 = __ldg(indptr + v), e1 = __ldg(indptr + v + 1);
+  const float4* ft4 = reinterpret_cast<const float4*>(ft);
+  const bool leader = (lane & (gs - 1)) == 0;
+  for (int c0 = 0; c0 < nchunks; c0 += 32) {
+    const int c = c0 + lane;
+    const bool valid = c < nchunks;
+    const int h = valid ? (c << 2) / D : 0;
+    const float4 q = valid ? __ldg(ft4 + (size_t)v * nchunks + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float m = -INFINITY, l = 0.f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = e0; e < e1; ++e) {
+      const int u = __ldg(esrc + e);
+      const float4 k = valid ? __ldg(ft4 + (size_t)u * nchunks + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float s = seg_sum(dot4(q, k), gs) * scale;
+      const float mn = fmaxf(m, s);
+      const float corr = expf(m - mn), p = expf(s - mn);
+      l = l * corr + p;
+      acc.x = acc.x * corr + p * k.x;
+      acc.y = acc.y * corr + p * k.y;
+      acc.z = acc.z * corr + p * k.z;
+      acc.w = acc.w * corr + p * k.w;
+      m = mn;
+      if (valid && leader && alpha) alpha[(size_t)e * H + h] = s;
+    }
+    const float il = l > 0.f ? 1.f / l : 0.f;
+    if (valid)
+      reinterpret_cast<float4*>(out)[(size_t)v * nchunks + c] = make_float4(acc.x * il, acc.y * il, acc.z * il, acc.w * il);
+    if (valid && leader && alpha)
+      for (int e = e0; e < e1; ++e) alpha[(size_t)e * H + h] = expf(alpha[(size_t)e * H + h] - m) * il;
+  }
+}
+
+// pass 1: ds[e,h] = alpha_e (dalpha_e - sum_e' alpha_e' dalpha_e') / sqrt(D),  dalpha_e = <dout_v, ft_u>
+__global__ void __launch_bounds__(256) edge_attn_bwd1_kernel(const float* __restrict__ ft, const float* __restrict__ alpha,
+                                                             const float* __restrict__ dout, const int* __restrict__ indptr,
+                                                             const int* __restrict__ esrc, float* __restrict__ ds,
+                                                             int n_nodes, int H, int D) {
+  const int lane = threadIdx.x & 31;
+  const int v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (v >= n_nodes) return;
+  const int nchunks = (H * D) >> 2, gs = D >> 2;
+  const float scale = rsqrtf((float)D);
+  const int e0 = __ldg(indptr + v), e1 = __ldg(indptr + v + 1);
+  const float4* ft4 = reinterpret_cast<const float4*>(ft);
+  const bool leader = (lane & (gs - 1)) == 0;
+  for (int c0 = 0; c0 < nchunks; c0 += 32) {
+    const int c = c0 + lane;
+    const bool valid = c < nchunks;
+    const int h = valid ? (c << 2) / D : 0;
+    const float4 g = valid ? __ldg(reinterpret_cast<const float4*>(dout) + (size_t)v * nchunks + c)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+    float dsum = 0.f;
+    for (int e = e0; e < e1; ++e) {
+      const int u = __ldg(esrc + e);
+      const float4 k = valid ? __ldg(ft4 + (size_t)u * nchunks + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float da = seg_sum(dot4(g, k), gs);
+      const float a = valid ? __ldg(alpha + (size_t)e * H + h) : 0.f;
+      dsum += a * da;
+      if (valid && leader) ds[(size_t)e * H + h] = da;
+    }
+    if (valid && leader)
+      for (int e = e0; e < e1; ++e)
+        ds[(size_t)e * H + h] = __ldg(alpha + (size_t)e * H + h) * (ds[(size_t)e * H + h] - dsum) * scale;
+  }
+}
+
+// pass 2: dft_u = sum over in-edges e = (w -> u), r = reverse(e) = (u -> w):
+//           (ds_e + ds_r) * ft_w + alpha_r * dout_w
+__global__ void __launch_bounds__(256) edge_attn_bwd2_kernel(const float* __restrict__ ft, const float* __restrict__ alpha,
+                                                             const float* __restrict__ dout, const float* __restrict__ ds,
+                                                             const int* __restrict__ indptr, const int* __restrict__ esrc,
+                                                             const int* __restrict__ erev, float* __restrict__ dft,
+                                                             int n_nodes, int H, int D) {
+  const int lane = threadIdx.x & 31;
+  const int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (u >= n_nodes) return;
+  const int nchunks = (H * D) >> 2;
+  const int e0 = __ldg(indptr + u), e1 = __ldg(indptr + u + 1);
+  const float4* ft4 = reinterpret_cast<const float4*>(ft);
+  const float4* do4 = reinterpret_cast<const float4*>(dout);
+  for (int c = lane; c < nchunks; c += 32) {
+    const int h = (c << 2) / D;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = e0; e < e1; ++e) {
+      const int w = __ldg(esrc + e), r = __ldg(erev + e);
+      const float4 fw = __ldg(ft4 + (size_t)w * nchunks + c);
+      const float4 gw = __ldg(do4 + (size_t)w * nchunks + c);
+      const float sc = ds[(size_t)e * H + h] + ds[(size_t)r * H + h];
+      const float ar = __ldg(alpha + (size_t)r * H + h);
+      acc.x += sc * fw.x + ar * gw.x;
+      acc.y += sc * fw.y + ar * gw.y;
+      acc.z += sc * fw.z + ar * gw.z;
+      acc.w += sc * fw.w + ar * gw.w;
+    }
+    reinterpret_cast<float4*>(dft)[(size_t)u * nchunks + c] = acc;
+  }
+}
+
+static int check_shape(const char* who, int n, int H, int D) {
+  GB_REQUIRE(n >= 0 && H > 0 && D > 0, "%s: bad shape", who);
+  GB_REQUIRE(D % 4 == 0 && D <= 128 && ((D / 4) & (D / 4 - 1)) == 0,
+             "%s: head dim must be 4, 8, 16, 32, 64 or 128 (got %d)", who, D);
+  return GB_OK;
+}
+
+}  // namespace gb
+
+using namespace gb;
+
+extern "C" int grappa_b200_edge_attention_fwd(const float* ft, const int32_t* indptr, const int32_t* esrc, float* out,
+                                              float* alpha, int32_t n_nodes, int32_t heads, int32_t dim, void* stream_) {
+  int rc = check_shape("edge_attention_fwd", n_nodes, heads, dim);
+  if (rc) return rc;
+  if (n_nodes == 0) return GB_OK;
+  GB_REQUIRE(ft && indptr && esrc && out, "edge_attention_fwd: NULL pointer");
+  edge_attn_fwd_kernel<<<(n_nodes + 7) / 8, 256, 0, (cudaStream_t)stream_>>>(ft, indptr, esrc, out, alpha, n_nodes, heads, dim);
+  GB_CHECK_LAUNCH();
+  return GB_OK;
+}
+
+extern "C" int grappa_b200_edge_attention_bwd(const float* ft, const float* alpha, const float* dout,
+                                              const int32_t* indptr, const int32_t* esrc, const int32_t* erev, float* ds,
+                                              float* dft, int32_t n_nodes, int32_t heads, int32_t dim, void* stream_) {
+  int rc = check_shape("edge_attention_bwd", n_nodes, heads, dim);
+  if (rc) return rc;
+  if (n_nodes == 0) return GB_OK;
+  GB_REQUIRE(ft && alpha && dout && indptr && esrc && erev && ds && dft, "edge_attention_bwd: NULL pointer");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  edge_attn_bwd1_kernel<<<(n_nodes + 7) / 8, 256, 0, stream>>>(ft, alpha, dout, indptr, esrc, ds, n_nodes, heads, dim);
+  GB_CHECK_LAUNCH();
+  edge_attn_bwd2_kernel<<<(n_nodes + 7) / 8, 256, 0, stream>>>(ft, alpha, dout, ds, indptr, esrc, erev, dft, n_nodes, heads, dim);
+  GB_CHECK_LAUNCH();
+  return GB_OK;
+}

@@ -1,0 +1,398 @@
+// Small fused kernels around the GEMMs: input featurisation, writer output maps (+ permutation sum),
+// dropout, axpby, squared-norm, Adam with global-norm clipping, molecule-wise loss.
+#include "common.cuh"
+
+namespace gb {
+
+// ------------------------------------------------------------------------------------------------
+// featurisation: concat + sinusoidal charge encoding (reference models/graph_attention.py:157-164,428-444)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) featurize_kernel(gb_featurize_args a, float* __restrict__ out, int n, int ld,
+                                                        int width_total) {
+  const long long total = (long long)n * ld;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int row = (int)(i / ld);
+    int c = (int)(i - (long long)row * ld);
+    float v = 0.f;
+    if (c < width_total) {
+      for (int f = 0; f < a.n_feats; ++f) {
+        if (c < a.width[f]) { v = __ldg(a.feats[f] + (size_t)row * a.width[f] + c); break; }
+        c -= a.width[f];
+      }
+    } else if (a.charge && c < width_total + a.enc_dim) {
+      const int j = c - width_total;
+      float q = fminf(fmaxf(__ldg(a.charge + row), -2.f), 2.f);
+      const float s = (q + 2.f) / 4.f;
+      const float freq = expf((float)(j >> 1) * -logf(10000.f) / (float)(a.enc_dim >> 1));
+      v = (j & 1) ? cosf(s * freq) : sinf(s * freq);
+    }
+    out[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// writer output maps
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float to_positive(float x, float mos, float sd, float mn) {
+  return sd * (elu1(mos + x - 1.f) + 1.f) + mn;
+}
+__device__ __forceinline__ float to_positive_grad(float x, float mos, float sd) {
+  const float z = mos + x - 1.f;
+  return sd * (z > 0.f ? 1.f : expf(z));
+}
+
+__global__ void __launch_bounds__(256) head_output_fwd_kernel(gb_head_out_args a, const float* __restrict__ scores,
+                                                              float* __restrict__ k, float* __restrict__ eq) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a.T) return;
+  float c[12];
+#pragma unroll
+  for (int j = 0; j < 12; ++j) {
+    c[j] = 0.f;
+    if (j < a.n_out)
+      for (int p = 0; p < a.n_perm; ++p) c[j] += __ldg(scores + ((size_t)p * a.T + t) * a.n_out + j);
+  }
+  if (a.kind == 0) {
+    eq[t] = to_positive(c[0], a.eq_mean_over_std, a.eq_std, a.eq_min);
+    k[t] = to_positive(c[1], a.k_mean_over_std, a.k_std, a.k_min);
+  } else if (a.kind == 1) {
+    eq[t] = a.eq_max * sigmoidf_(a.eq_std_over_max * c[0]);
+    k[t] = to_positive(c[1], a.k_mean_over_std, a.k_std, a.k_min);
+  } else {
+#pragma unroll
+    for (int n = 0; n < 6; ++n) {
+      if (n < a.n_per) {
+        float v = a.gated ? c[n] * sigmoidf_(c[n + a.n_per]) * a.tk_std[n] : c[n] * a.tk_std[n] + a.tk_mean[n];
+        if (a.cutoff > 0.f && !(fabsf(v) > a.cutoff)) v = 0.f;
+        k[(size_t)t * a.n_per + n] = v;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) head_output_bwd_kernel(gb_head_out_args a, const float* __restrict__ scores,
+                                                              const float* __restrict__ dk, const float* __restrict__ deq,
+                                                              float* __restrict__ dscores) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a.T) return;
+  float c[12], d[12];
+#pragma unroll
+  for (int j = 0; j < 12; ++j) {
+    c[j] = 0.f;
+    d[j] = 0.f;
+    if (j < a.n_out)
+      for (int p = 0; p < a.n_perm; ++p) c[j] += __ldg(scores + ((size_t)p * a.T + t) * a.n_out + j);
+  }
+  if (a.kind == 0) {
+    if (deq) d[0] = __ldg(deq + t) * to_positive_grad(c[0], a.eq_mean_over_std, a.eq_std);
+    if (dk) d[1] = __ldg(dk + t) * to_positive_grad(c[1], a.k_mean_over_std, a.k_std);
+  } else if (a.kind == 1) {
+    if (deq) {
+      const float s = sigmoidf_(a.eq_std_over_max * c[0]);
+      d[0] = __ldg(deq + t) * a.eq_max * a.eq_std_over_max * s * (1.f - s);
+    }
+    if (dk) d[1] = __ldg(dk + t) * to_positive_grad(c[1], a.k_mean_over_std, a.k_std);
+  } else if (dk) {
+#pragma unroll
+    for (int n = 0; n < 6; ++n) {
+      if (n < a.n_per) {
+        const float g = __ldg(dk + (size_t)t * a.n_per + n);
+        if (a.gated) {
+          const float s = sigmoidf_(c[n + a.n_per]);
+          const float v = c[n] * s * a.tk_std[n];
+          const bool keep = !(a.cutoff > 0.f) || fabsf(v) > a.cutoff;
+          d[n] = keep ? g * s * a.tk_std[n] : 0.f;
+          d[n + a.n_per] = keep ? g * c[n] * s * (1.f - s) * a.tk_std[n] : 0.f;
+        } else {
+          const float v = c[n] * a.tk_std[n] + a.tk_mean[n];
+          const bool keep = !(a.cutoff > 0.f) || fabsf(v) > a.cutoff;
+          d[n] = keep ? g * a.tk_std[n] : 0.f;
+        }
+      }
+    }
+  }
+  for (int p = 0; p < a.n_perm; ++p)
+#pragma unroll
+    for (int j = 0; j < 12; ++j)
+      if (j < a.n_out) dscores[((size_t)p * a.T + t) * a.n_out + j] = d[j];
+}
+
+// ------------------------------------------------------------------------------------------------
+// dropout / axpby / sumsq / adam
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ x, float* __restrict__ y, long long n,
+                                                      uint32_t thresh, float inv_keep, uint64_t seed) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = x[i] * dropout_scale(seed, (uint64_t)i, thresh, inv_keep);
+}
+
+__global__ void __launch_bounds__(256) act_dropout_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ act_out,
+                                                              float* __restrict__ dx, long long n, uint32_t thresh,
+                                                              float inv_keep, uint64_t seed) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = dy[i];
+    if (thresh) v *= dropout_scale(seed, (uint64_t)i, thresh, inv_keep);
+    if (act_out) v *= elu1_grad_from_out(act_out[i]);
+    dx[i] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) axpby_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float a,
+                                                    float b) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = b == 0.f ? a * x[i] : a * x[i] + b * y[i];
+}
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, long long n, float* out) {
+  __shared__ float sh[8];
+  float s = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    s += x[i] * x[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += sh[i];
+    atomicAdd(out, t);
+  }
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
+                                                   float bc1, float bc2_sqrt, const float* __restrict__ gnorm_sq, float clip,
+                                                   float grad_scale) {
+  float coef = grad_scale;
+  if (gnorm_sq && clip > 0.f) {
+    // the norm was accumulated on UNSCALED gradients: total norm of the scaled gradient = scale * sqrt(sumsq)
+    const float total = grad_scale * sqrtf(__ldg(gnorm_sq));
+    coef *= fminf(1.f, clip / (total + 1e-6f));
+  }
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * coef;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= (lr / bc1) * mi / (sqrtf(vi) / bc2_sqrt + eps);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// molecule-wise loss: one CTA per molecule
+// ------------------------------------------------------------------------------------------------
+__device__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];
+  return t;
+}
+
+__global__ void __launch_bounds__(256) molwise_loss_kernel(gb_loss_args a) {
+  __shared__ float sh[8];
+  const int b = blockIdx.x, tid = threadIdx.x, C = a.C;
+  const float invB = 1.f / a.B;
+  float term = 0.f;
+  // energies
+  if (a.w_energy != 0.f && a.energy) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = tid; c < C; c += blockDim.x) {
+      s1 += a.energy[(size_t)b * C + c];
+      s2 += a.energy_ref[(size_t)b * C + c];
+    }
+    const float me = block_sum(s1, sh) / C, mr = block_sum(s2, sh) / C;
+    float q = 0.f;
+    for (int c = tid; c < C; c += blockDim.x) {
+      const float d = (a.energy[(size_t)b * C + c] - me) - (a.energy_ref[(size_t)b * C + c] - mr);
+      q += d * d;
+      if (a.g_energy) a.g_energy[(size_t)b * C + c] = a.w_energy * invB * 2.f * d / C;
+    }
+    term += a.w_energy * block_sum(q, sh) / C;
+  } else if (a.g_energy) {
+    for (int c = tid; c < C; c += blockDim.x) a.g_energy[(size_t)b * C + c] = 0.f;
+  }
+  // gradients
+  const int a0 = a.atom_off[b], a1 = a.atom_off[b + 1];
+  const long long n0 = (long long)a0 * C * 3, n1 = (long long)a1 * C * 3;
+  if (a.w_grad != 0.f && a.grad) {
+    float q = 0.f;
+    const float sc = a.w_grad * invB * 2.f / (float)(n1 - n0);
+    for (long long i = n0 + tid; i < n1; i += blockDim.x) {
+      const float d = a.grad[i] - a.grad_ref[i];
+      q += d * d;
+      if (a.g_grad) a.g_grad[i] = sc * d;
+    }
+    term += a.w_grad * block_sum(q, sh) / (float)(n1 - n0);
+  } else if (a.g_grad) {
+    for (long long i = n0 + tid; i < n1; i += blockDim.x) a.g_grad[i] = 0.f;
+  }
+  // torsion L2 regularisers
+  for (int which = 0; which < 2; ++which) {
+    const float* k = which ? a.k_improper : a.k_proper;
+    float* gk = which ? a.g_k_improper : a.g_k_proper;
+    const int32_t* off = which ? a.improper_off : a.proper_off;
+    const int nper = which ? a.n_per_i : a.n_per_p;
+    const float w = which ? a.w_improper : a.w_proper;
+    if (!k || !off) continue;
+    const long long i0 = (long long)off[b] * nper, i1 = (long long)off[b + 1] * nper;
+    if (i1 <= i0) continue;
+    float q = 0.f;
+    const float sc = w * invB * 2.f / (float)(i1 - i0);
+    for (long long i = i0 + tid; i < i1; i += blockDim.x) {
+      const float v = k[i];
+      q += v * v;
+      if (gk) gk[i] = sc * v;
+    }
+    term += w * block_sum(q, sh) / (float)(i1 - i0);
+  }
+  if (tid == 0) a.mol_loss[b] = term * invB;
+}
+
+__global__ void __launch_bounds__(256) loss_final_kernel(const float* __restrict__ mol_loss, int B, float* loss) {
+  __shared__ float sh[8];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) s += mol_loss[i];
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) loss[0] = s;
+}
+
+static int grid_for(long long n) {
+  long long b = (n + 255) / 256;
+  long long cap = (long long)sm_count() * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace gb
+
+using namespace gb;
+
+extern "C" int grappa_b200_featurize(const gb_featurize_args* a, float* out, int32_t n, int32_t ld, void* stream_) {
+  GB_REQUIRE(a && out, "featurize: NULL pointer");
+  GB_REQUIRE(a->n_feats >= 0 && a->n_feats <= 8, "featurize: at most 8 feature tensors");
+  int w = 0;
+  for (int f = 0; f < a->n_feats; ++f) {
+    GB_REQUIRE(a->feats[f] != nullptr && a->width[f] > 0, "featurize: feature %d is NULL / empty", f);
+    w += a->width[f];
+  }
+  const int enc = a->charge ? a->enc_dim : 0;
+  GB_REQUIRE(enc % 2 == 0, "featurize: encoding dimension must be even");
+  GB_REQUIRE(ld >= w + enc, "featurize: ld %d < %d features", ld, w + enc);
+  if (n == 0) return GB_OK;
+  featurize_kernel<<<grid_for((long long)n * ld), 256, 0, (cudaStream_t)stream_>>>(*a, out, n, ld, w);
+  GB_CHECK_LAUNCH();
+  return GB_OK;
+}
+
+static int check_head(const gb_head_out_args* a) {
+  GB_REQUIRE(a != nullptr, "head_output: args is NULL");
+  GB_REQUIRE(a->kind >= 0 && a->kind <= 2, "head_output: kind must be 0, 1 or 2");
+  GB_REQUIRE(a->n_perm >= 1 && a->n_perm <= 6 && a->n_out >= 1 && a->n_out <= 12, "head_output: bad n_perm / n_out");
+  if (a->kind == 2) {
+    GB_REQUIRE(a->n_per >= 1 && a->n_per <= 6, "head_output: n_periodicity must be 1..6");
+    GB_REQUIRE(a->n_out == (a->gated ? 2 : 1) * a->n_per, "head_output: n_out does not match n_periodicity / gating");
+  } else {
+    GB_REQUIRE(a->n_out >= 2, "head_output: bonds / angles need >= 2 outputs");
+  }
+  return GB_OK;
+}
+
+extern "C" int grappa_b200_head_output_fwd(const gb_head_out_args* a, const float* scores, float* k, float* eq,
+                                           void* stream_) {
+  int rc = check_head(a);
+  if (rc) return rc;
+  if (a->T == 0) return GB_OK;
+  GB_REQUIRE(scores && k && (a->kind == 2 || eq), "head_output_fwd: NULL pointer");
+  head_output_fwd_kernel<<<(a->T + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(*a, scores, k, eq);
+  GB_CHECK_LAUNCH();
+  return GB_OK;
+}
+
+extern "C" int grappa_b200_head_output_bwd(const gb_head_out_args* a, const float* scores, const float* dk,
+                                           const float* deq, float* dscores, void* stream_) {
+  int rc = check_head(a);
+  if (rc) return rc;
+  if (a->T == 0) return GB_OK;
+  GB_REQUIRE(scores && dscores, "head_output_bwd: NULL pointer");
+  head_output_bwd_kernel<<<(a->T + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(*a, scores, dk, deq, dscores);
+  GB_CHECK_LAUNCH();
+  return GB_OK;
+}
+
+extern "C" int grappa_b200_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, void* stream_) {
+  GB_REQUIRE(p >= 0.f && p < 1.f, "dropout: p must be in [0,1)");
+  if (n == 0) return GB_OK;
+  GB_REQUIRE(x && y, "dropout: NULL pointer");
+  double t = (double)p * 4294967296.0;
+  uint32_t thresh = t >= 4294967295.0 ? 0xffffffffu : (uint32_t)t;
+  if (p > 0.f && thresh == 0) thresh = 1;
+  if (p == 0.f) thresh = 0;
+  dropout_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream_>>>(x, y, n, thresh, 1.f / (1.f - p), seed);
+  GB_CHECK_LAUNCH();
+  return GB_OK;
+}
+
+extern "C" int grappa_b200_act_dropout_bwd(const float* dy, const float* act_out, float* dx, int64_t n, float p,
+                                           uint64_t seed, void* stream_) {
+  GB_REQUIRE(p >= 0.f && p < 1.f, "act_dropout_bwd: p must be in [0,1)");
+  if (n == 0) return GB_OK;
+  GB_REQUIRE(dy && dx, "act_dropout_bwd: NULL pointer");
+  uint32_t thresh = 0;
+  if (p > 0.f) {
+    double t = (double)p * 4294967296.0;
+    thresh = t >= 4294967295.0 ? 0xffffffffu : (uint32_t)t;
+    if (thresh == 0) thresh = 1;
+  }
+  act_dropout_bwd_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream_>>>(dy, act_out, dx, n, thresh, 1.f / (1.f - p), seed);
+  GB_CHECK_LAUNCH();
+  return GB_OK;
+}
+
+extern "C" int grappa_b200_axpby(const float* x, float* y, int64_t n, float a, float b, void* stream_) {
+  if (n == 0) return GB_OK;
+  GB_REQUIRE(x && y, "axpby: NULL pointer");
+  axpby_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream_>>>(x, y, n, a, b);
+  GB_CHECK_LAUNCH();
+  return GB_OK;
+}
+
+extern "C" int grappa_b200_sumsq(const float* x, int64_t n, float* out, void* stream_) {
+  if (n == 0) return GB_OK;
+  GB_REQUIRE(x && out, "sumsq: NULL pointer");
+  sumsq_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream_>>>(x, n, out);
+  GB_CHECK_LAUNCH();
+  return GB_OK;
+}
+
+extern "C" int grappa_b200_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                                     float beta2, float eps, int32_t step, const float* gnorm_sq, float clip,
+                                     float grad_scale, void* stream_) {
+  if (n == 0) return GB_OK;
+  GB_REQUIRE(p && g && m && v, "adam_step: NULL pointer");
+  GB_REQUIRE(step >= 1, "adam_step: step counts from 1");
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
+  adam_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream_>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2s, gnorm_sq, clip,
+                                                             grad_scale);
+  GB_CHECK_LAUNCH();
+  return GB_OK;
+}
+
+extern "C" int grappa_b200_molwise_loss(const gb_loss_args* a, void* stream_) {
+  GB_REQUIRE(a != nullptr, "molwise_loss: args is NULL");
+  GB_REQUIRE(a->B > 0 && a->C > 0, "molwise_loss: empty batch");
+  GB_REQUIRE(a->atom_off && a->loss && a->mol_loss, "molwise_loss: NULL pointer");
+  GB_REQUIRE(!a->energy || a->energy_ref, "molwise_loss: energy without energy_ref");
+  GB_REQUIRE(!a->grad || a->grad_ref, "molwise_loss: gradient without gradient_ref");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  molwise_loss_kernel<<<a->B, 256, 0, stream>>>(*a);
+  GB_CHECK_LAUNCH();
+  loss_final_kernel<<<1, 256, 0, stream>>>(a->mol_loss, a->B, a->loss);
+  GB_CHECK_LAUNCH();
+  return GB_OK;
+}

@@ -1,0 +1,192 @@
+// fp32 FFMA GEMM (CUDA cores) with the fused epilogue -- the bit-faithful fp32 path used for 1e-5
+// parity against the reference and for shapes the tcgen05 path cannot take (unaligned rows, K = 85).
+// 128x128x8 tiles, 256 threads, 8x8 micro-tiles split 2x2 so shared-memory reads are conflict-free,
+// register-staged double buffering, optional deterministic split-K through a workspace.
+#include "common.cuh"
+#include "gemm_epilogue.cuh"
+
+namespace gb {
+
+constexpr int BM = 128, BN = 128, BK = 8, PAD = 4;
+
+// rows x K operand tile -> smem[k][row].  TR = 0: global is [rows, K] (K contiguous); TR = 1: [K, rows].
+template <int TR>
+struct TileLoader {
+  float v[4];
+  __device__ __forceinline__ void load(const float* __restrict__ g, int ld, int row0, int k0, int rows, int k_end,
+                                       int tid, bool vec) {
+    if (TR == 0) {
+      const int r = row0 + (tid >> 1), k = k0 + (tid & 1) * 4;
+      if (vec && r < rows && k + 3 < k_end) {
+        float4 t = __ldg(reinterpret_cast<const float4*>(g + (size_t)r * ld + k));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = (r < rows && k + i < k_end) ? __ldg(g + (size_t)r * ld + k + i) : 0.f;
+      }
+    } else {
+      const int k = k0 + (tid >> 5), r = row0 + (tid & 31) * 4;
+      if (vec && k < k_end && r + 3 < rows) {
+        float4 t = __ldg(reinterpret_cast<const float4*>(g + (size_t)k * ld + r));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = (k < k_end && r + i < rows) ? __ldg(g + (size_t)k * ld + r + i) : 0.f;
+      }
+    }
+  }
+  __device__ __forceinline__ void store(float (*s)[BM + PAD], int tid) const {
+    if (TR == 0) {
+      const int r = tid >> 1, kq = (tid & 1) * 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s[kq + i][r] = v[i];
+    } else {
+      const int k = tid >> 5, rq = (tid & 31) * 4;
+      *reinterpret_cast<float4*>(&s[k][rq]) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
+};
+
+template <int TA, int TB>
+__global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, const float* __restrict__ B, int M,
+                                                    int N, int K, int lda, int ldb, bool vec_a, bool vec_b,
+                                                    int k_chunk, float* __restrict__ partial, Epilogue ep) {
+  __shared__ __align__(16) float As[2][BK][BM + PAD];
+  __shared__ __align__(16) float Bs[2][BK][BN + PAD];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int k_begin = blockIdx.z * k_chunk;
+  const int k_end = min(K, k_begin + k_chunk);
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  TileLoader<TA> la;
+  TileLoader<TB> lb;
+  la.load(A, lda, m0, k_begin, M, k_end, tid, vec_a);
+  lb.load(B, ldb, n0, k_begin, N, k_end, tid, vec_b);
+  // TileLoader indexes rows relative to row0 through its own arithmetic: shift to tile-local on store
+  la.store(As[0], tid);
+  lb.store(Bs[0], tid);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+    const bool more = k0 + BK < k_end;
+    if (more) {
+      la.load(A, lda, m0, k0 + BK, M, k_end, tid, vec_a);
+      lb.load(B, ldb, n0, k0 + BK, N, k_end, tid, vec_b);
+    }
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[8], b[8];
+      *reinterpret_cast<float4*>(&a[0]) = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      *reinterpret_cast<float4*>(&a[4]) = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      *reinterpret_cast<float4*>(&b[0]) = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      *reinterpret_cast<float4*>(&b[4]) = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (more) {
+      la.store(As[buf ^ 1], tid);
+      lb.store(Bs[buf ^ 1], tid);
+    }
+    __syncthreads();
+    buf ^= 1;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (n >= N) continue;
+      if (partial) partial[((size_t)blockIdx.z * M + m) * N + n] = acc[i][j];
+      else ep.store(acc[i][j], m, n);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N,
+                                                            Epilogue ep) {
+  const size_t total = (size_t)M * N;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += partial[(size_t)z * total + i];
+    ep.store(s, (int)(i / N), (int)(i % N));
+  }
+}
+
+int launch_splitk_reduce(const float* partial, int splits, int M, int N, const Epilogue& ep, cudaStream_t stream) {
+  size_t total = (size_t)M * N;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(partial, splits, M, N, ep);
+  GB_CHECK_LAUNCH();
+  return GB_OK;
+}
+
+int gemm_simt(const gb_gemm_args* a, cudaStream_t stream) {
+  Epilogue ep = make_epilogue(a);
+  const int M = a->M, N = a->N, K = a->K;
+  const int gx = (N + BN - 1) / BN, gy = (M + BM - 1) / BM;
+  // split-K when the output grid cannot fill the machine and K is long (weight gradients)
+  int splits = 1;
+  const int sms = sm_count();
+  if (a->workspace && gx * gy < sms && K >= 1024) {
+    splits = (2 * sms + gx * gy - 1) / (gx * gy);
+    int max_by_k = K / 256;
+    if (splits > max_by_k) splits = max_by_k;
+    long long max_by_ws = a->workspace_bytes / ((long long)M * N * 4);
+    if (splits > max_by_ws) splits = (int)max_by_ws;
+    if (splits < 1) splits = 1;
+  }
+  int k_chunk = ((K + splits - 1) / splits + BK - 1) / BK * BK;
+  if (k_chunk <= 0) k_chunk = BK;
+  splits = (K + k_chunk - 1) / k_chunk;
+  if (splits < 1) splits = 1;
+  const bool a16 = ((uintptr_t)a->A % 16 == 0) && (a->lda % 4 == 0);
+  const bool b16 = ((uintptr_t)a->B % 16 == 0) && (a->ldb % 4 == 0);
+  float* partial = splits > 1 ? a->workspace : nullptr;
+  dim3 grid(gx, gy, splits);
+#define GB_LAUNCH(TA, TB) \
+  sgemm_kernel<TA, TB><<<grid, 256, 0, stream>>>(a->A, a->B, M, N, K, a->lda, a->ldb, a16, b16, k_chunk, partial, ep)
+  if (!a->trans_a && !a->trans_b) GB_LAUNCH(0, 0);
+  else if (!a->trans_a && a->trans_b) GB_LAUNCH(0, 1);
+  else if (a->trans_a && !a->trans_b) GB_LAUNCH(1, 0);
+  else GB_LAUNCH(1, 1);
+#undef GB_LAUNCH
+  GB_CHECK_LAUNCH();
+  if (splits > 1) return launch_splitk_reduce(partial, splits, M, N, ep, stream);
+  return GB_OK;
+}
+
+int gemm_tcgen05(const gb_gemm_args* a, cudaStream_t stream, bool* handled);
+
+}  // namespace gb
+
+extern "C" int grappa_b200_gemm(const gb_gemm_args* a, void* stream_) {
+  GB_REQUIRE(a != nullptr, "gemm: args is NULL");
+  GB_REQUIRE(a->M >= 0 && a->N >= 0 && a->K >= 0, "gemm: negative dimension");
+  if (a->M == 0 || a->N == 0) return GB_OK;
+  GB_REQUIRE(a->A && a->B && a->C, "gemm: NULL operand");
+  GB_REQUIRE(a->lda >= (a->trans_a ? a->M : a->K) && a->ldb >= (a->trans_b ? a->N : a->K) && a->ldc >= a->N,
+             "gemm: leading dimension too small (M=%d N=%d K=%d lda=%d ldb=%d ldc=%d ta=%d tb=%d)", a->M, a->N, a->K,
+             a->lda, a->ldb, a->ldc, a->trans_a, a->trans_b);
+  GB_REQUIRE(a->dropout_p >= 0.f && a->dropout_p < 1.f, "gemm: dropout_p must be in [0,1)");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (a->precision == 1 || a->precision == 2) {
+    bool handled = false;
+    int rc = gb::gemm_tcgen05(a, stream, &handled);
+    if (rc != GB_OK) return rc;
+    if (handled) return GB_OK;
+    GB_REQUIRE(a->precision == 2, "gemm: tcgen05 path cannot take this shape/alignment (M=%d N=%d K=%d lda=%d ldb=%d)",
+               a->M, a->N, a->K, a->lda, a->ldb);
+  }
+  return gb::gemm_simt(a, stream);
+}

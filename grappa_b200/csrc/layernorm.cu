@@ -1,0 +1,210 @@
+// LayerNorm forward / backward (dx) and the deterministic column reductions that give the parameter
+// gradients of LayerNorm (gamma, beta) and of every Linear bias.
+// torch.nn.LayerNorm semantics: biased variance, eps inside the sqrt, affine
+// (reference models/graph_attention.py:258,265; models/network_utils.py:38,100).
+#include "common.cuh"
+
+namespace gb {
+
+// one warp per row; the row lives in registers (VPT float4 per lane), two-pass mean / variance
+template <int VPT>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float* __restrict__ y,
+                                                            float* __restrict__ mean, float* __restrict__ rstd, int rows,
+                                                            int cols, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = cols >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * cols);
+  float4 v[VPT];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = lane + i * 32;
+    v[i] = c < nvec ? __ldg(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+  const float mu = warp_sum(s) / cols;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      float a = v[i].x - mu, b = v[i].y - mu, c2 = v[i].z - mu, d = v[i].w - mu;
+      q += a * a + b * b + c2 * c2 + d * d;
+    }
+  }
+  const float rs = rsqrtf(warp_sum(q) / cols + eps);
+  if (lane == 0) {
+    if (mean) mean[row] = mu;
+    if (rstd) rstd[row] = rs;
+  }
+  float4* yr = reinterpret_cast<float4*>(y + (size_t)row * cols);
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+      float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c);
+      float4 o;
+      o.x = (v[i].x - mu) * rs * g.x + b.x;
+      o.y = (v[i].y - mu) * rs * g.y + b.y;
+      o.z = (v[i].z - mu) * rs * g.z + b.z;
+      o.w = (v[i].w - mu) * rs * g.w + b.w;
+      yr[c] = o;
+    }
+  }
+}
+
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
+template <int VPT>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                            const float* __restrict__ gamma, float* __restrict__ dx,
+                                                            int rows, int cols) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = cols >> 2;
+  const float mu = __ldg(mean + row), rs = __ldg(rstd + row);
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * cols);
+  const float4* dr = reinterpret_cast<const float4*>(dy + (size_t)row * cols);
+  float4 xh[VPT], g[VPT];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      float4 xv = __ldg(xr + c), dv = __ldg(dr + c), gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+      xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+      g[i] = make_float4(dv.x * gm.x, dv.y * gm.y, dv.z * gm.z, dv.w * gm.w);
+      s1 += g[i].x + g[i].y + g[i].z + g[i].w;
+      s2 += g[i].x * xh[i].x + g[i].y * xh[i].y + g[i].z * xh[i].z + g[i].w * xh[i].w;
+    } else {
+      xh[i] = g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  s1 = warp_sum(s1) / cols;
+  s2 = warp_sum(s2) / cols;
+  float4* o = reinterpret_cast<float4*>(dx + (size_t)row * cols);
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      o[c] = make_float4(rs * (g[i].x - s1 - xh[i].x * s2), rs * (g[i].y - s1 - xh[i].y * s2),
+                         rs * (g[i].z - s1 - xh[i].z * s2), rs * (g[i].w - s1 - xh[i].w * s2));
+    }
+  }
+}
+
+// Column reduction stage 1: block = 32 columns x 8 row lanes; grid.y row slices.
+__global__ void __launch_bounds__(256) col_reduce_kernel(const float* __restrict__ dy, int ld, const float* __restrict__ x,
+                                                         const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                         float* __restrict__ part_sum, float* __restrict__ part_xhat,
+                                                         int rows, int cols) {
+  __shared__ float sh[2][8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + cx;
+  float a = 0.f, b = 0.f;
+  if (col < cols) {
+    for (int r = blockIdx.y * 8 + ry; r < rows; r += gridDim.y * 8) {
+      const float d = __ldg(dy + (size_t)r * ld + col);
+      a += d;
+      if (x) b += d * (__ldg(x + (size_t)r * cols + col) - __ldg(mean + r)) * __ldg(rstd + r);
+    }
+  }
+  sh[0][ry][cx] = a;
+  sh[1][ry][cx] = b;
+  __syncthreads();
+  if (ry == 0 && col < cols) {
+    float sa = 0.f, sb = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sa += sh[0][i][cx]; sb += sh[1][i][cx]; }
+    part_sum[(size_t)blockIdx.y * cols + col] = sa;
+    if (x) part_xhat[(size_t)blockIdx.y * cols + col] = sb;
+  }
+}
+
+__global__ void __launch_bounds__(256) col_reduce_final_kernel(const float* __restrict__ part_sum,
+                                                               const float* __restrict__ part_xhat, float* out_sum,
+                                                               float* out_xhat, int slices, int cols, int accumulate) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= cols) return;
+  float a = 0.f, b = 0.f;
+  for (int s = 0; s < slices; ++s) {
+    a += part_sum[(size_t)s * cols + col];
+    if (part_xhat) b += part_xhat[(size_t)s * cols + col];
+  }
+  if (out_sum) out_sum[col] = accumulate ? out_sum[col] + a : a;
+  if (out_xhat && part_xhat) out_xhat[col] = accumulate ? out_xhat[col] + b : b;
+}
+
+static int col_slices(int rows) {
+  int s = (rows + 63) / 64;
+  if (s > 64) s = 64;
+  if (s < 1) s = 1;
+  return s;
+}
+
+}  // namespace gb
+
+using namespace gb;
+
+#define GB_LN_DISPATCH(KERNEL, ...)                                                     \
+  do {                                                                                  \
+    const int nvec = cols / 4;                                                          \
+    const int blocks = (rows + 7) / 8;                                                  \
+    if (nvec <= 32) KERNEL<1><<<blocks, 256, 0, stream>>>(__VA_ARGS__);                 \
+    else if (nvec <= 64) KERNEL<2><<<blocks, 256, 0, stream>>>(__VA_ARGS__);            \
+    else if (nvec <= 128) KERNEL<4><<<blocks, 256, 0, stream>>>(__VA_ARGS__);           \
+    else if (nvec <= 256) KERNEL<8><<<blocks, 256, 0, stream>>>(__VA_ARGS__);           \
+    else if (nvec <= 384) KERNEL<12><<<blocks, 256, 0, stream>>>(__VA_ARGS__);          \
+    else KERNEL<16><<<blocks, 256, 0, stream>>>(__VA_ARGS__);                           \
+  } while (0)
+
+extern "C" int grappa_b200_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean,
+                                         float* rstd, int32_t rows, int32_t cols, float eps, void* stream_) {
+  GB_REQUIRE(rows >= 0 && cols > 0, "layernorm_fwd: bad shape %d x %d", rows, cols);
+  GB_REQUIRE(cols % 4 == 0 && cols <= 2048, "layernorm_fwd: cols must be a multiple of 4 and <= 2048 (got %d)", cols);
+  if (rows == 0) return GB_OK;
+  GB_REQUIRE(x && gamma && beta && y, "layernorm_fwd: NULL pointer");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GB_LN_DISPATCH(layernorm_fwd_kernel, x, gamma, beta, y, mean, rstd, rows, cols, eps);
+  GB_CHECK_LAUNCH();
+  return GB_OK;
+}
+
+extern "C" int grappa_b200_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
+                                         const float* gamma, float* dx, int32_t rows, int32_t cols, void* stream_) {
+  GB_REQUIRE(rows >= 0 && cols > 0, "layernorm_bwd: bad shape %d x %d", rows, cols);
+  GB_REQUIRE(cols % 4 == 0 && cols <= 2048, "layernorm_bwd: cols must be a multiple of 4 and <= 2048 (got %d)", cols);
+  if (rows == 0) return GB_OK;
+  GB_REQUIRE(dy && x && mean && rstd && gamma && dx, "layernorm_bwd: NULL pointer");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GB_LN_DISPATCH(layernorm_bwd_kernel, dy, x, mean, rstd, gamma, dx, rows, cols);
+  GB_CHECK_LAUNCH();
+  return GB_OK;
+}
+
+extern "C" int64_t grappa_b200_col_reduce_workspace(int32_t rows, int32_t cols) {
+  return (int64_t)2 * col_slices(rows) * cols * sizeof(float);
+}
+
+extern "C" int grappa_b200_col_reduce(const float* dy, int32_t ld, const float* x, const float* mean, const float* rstd,
+                                      float* out_sum, float* out_xhat, float* workspace, int32_t rows, int32_t cols,
+                                      int32_t accumulate, void* stream_) {
+  GB_REQUIRE(rows >= 0 && cols > 0 && ld >= cols, "col_reduce: bad shape %d x %d (ld %d)", rows, cols, ld);
+  GB_REQUIRE(workspace != nullptr, "col_reduce: workspace is NULL");
+  GB_REQUIRE(!x || (mean && rstd), "col_reduce: x given without mean/rstd");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int slices = col_slices(rows);
+  float* ps = workspace;
+  float* px = x ? workspace + (size_t)slices * cols : nullptr;
+  dim3 grid((cols + 31) / 32, slices);
+  col_reduce_kernel<<<grid, 256, 0, stream>>>(dy, ld, x, mean, rstd, ps, px, rows, cols);
+  GB_CHECK_LAUNCH();
+  col_reduce_final_kernel<<<(cols + 255) / 256, 256, 0, stream>>>(ps, px, out_sum, out_xhat, slices, cols, accumulate);
+  GB_CHECK_LAUNCH();
+  return GB_OK;
+}

@@ -1,0 +1,284 @@
+"""Tensor-level wrappers over the C ABI: torch owns memory and streams, the kernels do the math.
+
+Every function takes contiguous fp32 CUDA tensors, allocates its outputs with torch (caching
+allocator, graph-capture safe) and enqueues on torch's current stream.  No function here computes
+anything with torch ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib_ops import FeaturizeArgs, GemmArgs, HeadOutArgs, LossArgs, Perms
+
+FP32, TF32, AUTO = 0, 1, 2
+_precision = FP32
+
+
+def set_matmul_precision(mode: str):
+    """'fp32' (FFMA, 1e-5 parity) | 'tf32' (tcgen05 tensor cores where legal, 1e-3 parity)."""
+    global _precision
+    if mode not in ("fp32", "tf32"):
+        raise ValueError("matmul precision must be 'fp32' or 'tf32'")
+    _precision = FP32 if mode == "fp32" else AUTO
+
+
+def get_matmul_precision() -> str:
+    return "fp32" if _precision == FP32 else "tf32"
+
+
+def _p(t: Optional[torch.Tensor]) -> int:
+    return 0 if t is None or t.numel() == 0 else t.data_ptr()
+
+
+def _s() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+_ws_cache = {}
+
+
+def workspace(nbytes: int, device, tag: str = "ws") -> torch.Tensor:
+    """A reusable scratch buffer per (device, stream, tag); grows monotonically."""
+    key = (device, torch.cuda.current_stream().cuda_stream, tag)
+    t = _ws_cache.get(key)
+    if t is None or t.numel() * 4 < nbytes:
+        t = torch.empty(max((nbytes + 3) // 4, 1 << 20), dtype=torch.float32, device=device)
+        _ws_cache[key] = t
+    return t
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a=False, trans_b=False, bias=None, act=0, mul_elu_out=None,
+         dropout_p=0.0, dropout_seed=0, residual=None, out=None, accumulate=False, m=None, n=None, k=None,
+         precision=None, act_out=None) -> torch.Tensor:
+    """C[M,N] = opA(a) opB(b)^T (+ fused epilogue), see gb_gemm_args.  a/b may be column-sliced views
+    (last-dim stride 1); leading dimensions are taken from the row strides."""
+    lib = _lib.lib()
+    _lib.require_cuda(a, b)
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+    M = m if m is not None else (a.shape[1] if trans_a else a.shape[0])
+    K = k if k is not None else (a.shape[0] if trans_a else a.shape[1])
+    N = n if n is not None else (b.shape[1] if trans_b else b.shape[0])
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=torch.float32)
+    g = GemmArgs()
+    g.A, g.B, g.C = a.data_ptr(), b.data_ptr(), out.data_ptr()
+    g.M, g.N, g.K = M, N, K
+    g.lda, g.ldb, g.ldc = a.stride(0), b.stride(0), out.stride(0)
+    g.trans_a, g.trans_b = int(trans_a), int(trans_b)
+    g.bias = _p(bias)
+    g.act = act
+    g.mul_elu_out = _p(mul_elu_out)
+    g.ldm = mul_elu_out.stride(0) if mul_elu_out is not None else 0
+    g.dropout_p = float(dropout_p)
+    g.dropout_seed = int(dropout_seed) & 0xFFFFFFFFFFFFFFFF
+    g.residual = _p(residual)
+    g.ldr = residual.stride(0) if residual is not None else 0
+    g.accumulate = int(accumulate)
+    g.act_out = _p(act_out)
+    g.ldact = act_out.stride(0) if act_out is not None else 0
+    g.precision = _precision if precision is None else precision
+    if trans_a and M * N <= (1 << 22) and K >= 1024:
+        ws = workspace(64 << 20, a.device, "splitk")
+        g.workspace, g.workspace_bytes = ws.data_ptr(), ws.numel() * 4
+    _lib.check(lib.grappa_b200_gemm(C.byref(g), _s()), "gemm")
+    return out
+
+
+def layernorm_fwd(x, gamma, beta, eps=1e-5):
+    lib = _lib.lib()
+    rows, cols = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty(rows, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+    _lib.check(lib.grappa_b200_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(),
+                                             mean.data_ptr(), rstd.data_ptr(), rows, cols, eps, _s()), "layernorm_fwd")
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma):
+    lib = _lib.lib()
+    rows, cols = x.shape
+    dx = torch.empty_like(x)
+    _lib.check(lib.grappa_b200_layernorm_bwd(dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                             gamma.data_ptr(), dx.data_ptr(), rows, cols, _s()), "layernorm_bwd")
+    return dx
+
+
+def col_reduce(dy, out_sum=None, x=None, mean=None, rstd=None, out_xhat=None, accumulate=False, cols=None):
+    """out_sum[c] = sum_r dy[r,c];  out_xhat[c] = sum_r dy[r,c] * xhat[r,c]  (LayerNorm gamma grad)."""
+    lib = _lib.lib()
+    rows = dy.shape[0]
+    cols = cols if cols is not None else dy.shape[1]
+    if out_sum is None:
+        out_sum = torch.empty(cols, device=dy.device, dtype=torch.float32)
+        accumulate = False
+    if x is not None and out_xhat is None:
+        out_xhat = torch.empty(cols, device=dy.device, dtype=torch.float32)
+    if rows == 0:
+        if not accumulate:
+            out_sum.zero_()
+            if out_xhat is not None:
+                out_xhat.zero_()
+        return out_sum, out_xhat
+    nb = lib.grappa_b200_col_reduce_workspace(rows, cols)
+    ws = workspace(nb, dy.device, "colred")
+    _lib.check(lib.grappa_b200_col_reduce(dy.data_ptr(), dy.stride(0), _p(x), _p(mean), _p(rstd), out_sum.data_ptr(),
+                                          _p(out_xhat), ws.data_ptr(), rows, cols, int(accumulate), _s()), "col_reduce")
+    return out_sum, out_xhat
+
+
+def edge_attention_fwd(ft, pack, heads):
+    lib = _lib.lib()
+    n, hd = ft.shape
+    out = torch.empty_like(ft)
+    alpha = torch.empty((pack.n_edges, heads), device=ft.device, dtype=torch.float32)
+    _lib.check(lib.grappa_b200_edge_attention_fwd(ft.data_ptr(), pack.ptr("indptr"), pack.ptr("esrc"), out.data_ptr(),
+                                                  _p(alpha), n, heads, hd // heads, _s()), "edge_attention_fwd")
+    return out, alpha
+
+
+def edge_attention_bwd(ft, alpha, dout, pack, heads):
+    lib = _lib.lib()
+    n, hd = ft.shape
+    ds = torch.empty_like(alpha)
+    dft = torch.empty_like(ft)
+    _lib.check(lib.grappa_b200_edge_attention_bwd(ft.data_ptr(), alpha.data_ptr(), dout.data_ptr(), pack.ptr("indptr"),
+                                                  pack.ptr("esrc"), pack.ptr("erev"), _p(ds), dft.data_ptr(), n, heads,
+                                                  hd // heads, _s()), "edge_attention_bwd")
+    return dft
+
+
+def tuple_attention_fwd(qkv, T, L, heads):
+    lib = _lib.lib()
+    E = qkv.shape[1] // 3
+    out = torch.empty((L * T, E), device=qkv.device, dtype=torch.float32)
+    _lib.check(lib.grappa_b200_tuple_attention_fwd(_p(qkv), _p(out), T, L, heads, E // heads, _s()), "tuple_attention_fwd")
+    return out
+
+
+def tuple_attention_bwd(qkv, dout, T, L, heads):
+    lib = _lib.lib()
+    E = qkv.shape[1] // 3
+    dqkv = torch.empty_like(qkv)
+    _lib.check(lib.grappa_b200_tuple_attention_bwd(_p(qkv), _p(dout), _p(dqkv), T, L, heads, E // heads, _s()),
+               "tuple_attention_bwd")
+    return dqkv
+
+
+def tuple_gather_fwd(p, idx, pe, T, L, F, E):
+    lib = _lib.lib()
+    x = torch.empty((L * T, E), device=p.device, dtype=torch.float32)
+    _lib.check(lib.grappa_b200_tuple_gather_fwd(_p(p), p.stride(0), _p(idx), _p(pe), _p(x), T, L, F, E, _s()),
+               "tuple_gather_fwd")
+    return x
+
+
+def tuple_gather_bwd(dx, inv_ptr, inv_ent, n_atoms, ldp, T, L, F, E, out=None, accumulate=False):
+    lib = _lib.lib()
+    if out is None:
+        out = torch.empty((n_atoms, ldp), device=dx.device, dtype=torch.float32)
+    _lib.check(lib.grappa_b200_tuple_gather_bwd(_p(dx), _p(inv_ptr), _p(inv_ent), out.data_ptr(), out.stride(0), n_atoms, T,
+                                                L, F, E, int(accumulate), _s()), "tuple_gather_bwd")
+    return out
+
+
+def make_perms(perms: Sequence[Sequence[int]]) -> Perms:
+    p = Perms()
+    p.n_perm = len(perms)
+    for i, row in enumerate(perms):
+        for j, v in enumerate(row):
+            p.perm[i][j] = int(v)
+    return p
+
+
+def perm_concat_fwd(x, perms: Perms, T, L, E):
+    lib = _lib.lib()
+    s = torch.empty((perms.n_perm * T, L * E), device=x.device, dtype=torch.float32)
+    _lib.check(lib.grappa_b200_perm_concat_fwd(_p(x), _p(s), C.byref(perms), T, L, E, _s()), "perm_concat_fwd")
+    return s
+
+
+def perm_concat_bwd(ds, perms: Perms, T, L, E):
+    lib = _lib.lib()
+    dx = torch.empty((L * T, E), device=ds.device, dtype=torch.float32)
+    _lib.check(lib.grappa_b200_perm_concat_bwd(_p(ds), _p(dx), C.byref(perms), T, L, E, _s()), "perm_concat_bwd")
+    return dx
+
+
+def featurize(feats: Sequence[torch.Tensor], charge: Optional[torch.Tensor], ld: int, enc_dim: int = 16):
+    lib = _lib.lib()
+    n = feats[0].shape[0]
+    a = FeaturizeArgs()
+    a.n_feats = len(feats)
+    keep = []
+    for i, f in enumerate(feats):
+        f = f.float().contiguous()
+        keep.append(f)
+        a.feats[i] = f.data_ptr()
+        a.width[i] = 1 if f.dim() == 1 else f.shape[1]
+    if charge is not None:
+        charge = charge.float().contiguous()
+    a.charge = _p(charge)
+    a.enc_dim = enc_dim
+    out = torch.empty((n, ld), device=feats[0].device, dtype=torch.float32)
+    _lib.check(lib.grappa_b200_featurize(C.byref(a), out.data_ptr(), n, ld, _s()), "featurize")
+    return out
+
+
+def head_output_fwd(args: HeadOutArgs, scores):
+    lib = _lib.lib()
+    T = args.T
+    dev = scores.device
+    if args.kind == 2:
+        k = torch.empty((T, args.n_per), device=dev, dtype=torch.float32)
+        eq = None
+    else:
+        k = torch.empty(T, device=dev, dtype=torch.float32)
+        eq = torch.empty(T, device=dev, dtype=torch.float32)
+    _lib.check(lib.grappa_b200_head_output_fwd(C.byref(args), _p(scores), _p(k), _p(eq), _s()), "head_output_fwd")
+    return k, eq
+
+
+def head_output_bwd(args: HeadOutArgs, scores, dk, deq):
+    lib = _lib.lib()
+    ds = torch.empty_like(scores)
+    _lib.check(lib.grappa_b200_head_output_bwd(C.byref(args), _p(scores), _p(dk), _p(deq), _p(ds), _s()), "head_output_bwd")
+    return ds
+
+
+def dropout(x, p, seed, out=None):
+    lib = _lib.lib()
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.check(lib.grappa_b200_dropout(_p(x), _p(out), x.numel(), float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, _s()), "dropout")
+    return out
+
+
+def act_dropout_bwd(dy, act_out, p, seed):
+    lib = _lib.lib()
+    dx = torch.empty_like(dy)
+    _lib.check(lib.grappa_b200_act_dropout_bwd(_p(dy), _p(act_out), _p(dx), dy.numel(), float(p),
+                                               int(seed) & 0xFFFFFFFFFFFFFFFF, _s()), "act_dropout_bwd")
+    return dx
+
+
+def axpby(x, y, a=1.0, b=1.0):
+    lib = _lib.lib()
+    _lib.check(lib.grappa_b200_axpby(_p(x), _p(y), x.numel(), float(a), float(b), _s()), "axpby")
+    return y
+
+
+def sumsq(x, out):
+    lib = _lib.lib()
+    _lib.check(lib.grappa_b200_sumsq(_p(x), x.numel(), out.data_ptr(), _s()), "sumsq")
+    return out
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, gnorm_sq=None, clip=0.0, grad_scale=1.0):
+    lib = _lib.lib()
+    _lib.check(lib.grappa_b200_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2,
+                                         eps, step, _p(gnorm_sq), float(clip), float(grad_scale), _s()), "adam_step")

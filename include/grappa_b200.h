@@ -97,6 +97,190 @@ typedef struct {
 int64_t grappa_b200_energy_bwd_workspace(const gb_energy_args* a);
 int grappa_b200_energy_bwd(const gb_energy_bwd_args* a, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Dense linear layer GEMM with fused epilogue.  Replaces every torch.nn.Linear on the path
+ * (reference models/graph_attention.py:98-101,125-127,261,267-272; DGL DotGatConv.fc;
+ * interaction_parameters.py:148-151; network_utils.py:31-32,105; perm_equiv_transformer.py:231-237)
+ * and their autograd backward (dgrad / wgrad).
+ *
+ *   acc[m,n] = sum_k opA(A)[m,k] * opB(B)[n,k]
+ *   v = acc + bias[n]; v = act(v); [act_out[m,n] = v;] v *= elu'(y = mul_elu_out[m,n]);
+ *   v *= dropout_mask(seed, m*N+n)/(1-p);
+ *   v += residual[m,n];  C[m,n] = accumulate ? C[m,n] + v : v
+ *
+ * trans_a = 0: A is [M,K] row-major (lda >= K);  1: A is stored [K,M] row-major (lda >= M)
+ * trans_b = 0: B is [N,K] row-major (nn.Linear weight layout, C = A B^T);  1: B is stored [K,N]
+ * precision: 0 = fp32 FFMA (CUDA cores), 1 = TF32 tcgen05 tensor cores (TMA-staged, TMEM accumulator;
+ *            needs 16-byte aligned rows, otherwise GB_ERR_INVALID), 2 = auto (tcgen05 when legal)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* A;
+  const float* B;
+  float* C;
+  int32_t M, N, K;
+  int32_t lda, ldb, ldc;
+  int32_t trans_a, trans_b;
+  const float* bias;          /* [N] or NULL */
+  int32_t act;                /* 0 none, 1 ELU(alpha=1) */
+  const float* mul_elu_out;   /* [M,N] (ld = ldm) saved ELU OUTPUT y: multiply by (y > 0 ? 1 : y + 1) */
+  int32_t ldm;
+  float dropout_p;            /* 0 = off */
+  uint64_t dropout_seed;
+  const float* residual;      /* [M,N] (ld = ldr) or NULL */
+  int32_t ldr;
+  int32_t accumulate;
+  int32_t precision;
+  float* workspace;           /* optional split-K scratch (deterministic partial sums), or NULL */
+  int64_t workspace_bytes;
+  float* act_out;             /* optional [M,N] (ld = ldact): value after bias+activation, before dropout/residual */
+  int32_t ldact;
+} gb_gemm_args;
+
+int grappa_b200_gemm(const gb_gemm_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * LayerNorm over the last dimension (eps, affine, biased variance = torch.nn.LayerNorm defaults;
+ * reference models/graph_attention.py:258,265, network_utils.py:38,100).
+ * ------------------------------------------------------------------------------------------- */
+int grappa_b200_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean,
+                              float* rstd, int32_t rows, int32_t cols, float eps, void* stream);
+/* dx only; parameter gradients come from grappa_b200_col_reduce below */
+int grappa_b200_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
+                              const float* gamma, float* dx, int32_t rows, int32_t cols, void* stream);
+/* Column reductions over rows (deterministic two-stage):
+ *   out_sum[c]  = sum_r dy[r,c]                                  (bias gradients, LayerNorm beta)
+ *   out_xhat[c] = sum_r dy[r,c] * (x[r,c] - mean[r]) * rstd[r]   (LayerNorm gamma; skipped if x NULL)
+ * workspace: >= grappa_b200_col_reduce_workspace(rows, cols) bytes. accumulate: add to outputs. */
+int64_t grappa_b200_col_reduce_workspace(int32_t rows, int32_t cols);
+int grappa_b200_col_reduce(const float* dy, int32_t ld, const float* x, const float* mean, const float* rstd,
+                           float* out_sum, float* out_xhat, float* workspace, int32_t rows, int32_t cols,
+                           int32_t accumulate, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Graph attention over bonded neighbours (DGL DotGatConv body: u_dot_v / sqrt(d) -> edge softmax over
+ * the in-edges of each destination -> u_mul_e + sum; call site reference models/graph_attention.py:283).
+ * CSR by destination: indptr[n+1], esrc[E]; erev[e] = position of the reverse edge.
+ * ft/out/dout/dft: [n_nodes, heads*dim]; alpha, ds: [E, heads].
+ * ------------------------------------------------------------------------------------------- */
+int grappa_b200_edge_attention_fwd(const float* ft, const int32_t* indptr, const int32_t* esrc, float* out,
+                                   float* alpha, int32_t n_nodes, int32_t heads, int32_t dim, void* stream);
+int grappa_b200_edge_attention_bwd(const float* ft, const float* alpha, const float* dout, const int32_t* indptr,
+                                   const int32_t* esrc, const int32_t* erev, float* ds, float* dft,
+                                   int32_t n_nodes, int32_t heads, int32_t dim, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Self-attention over the L <= 4 atoms of every tuple (torch.nn.MultiheadAttention core, reference
+ * models/network_utils.py:105,122): qkv [L*T, 3E] (row = l*T + t; q | k | v; heads are contiguous
+ * head_dim slices), out [L*T, E].  scores = (q / sqrt(head_dim)) k^T, softmax over keys.
+ * ------------------------------------------------------------------------------------------- */
+int grappa_b200_tuple_attention_fwd(const float* qkv, float* out, int32_t T, int32_t L, int32_t heads,
+                                    int32_t head_dim, void* stream);
+int grappa_b200_tuple_attention_bwd(const float* qkv, const float* dout, float* dqkv, int32_t T, int32_t L,
+                                    int32_t heads, int32_t head_dim, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Tuple gather (RepProjector: atom_feats[idxs].transpose(0,1), reference
+ * interaction_parameters.py:173-178) fused with the positional-encoding column
+ * (perm_equiv_transformer.py:134-141):  x[l*T+t, 0:F] = p[idx[t,l], 0:F];  x[l*T+t, F:E] = pe[l].
+ * Backward is a deterministic segmented sum over the atom -> (tuple, slot) incidence CSR.
+ * ------------------------------------------------------------------------------------------- */
+int grappa_b200_tuple_gather_fwd(const float* p, int32_t ldp, const int32_t* idx, const float* pe, float* x,
+                                 int32_t T, int32_t L, int32_t F, int32_t E, void* stream);
+int grappa_b200_tuple_gather_bwd(const float* dx, const int32_t* inv_ptr, const int32_t* inv_ent, float* dp,
+                                 int32_t ldp, int32_t n_atoms, int32_t T, int32_t L, int32_t F, int32_t E,
+                                 int32_t accumulate, void* stream);
+
+/* Symmetriser input (reference perm_equiv_transformer.py:239-262): for each permutation p of the L
+ * positions, s[p*T+t, j*E:(j+1)*E] = x[perm[p][j]*T + t, :].  bwd sums the contributions back. */
+typedef struct {
+  int32_t n_perm;
+  int32_t perm[6][4];
+} gb_perms;
+int grappa_b200_perm_concat_fwd(const float* x, float* s, const gb_perms* perms, int32_t T, int32_t L, int32_t E,
+                                void* stream);
+int grappa_b200_perm_concat_bwd(const float* ds, float* dx, const gb_perms* perms, int32_t T, int32_t L, int32_t E,
+                                void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Input featurisation: concat of per-atom feature tensors + 16-d sinusoidal charge encoding
+ * (reference models/graph_attention.py:157-164, 418-444).  feats[i] is [n, width[i]] row-major.
+ * out is [n, ld] with ld >= sum(width) + 16; padding columns are zeroed.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t n_feats;
+  const float* feats[8];
+  int32_t width[8];
+  const float* charge;   /* [n] partial charges for the encoding, or NULL (charge_encoding=False) */
+  int32_t enc_dim;       /* 16 */
+} gb_featurize_args;
+int grappa_b200_featurize(const gb_featurize_args* a, float* out, int32_t n, int32_t ld, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Output maps of the writers, fused with the sum over the two symmetriser permutations
+ * (reference interaction_parameters.py:244-266, 337-362, 519-562; final_layer.py:48-52, 91-97;
+ * network_utils.py:144-145).  scores: [n_perm*T, n_out] (row = p*T + t).
+ *   kind 0 bond    : eq = ToPositive(c0; eq stats), k = ToPositive(c1; k stats)
+ *   kind 1 angle   : eq = max * sigmoid(std_over_max * c0),  k = ToPositive(c1)
+ *   kind 2 torsion : gated: k_n = c_n * sigmoid(c_{n+n_per}) * k_std[n]; else c_n * k_std[n] + k_mean[n];
+ *                    then zeroed where |k| <= cutoff
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t kind, T, n_perm, n_out, n_per, gated;
+  float k_mean_over_std, k_std, k_min;        /* ToPositive for k  (kinds 0, 1) */
+  float eq_mean_over_std, eq_std, eq_min;     /* ToPositive for eq (kind 0)     */
+  float eq_std_over_max, eq_max;              /* ToRange for eq    (kind 1)     */
+  float tk_std[6], tk_mean[6];                /* torsion statistics (kind 2)    */
+  float cutoff;
+} gb_head_out_args;
+int grappa_b200_head_output_fwd(const gb_head_out_args* a, const float* scores, float* k, float* eq, void* stream);
+/* dscores [n_perm*T, n_out] from dk, deq (either may be NULL = zero) */
+int grappa_b200_head_output_bwd(const gb_head_out_args* a, const float* scores, const float* dk, const float* deq,
+                                float* dscores, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Small fused elementwise kernels.
+ * ------------------------------------------------------------------------------------------- */
+/* y[i] = x[i] * keep(seed, i) / (1 - p)   (same call regenerates the mask in the backward pass) */
+int grappa_b200_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, void* stream);
+/* dx[i] = dy[i] * keep(seed, i)/(1-p) * elu'(act_out[i])   (act_out NULL: no activation; p = 0: no mask) */
+int grappa_b200_act_dropout_bwd(const float* dy, const float* act_out, float* dx, int64_t n, float p, uint64_t seed,
+                                void* stream);
+/* y = a*x + b*y */
+int grappa_b200_axpby(const float* x, float* y, int64_t n, float a, float b, void* stream);
+/* out[0] += sum x^2  (out must be zeroed by the caller; deterministic two-stage when ws given) */
+int grappa_b200_sumsq(const float* x, int64_t n, float* out, void* stream);
+/* Adam (torch.optim.Adam semantics, weight_decay = 0) with the gradient pre-scaled by
+ * min(1, clip / (sqrt(*gnorm_sq) + 1e-6)) * grad_scale -- gnorm_sq is a device scalar or NULL. */
+int grappa_b200_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                          float eps, int32_t step, const float* gnorm_sq, float clip, float grad_scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Molecule-wise loss (reference training/loss.py:45-167, terms active in grappa-1.2 training):
+ *   loss = mean_b [ w_e * MSE_c(E_b - mean_c E_b, Eref_b - mean_c Eref_b) + w_g * MSE(grad_b, gradref_b)
+ *                   + w_p * mean(k_proper_b^2) + w_i * mean(k_improper_b^2) ]
+ * and its gradients w.r.t. energy, gradient and the torsion parameters, in one pass.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* energy;      /* [B,C] */
+  const float* energy_ref;  /* [B,C] */
+  const float* grad;        /* [N,C,3] */
+  const float* grad_ref;    /* [N,C,3] */
+  const int32_t* atom_off;  /* [B+1] */
+  const float* k_proper;    /* [T4, n_per_p] or NULL */
+  const float* k_improper;  /* [T4i, n_per_i] or NULL */
+  const int32_t* proper_off;   /* [B+1] */
+  const int32_t* improper_off; /* [B+1] */
+  int32_t B, C, n_per_p, n_per_i;
+  float w_energy, w_grad, w_proper, w_improper;
+  float* loss;              /* [1]  (overwritten) */
+  float* mol_loss;          /* [B] per-molecule terms (workspace / diagnostics) */
+  float* g_energy;          /* [B,C] dloss/denergy   or NULL */
+  float* g_grad;            /* [N,C,3]               or NULL */
+  float* g_k_proper;        /* like k_proper         or NULL */
+  float* g_k_improper;      /* like k_improper       or NULL */
+} gb_loss_args;
+int grappa_b200_molwise_loss(const gb_loss_args* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,301 @@
+"""Per-kernel parity through the C ABI against plain torch restatements of the same op (fp64 where
+cheap).  fp32 kernels: 1e-5 relative (norm-wise); TF32 tensor-core GEMM: 1e-3."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def R(a, b):
+    return rel_err(a.detach().double().cpu().numpy(), b.detach().double().cpu().numpy())
+
+
+@pytest.fixture(autouse=True)
+def _seed():
+    torch.manual_seed(0)
+
+
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (37, 85, 19), (128, 128, 64), (300, 511, 256), (1664, 512, 85), (130, 6, 256)])
+def test_gemm_fp32_all_layouts(ta, tb, M, N, K):
+    from grappa_b200 import ops
+    dev = "cuda"
+    A = torch.randn((K, M) if ta else (M, K), device=dev)
+    B = torch.randn((K, N) if tb else (N, K), device=dev)
+    ref = (A.double().T if ta else A.double()) @ (B.double() if tb else B.double().T)
+    out = ops.gemm(A, B, trans_a=ta, trans_b=tb, precision=ops.FP32)
+    assert R(out, ref) < 1e-5
+
+
+def test_gemm_fp32_epilogue_and_strided_views():
+    from grappa_b200 import ops
+    dev = "cuda"
+    M, N, K = 203, 511, 256
+    X = torch.randn(M, K, device=dev)
+    W = torch.randn(N, K, device=dev) / math.sqrt(K)
+    b = torch.randn(N, device=dev)
+    res = torch.randn(M, 512, device=dev)
+    out = torch.zeros(M, 512, device=dev)
+    ops.gemm(X, W, bias=b, act=1, residual=res[:, :N], out=out[:, :N], precision=ops.FP32)
+    ref = F.elu(X.double() @ W.double().T + b.double()) + res[:, :N].double()
+    assert R(out[:, :N], ref) < 1e-5
+    assert out[:, N:].abs().max() == 0
+    # dgrad with ELU-derivative mask and accumulate
+    Y = F.elu(torch.randn(M, K, device=dev))
+    dY = torch.randn(M, N, device=dev)
+    acc = torch.randn(M, K, device=dev)
+    ref = acc.double() + (dY.double() @ W.double()) * torch.where(Y > 0, 1.0, Y.double() + 1.0)
+    got = ops.gemm(dY, W, trans_b=True, mul_elu_out=Y, out=acc.clone(), accumulate=True, precision=ops.FP32)
+    assert R(got, ref) < 1e-5
+    # wgrad (split-K path: long reduction, small output)
+    rows = 9000
+    dYl = torch.randn(rows, 64, device=dev)
+    Xl = torch.randn(rows, 96, device=dev)
+    got = ops.gemm(dYl, Xl, trans_a=True, trans_b=True, precision=ops.FP32)
+    assert R(got, dYl.double().T @ Xl.double()) < 1e-5
+
+
+def test_gemm_dropout_mask_is_reproducible_and_unbiased():
+    from grappa_b200 import ops
+    dev = "cuda"
+    X = torch.randn(512, 64, device=dev)
+    W = torch.randn(256, 64, device=dev)
+    plain = ops.gemm(X, W, precision=ops.FP32)
+    d1 = ops.gemm(X, W, dropout_p=0.3, dropout_seed=77, precision=ops.FP32)
+    d2 = ops.gemm(X, W, dropout_p=0.3, dropout_seed=77, precision=ops.FP32)
+    assert torch.equal(d1, d2)
+    keep = d1 != 0
+    assert abs(keep.float().mean().item() - 0.7) < 0.01
+    assert R(d1[keep], plain[keep] / 0.7) < 1e-6
+    # the standalone dropout kernel regenerates the same mask (used by the backward pass)
+    m = ops.dropout(torch.ones_like(plain), 0.3, 77)
+    assert torch.equal(m != 0, keep)
+
+
+@pytest.mark.parametrize("rows,cols", [(1, 256), (77, 512), (1000, 1024), (333, 1536), (64, 2048), (5, 128), (9, 64)])
+def test_layernorm_fwd_bwd(rows, cols):
+    from grappa_b200 import ops
+    dev = "cuda"
+    x = torch.randn(rows, cols, device=dev) * 2 + 0.3
+    g = torch.randn(cols, device=dev)
+    b = torch.randn(cols, device=dev)
+    y, mean, rstd = ops.layernorm_fwd(x, g, b)
+    xd = x.double().requires_grad_(True)
+    gd = g.double().requires_grad_(True)
+    bd = b.double().requires_grad_(True)
+    ref = F.layer_norm(xd, (cols,), gd, bd, 1e-5)
+    assert R(y, ref) < 1e-5
+    dy = torch.randn(rows, cols, device=dev)
+    ref.backward(dy.double())
+    dx = ops.layernorm_bwd(dy, x, mean, rstd, g)
+    assert R(dx, xd.grad) < 1e-5
+    dbeta, dgamma = ops.col_reduce(dy, x=x, mean=mean, rstd=rstd)
+    assert R(dbeta, bd.grad) < 1e-5
+    assert R(dgamma, gd.grad) < 1e-5
+
+
+def _random_graph(n_mols=5):
+    from grappa_b200 import synthetic
+    from grappa_b200.pack import PackedBatch
+    g = synthetic.espaloma_mix_batch(seed=4, batch_size=n_mols, n_confs=2).to("cuda")
+    return g, PackedBatch(g, device="cuda")
+
+
+@pytest.mark.parametrize("H,D", [(16, 32), (4, 32), (2, 8), (8, 64)])
+def test_edge_attention_fwd_bwd(H, D):
+    import grappa_oracle as orc
+    from grappa_b200 import ops
+    g, pack = _random_graph()
+    n = g.num_nodes("n1")
+    ft = torch.randn(n, H * D, device="cuda")
+    out, alpha = ops.edge_attention_fwd(ft, pack, H)
+    src, dst = g.edges()
+    ftd = ft.double().cpu().view(n, H, D).requires_grad_(True)
+    ref = orc.dot_gat(ftd, src.long().cpu(), dst.long().cpu())
+    assert R(out.cpu(), ref.flatten(1)) < 1e-5
+    # attention weights sum to one over the in-edges of every destination
+    sums = torch.zeros(n, H, device="cuda").index_add(0, torch.repeat_interleave(
+        torch.arange(n, device="cuda"), torch.diff(pack["indptr"]).long()), alpha)
+    assert (sums - 1).abs().max() < 1e-5
+    dout = torch.randn(n, H * D, device="cuda")
+    ref.backward(dout.double().cpu().view(n, H, D))
+    dft = ops.edge_attention_bwd(ft, alpha, dout, pack, H)
+    assert R(dft.cpu(), ftd.grad.flatten(1)) < 1e-5
+
+
+@pytest.mark.parametrize("L,heads,HD,T", [(2, 8, 64, 50), (3, 8, 64, 33), (4, 8, 64, 129), (4, 4, 32, 7), (3, 2, 16, 1)])
+def test_tuple_attention_fwd_bwd(L, heads, HD, T):
+    from grappa_b200 import ops
+    E = heads * HD
+    qkv = torch.randn(L * T, 3 * E, device="cuda")
+    out = ops.tuple_attention_fwd(qkv, T, L, heads)
+    qd = qkv.double().requires_grad_(True)
+    q, k, v = qd.view(L, T, 3 * E).split(E, dim=-1)
+    sh = lambda t: t.reshape(L, T, heads, HD).permute(1, 2, 0, 3)
+    att = torch.softmax(sh(q) / math.sqrt(HD) @ sh(k).transpose(-1, -2), dim=-1)
+    ref = (att @ sh(v)).permute(2, 0, 1, 3).reshape(L * T, E)
+    assert R(out, ref) < 1e-5
+    dout = torch.randn(L * T, E, device="cuda")
+    ref.backward(dout.double())
+    dqkv = ops.tuple_attention_bwd(qkv, dout, T, L, heads)
+    assert R(dqkv, qd.grad) < 1e-5
+
+
+@pytest.mark.parametrize("lvl,F,E", [(0, 512, 512), (1, 511, 512), (2, 511, 512), (3, 127, 128)])
+def test_tuple_gather_and_perm_concat(lvl, F, E):
+    from grappa_b200 import ops
+    g, pack = _random_graph(8)
+    L = (2, 3, 4, 4)[lvl]
+    T = pack.n_tuples[lvl]
+    n = pack.n_atoms
+    p = torch.randn(n, E, device="cuda")
+    pe = torch.tensor([0.0, 1.0, 1.0, 0.0][:L], device="cuda") if F < E else None
+    idx = pack[f"idx{lvl}"]
+    x = ops.tuple_gather_fwd(p, idx, pe, T, L, F, E)
+    ref = p[idx.long()].transpose(0, 1).reshape(L * T, E).clone()
+    if F < E:
+        ref[:, F:] = pe.repeat_interleave(T)[:, None]
+    assert torch.equal(x, ref)
+    dx = torch.randn(L * T, E, device="cuda")
+    dp = ops.tuple_gather_bwd(dx, pack[f"inv_ptr{lvl}"], pack[f"inv_ent{lvl}"], n, E, T, L, F, E)
+    refd = torch.zeros(n, E, device="cuda", dtype=torch.float64)
+    refd.index_add_(0, idx.long().T.reshape(-1), dx.double())
+    refd[:, F:] = 0
+    assert R(dp, refd) < 1e-5
+    perms = [[0, 1, 2, 3][:L], {2: [1, 0], 3: [2, 1, 0], 4: [3, 1, 2, 0] if lvl == 3 else [3, 2, 1, 0]}[L]]
+    P = ops.make_perms(perms)
+    s = ops.perm_concat_fwd(x, P, T, L, E)
+    xr = x.view(L, T, E)
+    refs = torch.stack([torch.cat([xr[j] for j in pm], dim=-1) for pm in perms]).reshape(2 * T, L * E)
+    assert torch.equal(s, refs)
+    ds = torch.randn_like(s)
+    dxx = ops.perm_concat_bwd(ds, P, T, L, E)
+    xg = x.double().requires_grad_(True)
+    xr = xg.view(L, T, E)
+    torch.stack([torch.cat([xr[j] for j in pm], dim=-1) for pm in perms]).reshape(2 * T, L * E).backward(ds.double())
+    assert R(dxx, xg.grad) < 1e-6
+
+
+def test_featurize_matches_oracle():
+    import grappa_oracle as orc
+    from grappa_b200 import ops
+    g, _ = _random_graph(6)
+    names = ["atomic_number", "partial_charge", "ring_encoding", "degree", "charge_model"]
+    feats = [g.nodes["n1"].data[k] for k in names]
+    out = ops.featurize(feats, g.nodes["n1"].data["partial_charge"], 96)
+    ref = orc.input_features(g.cpu(), names)
+    assert ref.shape[1] == 85
+    assert R(out[:, :85].cpu(), ref) < 1e-6
+    assert out[:, 85:].abs().max() == 0
+
+
+def test_head_outputs_fwd_bwd():
+    import grappa_oracle as orc
+    from grappa_b200 import ops
+    from grappa_b200._lib_ops import HeadOutArgs
+    T = 77
+    dev = "cuda"
+    # bonds
+    a = HeadOutArgs(kind=0, T=T, n_perm=2, n_out=2, n_per=0, gated=0, k_mean_over_std=4.7342, k_std=161.2278, k_min=0.0,
+                    eq_mean_over_std=6.3251, eq_std=0.1953, eq_min=0.0)
+    sc = torch.randn(2 * T, 2, device=dev) * 3
+    k, eq = ops.head_output_fwd(a, sc)
+    sd = {"p.to_k.std": torch.tensor(161.2278), "p.to_k.mean_over_std": torch.tensor(4.7342), "p.to_k.min_": torch.tensor(0.0),
+          "p.to_eq.std": torch.tensor(0.1953), "p.to_eq.mean_over_std": torch.tensor(6.3251), "p.to_eq.min_": torch.tensor(0.0)}
+    c = (sc[:T] + sc[T:]).double().cpu().requires_grad_(True)
+    rk = orc.to_positive(sd, "p.to_k", c[:, 1])
+    req = orc.to_positive(sd, "p.to_eq", c[:, 0])
+    assert R(k.cpu(), rk) < 1e-5 and R(eq.cpu(), req) < 1e-5
+    dk, deq = torch.randn(T, device=dev), torch.randn(T, device=dev)
+    (rk * dk.double().cpu()).sum().backward(retain_graph=True)
+    (req * deq.double().cpu()).sum().backward()
+    ds = ops.head_output_bwd(a, sc, dk, deq)
+    assert R(ds[:T].cpu(), c.grad) < 1e-5 and torch.equal(ds[:T], ds[T:])
+    # angles
+    a = HeadOutArgs(kind=1, T=T, n_perm=2, n_out=2, k_mean_over_std=3.9726, k_std=26.5965, k_min=0.0,
+                    eq_std_over_max=0.029189, eq_max=math.pi)
+    k, eq = ops.head_output_fwd(a, sc)
+    cc = (sc[:T] + sc[T:]).double().cpu().requires_grad_(True)
+    req = math.pi * torch.sigmoid(0.029189 * cc[:, 0])
+    assert R(eq.cpu(), req) < 1e-5
+    (req * deq.double().cpu()).sum().backward()
+    ds = ops.head_output_bwd(a, sc, None, deq)
+    assert R(ds[:T, 0].cpu(), cc.grad[:, 0]) < 1e-5 and ds[:, 1].abs().max() == 0
+    # gated torsions with cutoff
+    a = HeadOutArgs(kind=2, T=T, n_perm=2, n_out=6, n_per=3, gated=1, cutoff=1e-4)
+    for i, v in enumerate([0.5977, 1.3465, 0.2466]):
+        a.tk_std[i] = v
+    sc = torch.randn(2 * T, 6, device=dev)
+    sc[5] = 0.0; sc[T + 5] = 0.0           # a tuple that lands below the cutoff
+    k, _ = ops.head_output_fwd(a, sc)
+    c = (sc[:T] + sc[T:]).double().cpu().requires_grad_(True)
+    rk = c[:, :3] * torch.sigmoid(c[:, 3:]) * torch.tensor([0.5977, 1.3465, 0.2466], dtype=torch.float64)
+    rk = torch.where(rk.abs() > 1e-4, rk, torch.zeros_like(rk))
+    assert R(k.cpu(), rk) < 1e-5 and k[5].abs().max() == 0
+    dk = torch.randn(T, 3, device=dev)
+    (rk * dk.double().cpu()).sum().backward()
+    ds = ops.head_output_bwd(a, sc, dk, None)
+    assert R(ds[:T].cpu(), c.grad) < 1e-5
+
+
+def test_adam_and_clip_match_torch():
+    from grappa_b200 import ops
+    dev = "cuda"
+    n = 100_003
+    p = torch.randn(n, device=dev)
+    g = torch.randn(n, device=dev) * 3
+    ref_p = torch.nn.Parameter(p.clone())
+    opt = torch.optim.Adam([ref_p], lr=1e-3)
+    m, v = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    mine = p.clone()
+    for step in range(1, 4):
+        ref_p.grad = g.clone() * step
+        torch.nn.utils.clip_grad_norm_([ref_p], 10.0)
+        opt.step()
+        gi = g * step
+        nsq = torch.zeros(1, device=dev)
+        ops.sumsq(gi, nsq)
+        ops.adam_step(mine, gi, m, v, 1e-3, 0.9, 0.999, 1e-8, step, gnorm_sq=nsq, clip=10.0)
+    assert R(mine, ref_p.data) < 1e-5
+
+
+def test_molwise_loss_matches_oracle():
+    import ctypes as C
+    import grappa_oracle as orc
+    from grappa_b200 import _lib, synthetic
+    from grappa_b200._lib_ops import LossArgs
+    from grappa_b200.pack import PackedBatch
+    g = synthetic.espaloma_mix_batch(seed=8, batch_size=6, n_confs=5)
+    N, Cn, B = g.num_nodes("n1"), 5, 6
+    e = torch.randn(B, Cn) * 5
+    gr = torch.randn(N, Cn, 3) * 4
+    kp = torch.randn(g.num_nodes("n4"), 3)
+    ki = torch.randn(g.num_nodes("n4_improper"), 3)
+    e64, gr64 = e.double().requires_grad_(True), gr.double().requires_grad_(True)
+    kp64, ki64 = kp.double().requires_grad_(True), ki.double().requires_grad_(True)
+    ref = orc.molwise_loss({"energy": e64, "gradient": gr64}, {"n4": {"k": kp64}, "n4_improper": {"k": ki64}}, g)
+    ref.backward()
+    gd = g.to("cuda")
+    pack = PackedBatch(gd, device="cuda")
+    dev = "cuda"
+    t = {k: v.to(dev) for k, v in dict(e=e, gr=gr, kp=kp, ki=ki).items()}
+    outs = {k: torch.empty_like(v) for k, v in t.items()}
+    loss, mol = torch.zeros(1, device=dev), torch.zeros(B, device=dev)
+    a = LossArgs(energy=t["e"].data_ptr(), energy_ref=gd.nodes["g"].data["energy_ref"].data_ptr(), grad=t["gr"].data_ptr(),
+                 grad_ref=gd.nodes["n1"].data["gradient_ref"].data_ptr(), atom_off=pack.ptr("atom_off"),
+                 k_proper=t["kp"].data_ptr(), k_improper=t["ki"].data_ptr() if ki.numel() else 0,
+                 proper_off=pack.ptr("tup_off2"), improper_off=pack.ptr("tup_off3"), B=B, C=Cn, n_per_p=3, n_per_i=3,
+                 w_energy=1.0, w_grad=0.8, w_proper=1e-3, w_improper=2e-3, loss=loss.data_ptr(), mol_loss=mol.data_ptr(),
+                 g_energy=outs["e"].data_ptr(), g_grad=outs["gr"].data_ptr(), g_k_proper=outs["kp"].data_ptr(),
+                 g_k_improper=outs["ki"].data_ptr() if ki.numel() else 0)
+    _lib.check(_lib.lib().grappa_b200_molwise_loss(C.byref(a), torch.cuda.current_stream().cuda_stream), "loss")
+    assert abs(loss.item() - ref.item()) < 1e-5 * abs(ref.item())
+    assert R(outs["e"], e64.grad) < 1e-5 and R(outs["gr"], gr64.grad) < 1e-5 and R(outs["kp"], kp64.grad) < 1e-5
+    if ki.numel():
+        assert R(outs["ki"], ki64.grad) < 1e-5
