@@ -195,7 +195,8 @@ __device__ float block_sum(float v, float* sh) {
 __global__ void __launch_bounds__(256) molwise_loss_kernel(gb_loss_args a) {
   __shared__ float sh[8];
   const int b = blockIdx.x, tid = threadIdx.x, C = a.C;
-  const float invB = 1.f / a.B;
+  const float invB = (a.grad_scale ? __ldg(a.grad_scale) : 1.f) / a.B;
+  const float invB_loss = 1.f / a.B;
   float term = 0.f;
   // energies
   if (a.w_energy != 0.f && a.energy) {
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(256) molwise_loss_kernel(gb_loss_args a) {
     }
     term += w * block_sum(q, sh) / (float)(i1 - i0);
   }
-  if (tid == 0) a.mol_loss[b] = term * invB;
+  if (tid == 0) a.mol_loss[b] = term * invB_loss;
 }
 
 __global__ void __launch_bounds__(256) loss_final_kernel(const float* __restrict__ mol_loss, int B, float* loss) {

@@ -1,5 +1,348 @@
-// placeholder until the tcgen05 kernel lands (next commit): report "not handled"
+// TF32 tensor-core GEMM for sm_100a: TMA-staged operand tiles, tcgen05.mma with the accumulator in
+// TMEM, mbarrier producer/consumer pipeline, fused epilogue straight out of TMEM.
+//
+//   C[M,N] = opA(A)[M,K] * opB(B)[N,K]^T  (+ epilogue of gemm_epilogue.cuh)
+//
+// One CTA computes one BLOCK_M x BLOCK_N output tile (BLOCK_M = 128, BLOCK_N = 128 or 64) for one
+// K-slice (grid.z = split-K slices; partial tiles go to a workspace and a reduce kernel applies the
+// epilogue, which keeps weight-gradient GEMMs -- tiny output, very long K -- on all SMs and
+// deterministic).  Warp roles (192 threads):
+//     warp 0   : TMA producer   (cp.async.bulk.tensor.2d -> 128B-swizzled smem, 4-stage ring)
+//     warp 1   : TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma.kind::tf32)
+//     warps 2-5: epilogue       (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
+// Operands are fp32 in HBM; the tensor maps use the TFLOAT32 data type and the MMA reads them as
+// TF32, so no conversion pass or shadow copy exists.  Both operand majors are supported because the
+// backward pass needs them (dgrad: B is [K,N]; wgrad: A is [K,M] and B is [K,N]):
+//     K-major  (trans = 0): smem tile = rows x 32 floats, one 128-byte swizzle row per tile row
+//     MN-major (trans = 1): smem tile = (rows/32) boxes of [BLOCK_K x 32 floats]
+// Rows / K tails are handled by TMA out-of-bounds zero fill and predicated stores.
+#include <cuda.h>
+
 #include "common.cuh"
+#include "gemm_epilogue.cuh"
+
 namespace gb {
-int gemm_tcgen05(const gb_gemm_args*, cudaStream_t, bool* handled) { *handled = false; return GB_OK; }
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;          // floats per stage along K = one 128-byte swizzle atom
+constexpr int TC_STAGES = 4;
+constexpr int TC_THREADS = 192;
+constexpr uint32_t SPIN_LIMIT = 1u << 28;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0, spins = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!done && ++spins > SPIN_LIMIT) __trap();   // never hang the device: surface a launch failure instead
+  }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t.reg .b32 r;\n\t"
+      "elect.sync r|P, %1;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred)
+      : "r"(0xffffffffu));
+  return pred != 0;
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 64-bit shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 128-byte swizzle, version 1
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;   // LayoutType::SWIZZLE_128B
+  return d;
+}
+
+struct TcParams {
+  int M, N, K;
+  int k_blocks_per_split;   // K blocks (of TC_BK) handled by one grid.z slice
+  float* partial;           // split-K workspace or NULL
+  Epilogue ep;
+};
+
+template <int BN, int TA, int TB>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
+  constexpr int B_BYTES = BN * TC_BK * 4;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + TC_STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + TC_STAGES;
+  uint64_t* acc_bar = empty_bar + TC_STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(acc_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+  const int total_kb = (p.K + TC_BK - 1) / TC_BK;
+  const int kb0 = blockIdx.z * p.k_blocks_per_split;
+  const int kb1 = min(total_kb, kb0 + p.k_blocks_per_split);
+  const int num_kb = kb1 - kb0;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_b) : "memory");
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(acc_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // TMEM: BN fp32 accumulator columns (power of two >= 32)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % TC_STAGES;
+        const uint32_t ph = (i / TC_STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = smem + s * STAGE_BYTES;
+        uint8_t* sb = sa + A_BYTES;
+        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+        const int k = (kb0 + i) * TC_BK;
+        if (TA == 0) {
+          tma_load_2d(&map_a, &full_bar[s], sa, k, m0);                     // box {32 k, 128 rows}
+        } else {
+#pragma unroll
+          for (int j = 0; j < TC_BM / 32; ++j)                              // boxes {32 rows, 32 k}
+            tma_load_2d(&map_a, &full_bar[s], sa + j * (TC_BK * 128), m0 + j * 32, k);
+        }
+        if (TB == 0) {
+          tma_load_2d(&map_b, &full_bar[s], sb, k, n0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 32; ++j)
+            tma_load_2d(&map_b, &full_bar[s], sb + j * (TC_BK * 128), n0 + j * 32, k);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, majors, N >> 3, M >> 4
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)TA << 15) | ((uint32_t)TB << 16) |
+                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    for (int i = 0; i < num_kb; ++i) {
+      const int s = i % TC_STAGES;
+      const uint32_t ph = (i / TC_STAGES) & 1;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < TC_BK / 8; ++kk) {   // UMMA_K = 8 for TF32
+          // K-major : 8 rows x 128 B atoms, SBO = 1024 B between 8-row groups; k step = 32 B inside the atom
+          // MN-major: atom = 8 k-rows x 128 B; LBO = box size between 32-wide MN chunks; k step = 1024 B
+          const uint64_t da = TA == 0 ? make_smem_desc(sa + kk * 32, 16, 1024) : make_smem_desc(sa + kk * 1024, TC_BK * 128, 1024);
+          const uint64_t db = TB == 0 ? make_smem_desc(sb + kk * 32, 16, 1024) : make_smem_desc(sb + kk * 1024, TC_BK * 128, 1024);
+          tc_mma_tf32(tmem_base, da, db, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+        }
+        tc_commit(&empty_bar[s]);                       // frees the smem stage when these MMAs retire
+        if (i == num_kb - 1) tc_commit(acc_bar);        // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                            // TMEM lane quarter this warp may access
+    const int row = m0 + q * 32 + lane;
+    if (num_kb > 0) {
+      mbar_wait(acc_bar, 0);
+      tc_fence_after();
+    }
+    const bool row_ok = row < p.M;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      float v[16];
+      if (num_kb > 0) {
+        tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0.f;
+      }
+      if (row_ok) {
+        if (p.partial) {
+          float* dst = p.partial + ((size_t)blockIdx.z * p.M + row) * p.N + n0 + c0;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (n0 + c0 + i < p.N) dst[i] = v[i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (n0 + c0 + i < p.N) p.ep.store(v[i], row, n0 + c0 + i);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN));
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)sym;
+    cudaGetLastError();
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor [rows, cols] with row pitch ld; box = {32 floats, box_rows}; 128-byte swizzle
+static bool make_map(CUtensorMap* map, const float* base, int rows, int cols, int ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, (void*)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int BN, int TA, int TB>
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, dim3 grid, cudaStream_t stream) {
+  constexpr int smem = TC_STAGES * (TC_BM * TC_BK * 4 + BN * TC_BK * 4) + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    GB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN, TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  gemm_tf32_kernel<BN, TA, TB><<<grid, TC_THREADS, smem, stream>>>(ma, mb, p);
+  GB_CHECK_LAUNCH();
+  return GB_OK;
+}
+
+int launch_splitk_reduce(const float* partial, int splits, int M, int N, const Epilogue& ep, cudaStream_t stream);
+
+int gemm_tcgen05(const gb_gemm_args* a, cudaStream_t stream, bool* handled) {
+  *handled = false;
+  const int M = a->M, N = a->N, K = a->K;
+  // legality: 16-byte aligned bases and row pitches (TMA), enough work to fill a tile
+  if (((uintptr_t)a->A & 15) || ((uintptr_t)a->B & 15) || (a->lda & 3) || (a->ldb & 3)) return GB_OK;
+  if (K < 8 || N < 16 || M < 1) return GB_OK;
+  const int BN = (N <= 64 || ((N + 127) / 128) * ((M + 127) / 128) < sm_count() / 2) ? 64 : 128;
+  CUtensorMap ma, mb;
+  bool ok = a->trans_a ? make_map(&ma, a->A, K, M, a->lda, TC_BK) : make_map(&ma, a->A, M, K, a->lda, TC_BM);
+  ok = ok && (a->trans_b ? make_map(&mb, a->B, K, N, a->ldb, TC_BK) : make_map(&mb, a->B, N, K, a->ldb, BN));
+  if (!ok) return GB_OK;   // descriptor could not be encoded (e.g. no driver): let the FFMA path handle it
+
+  TcParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.ep = make_epilogue(a);
+  const int gx = (N + BN - 1) / BN, gy = (M + TC_BM - 1) / TC_BM;
+  const int total_kb = (K + TC_BK - 1) / TC_BK;
+  int splits = 1;
+  const int sms = sm_count();
+  if (a->workspace && gx * gy * 2 <= sms && total_kb >= 16) {
+    splits = sms / (gx * gy);
+    if (splits > total_kb / 8) splits = total_kb / 8;
+    long long by_ws = a->workspace_bytes / ((long long)M * N * 4);
+    if (splits > by_ws) splits = (int)by_ws;
+    if (splits < 1) splits = 1;
+  }
+  p.k_blocks_per_split = (total_kb + splits - 1) / splits;
+  splits = (total_kb + p.k_blocks_per_split - 1) / p.k_blocks_per_split;
+  p.partial = splits > 1 ? a->workspace : nullptr;
+  dim3 grid(gx, gy, splits);
+  int rc;
+#define GB_TC(BN_, TA_, TB_) rc = launch<BN_, TA_, TB_>(ma, mb, p, grid, stream)
+  if (BN == 128) {
+    if (!a->trans_a && !a->trans_b) GB_TC(128, 0, 0);
+    else if (!a->trans_a && a->trans_b) GB_TC(128, 0, 1);
+    else if (a->trans_a && !a->trans_b) GB_TC(128, 1, 0);
+    else GB_TC(128, 1, 1);
+  } else {
+    if (!a->trans_a && !a->trans_b) GB_TC(64, 0, 0);
+    else if (!a->trans_a && a->trans_b) GB_TC(64, 0, 1);
+    else if (a->trans_a && !a->trans_b) GB_TC(64, 1, 0);
+    else GB_TC(64, 1, 1);
+  }
+#undef GB_TC
+  if (rc) return rc;
+  if (splits > 1) {
+    rc = launch_splitk_reduce(p.partial, splits, M, N, p.ep, stream);
+    if (rc) return rc;
+  }
+  *handled = true;
+  return GB_OK;
+}
+
+}  // namespace gb

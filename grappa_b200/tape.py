@@ -1,0 +1,208 @@
+"""A small reverse-mode tape over the CUDA operators (replaces torch autograd inside the modules).
+
+The reference relies on torch autograd over ~150 ATen/DGL ops per forward; here each fused stage
+(GNN, one writer) records its handful of kernel-level ops on a `Tape` and the stage's
+torch.autograd.Function replays the tape backwards with hand-written backward kernels:
+
+    linear      dgrad / wgrad GEMMs with fused residual-gradient add and ELU'-mask epilogues
+    layernorm   dx kernel + deterministic column reductions for gamma / beta
+    edge / tuple attention, tuple gather, permuted concat, output maps: dedicated backward kernels
+
+Gradient accumulation for values with several consumers is fused into the producing GEMM epilogue
+where possible (`residual=` existing gradient) instead of separate add kernels.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional
+
+import torch
+
+from . import ops
+
+
+class Var:
+    """A value on the tape with its (lazily created) gradient."""
+    __slots__ = ("v", "g", "needs", "elu_fusable", "g_is_pre")
+
+    def __init__(self, v: torch.Tensor, needs: bool = True):
+        self.v = v
+        self.g: Optional[torch.Tensor] = None
+        self.needs = needs
+        self.elu_fusable = False   # v == ELU(pre) exactly and the single consumer is a linear layer
+        self.g_is_pre = False      # g already holds d/d(pre-activation)
+
+
+class Tape:
+    def __init__(self, record: bool, train: bool, seed: int):
+        self.record = record
+        self.train = train
+        self.seed = int(seed)
+        self._n = 0
+        self.fns: List[Callable[[], None]] = []
+        self.pgrads: Dict[int, torch.Tensor] = {}   # id(param tensor) -> grad
+
+    def next_seed(self) -> int:
+        self._n += 1
+        return (self.seed * 0x9E3779B1 + self._n * 0x85EBCA77) & 0xFFFFFFFFFFFFFFFF
+
+    def push(self, fn):
+        if self.record:
+            self.fns.append(fn)
+
+    def backward(self):
+        for fn in reversed(self.fns):
+            fn()
+        self.fns = []
+
+    def add_pgrad(self, p: torch.Tensor, g: torch.Tensor):
+        k = id(p)
+        if k in self.pgrads:
+            ops.axpby(g, self.pgrads[k], 1.0, 1.0)
+        else:
+            self.pgrads[k] = g
+
+
+def add_grad(var: Var, g: torch.Tensor):
+    if not var.needs:
+        return
+    if var.g is None:
+        var.g = g
+    else:
+        out = var.g.clone()
+        ops.axpby(g, out, 1.0, 1.0)
+        var.g = out
+
+
+# --------------------------------------------------------------------------------------------------
+# primitives
+# --------------------------------------------------------------------------------------------------
+def linear(t: Tape, x: Var, W: torch.Tensor, b: Optional[torch.Tensor], *, act: int = 0, dropout_p: float = 0.0,
+           residual: Optional[Var] = None, k: Optional[int] = None, out_ld: Optional[int] = None,
+           fuse_elu_into_consumer: bool = False) -> Var:
+    """y = dropout(act(x[:, :k] W^T + b)) + residual.  `out_ld` > N gives a padded output buffer."""
+    xv = x.v
+    N = W.shape[0]
+    K = k if k is not None else W.shape[1]
+    M = xv.shape[0]
+    p = dropout_p if t.train else 0.0
+    seed = t.next_seed() if p > 0.0 else 0
+    need_act_out = t.record and act != 0 and (p > 0.0 or residual is not None)
+    if out_ld is not None and out_ld != N:
+        buf = torch.zeros((M, out_ld), device=xv.device, dtype=torch.float32)
+        out = buf[:, :N]
+        assert p == 0.0, "dropout on a padded output is not supported"
+    else:
+        buf = torch.empty((M, N), device=xv.device, dtype=torch.float32)
+        out = buf
+    act_out = torch.empty((M, N), device=xv.device, dtype=torch.float32) if need_act_out else None
+    ops.gemm(xv, W, bias=b, act=act, dropout_p=p, dropout_seed=seed, residual=None if residual is None else residual.v,
+             out=out, k=K, m=M, n=N, act_out=act_out)
+    y = Var(buf)
+    if act != 0 and p == 0.0 and residual is None and fuse_elu_into_consumer:
+        y.elu_fusable = True
+
+    def bwd():
+        dy_full = y.g
+        if dy_full is None:
+            return
+        if residual is not None:
+            add_grad(residual, dy_full)
+        # elementwise part on the full (possibly padded, contiguous) buffers; padded columns carry zeros
+        if y.g_is_pre:
+            dpre_full = dy_full
+        elif act != 0 or p > 0.0:
+            saved = act_out if need_act_out else (y.v if act != 0 else None)
+            dpre_full = ops.act_dropout_bwd(dy_full.contiguous(), saved, p, seed)
+        else:
+            dpre_full = dy_full
+        dpre = dpre_full[:, :N] if dpre_full.shape[1] != N else dpre_full
+        # weight / bias gradients
+        dW = ops.gemm(dpre, xv, trans_a=True, trans_b=True, m=N, n=K, k=M)
+        t.add_pgrad(W, dW)
+        if b is not None:
+            db, _ = ops.col_reduce(dpre, cols=N)
+            t.add_pgrad(b, db)
+        if x.needs:
+            fuse = x.elu_fusable and x.g is None
+            if K == xv.shape[1]:
+                dx = ops.gemm(dpre, W, trans_b=True, m=M, n=K, k=N, residual=x.g,
+                              mul_elu_out=xv if fuse else None)
+                x.g = dx
+                x.g_is_pre = fuse
+            else:   # consumer read only the first K columns of a wider buffer
+                dx = torch.zeros_like(xv)
+                ops.gemm(dpre, W, trans_b=True, m=M, n=K, k=N, out=dx[:, :K])
+                add_grad(x, dx)
+
+    t.push(bwd)
+    return y
+
+
+def layernorm(t: Tape, x: Var, gamma: torch.Tensor, beta: torch.Tensor) -> Var:
+    yv, mean, rstd = ops.layernorm_fwd(x.v, gamma, beta)
+    y = Var(yv)
+
+    def bwd():
+        dy = y.g
+        if dy is None:
+            return
+        dbeta, dgamma = ops.col_reduce(dy, x=x.v, mean=mean, rstd=rstd)
+        t.add_pgrad(gamma, dgamma)
+        t.add_pgrad(beta, dbeta)
+        if x.needs:
+            add_grad(x, ops.layernorm_bwd(dy, x.v, mean, rstd, gamma))
+
+    t.push(bwd)
+    return y
+
+
+def edge_attention(t: Tape, ft: Var, pack, heads: int) -> Var:
+    out, alpha = ops.edge_attention_fwd(ft.v, pack, heads)
+    y = Var(out)
+
+    def bwd():
+        if y.g is None:
+            return
+        add_grad(ft, ops.edge_attention_bwd(ft.v, alpha, y.g, pack, heads))
+
+    t.push(bwd)
+    return y
+
+
+def tuple_attention(t: Tape, qkv: Var, T: int, L: int, heads: int) -> Var:
+    y = Var(ops.tuple_attention_fwd(qkv.v, T, L, heads))
+
+    def bwd():
+        if y.g is None:
+            return
+        add_grad(qkv, ops.tuple_attention_bwd(qkv.v, y.g, T, L, heads))
+
+    t.push(bwd)
+    return y
+
+
+def tuple_gather(t: Tape, p: Var, pack, level: int, pe: Optional[torch.Tensor], F: int, E: int) -> Var:
+    L = (2, 3, 4, 4)[level]
+    T = pack.n_tuples[level]
+    y = Var(ops.tuple_gather_fwd(p.v, pack[f"idx{level}"], pe, T, L, F, E))
+
+    def bwd():
+        if y.g is None or not p.needs:
+            return
+        add_grad(p, ops.tuple_gather_bwd(y.g, pack[f"inv_ptr{level}"], pack[f"inv_ent{level}"], pack.n_atoms,
+                                         p.v.shape[1], T, L, F, E))
+
+    t.push(bwd)
+    return y
+
+
+def perm_concat(t: Tape, x: Var, perms, T: int, L: int, E: int) -> Var:
+    y = Var(ops.perm_concat_fwd(x.v, perms, T, L, E))
+
+    def bwd():
+        if y.g is None:
+            return
+        add_grad(x, ops.perm_concat_bwd(y.g, perms, T, L, E))
+
+    t.push(bwd)
+    return y

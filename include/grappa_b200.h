@@ -278,6 +278,7 @@ typedef struct {
   float* g_grad;            /* [N,C,3]               or NULL */
   float* g_k_proper;        /* like k_proper         or NULL */
   float* g_k_improper;      /* like k_improper       or NULL */
+  const float* grad_scale;  /* device scalar multiplied into every g_* output (upstream dL), or NULL = 1 */
 } gb_loss_args;
 int grappa_b200_molwise_loss(const gb_loss_args* a, void* stream);
 

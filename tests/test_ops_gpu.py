@@ -299,3 +299,65 @@ def test_molwise_loss_matches_oracle():
     assert R(outs["e"], e64.grad) < 1e-5 and R(outs["gr"], gr64.grad) < 1e-5 and R(outs["kp"], kp64.grad) < 1e-5
     if ki.numel():
         assert R(outs["ki"], ki64.grad) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------
+# tcgen05 / TMA tensor-core GEMM (TF32 operands, fp32 accumulation in TMEM)
+# ---------------------------------------------------------------------------------------------------
+TC_SHAPES = [(128, 128, 32), (128, 64, 64), (256, 256, 256), (1664, 512, 512), (300, 511, 256), (77, 96, 40),
+             (1000, 2048, 512), (130, 1536, 512), (3264, 512, 2048), (64, 16, 8)]
+
+
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", TC_SHAPES)
+def test_gemm_tcgen05_exact_on_tf32_representable_inputs(ta, tb, M, N, K):
+    """Small-integer operands are exactly representable in TF32 and the fp32 accumulation is exact,
+    so the tensor-core result must equal the fp64 product bit for bit: any descriptor / swizzle /
+    layout mistake shows up as a wrong number, not as a tolerance question."""
+    from grappa_b200 import ops
+    dev = "cuda"
+    ld_a = ((M if ta else K) + 3) // 4 * 4
+    ld_b = ((N if tb else K) + 3) // 4 * 4
+    A = torch.randint(-3, 4, ((K if ta else M), ld_a), device=dev).float()[:, :(M if ta else K)]
+    B = torch.randint(-3, 4, ((K if tb else N), ld_b), device=dev).float()[:, :(N if tb else K)]
+    ref = ((A.double().T if ta else A.double()) @ (B.double() if tb else B.double().T)).float()
+    out = ops.gemm(A, B, trans_a=ta, trans_b=tb, precision=ops.TF32)
+    assert torch.equal(out, ref), f"max abs diff {(out - ref).abs().max().item()}"
+
+
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, True)])
+def test_gemm_tcgen05_tf32_accuracy_and_epilogue(ta, tb):
+    from grappa_b200 import ops
+    dev = "cuda"
+    M, N, K = 1111, 511, 512
+    A = torch.randn((K, 1112) if ta else (M, K), device=dev)[:, :(M if ta else K)]
+    B = torch.randn((K, 512) if tb else (N, K), device=dev)[:, :(N if tb else K)] / math.sqrt(K)
+    bias = torch.randn(N, device=dev)
+    res = torch.randn(M, N, device=dev)
+    ref = F.elu((A.double().T if ta else A.double()) @ (B.double() if tb else B.double().T) + bias.double()) + res.double()
+    out = ops.gemm(A, B, trans_a=ta, trans_b=tb, bias=bias, act=1, residual=res, precision=ops.TF32)
+    assert R(out, ref) < 1e-3
+    same = ops.gemm(A, B, trans_a=ta, trans_b=tb, bias=bias, act=1, residual=res, precision=ops.TF32)
+    assert torch.equal(out, same)       # deterministic
+
+
+def test_gemm_tcgen05_splitk_wgrad():
+    from grappa_b200 import ops
+    dev = "cuda"
+    rows, n_out, k_in = 14848, 512, 512
+    dY = torch.randint(-2, 3, (rows, n_out), device=dev).float()
+    X = torch.randint(-2, 3, (rows, k_in), device=dev).float()
+    ref = (dY.double().T @ X.double()).float()
+    out = ops.gemm(dY, X, trans_a=True, trans_b=True, precision=ops.TF32)     # ops.gemm hands in a split-K workspace
+    assert torch.equal(out, ref)
+
+
+def test_gemm_tcgen05_rejects_unaligned_and_auto_falls_back():
+    from grappa_b200 import GrappaB200Error, ops
+    dev = "cuda"
+    A = torch.randn(64, 85, device=dev)          # row pitch 85 floats: not 16-byte aligned -> TMA illegal
+    B = torch.randn(32, 85, device=dev)
+    with pytest.raises(GrappaB200Error):
+        ops.gemm(A, B, precision=ops.TF32)
+    out = ops.gemm(A, B, precision=ops.AUTO)     # same call, automatic kernel choice: FFMA path
+    assert R(out, A.double() @ B.double().T) < 1e-5
