@@ -62,6 +62,7 @@ def _declare(lib):
     lib.grappa_b200_last_error.restype = C.c_char_p
     lib.grappa_b200_abi_version.restype = C.c_int
     lib.grappa_b200_sm_count.restype = C.c_int
+    lib.grappa_b200_launch_count.restype = C.c_int64
     lib.grappa_b200_tuples_count.argtypes = [C.c_void_p, C.c_int64, i64p, i64p]
     lib.grappa_b200_tuples_build.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.grappa_b200_torsions_classify.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int,
@@ -110,3 +111,8 @@ def require_cuda(*tensors):
             raise GrappaB200Error(
                 "grappa_b200 kernels need CUDA tensors (got a CPU tensor); there is no CPU fallback. "
                 "Move the graph and the module to a B200 device first.")
+
+
+def launch_count() -> int:
+    """Kernels launched by libgrappa_b200.so so far in this process."""
+    return int(lib().grappa_b200_launch_count())

@@ -22,6 +22,7 @@ void set_error(const char* fmt, ...);
 
 #define GB_CHECK_LAUNCH()                                                                   \
   do {                                                                                      \
+    gb::count_launch();                                                                     \
     cudaError_t _e = cudaGetLastError();                                                    \
     if (_e != cudaSuccess) {                                                                \
       gb::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
@@ -37,6 +38,7 @@ void set_error(const char* fmt, ...);
     }                                        \
   } while (0)
 
+void count_launch();  // bumps the process-wide kernel launch counter (grappa_b200_launch_count)
 int sm_count();  // cached multiprocessor count of the current device (148 on B200)
 
 #ifdef __CUDACC__

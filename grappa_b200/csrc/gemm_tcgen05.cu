@@ -14,7 +14,10 @@
 // TF32, so no conversion pass or shadow copy exists.  Both operand majors are supported because the
 // backward pass needs them (dgrad: B is [K,N]; wgrad: A is [K,M] and B is [K,N]):
 //     K-major  (trans = 0): smem tile = rows x 32 floats, one 128-byte swizzle row per tile row
-//     MN-major (trans = 1): smem tile = (rows/32) boxes of [BLOCK_K x 32 floats]
+//                           (TMA SWIZZLE_128B, UMMA layout SWIZZLE_128B)
+//     MN-major (trans = 1): smem tile = (rows/32) boxes of [BLOCK_K x 32 floats]; 32-bit MN-major
+//                           operands only exist in the 32-byte-atom flavour of the 128-byte swizzle
+//                           (TMA SWIZZLE_128B_ATOM_32B, UMMA layout SWIZZLE_128B_BASE32B, atoms of 4 k-rows)
 // Rows / K tails are handled by TMA out-of-bounds zero fill and predicated stores.
 #include <cuda.h>
 
@@ -94,13 +97,14 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
 }
 
 // 64-bit shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 128-byte swizzle, version 1
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;   // LayoutType::SWIZZLE_128B
+  d |= (uint64_t)layout_type << 61;   // LayoutType: 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
   return d;
 }
 
@@ -193,9 +197,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
         for (int kk = 0; kk < TC_BK / 8; ++kk) {   // UMMA_K = 8 for TF32
           // K-major : 8 rows x 128 B atoms, SBO = 1024 B between 8-row groups; k step = 32 B inside the atom
-          // MN-major: atom = 8 k-rows x 128 B; LBO = box size between 32-wide MN chunks; k step = 1024 B
-          const uint64_t da = TA == 0 ? make_smem_desc(sa + kk * 32, 16, 1024) : make_smem_desc(sa + kk * 1024, TC_BK * 128, 1024);
-          const uint64_t db = TB == 0 ? make_smem_desc(sb + kk * 32, 16, 1024) : make_smem_desc(sb + kk * 1024, TC_BK * 128, 1024);
+          // MN-major: atom = 4 k-rows x 128 B (32-byte swizzle base); SBO = 512 B between the two atoms of one
+          //           UMMA_K = 8 step, LBO = box size between 32-wide MN chunks; k step = 1024 B
+          const uint64_t da = TA == 0 ? make_smem_desc(sa + kk * 32, 16, 1024, 2) : make_smem_desc(sa + kk * 1024, TC_BK * 128, 512, 1);
+          const uint64_t db = TB == 0 ? make_smem_desc(sb + kk * 32, 16, 1024, 2) : make_smem_desc(sb + kk * 1024, TC_BK * 128, 512, 1);
           tc_mma_tf32(tmem_base, da, db, idesc, (i > 0 || kk > 0) ? 1u : 0u);
         }
         tc_commit(&empty_bar[s]);                       // frees the smem stage when these MMAs retire
@@ -264,7 +269,7 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2-D fp32 tensor [rows, cols] with row pitch ld; box = {32 floats, box_rows}; 128-byte swizzle
-static bool make_map(CUtensorMap* map, const float* base, int rows, int cols, int ld, int box_rows) {
+static bool make_map(CUtensorMap* map, const float* base, int rows, int cols, int ld, int box_rows, bool mn_major) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -272,7 +277,8 @@ static bool make_map(CUtensorMap* map, const float* base, int rows, int cols, in
   cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, (void*)base, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
@@ -300,8 +306,8 @@ int gemm_tcgen05(const gb_gemm_args* a, cudaStream_t stream, bool* handled) {
   if (K < 8 || N < 16 || M < 1) return GB_OK;
   const int BN = (N <= 64 || ((N + 127) / 128) * ((M + 127) / 128) < sm_count() / 2) ? 64 : 128;
   CUtensorMap ma, mb;
-  bool ok = a->trans_a ? make_map(&ma, a->A, K, M, a->lda, TC_BK) : make_map(&ma, a->A, M, K, a->lda, TC_BM);
-  ok = ok && (a->trans_b ? make_map(&mb, a->B, K, N, a->ldb, TC_BK) : make_map(&mb, a->B, N, K, a->ldb, BN));
+  bool ok = a->trans_a ? make_map(&ma, a->A, K, M, a->lda, TC_BK, true) : make_map(&ma, a->A, M, K, a->lda, TC_BM, false);
+  ok = ok && (a->trans_b ? make_map(&mb, a->B, K, N, a->ldb, TC_BK, true) : make_map(&mb, a->B, N, K, a->ldb, BN, false));
   if (!ok) return GB_OK;   // descriptor could not be encoded (e.g. no driver): let the FFMA path handle it
 
   TcParams p;

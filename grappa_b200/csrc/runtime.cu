@@ -1,7 +1,11 @@
 // Device-property cache and small runtime helpers shared by all kernels.
 #include "common.cuh"
 
+#include <atomic>
 namespace gb {
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launches() { return g_launches.load(std::memory_order_relaxed); }
 int sm_count() {
   static int cached = 0;
   if (cached > 0) return cached;
@@ -11,6 +15,7 @@ int sm_count() {
   cached = n;
   return n;
 }
+long long launches();
 }  // namespace gb
 
 extern "C" int grappa_b200_sm_count(void) {
@@ -24,3 +29,5 @@ extern "C" int grappa_b200_sm_count(void) {
   }
   return n;
 }
+
+extern "C" int64_t grappa_b200_launch_count(void) { return gb::launches(); }

@@ -100,7 +100,8 @@ class MolGraph:
         g._ndata = {nt: {k: v.to(device, non_blocking=non_blocking) for k, v in d.items()}
                     for nt, d in self._ndata.items()}
         g._batch_num_nodes = dict(self._batch_num_nodes)  # counts stay on the host
-        g._pack_cache = None
+        # a host-built pack (index tables, see pack.py) travels with the graph: one extra H2D copy
+        g._pack_cache = self._pack_cache.to(device) if self._pack_cache is not None else None
         return g
 
     def cpu(self):
@@ -113,7 +114,7 @@ class MolGraph:
         g._dst = self._dst.pin_memory()
         g._ndata = {nt: {k: v.pin_memory() for k, v in d.items()} for nt, d in self._ndata.items()}
         g._batch_num_nodes = dict(self._batch_num_nodes)
-        g._pack_cache = None
+        g._pack_cache = self._pack_cache
         return g
 
     def host_bytes(self) -> int:
@@ -122,6 +123,8 @@ class MolGraph:
         for d in self._ndata.values():
             for v in d.values():
                 n += v.numel() * v.element_size()
+        if self._pack_cache is not None:
+            n += self._pack_cache.bytes
         return n
 
 

@@ -53,12 +53,32 @@ def get_default_statistics():
 # ==================================================================================================
 # stage runner: one torch.autograd.Function per fused stage, backward = tape replay
 # ==================================================================================================
+_BACKWARD_HOOK = None
+
+
+def set_backward_hook(fn):
+    """fn(tag) is called during backward when all gradients of a stage (('writer', module)), of one GNN
+    block (('gnn_block', i)) or of the rest of the GNN (('gnn_rest', None)) are final -- used by
+    training.Trainer to start the bucketed gradient all-reduce while backward is still running."""
+    global _BACKWARD_HOOK
+    _BACKWARD_HOOK = fn
+
+
+def _fire(tag):
+    if _BACKWARD_HOOK is not None:
+        _BACKWARD_HOOK(tag)
+
+
 class _StageFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, runner, record, train, seed, n_inputs, *tensors):
         tape = Tape(record, train, seed)
         ins = [Var(t.detach().contiguous().float(), needs=bool(t.requires_grad)) for t in tensors[:n_inputs]]
         params = [t.detach() for t in tensors[n_inputs:]]
+        for raw, det in zip(tensors[n_inputs:], params):
+            sink = getattr(raw, "_gb_sink", None)
+            if sink is not None:
+                tape.sinks[id(det)] = sink
         outs = runner(tape, ins, params)
         ctx.tape, ctx.ins, ctx.params, ctx.outs = tape, ins, params, outs
         ctx.set_materialize_grads(False)
@@ -71,7 +91,7 @@ class _StageFn(torch.autograd.Function):
             o.g = None if g is None else g.contiguous().float()
         tape.backward()
         gin = [v.g if v.needs else None for v in ctx.ins]
-        gp = [tape.pgrads.get(id(p)) for p in ctx.params]
+        gp = [None if id(p) in tape.sinks else tape.pgrads.get(id(p)) for p in ctx.params]
         ctx.tape = ctx.outs = None
         return (None, None, None, None, None, *gin, *gp)
 
@@ -169,10 +189,12 @@ class GrappaGNN(nn.Module):
         def run(t: Tape, ins, params):
             P = lambda p: params[index[id(p)]]
             x = ins[0]
+            t.push(lambda: _fire(("gnn_rest", None)))          # runs last in backward
             h = T_.linear(t, x, P(self.pre_dense[0].weight), P(self.pre_dense[0].bias), act=ELU,
                           dropout_p=self.p_initial, k=self.in_feats)
             if not self.no_convs:
-                for blk in self.att_blocks:
+                for i, blk in enumerate(self.att_blocks):
+                    t.push(lambda i=i: _fire(("gnn_block", i)))  # runs after block i's backward ops
                     h = blk.tape_forward(t, pack, h, P)
             h = T_.linear(t, h, P(self.post_dense[0].weight), P(self.post_dense[0].bias), dropout_p=self.p_final)
             return [h]
@@ -386,6 +408,7 @@ class _TupleWriter(nn.Module):
         def run(t: Tape, ins, params):
             P = lambda p: params[index[id(p)]]
             h = ins[0]
+            t.push(lambda: _fire(("writer", self)))
             proj = T_.linear(t, h, P(self.rep_projector.mlp[0].weight), P(self.rep_projector.mlp[0].bias), act=ELU,
                              out_ld=(E if E % 4 == 0 else (E + 3) // 4 * 4))
             x = T_.tuple_gather(t, proj, pack, self.level_id, pe, F, E)

@@ -30,6 +30,15 @@ def get_matmul_precision() -> str:
     return "fp32" if _precision == FP32 else "tf32"
 
 
+_gemm_profile = None   # list collecting (flops, start_event, stop_event, kernel) when profiling is on
+
+
+def set_gemm_profiler(sink):
+    """bench.py: pass a list to time every GEMM launch with CUDA events on the launching stream; None = off."""
+    global _gemm_profile
+    _gemm_profile = sink
+
+
 def _p(t: Optional[torch.Tensor]) -> int:
     return 0 if t is None or t.numel() == 0 else t.data_ptr()
 
@@ -84,6 +93,13 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a=False, trans_b=False, bias
     if trans_a and M * N <= (1 << 22) and K >= 1024:
         ws = workspace(64 << 20, a.device, "splitk")
         g.workspace, g.workspace_bytes = ws.data_ptr(), ws.numel() * 4
+    if _gemm_profile is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(lib.grappa_b200_gemm(C.byref(g), _s()), "gemm")
+        e1.record()
+        _gemm_profile.append((2.0 * M * N * K, e0, e1, (M, N, K, int(trans_a), int(trans_b))))
+        return out
     _lib.check(lib.grappa_b200_gemm(C.byref(g), _s()), "gemm")
     return out
 

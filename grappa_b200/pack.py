@@ -90,24 +90,40 @@ class PackedBatch:
             raise ValueError("every atom must be part of a bond (zero in-degree atom; reference data/Molecule.py:470)")
         self.max_degree = int(deg.max()) if n_atoms else 0
         self.host = host
-        self._dev: Dict[str, torch.Tensor] = {}
-        names = list(host.keys())
-        # one pinned staging buffer + one H2D copy for all tables
-        sizes = [host[k].size for k in names]
-        total = int(sum(sizes))
+        self._names = list(host.keys())
+        self._sizes = [host[k].size for k in self._names]
+        total = int(sum(self._sizes))
+        # one (pinned) staging buffer so that the whole pack moves with a single H2D copy
         stage = torch.empty(total, dtype=torch.int32)
-        if self.device.type == "cuda":
-            stage = stage.pin_memory()
         off = 0
-        for k, s in zip(names, sizes):
+        for k, s in zip(self._names, self._sizes):
             stage[off:off + s] = torch.from_numpy(host[k].reshape(-1))
             off += s
-        flat = stage.to(self.device, non_blocking=True)
+        if torch.cuda.is_available():
+            try:
+                stage = stage.pin_memory()
+            except RuntimeError:  # pragma: no cover
+                pass
+        self._stage = stage
         self.bytes = total * 4
+        self._dev: Dict[str, torch.Tensor] = {}
+        self._materialise(self.device)
+
+    def _materialise(self, device):
+        self.device = torch.device(device)
+        flat = self._stage.to(self.device, non_blocking=True)
         off = 0
-        for k, s in zip(names, sizes):
-            self._dev[k] = flat[off:off + s].view(host[k].shape)
+        self._dev = {}
+        for k, s in zip(self._names, self._sizes):
+            self._dev[k] = flat[off:off + s].view(self.host[k].shape)
             off += s
+
+    def to(self, device) -> "PackedBatch":
+        """Copy of the pack on another device (one H2D transfer of the staging buffer)."""
+        import copy as _copy
+        p = _copy.copy(self)
+        p._materialise(device)
+        return p
 
     def __getitem__(self, k) -> torch.Tensor:
         return self._dev[k]

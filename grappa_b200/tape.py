@@ -40,6 +40,8 @@ class Tape:
         self._n = 0
         self.fns: List[Callable[[], None]] = []
         self.pgrads: Dict[int, torch.Tensor] = {}   # id(param tensor) -> grad
+        self.sinks: Dict[int, torch.Tensor] = {}    # id(param tensor) -> preallocated gradient buffer (flat-buffer view)
+        self._sink_written = set()
 
     def next_seed(self) -> int:
         self._n += 1
@@ -53,6 +55,15 @@ class Tape:
         for fn in reversed(self.fns):
             fn()
         self.fns = []
+
+    def grad_target(self, p: torch.Tensor):
+        """(buffer, accumulate) if the parameter's gradient is written in place by the kernels, else (None, False)."""
+        s = self.sinks.get(id(p))
+        if s is None:
+            return None, False
+        acc = id(p) in self._sink_written
+        self._sink_written.add(id(p))
+        return s, acc
 
     def add_pgrad(self, p: torch.Tensor, g: torch.Tensor):
         k = id(p)
@@ -117,11 +128,18 @@ def linear(t: Tape, x: Var, W: torch.Tensor, b: Optional[torch.Tensor], *, act: 
             dpre_full = dy_full
         dpre = dpre_full[:, :N] if dpre_full.shape[1] != N else dpre_full
         # weight / bias gradients
-        dW = ops.gemm(dpre, xv, trans_a=True, trans_b=True, m=N, n=K, k=M)
-        t.add_pgrad(W, dW)
+        tgt, acc = t.grad_target(W)
+        if tgt is None:
+            t.add_pgrad(W, ops.gemm(dpre, xv, trans_a=True, trans_b=True, m=N, n=K, k=M))
+        else:
+            ops.gemm(dpre, xv, trans_a=True, trans_b=True, m=N, n=K, k=M, out=tgt, accumulate=acc)
         if b is not None:
-            db, _ = ops.col_reduce(dpre, cols=N)
-            t.add_pgrad(b, db)
+            tgt, acc = t.grad_target(b)
+            if tgt is None:
+                db, _ = ops.col_reduce(dpre, cols=N)
+                t.add_pgrad(b, db)
+            else:
+                ops.col_reduce(dpre, out_sum=tgt, cols=N, accumulate=acc)
         if x.needs:
             fuse = x.elu_fusable and x.g is None
             if K == xv.shape[1]:
@@ -146,9 +164,14 @@ def layernorm(t: Tape, x: Var, gamma: torch.Tensor, beta: torch.Tensor) -> Var:
         dy = y.g
         if dy is None:
             return
-        dbeta, dgamma = ops.col_reduce(dy, x=x.v, mean=mean, rstd=rstd)
-        t.add_pgrad(gamma, dgamma)
-        t.add_pgrad(beta, dbeta)
+        tg, acc = t.grad_target(gamma)
+        tb, _ = t.grad_target(beta)
+        if tg is None or tb is None:
+            dbeta, dgamma = ops.col_reduce(dy, x=x.v, mean=mean, rstd=rstd)
+            t.add_pgrad(gamma, dgamma)
+            t.add_pgrad(beta, dbeta)
+        else:
+            ops.col_reduce(dy, out_sum=tb, x=x.v, mean=mean, rstd=rstd, out_xhat=tg, accumulate=acc)
         if x.needs:
             add_grad(x, ops.layernorm_bwd(dy, x.v, mean, rstd, gamma))
 

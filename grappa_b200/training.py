@@ -1,0 +1,174 @@
+"""Data-parallel training step around the drop-in modules (SURVEY.md sections 3.1, 8e).
+
+The reference trains `Sequential(GrappaModel, Energy)` under PyTorch Lightning on ONE GPU
+(training/trainrun.py:112-166, lightning_model.py:205-230: forward, MolwiseLoss, backward,
+clip_grad_norm 10, Adam).  Lightning is neither available here nor on the hot path, so this module
+provides the equivalent plain loop, B200-first:
+
+  * parameters, gradients and Adam moments live in ONE flat fp32 buffer each (`FlatParams`); the
+    modules' Parameters are views into it, so checkpoints / state_dict are unchanged
+  * the backward kernels write weight gradients straight into the flat gradient buffer (no
+    per-parameter accumulate kernels, no flatten / unflatten copies)
+  * one process per GPU; gradients are averaged with bucketed NCCL all-reduces on a side stream that
+    start as soon as a bucket's backward has finished (4 writer buckets first, then GNN blocks
+    last-to-first), overlapping communication with the remaining backward kernels
+  * global-norm clipping + Adam are two fused kernels over the flat buffers
+
+Each rank draws its own batch (weak scaling); the global loss is the mean of the rank losses.
+"""
+from __future__ import annotations
+
+import os
+from typing import Callable, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import models, ops
+
+
+class FlatParams:
+    """Re-homes all parameters of a module into one flat buffer (+ flat grads, Adam m / v)."""
+
+    def __init__(self, module: torch.nn.Module, device):
+        self.module = module
+        params = [p for p in module.parameters() if p.requires_grad]
+        self.params = params
+        sizes = [p.numel() for p in params]
+        # 16-byte aligned slices so that TMA descriptors stay legal on the views
+        offs, off = [], 0
+        for n in sizes:
+            offs.append(off)
+            off += (n + 3) // 4 * 4
+        self.offsets, self.total = offs, off
+        self.flat = torch.zeros(off, device=device, dtype=torch.float32)
+        self.grad = torch.zeros(off, device=device, dtype=torch.float32)
+        self.m = torch.zeros(off, device=device, dtype=torch.float32)
+        self.v = torch.zeros(off, device=device, dtype=torch.float32)
+        with torch.no_grad():
+            for p, o in zip(params, offs):
+                view = self.flat[o:o + p.numel()].view_as(p)
+                view.copy_(p.data.to(device))
+                p.data = view
+                gv = self.grad[o:o + p.numel()].view_as(p)
+                p.grad = gv
+                p._gb_sink = gv          # backward kernels write here directly (models._StageFn)
+        self._index = {id(p): i for i, p in enumerate(params)}
+
+    def span(self, module: torch.nn.Module) -> Tuple[int, int]:
+        """[start, end) of the flat slice covering all parameters of a sub-module (must be contiguous)."""
+        idx = sorted(self._index[id(p)] for p in module.parameters() if id(p) in self._index)
+        if not idx:
+            return 0, 0
+        assert idx == list(range(idx[0], idx[-1] + 1)), "sub-module parameters are not contiguous in the flat buffer"
+        last = idx[-1]
+        return self.offsets[idx[0]], self.offsets[last] + (self.params[last].numel() + 3) // 4 * 4
+
+
+class Trainer:
+    """forward -> loss -> backward -> (bucketed all-reduce) -> clip + Adam, all on the GPU."""
+
+    def __init__(self, model: models.GrappaModel, energy, loss_fn, lr: float = 1.5e-5, clip: float = 10.0,
+                 betas=(0.9, 0.999), eps: float = 1e-8, device="cuda", distributed: Optional[bool] = None):
+        self.model, self.energy, self.loss_fn = model, energy, loss_fn
+        self.lr, self.clip, self.betas, self.eps = lr, clip, betas, eps
+        self.device = torch.device(device)
+        model.to(self.device)
+        self.fp = FlatParams(model, self.device)
+        self.step_count = 0
+        self.distributed = dist.is_available() and dist.is_initialized() if distributed is None else distributed
+        self.world = dist.get_world_size() if self.distributed else 1
+        self.gnorm_sq = torch.zeros(1, device=self.device, dtype=torch.float32)
+        # buckets in the order their gradients become available during backward
+        w = model.parameter_writer
+        g = model.gnn
+        self.buckets: List[Tuple[str, torch.nn.Module]] = [
+            ("improper", w.improper_writer), ("proper", w.proper_writer), ("angle", w.angle_writer), ("bond", w.bond_writer)]
+        self._gnn_span = self.fp.span(g)
+        self._bucket_spans = {name: self.fp.span(mod) for name, mod in self.buckets}
+        self._block_spans = [self.fp.span(b) for b in g.att_blocks] if not g.no_convs else []
+        self.comm_stream = torch.cuda.Stream(device=self.device) if self.distributed and self.device.type == "cuda" else None
+        self._pending: List = []
+        if self.distributed:
+            models.set_backward_hook(self._on_stage_backward)
+
+    # ---- gradient exchange ---------------------------------------------------------------------
+    def _launch_allreduce(self, start: int, end: int):
+        if end <= start:
+            return
+        buf = self.fp.grad[start:end]
+        if self.comm_stream is not None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                self.comm_stream.wait_event(ev)
+                dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+                done = torch.cuda.Event()
+                done.record(self.comm_stream)
+            self._pending.append(done)
+        else:   # gloo / CPU tests
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+
+    def _on_stage_backward(self, tag):
+        """Called from the backward pass when all gradients of a stage / GNN block are final."""
+        kind, obj = tag
+        if kind == "writer":
+            for name, mod in self.buckets:
+                if mod is obj:
+                    self._launch_allreduce(*self._bucket_spans[name])
+        elif kind == "gnn_block":
+            self._launch_allreduce(*self._block_spans[obj])
+        elif kind == "gnn_rest":
+            # pre_dense / post_dense: everything of the GNN span outside the blocks
+            s, e = self._gnn_span
+            if self._block_spans:
+                b0, b1 = self._block_spans[0][0], self._block_spans[-1][1]
+                self._launch_allreduce(s, b0)
+                self._launch_allreduce(b1, e)
+            else:
+                self._launch_allreduce(s, e)
+
+    def _wait_comm(self):
+        for ev in self._pending:
+            torch.cuda.current_stream().wait_event(ev)
+        self._pending = []
+
+    # ---- one optimisation step -----------------------------------------------------------------
+    def forward_backward(self, g) -> torch.Tensor:
+        g = self.model(g)
+        g = self.energy(g)
+        loss = self.loss_fn(g)
+        loss.backward()
+        return loss.detach()
+
+    def optimizer_step(self):
+        self._wait_comm()
+        self.step_count += 1
+        self.gnorm_sq.zero_()
+        ops.sumsq(self.fp.grad, self.gnorm_sq)
+        ops.adam_step(self.fp.flat, self.fp.grad, self.fp.m, self.fp.v, self.lr, self.betas[0], self.betas[1], self.eps,
+                      self.step_count, gnorm_sq=self.gnorm_sq, clip=self.clip, grad_scale=1.0 / self.world)
+
+    def step(self, g) -> torch.Tensor:
+        loss = self.forward_backward(g)
+        self.optimizer_step()
+        return loss
+
+
+def init_distributed(backend: Optional[str] = None) -> Tuple[int, int, int]:
+    """(rank, local_rank, world) from the torchrun environment; initialises the process group."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, local, world
+
+
+def shard_molecules(n_items: int, rank: int, world: int) -> range:
+    """Inference / energy sweeps: molecule i -> rank i mod world, no communication."""
+    return range(rank, n_items, world)

@@ -31,6 +31,8 @@ const char* grappa_b200_last_error(void);
 int grappa_b200_abi_version(void);
 /* number of SMs of the current device (negative error code without a GPU) */
 int grappa_b200_sm_count(void);
+/* number of CUDA kernels this library has launched in the current process (for bench.py's gpu_launches) */
+int64_t grappa_b200_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Tuple index construction (host code, no GPU needed).

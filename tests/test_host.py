@@ -1,0 +1,190 @@
+"""CPU-side coverage: C ABI surface, bit-exact tuple indices, graph batching, pack tables, module
+state_dict layout, flat parameter buffers.  No kernel is launched here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from util import LEVELS, load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from grappa_b200 import _lib
+    lib = _lib.lib()
+    header = open(os.path.join(ROOT, "include", "grappa_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(grappa_b200_[a-z0-9_]+)\s*\(", header)))
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"libgrappa_b200.so does not export {n}"
+    assert lib.grappa_b200_abi_version() == 1
+    assert isinstance(_lib.launch_count(), int)
+
+
+def test_abi_reports_errors_instead_of_crashing():
+    from grappa_b200 import _lib
+    from grappa_b200._lib_ops import GemmArgs
+    lib = _lib.lib()
+    g = GemmArgs(M=4, N=4, K=4, lda=4, ldb=4, ldc=4)          # NULL operands
+    rc = lib.grappa_b200_gemm(ctypes.byref(g), None)
+    assert rc == -1 and b"NULL" in lib.grappa_b200_last_error()
+    with pytest.raises(_lib.GrappaB200Error):
+        _lib.check(rc, "gemm")
+    bad = np.array([[0, 0]], dtype=np.int64)                  # self-bond
+    na, npr = ctypes.c_int64(), ctypes.c_int64()
+    assert lib.grappa_b200_tuples_count(bad.ctypes.data, 1, ctypes.byref(na), ctypes.byref(npr)) == -1
+    assert b"self-bond" in lib.grappa_b200_last_error()
+
+
+def test_struct_layouts_match_the_header():
+    """sizeof of the ctypes mirrors == what the C compiler lays out (computed from the field lists: all
+    fields are naturally aligned 4/8-byte scalars, so ctypes and C agree; this guards field-count drift)."""
+    from grappa_b200._lib import EnergyArgs, EnergyBwdArgs
+    from grappa_b200._lib_ops import GemmArgs, HeadOutArgs, LossArgs, Perms
+    assert ctypes.sizeof(Perms) == 4 + 6 * 4 * 4
+    assert ctypes.sizeof(GemmArgs) % 8 == 0 and ctypes.sizeof(EnergyArgs) % 8 == 0
+    assert ctypes.sizeof(EnergyBwdArgs) > ctypes.sizeof(EnergyArgs)
+    assert ctypes.sizeof(HeadOutArgs) == 6 * 4 + 8 * 4 + 12 * 4 + 4
+    assert ctypes.sizeof(LossArgs) == 9 * 8 + 4 * 4 + 4 * 4 + 7 * 8
+
+
+@pytest.mark.parametrize("name", ["dipeptide", "peptide4", "tree", "rna", "protein30"])
+def test_tuple_indices_bit_exact_vs_reference_fixture(name):
+    from grappa_b200 import tuples
+    z = load_golden("tuple_indices.npz")
+    out = tuples.build_tuples(0, z[f"{name}.in_bonds"], z[f"{name}.in_improper_candidates"])
+    for k in ("bonds", "angles", "propers", "impropers"):
+        assert out[k].dtype == np.int64 and np.array_equal(out[k], z[f"{name}.{k}"]), k
+
+
+def test_tuple_indices_vs_bruteforce_path_enumeration():
+    import networkx as nx
+    from grappa_b200 import synthetic, tuples
+    rng = np.random.default_rng(0)
+    el, bonds, _ = synthetic.random_tree_topology(rng, 30, 2)
+    out = tuples.get_idx_tuples(bonds)
+    G = nx.Graph([tuple(b) for b in bonds.tolist()])
+    angles = {(a, b, c) if a < c else (c, b, a) for b in G for a in G[b] for c in G[b] if a != c}
+    propers = set()
+    for b, c in G.edges:
+        for a in G[b]:
+            for d in G[c]:
+                if a != c and d != b and a != d:
+                    propers.add((a, b, c, d) if a < d else (d, c, b, a))
+    assert {tuple(r) for r in out["angles"].tolist()} == angles
+    assert {tuple(r) for r in out["propers"].tolist()} == propers
+    assert len(out["angles"]) == len(angles) and len(out["propers"]) == len(propers)
+
+
+def test_synthetic_shapes_match_the_survey_table():
+    from grappa_b200 import synthetic
+    for n_res, want in [(1, (22, 21, 36, 41, 12)), (4, (52, 51, 90, 116, 30))]:
+        g = synthetic.make_molecule(np.random.default_rng(0), "peptide", n_confs=2, n_res=n_res)
+        got = (g.num_nodes("n1"),) + tuple(g.num_nodes(l) for l in LEVELS)
+        assert got == want
+    g = synthetic.protein(seed=0)
+    assert (g.num_nodes("n1"), g.num_nodes("n2"), g.num_nodes("n3"), g.num_nodes("n4"), g.num_nodes("n4_improper")) == \
+        (1502, 1501, 2700, 3741, 900)
+    assert g.nodes["n1"].data["atomic_number"].shape == (1502, 53)
+    gb = synthetic.peptide_batch(seed=0, batch_size=32)
+    assert gb.nodes["n1"].data["xyz"].shape == (32 * 52, 50, 3)
+
+
+def test_batch_unbatch_identity_and_offsets():
+    """reference tests/dgl_utils.py:34-53: batch -> unbatch is the identity on every feature; idxs are shifted."""
+    from grappa_b200 import graph as gbg, synthetic
+    rng = np.random.default_rng(1)
+    mols = [synthetic.make_molecule(rng, k, n_confs=3, **kw) for k, kw in
+            [("peptide", dict(n_res=1)), ("small", dict(n_atoms=12)), ("rna", dict(n_atoms=92))]]
+    b = gbg.batch(mols)
+    assert b.batch_size == 3 and b.num_nodes("g") == 3
+    assert b.nodes["n2"].data["idxs"].max() < b.num_nodes("n1")
+    off = mols[0].num_nodes("n1")
+    assert torch.equal(b.nodes["n3"].data["idxs"][mols[0].num_nodes("n3"):mols[0].num_nodes("n3") + mols[1].num_nodes("n3")],
+                       mols[1].nodes["n3"].data["idxs"] + off)
+    back = gbg.unbatch(b)
+    for a, c in zip(mols, back):
+        for nt in a.ntypes:
+            assert a.num_nodes(nt) == c.num_nodes(nt)
+            for k, v in a.nodes[nt].data.items():
+                assert torch.equal(v, c.nodes[nt].data[k]), (nt, k)
+        assert sorted(zip(*[t.tolist() for t in a.edges()])) == sorted(zip(*[t.tolist() for t in c.edges()]))
+    with pytest.raises(ValueError):
+        gbg.batch([mols[0], synthetic.make_molecule(rng, "small", n_confs=4, n_atoms=5)])
+
+
+def test_pack_tables():
+    from grappa_b200 import synthetic
+    from grappa_b200.pack import PackedBatch
+    g = synthetic.espaloma_mix_batch(seed=2, batch_size=5, n_confs=2)
+    p = PackedBatch(g, device="cpu")
+    n = g.num_nodes("n1")
+    src, dst = [t.numpy() for t in g.edges()]
+    indptr, esrc, erev = p.host["indptr"], p.host["esrc"], p.host["erev"]
+    edst = np.repeat(np.arange(n), np.diff(indptr))
+    assert sorted(zip(esrc.tolist(), edst.tolist())) == sorted(zip(src.tolist(), dst.tolist()))
+    assert np.array_equal(esrc[erev], edst) and np.array_equal(edst[erev], esrc)      # reverse edges
+    for l, lvl in enumerate(LEVELS):
+        idx = g.nodes[lvl].data["idxs"].numpy()
+        L = idx.shape[1]
+        assert np.array_equal(p.host[f"idx{l}"], idx.astype(np.int32))
+        ptr, ent = p.host[f"inv_ptr{l}"], p.host[f"inv_ent{l}"]
+        assert ptr[-1] == idx.size
+        for atom in (0, n // 2, n - 1):
+            assert all(idx.reshape(-1)[e] == atom for e in ent[ptr[atom]:ptr[atom + 1]])
+        assert np.array_equal(np.diff(p.host[f"tup_off{l}"]), g.batch_num_nodes(lvl).numpy())
+    g.nodes["n2"].data["idxs"][0, 0] = n + 3
+    with pytest.raises(AssertionError):
+        PackedBatch(g, device="cpu")
+    g.nodes["n2"].data["idxs"] = g.nodes["n2"].data["idxs"].float()
+    with pytest.raises(IndexError):
+        PackedBatch(g, device="cpu")
+
+
+def test_module_tree_state_dict_and_error_behaviour():
+    from grappa_b200 import GrappaB200Error, models, synthetic
+    from grappa_b200.energy import Energy
+    z = load_golden("dipeptide_grappa12.npz")
+    m = models.model_from_config(models.grappa_1_2_model_config())
+    sd = m.state_dict()
+    assert sorted(sd.keys()) == list(z["meta.state_dict_keys"])
+    assert [",".join(map(str, sd[k].shape)) for k in sorted(sd)] == list(z["meta.state_dict_shapes"])
+    assert sd["gnn.blocks.3.head_reducer.weight"].data_ptr() == sd["gnn.att_blocks.3.head_reducer.weight"].data_ptr()
+    assert m.field_of_view == 10 and sd["gnn.pre_dense.0.weight"].shape == (512, 85)
+    # Lightning checkpoints prefix keys with 'model.0.' (training/lightning_model.py); stripping it must load
+    m.load_state_dict({k: v for k, v in {("model.0." + k)[8:]: v for k, v in sd.items()}.items()})
+    with pytest.raises(NotImplementedError):
+        models.GrappaGNN(n_conv=2)
+    g = synthetic.dipeptide(seed=0, n_confs=2)
+    with pytest.raises(ValueError):
+        Energy(terms="n2")
+    with pytest.raises(GrappaB200Error):
+        m(g)                                   # CPU tensors: no fallback
+    del g.nodes["n1"].data["xyz"]
+    with pytest.raises(ValueError):
+        Energy()(g)
+
+
+def test_flat_params_are_views_and_buckets_tile_the_buffer():
+    import grappa_oracle as orc
+    from grappa_b200 import models
+    from grappa_b200.training import FlatParams
+    m = models.model_from_config(orc.small_model_config())
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    fp = FlatParams(m, "cpu")
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, before[k])
+    p = m.gnn.att_blocks[0].head_reducer.weight
+    assert p.data_ptr() >= fp.flat.data_ptr() and p._gb_sink.data_ptr() >= fp.grad.data_ptr()
+    spans = [fp.span(w) for w in (m.parameter_writer.bond_writer, m.parameter_writer.angle_writer,
+                                  m.parameter_writer.proper_writer, m.parameter_writer.improper_writer)]
+    spans.append(fp.span(m.gnn))
+    spans.sort()
+    assert spans[0][0] == 0 and spans[-1][1] == fp.total
+    assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    fp.flat.zero_()
+    assert all(float(q.abs().sum()) == 0 for q in m.parameters())

@@ -331,7 +331,7 @@ def test_gemm_tcgen05_tf32_accuracy_and_epilogue(ta, tb):
     dev = "cuda"
     M, N, K = 1111, 511, 512
     A = torch.randn((K, 1112) if ta else (M, K), device=dev)[:, :(M if ta else K)]
-    B = torch.randn((K, 512) if tb else (N, K), device=dev)[:, :(N if tb else K)] / math.sqrt(K)
+    B = (torch.randn((K, 512) if tb else (N, K), device=dev) / math.sqrt(K))[:, :(N if tb else K)]
     bias = torch.randn(N, device=dev)
     res = torch.randn(M, N, device=dev)
     ref = F.elu((A.double().T if ta else A.double()) @ (B.double() if tb else B.double().T) + bias.double()) + res.double()

@@ -1,0 +1,105 @@
+"""The CPU oracle (oracle/grappa_oracle.py) is pinned against fixtures generated from the UNMODIFIED
+reference (tests/golden/make_golden.py) and -- when /root/reference is mounted -- against the reference
+itself on fresh inputs."""
+import numpy as np
+import pytest
+import torch
+
+import grappa_oracle as orc
+from util import LEVELS, graph_from_fixture, load_golden, rel_err
+
+
+def _sd(cfg, seed):
+    from grappa_b200 import models, synthetic
+    m = models.model_from_config(dict(cfg))
+    return synthetic.deterministic_state_dict(m.state_dict(), seed=seed), m
+
+
+def _compare(h, params, en, z, tol):
+    assert rel_err(h.detach().numpy(), z["out.h"]) < tol
+    for l in LEVELS:
+        assert rel_err(params[l]["k"].detach().numpy(), z[f"out.{l}.k"]) < tol
+        if l in ("n2", "n3"):
+            assert rel_err(params[l]["eq"].detach().numpy(), z[f"out.{l}.eq"]) < tol
+        assert rel_err(en["term_energy"][l].numpy(), z[f"out.g.energy_{l}"]) < 20 * tol
+    assert rel_err(en["energy"].detach().numpy(), z["out.g.energy"]) < tol
+    assert rel_err(en["gradient"].detach().numpy(), z["out.n1.gradient"]) < tol
+
+
+def test_oracle_matches_reference_fixture_grappa12_dipeptide():
+    z = load_golden("dipeptide_grappa12.npz")
+    cfg = orc.grappa_1_2_model_config()
+    sd, model = _sd(cfg, seed=3)
+    assert sorted(sd.keys()) == list(z["meta.state_dict_keys"])          # 410 reference state_dict keys
+    assert len(sd) == 410 and sum(p.numel() for p in model.parameters()) == 40_801_805
+    g = graph_from_fixture(z)
+    with torch.no_grad():
+        pass
+    h, params, en = orc.path_forward(sd, g, cfg)
+    _compare(h, params, en, z, 2e-5)
+
+
+def test_oracle_matches_reference_fixture_loss_and_gradients():
+    z = load_golden("mixed_batch_small_model.npz")
+    cfg = orc.small_model_config()
+    sd, _ = _sd(cfg, seed=7)
+    leaves = {k: v.requires_grad_(True) for k, v in sd.items() if ("grad." + k) in z.files}
+    g = graph_from_fixture(z)
+    h, params, en = orc.path_forward(sd, g, cfg, create_graph=True)
+    _compare(h, params, en, z, 2e-5)
+    loss = orc.molwise_loss(en, params, g)
+    assert abs(float(loss) - float(z["out.loss"])) < 1e-5 * abs(float(z["out.loss"]))
+    grads = torch.autograd.grad(loss, list(leaves.values()))
+    for (k, _), gr in zip(leaves.items(), grads):
+        assert rel_err(gr.numpy(), z["grad." + k]) < 1e-4, k
+
+
+def test_oracle_energy_fixture_and_double_backward():
+    z = load_golden("energy_mixed_batch.npz")
+    g = graph_from_fixture(z)
+    prm = {l: {n: torch.from_numpy(z[f"in.{l}.{n}"]).requires_grad_(True) for n in ("k", "eq") if f"in.{l}.{n}" in z.files}
+           for l in LEVELS}
+    idxs = {l: g.nodes[l].data["idxs"] for l in LEVELS}
+    counts = {l: g.batch_num_nodes(l).tolist() for l in LEVELS}
+    en = orc.energy_forward(g.nodes["n1"].data["xyz"], idxs, prm, counts, create_graph=True)
+    assert rel_err(en["energy"].detach().numpy(), z["out.g.energy"]) < 1e-5
+    assert rel_err(en["gradient"].detach().numpy(), z["out.n1.gradient"]) < 1e-5
+    obj = (en["energy"] * torch.from_numpy(z["in.gE"])).sum() + (en["gradient"] * torch.from_numpy(z["in.gF"])).sum()
+    leaves = [(l, n, prm[l][n]) for l in LEVELS for n in sorted(prm[l])]
+    grads = torch.autograd.grad(obj, [t for _, _, t in leaves])
+    for (l, n, _), gr in zip(leaves, grads):
+        assert rel_err(gr.numpy(), z[f"grad.{l}.{n}"]) < 1e-4, (l, n)
+
+
+def test_oracle_known_answers_geometry():
+    """SURVEY.md appendix A.5 known answers."""
+    p = lambda *v: torch.tensor(v, dtype=torch.float64)
+    assert abs(float(orc.dihedral_angle(p(1, 0, 0), p(0, 0, 0), p(0, 0, 1), p(1, 0, 1)))) < 1e-12
+    assert abs(float(orc.dihedral_angle(p(1, 0, 0), p(0, 0, 0), p(0, 0, 1), p(0, 1, 1))) + np.pi / 2) < 1e-12
+    assert abs(float(orc.bond_angle(p(1, 0, 0), p(0, 0, 0), p(0, 1, 0))) - np.pi / 2) < 1e-12
+    assert abs(float(orc.bond_length(p(1, 2, 2), p(0, 0, 0))) - 3.0) < 1e-12
+
+
+def test_oracle_vs_live_reference_on_fresh_inputs():
+    """Only where the reference sources are mounted (build container)."""
+    from ref_import import import_reference, no_dihedral_noise, reference_available, to_reference_graph
+    if not reference_available():
+        pytest.skip("/root/reference not mounted (GPU box)")
+    from grappa_b200 import synthetic
+    ns = import_reference()
+    cfg = orc.small_model_config()
+    torch.manual_seed(0)
+    ref = ns.deploy.model_from_config(dict(cfg), param_statistics=ns.graph_utils.get_default_statistics()).eval()
+    sd = {k: v.clone() for k, v in ref.state_dict().items()}          # the reference's own random init
+    # n_confs != 3: the reference's angle() calls torch.cross WITHOUT dim (internal_coordinates.py:159), which picks the
+    # first axis of size 3 -- with exactly 3 conformations (or 3 angles) it crosses over the wrong axis.
+    g = synthetic.espaloma_mix_batch(seed=21, batch_size=4, n_confs=5)
+    dg = to_reference_graph(ns, g)
+    with no_dihedral_noise():
+        dg = torch.nn.Sequential(ref, ns.energy.Energy())(dg)
+    h, params, en = orc.path_forward(sd, g, cfg)
+    assert rel_err(h.detach().numpy(), dg.nodes["n1"].data["h"].detach().numpy()) < 2e-5
+    assert rel_err(en["energy"].detach().numpy(), dg.nodes["g"].data["energy"].detach().numpy()) < 1e-5
+    assert rel_err(en["gradient"].numpy(), dg.nodes["n1"].data["gradient"].detach().numpy()) < 1e-5
+    for l in LEVELS:
+        assert rel_err(params[l]["k"].detach().numpy(), dg.nodes[l].data["k"].detach().numpy()) < 2e-5
