@@ -28,6 +28,7 @@ class GemmArgs(C.Structure):
         ("workspace_bytes", i64),
         ("act_out", vp),
         ("ldact", i32),
+        ("dropout_offset", vp),
     ]
 
 
@@ -80,14 +81,16 @@ def declare(lib):
     lib.grappa_b200_featurize.argtypes = [P(FeaturizeArgs), vp, i32, i32, vp]
     lib.grappa_b200_head_output_fwd.argtypes = [P(HeadOutArgs), vp, vp, vp, vp]
     lib.grappa_b200_head_output_bwd.argtypes = [P(HeadOutArgs), vp, vp, vp, vp, vp]
-    lib.grappa_b200_dropout.argtypes = [vp, vp, i64, f32, u64, vp]
-    lib.grappa_b200_act_dropout_bwd.argtypes = [vp, vp, vp, i64, f32, u64, vp]
+    lib.grappa_b200_dropout.argtypes = [vp, vp, i64, f32, u64, vp, vp]
+    lib.grappa_b200_act_dropout_bwd.argtypes = [vp, vp, vp, i64, f32, u64, vp, vp]
     lib.grappa_b200_axpby.argtypes = [vp, vp, i64, f32, f32, vp]
     lib.grappa_b200_sumsq.argtypes = [vp, i64, vp, vp]
     lib.grappa_b200_adam_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, vp, f32, f32, vp]
+    lib.grappa_b200_adam_step_dev.argtypes = [vp, vp, vp, vp, i64, vp, f32, f32, f32, vp, vp, f32, f32, vp]
+    lib.grappa_b200_tick.argtypes = [vp, i32, vp]
     lib.grappa_b200_molwise_loss.argtypes = [P(LossArgs), vp]
     for name in ("gemm", "layernorm_fwd", "layernorm_bwd", "col_reduce", "edge_attention_fwd", "edge_attention_bwd",
                  "tuple_attention_fwd", "tuple_attention_bwd", "tuple_gather_fwd", "tuple_gather_bwd",
                  "perm_concat_fwd", "perm_concat_bwd", "featurize", "head_output_fwd", "head_output_bwd", "dropout",
-                 "act_dropout_bwd", "axpby", "sumsq", "adam_step", "molwise_loss"):
+                 "act_dropout_bwd", "axpby", "sumsq", "adam_step", "adam_step_dev", "tick", "molwise_loss"):
         getattr(lib, "grappa_b200_" + name).restype = C.c_int

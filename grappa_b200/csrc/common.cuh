@@ -65,6 +65,10 @@ __device__ __forceinline__ uint32_t mix32(uint64_t seed, uint64_t idx) {
   z = z ^ (z >> 31);
   return (uint32_t)(z >> 32);
 }
+// seed of this launch = static seed + run-time device counter * odd constant (fresh masks per graph replay)
+__device__ __forceinline__ uint64_t seed_with_offset(uint64_t seed, const uint64_t* offset) {
+  return offset ? seed + __ldg(reinterpret_cast<const unsigned long long*>(offset)) * 0xD1342543DE82EF95ull : seed;
+}
 __device__ __forceinline__ float dropout_scale(uint64_t seed, uint64_t idx, uint32_t thresh, float inv_keep) {
   return mix32(seed, idx) >= thresh ? inv_keep : 0.f;
 }

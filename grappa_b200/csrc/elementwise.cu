@@ -122,14 +122,18 @@ __global__ void __launch_bounds__(256) head_output_bwd_kernel(gb_head_out_args a
 // dropout / axpby / sumsq / adam
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ x, float* __restrict__ y, long long n,
-                                                      uint32_t thresh, float inv_keep, uint64_t seed) {
+                                                      uint32_t thresh, float inv_keep, uint64_t seed0,
+                                                      const uint64_t* __restrict__ seed_off) {
+  const uint64_t seed = seed_with_offset(seed0, seed_off);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = x[i] * dropout_scale(seed, (uint64_t)i, thresh, inv_keep);
 }
 
 __global__ void __launch_bounds__(256) act_dropout_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ act_out,
                                                               float* __restrict__ dx, long long n, uint32_t thresh,
-                                                              float inv_keep, uint64_t seed) {
+                                                              float inv_keep, uint64_t seed0,
+                                                              const uint64_t* __restrict__ seed_off) {
+  const uint64_t seed = seed_with_offset(seed0, seed_off);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float v = dy[i];
     if (thresh) v *= dropout_scale(seed, (uint64_t)i, thresh, inv_keep);
@@ -325,7 +329,8 @@ extern "C" int grappa_b200_head_output_bwd(const gb_head_out_args* a, const floa
   return GB_OK;
 }
 
-extern "C" int grappa_b200_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, void* stream_) {
+extern "C" int grappa_b200_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, const uint64_t* seed_offset,
+                                   void* stream_) {
   GB_REQUIRE(p >= 0.f && p < 1.f, "dropout: p must be in [0,1)");
   if (n == 0) return GB_OK;
   GB_REQUIRE(x && y, "dropout: NULL pointer");
@@ -333,13 +338,13 @@ extern "C" int grappa_b200_dropout(const float* x, float* y, int64_t n, float p,
   uint32_t thresh = t >= 4294967295.0 ? 0xffffffffu : (uint32_t)t;
   if (p > 0.f && thresh == 0) thresh = 1;
   if (p == 0.f) thresh = 0;
-  dropout_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream_>>>(x, y, n, thresh, 1.f / (1.f - p), seed);
+  dropout_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream_>>>(x, y, n, thresh, 1.f / (1.f - p), seed, seed_offset);
   GB_CHECK_LAUNCH();
   return GB_OK;
 }
 
 extern "C" int grappa_b200_act_dropout_bwd(const float* dy, const float* act_out, float* dx, int64_t n, float p,
-                                           uint64_t seed, void* stream_) {
+                                           uint64_t seed, const uint64_t* seed_offset, void* stream_) {
   GB_REQUIRE(p >= 0.f && p < 1.f, "act_dropout_bwd: p must be in [0,1)");
   if (n == 0) return GB_OK;
   GB_REQUIRE(dy && dx, "act_dropout_bwd: NULL pointer");
@@ -349,7 +354,8 @@ extern "C" int grappa_b200_act_dropout_bwd(const float* dy, const float* act_out
     thresh = t >= 4294967295.0 ? 0xffffffffu : (uint32_t)t;
     if (thresh == 0) thresh = 1;
   }
-  act_dropout_bwd_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream_>>>(dy, act_out, dx, n, thresh, 1.f / (1.f - p), seed);
+  act_dropout_bwd_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream_>>>(dy, act_out, dx, n, thresh, 1.f / (1.f - p), seed,
+                                                                                 seed_offset);
   GB_CHECK_LAUNCH();
   return GB_OK;
 }
@@ -380,6 +386,70 @@ extern "C" int grappa_b200_adam_step(float* p, const float* g, float* m, float* 
   const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
   adam_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream_>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2s, gnorm_sq, clip,
                                                              grad_scale);
+  GB_CHECK_LAUNCH();
+  return GB_OK;
+}
+
+__global__ void __launch_bounds__(256) adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                       float* __restrict__ v, long long n, const float* __restrict__ lr_dev,
+                                                       float b1, float b2, float eps, const uint64_t* __restrict__ step_dev,
+                                                       const float* __restrict__ gnorm_sq, float clip, float grad_scale) {
+  const float step = (float)(__ldg(reinterpret_cast<const unsigned long long*>(step_dev)) + 1ull);
+  const float lr = __ldg(lr_dev);
+  const float bc1 = 1.f - powf(b1, step);
+  const float bc2_sqrt = sqrtf(1.f - powf(b2, step));
+  float coef = grad_scale;
+  if (gnorm_sq && clip > 0.f) {
+    const float total = grad_scale * sqrtf(__ldg(gnorm_sq));
+    coef *= fminf(1.f, clip / (total + 1e-6f));
+  }
+  const long long n4 = n >> 2;   // flat buffers are 16-byte aligned (cudaMalloc / torch allocator)
+  float4* p4 = reinterpret_cast<float4*>(p);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  const float a = lr / bc1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 pp = p4[i], gg = g4[i], mm = m4[i], vv = v4[i];
+    float* pf = &pp.x; float* gf = &gg.x; float* mf = &mm.x; float* vf = &vv.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gi = gf[j] * coef;
+      mf[j] = b1 * mf[j] + (1.f - b1) * gi;
+      vf[j] = b2 * vf[j] + (1.f - b2) * gi * gi;
+      pf[j] -= a * mf[j] / (sqrtf(vf[j]) / bc2_sqrt + eps);
+    }
+    p4[i] = pp; m4[i] = mm; v4[i] = vv;
+  }
+  for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * coef;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= a * mi / (sqrtf(vi) / bc2_sqrt + eps);
+  }
+}
+
+__global__ void tick_kernel(uint64_t* counters, int n) {
+  if ((int)threadIdx.x < n) counters[threadIdx.x] += 1ull;
+}
+
+extern "C" int grappa_b200_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_dev,
+                                         float beta1, float beta2, float eps, const uint64_t* step_dev,
+                                         const float* gnorm_sq, float clip, float grad_scale, void* stream_) {
+  if (n == 0) return GB_OK;
+  GB_REQUIRE(p && g && m && v && lr_dev && step_dev, "adam_step_dev: NULL pointer");
+  GB_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "adam_step_dev: buffers must be 16-byte aligned");
+  adam_dev_kernel<<<grid_for(n / 4 + 1), 256, 0, (cudaStream_t)stream_>>>(p, g, m, v, n, lr_dev, beta1, beta2, eps, step_dev,
+                                                                         gnorm_sq, clip, grad_scale);
+  GB_CHECK_LAUNCH();
+  return GB_OK;
+}
+
+extern "C" int grappa_b200_tick(uint64_t* counters, int32_t n, void* stream_) {
+  GB_REQUIRE(counters && n >= 1 && n <= 32, "tick: need 1..32 counters");
+  tick_kernel<<<1, 32, 0, (cudaStream_t)stream_>>>(counters, n);
   GB_CHECK_LAUNCH();
   return GB_OK;
 }

@@ -16,16 +16,59 @@ struct Epilogue {
   uint32_t drop_thresh;   // 0 = dropout off
   float drop_inv_keep;
   uint64_t drop_seed;
+  const uint64_t* drop_offset;   // device counter mixed into the seed (CUDA-graph replays), or NULL
 
+  __device__ __forceinline__ uint64_t seed() const { return seed_with_offset(drop_seed, drop_offset); }
   __device__ __forceinline__ float apply(float acc, int m, int n) const {
     float v = acc;
     if (bias) v += __ldg(bias + n);
     if (act == 1) v = elu1(v);
     if (act_out) act_out[(size_t)m * ldact + n] = v;
     if (mul_elu_out) v *= elu1_grad_from_out(__ldg(mul_elu_out + (size_t)m * ldm + n));
-    if (drop_thresh) v *= dropout_scale(drop_seed, (uint64_t)m * (uint64_t)N + (uint64_t)n, drop_thresh, drop_inv_keep);
+    if (drop_thresh) v *= dropout_scale(seed(), (uint64_t)m * (uint64_t)N + (uint64_t)n, drop_thresh, drop_inv_keep);
     if (residual) v += __ldg(residual + (size_t)m * ldr + n);
     return v;
+  }
+  // 4 consecutive columns of one row (n % 4 == 0); every pointer / pitch is 16-byte aligned (vec_ok)
+  __device__ __forceinline__ bool vec_ok() const {
+    const uintptr_t ptrs = (uintptr_t)bias | (uintptr_t)mul_elu_out | (uintptr_t)residual | (uintptr_t)C | (uintptr_t)act_out;
+    const int lds = ldc | (mul_elu_out ? ldm : 0) | (residual ? ldr : 0) | (act_out ? ldact : 0) | N;
+    return (ptrs & 15) == 0 && (lds & 3) == 0;
+  }
+  // FAST: bias already added by the caller, ELU through ex2.approx (tensor-core path; |abs err| ~1e-7)
+  template <bool FAST>
+  __device__ __forceinline__ void store4(float4 acc, int m, int n) const {
+    float v[4] = {acc.x, acc.y, acc.z, acc.w};
+    if (!FAST && bias) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n));
+      v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+    }
+    if (act == 1) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = FAST ? (v[i] > 0.f ? v[i] : __expf(v[i]) - 1.f) : elu1(v[i]);
+    }
+    if (act_out) *reinterpret_cast<float4*>(act_out + (size_t)m * ldact + n) = make_float4(v[0], v[1], v[2], v[3]);
+    if (mul_elu_out) {
+      const float4 y = __ldg(reinterpret_cast<const float4*>(mul_elu_out + (size_t)m * ldm + n));
+      v[0] *= elu1_grad_from_out(y.x); v[1] *= elu1_grad_from_out(y.y);
+      v[2] *= elu1_grad_from_out(y.z); v[3] *= elu1_grad_from_out(y.w);
+    }
+    if (drop_thresh) {
+      const uint64_t base = (uint64_t)m * (uint64_t)N + (uint64_t)n;
+      const uint64_t sd = seed();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] *= dropout_scale(sd, base + i, drop_thresh, drop_inv_keep);
+    }
+    if (residual) {
+      const float4 r = __ldg(reinterpret_cast<const float4*>(residual + (size_t)m * ldr + n));
+      v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
+    }
+    float4* c = reinterpret_cast<float4*>(C + (size_t)m * ldc + n);
+    if (accumulate) {
+      const float4 o = *c;
+      v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;
+    }
+    *c = make_float4(v[0], v[1], v[2], v[3]);
   }
   __device__ __forceinline__ void store(float acc, int m, int n) const {
     float v = apply(acc, m, n);
@@ -59,6 +102,7 @@ inline Epilogue make_epilogue(const gb_gemm_args* a) {
     e.drop_inv_keep = 1.f;
   }
   e.drop_seed = a->dropout_seed;
+  e.drop_offset = a->dropout_offset;
   return e;
 }
 

@@ -28,8 +28,7 @@ namespace gb {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;          // floats per stage along K = one 128-byte swizzle atom
-constexpr int TC_STAGES = 4;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;        // TMA warp + MMA warp + 8 epilogue warps
 constexpr uint32_t SPIN_LIMIT = 1u << 28;
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -40,6 +39,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
@@ -110,43 +112,62 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 
 struct TcParams {
   int M, N, K;
-  int k_blocks_per_split;   // K blocks (of TC_BK) handled by one grid.z slice
+  int k_blocks_per_split;   // K blocks (of TC_BK) handled by one split-K slice
+  int splits;               // number of split-K slices (1 = none)
+  int tiles_m, tiles_n;     // output tile grid
   float* partial;           // split-K workspace or NULL
   Epilogue ep;
 };
 
+template <int BN>
+struct TcCfg {
+  static constexpr int A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
+  static constexpr int B_BYTES = BN * TC_BK * 4;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BN == 128 ? 5 : 7;      // 160-168 KB of operand ring
+  static constexpr int EPI_LD = 36;                     // floats per staged row (float4-aligned, conflict-free)
+  static constexpr int EPI_BYTES = 8 * 32 * EPI_LD * 4; // one 32x32 transpose patch per epilogue warp
+  static_assert(STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256 <= 232448, "shared memory budget");
+  static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// Persistent kernel: grid = min(#work items, #SMs); work item = (split-K slice, m tile, n tile), n fastest.
+// Two TMEM accumulator stages: the epilogue of item i overlaps the mainloop of item i+1.
 template <int BN, int TA, int TB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  constexpr int A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
-  constexpr int B_BYTES = BN * TC_BK * 4;
-  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  using Cfg = TcCfg<BN>;
+  constexpr int A_BYTES = Cfg::A_BYTES;
+  constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
+  constexpr int STAGES = Cfg::STAGES;
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = (uint64_t*)(smem + TC_STAGES * STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + TC_STAGES;
-  uint64_t* acc_bar = empty_bar + TC_STAGES;
-  uint32_t* tmem_slot = (uint32_t*)(acc_bar + 1);
+  float* epi = (float*)(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES + Cfg::EPI_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* acc_full = empty_bar + STAGES;    // [2] MMA -> epilogue
+  uint64_t* acc_empty = acc_full + 2;         // [2] epilogue -> MMA
+  uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
   const int total_kb = (p.K + TC_BK - 1) / TC_BK;
-  const int kb0 = blockIdx.z * p.k_blocks_per_split;
-  const int kb1 = min(total_kb, kb0 + p.k_blocks_per_split);
-  const int num_kb = kb1 - kb0;
+  const int n_items = p.tiles_m * p.tiles_n * p.splits;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_b) : "memory");
-    for (int s = 0; s < TC_STAGES; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(acc_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 8);   // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {   // TMEM: BN fp32 accumulator columns (power of two >= 32)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN));
+  if (warp == 1) {   // TMEM: 2 accumulator stages of BN fp32 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * BN)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -157,27 +178,37 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      for (int i = 0; i < num_kb; ++i) {
-        const int s = i % TC_STAGES;
-        const uint32_t ph = (i / TC_STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* sa = smem + s * STAGE_BYTES;
-        uint8_t* sb = sa + A_BYTES;
-        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-        const int k = (kb0 + i) * TC_BK;
-        if (TA == 0) {
-          tma_load_2d(&map_a, &full_bar[s], sa, k, m0);                     // box {32 k, 128 rows}
-        } else {
+      uint32_t it = 0;   // running k-block counter across work items (ring position)
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int nb = item % p.tiles_n;
+        const int rest = item / p.tiles_n;
+        const int mb = rest % p.tiles_m;
+        const int z = rest / p.tiles_m;
+        const int m0 = mb * TC_BM, n0 = nb * BN;
+        const int kb0 = z * p.k_blocks_per_split;
+        const int num_kb = min(total_kb, kb0 + p.k_blocks_per_split) - kb0;
+        for (int i = 0; i < num_kb; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+          const int k = (kb0 + i) * TC_BK;
+          if (TA == 0) {
+            tma_load_2d(&map_a, &full_bar[s], sa, k, m0);                     // box {32 k, 128 rows}
+          } else {
 #pragma unroll
-          for (int j = 0; j < TC_BM / 32; ++j)                              // boxes {32 rows, 32 k}
-            tma_load_2d(&map_a, &full_bar[s], sa + j * (TC_BK * 128), m0 + j * 32, k);
-        }
-        if (TB == 0) {
-          tma_load_2d(&map_b, &full_bar[s], sb, k, n0);
-        } else {
+            for (int j = 0; j < TC_BM / 32; ++j)                              // boxes {32 rows, 32 k}
+              tma_load_2d(&map_a, &full_bar[s], sa + j * (TC_BK * 128), m0 + j * 32, k);
+          }
+          if (TB == 0) {
+            tma_load_2d(&map_b, &full_bar[s], sb, k, n0);
+          } else {
 #pragma unroll
-          for (int j = 0; j < BN / 32; ++j)
-            tma_load_2d(&map_b, &full_bar[s], sb + j * (TC_BK * 128), n0 + j * 32, k);
+            for (int j = 0; j < BN / 32; ++j)
+              tma_load_2d(&map_b, &full_bar[s], sb + j * (TC_BK * 128), n0 + j * 32, k);
+          }
         }
       }
     }
@@ -186,57 +217,115 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, majors, N >> 3, M >> 4
     constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)TA << 15) | ((uint32_t)TB << 16) |
                                ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-    for (int i = 0; i < num_kb; ++i) {
-      const int s = i % TC_STAGES;
-      const uint32_t ph = (i / TC_STAGES) & 1;
-      mbar_wait(&full_bar[s], ph);
+    uint32_t it = 0, lt = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++lt) {
+      const int z = item / (p.tiles_n * p.tiles_m);
+      const int kb0 = z * p.k_blocks_per_split;
+      const int num_kb = min(total_kb, kb0 + p.k_blocks_per_split) - kb0;
+      const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
+      mbar_wait(&acc_empty[as], aph ^ 1);               // epilogue has drained this accumulator stage
       tc_fence_after();
-      if (elect_one()) {
-        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-        const uint32_t sb = sa + A_BYTES;
+      const uint32_t d_tmem = tmem_base + as * BN;
+      for (int i = 0; i < num_kb; ++i, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
 #pragma unroll
-        for (int kk = 0; kk < TC_BK / 8; ++kk) {   // UMMA_K = 8 for TF32
-          // K-major : 8 rows x 128 B atoms, SBO = 1024 B between 8-row groups; k step = 32 B inside the atom
-          // MN-major: atom = 4 k-rows x 128 B (32-byte swizzle base); SBO = 512 B between the two atoms of one
-          //           UMMA_K = 8 step, LBO = box size between 32-wide MN chunks; k step = 1024 B
-          const uint64_t da = TA == 0 ? make_smem_desc(sa + kk * 32, 16, 1024, 2) : make_smem_desc(sa + kk * 1024, TC_BK * 128, 512, 1);
-          const uint64_t db = TB == 0 ? make_smem_desc(sb + kk * 32, 16, 1024, 2) : make_smem_desc(sb + kk * 1024, TC_BK * 128, 512, 1);
-          tc_mma_tf32(tmem_base, da, db, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < TC_BK / 8; ++kk) {   // UMMA_K = 8 for TF32
+            // K-major : 8 rows x 128 B atoms, SBO = 1024 B between 8-row groups; k step = 32 B inside the atom
+            // MN-major: atom = 4 k-rows x 128 B (32-byte swizzle base); SBO = 512 B between the two atoms of one
+            //           UMMA_K = 8 step, LBO = box size between 32-wide MN chunks; k step = 1024 B
+            const uint64_t da = TA == 0 ? make_smem_desc(sa + kk * 32, 16, 1024, 2) : make_smem_desc(sa + kk * 1024, TC_BK * 128, 512, 1);
+            const uint64_t db = TB == 0 ? make_smem_desc(sb + kk * 32, 16, 1024, 2) : make_smem_desc(sb + kk * 1024, TC_BK * 128, 512, 1);
+            tc_mma_tf32(d_tmem, da, db, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[s]);                       // frees the smem stage when these MMAs retire
+          if (i == num_kb - 1) tc_commit(&acc_full[as]);  // accumulator complete
         }
-        tc_commit(&empty_bar[s]);                       // frees the smem stage when these MMAs retire
-        if (i == num_kb - 1) tc_commit(acc_bar);        // accumulator complete
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
+    // TMEM -> registers (one row per lane, 32 columns) -> per-warp smem transpose patch -> every lane owns
+    // 4 consecutive columns of a row, so all global traffic of the fused epilogue is 128-byte coalesced.
+    // Two warps share each TMEM lane quarter and split the tile's columns between them.
     const int q = warp & 3;                            // TMEM lane quarter this warp may access
-    const int row = m0 + q * 32 + lane;
-    if (num_kb > 0) {
-      mbar_wait(acc_bar, 0);
+    const int half = (warp - 2) >> 2;                  // which half of the tile's columns
+    float* patch = epi + (warp - 2) * (32 * Cfg::EPI_LD);
+    const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+    const bool vec_ok = p.partial ? ((p.N & 3) == 0) : p.ep.vec_ok();
+    uint32_t lt = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++lt) {
+      const int nb = item % p.tiles_n;
+      const int rest = item / p.tiles_n;
+      const int mb = rest % p.tiles_m;
+      const int z = rest / p.tiles_m;
+      const int m0 = mb * TC_BM + q * 32, n0 = nb * BN + half * (BN / 2);
+      const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
+      mbar_wait(&acc_full[as], aph);
       tc_fence_after();
-    }
-    const bool row_ok = row < p.M;
+      const uint32_t t_addr = tmem_base + as * BN + half * (BN / 2) + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      float v[16];
-      if (num_kb > 0) {
-        tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = 0.f;
-      }
-      if (row_ok) {
-        if (p.partial) {
-          float* dst = p.partial + ((size_t)blockIdx.z * p.M + row) * p.N + n0 + c0;
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (n0 + c0 + i < p.N) dst[i] = v[i];
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (n0 + c0 + i < p.N) p.ep.store(v[i], row, n0 + c0 + i);
+      for (int c0 = 0; c0 < BN / 2; c0 += 32) {
+        float v[32];
+        tc_ld16(t_addr + (uint32_t)c0, v);
+        tc_ld16(t_addr + (uint32_t)c0 + 16u, v + 16);
+        if (c0 + 32 >= BN / 2) {   // accumulator fully read: hand the TMEM stage back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[as]);
         }
+        if (n0 + c0 >= p.N) continue;   // warp-uniform
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(patch + lane * Cfg::EPI_LD + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        const int col = n0 + c0 + sub_c;
+        if (col < p.N) {
+          if (p.partial) {
+            float* dst0 = p.partial + ((size_t)z * p.M + m0) * p.N + col;
+#pragma unroll 2
+            for (int i = 0; i < 8; ++i) {
+              const int r = sub_r + 4 * i;
+              if (m0 + r >= p.M) break;
+              const float4 acc = *reinterpret_cast<const float4*>(patch + r * Cfg::EPI_LD + sub_c);
+              float* dst = dst0 + (size_t)r * p.N;
+              if (vec_ok) {
+                *reinterpret_cast<float4*>(dst) = acc;
+              } else {
+                const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
+                for (int e = 0; e < 4; ++e)
+                  if (col + e < p.N) dst[e] = a4[e];
+              }
+            }
+          } else if (vec_ok) {
+            const float4 b4 = p.ep.bias ? __ldg(reinterpret_cast<const float4*>(p.ep.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+            for (int i = 0; i < 8; ++i) {
+              const int r = sub_r + 4 * i;
+              if (m0 + r >= p.M) break;
+              float4 acc = *reinterpret_cast<const float4*>(patch + r * Cfg::EPI_LD + sub_c);
+              acc.x += b4.x; acc.y += b4.y; acc.z += b4.z; acc.w += b4.w;
+              p.ep.template store4<true>(acc, m0 + r, col);
+            }
+          } else {
+#pragma unroll 1
+            for (int i = 0; i < 8; ++i) {
+              const int r = sub_r + 4 * i;
+              if (m0 + r >= p.M) break;
+              const float4 acc = *reinterpret_cast<const float4*>(patch + r * Cfg::EPI_LD + sub_c);
+              const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
+              for (int e = 0; e < 4; ++e)
+                if (col + e < p.N) p.ep.store(a4[e], m0 + r, col + e);
+            }
+          }
+        }
+        __syncwarp();
       }
     }
   }
@@ -244,7 +333,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)));
   }
 }
 
@@ -284,8 +373,8 @@ static bool make_map(CUtensorMap* map, const float* base, int rows, int cols, in
 }
 
 template <int BN, int TA, int TB>
-static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, dim3 grid, cudaStream_t stream) {
-  constexpr int smem = TC_STAGES * (TC_BM * TC_BK * 4 + BN * TC_BK * 4) + 1024 + 256;
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int grid, cudaStream_t stream) {
+  constexpr int smem = TcCfg<BN>::SMEM;
   static bool configured = false;
   if (!configured) {
     GB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN, TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -326,8 +415,12 @@ int gemm_tcgen05(const gb_gemm_args* a, cudaStream_t stream, bool* handled) {
   }
   p.k_blocks_per_split = (total_kb + splits - 1) / splits;
   splits = (total_kb + p.k_blocks_per_split - 1) / p.k_blocks_per_split;
+  p.splits = splits;
+  p.tiles_m = gy;
+  p.tiles_n = gx;
   p.partial = splits > 1 ? a->workspace : nullptr;
-  dim3 grid(gx, gy, splits);
+  const int n_items = gx * gy * splits;
+  const int grid = n_items < sms ? n_items : sms;
   int rc;
 #define GB_TC(BN_, TA_, TB_) rc = launch<BN_, TA_, TB_>(ma, mb, p, grid, stream)
   if (BN == 128) {

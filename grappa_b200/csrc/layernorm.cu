@@ -98,17 +98,43 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   }
 }
 
-// Column reduction stage 1: block = 32 columns x 8 row lanes; grid.y row slices.
+// Column reduction, ONE kernel: block = 32 columns x 8 row lanes, grid.y row slices.  Every block writes its
+// partial sums; the last block to finish a column group (ticket counter, self-resetting) adds the partials in
+// slice order, so the result is deterministic and no second launch is needed.
 __global__ void __launch_bounds__(256) col_reduce_kernel(const float* __restrict__ dy, int ld, const float* __restrict__ x,
                                                          const float* __restrict__ mean, const float* __restrict__ rstd,
                                                          float* __restrict__ part_sum, float* __restrict__ part_xhat,
-                                                         int rows, int cols) {
+                                                         unsigned int* __restrict__ tickets, float* __restrict__ out_sum,
+                                                         float* __restrict__ out_xhat, int rows, int cols, int accumulate) {
   __shared__ float sh[2][8][33];
+  __shared__ bool is_last;
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + cx;
+  const int slices = gridDim.y;
   float a = 0.f, b = 0.f;
   if (col < cols) {
-    for (int r = blockIdx.y * 8 + ry; r < rows; r += gridDim.y * 8) {
+    const int stride = slices * 8;
+    int r = blockIdx.y * 8 + ry;
+    // 4 independent rows in flight per thread
+    for (; r + 3 * stride < rows; r += 4 * stride) {
+      float d[4], xv[4], mu[4], rs[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) d[u] = __ldg(dy + (size_t)(r + u * stride) * ld + col);
+      if (x) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          xv[u] = __ldg(x + (size_t)(r + u * stride) * cols + col);
+          mu[u] = __ldg(mean + r + u * stride);
+          rs[u] = __ldg(rstd + r + u * stride);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a += d[u];
+        if (x) b += d[u] * (xv[u] - mu[u]) * rs[u];
+      }
+    }
+    for (; r < rows; r += stride) {
       const float d = __ldg(dy + (size_t)r * ld + col);
       a += d;
       if (x) b += d * (__ldg(x + (size_t)r * cols + col) - __ldg(mean + r)) * __ldg(rstd + r);
@@ -121,23 +147,39 @@ __global__ void __launch_bounds__(256) col_reduce_kernel(const float* __restrict
     float sa = 0.f, sb = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) { sa += sh[0][i][cx]; sb += sh[1][i][cx]; }
-    part_sum[(size_t)blockIdx.y * cols + col] = sa;
-    if (x) part_xhat[(size_t)blockIdx.y * cols + col] = sb;
+    if (slices == 1) {
+      if (out_sum) out_sum[col] = accumulate ? out_sum[col] + sa : sa;
+      if (x && out_xhat) out_xhat[col] = accumulate ? out_xhat[col] + sb : sb;
+    } else {
+      __stcg(part_sum + (size_t)blockIdx.y * cols + col, sa);
+      if (x) __stcg(part_xhat + (size_t)blockIdx.y * cols + col, sb);
+    }
   }
-}
-
-__global__ void __launch_bounds__(256) col_reduce_final_kernel(const float* __restrict__ part_sum,
-                                                               const float* __restrict__ part_xhat, float* out_sum,
-                                                               float* out_xhat, int slices, int cols, int accumulate) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= cols) return;
-  float a = 0.f, b = 0.f;
-  for (int s = 0; s < slices; ++s) {
-    a += part_sum[(size_t)s * cols + col];
-    if (part_xhat) b += part_xhat[(size_t)s * cols + col];
+  if (slices == 1) return;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(tickets + blockIdx.x, 1u) == (unsigned int)(slices - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  a = 0.f; b = 0.f;
+  if (col < cols) {
+    for (int s2 = ry; s2 < slices; s2 += 8) {
+      a += __ldcg(part_sum + (size_t)s2 * cols + col);
+      if (x) b += __ldcg(part_xhat + (size_t)s2 * cols + col);
+    }
   }
-  if (out_sum) out_sum[col] = accumulate ? out_sum[col] + a : a;
-  if (out_xhat && part_xhat) out_xhat[col] = accumulate ? out_xhat[col] + b : b;
+  sh[0][ry][cx] = a;
+  sh[1][ry][cx] = b;
+  __syncthreads();
+  if (ry == 0 && col < cols) {
+    float sa = 0.f, sb = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sa += sh[0][i][cx]; sb += sh[1][i][cx]; }
+    if (out_sum) out_sum[col] = accumulate ? out_sum[col] + sa : sa;
+    if (x && out_xhat) out_xhat[col] = accumulate ? out_xhat[col] + sb : sb;
+  }
+  if (threadIdx.x == 0) tickets[blockIdx.x] = 0u;   // ready for the next launch on this workspace
 }
 
 static int col_slices(int rows) {
@@ -187,8 +229,9 @@ extern "C" int grappa_b200_layernorm_bwd(const float* dy, const float* x, const 
   return GB_OK;
 }
 
+// workspace layout: [256 B ticket counters (MUST be zero on first use; the kernel resets them)] [partials]
 extern "C" int64_t grappa_b200_col_reduce_workspace(int32_t rows, int32_t cols) {
-  return (int64_t)2 * col_slices(rows) * cols * sizeof(float);
+  return 256 + (int64_t)2 * col_slices(rows) * cols * sizeof(float);
 }
 
 extern "C" int grappa_b200_col_reduce(const float* dy, int32_t ld, const float* x, const float* mean, const float* rstd,
@@ -198,13 +241,20 @@ extern "C" int grappa_b200_col_reduce(const float* dy, int32_t ld, const float* 
   GB_REQUIRE(workspace != nullptr, "col_reduce: workspace is NULL");
   GB_REQUIRE(!x || (mean && rstd), "col_reduce: x given without mean/rstd");
   cudaStream_t stream = (cudaStream_t)stream_;
+  GB_REQUIRE(cols <= 2048, "col_reduce: cols must be <= 2048 (got %d)", cols);
+  if (rows == 0) {
+    if (!accumulate) {
+      if (out_sum) GB_CHECK_CUDA(cudaMemsetAsync(out_sum, 0, sizeof(float) * cols, stream));
+      if (out_xhat && x) GB_CHECK_CUDA(cudaMemsetAsync(out_xhat, 0, sizeof(float) * cols, stream));
+    }
+    return GB_OK;
+  }
   const int slices = col_slices(rows);
-  float* ps = workspace;
-  float* px = x ? workspace + (size_t)slices * cols : nullptr;
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(workspace);
+  float* ps = workspace + 64;
+  float* px = x ? ps + (size_t)slices * cols : nullptr;
   dim3 grid((cols + 31) / 32, slices);
-  col_reduce_kernel<<<grid, 256, 0, stream>>>(dy, ld, x, mean, rstd, ps, px, rows, cols);
-  GB_CHECK_LAUNCH();
-  col_reduce_final_kernel<<<(cols + 255) / 256, 256, 0, stream>>>(ps, px, out_sum, out_xhat, slices, cols, accumulate);
+  col_reduce_kernel<<<grid, 256, 0, stream>>>(dy, ld, x, mean, rstd, ps, px, tickets, out_sum, out_xhat, rows, cols, accumulate);
   GB_CHECK_LAUNCH();
   return GB_OK;
 }

@@ -189,12 +189,13 @@ class GrappaGNN(nn.Module):
         def run(t: Tape, ins, params):
             P = lambda p: params[index[id(p)]]
             x = ins[0]
-            t.push(lambda: _fire(("gnn_rest", None)))          # runs last in backward
+            t.push(lambda: (t.join_side(), _fire(("gnn_rest", None))))          # runs last in backward
             h = T_.linear(t, x, P(self.pre_dense[0].weight), P(self.pre_dense[0].bias), act=ELU,
                           dropout_p=self.p_initial, k=self.in_feats)
             if not self.no_convs:
                 for i, blk in enumerate(self.att_blocks):
-                    t.push(lambda i=i: _fire(("gnn_block", i)))  # runs after block i's backward ops
+                    if _BACKWARD_HOOK is not None:               # runs after block i's backward ops
+                        t.push(lambda i=i: (t.join_side(), _fire(("gnn_block", i))))
                     h = blk.tape_forward(t, pack, h, P)
             h = T_.linear(t, h, P(self.post_dense[0].weight), P(self.post_dense[0].bias), dropout_p=self.p_final)
             return [h]
@@ -408,7 +409,7 @@ class _TupleWriter(nn.Module):
         def run(t: Tape, ins, params):
             P = lambda p: params[index[id(p)]]
             h = ins[0]
-            t.push(lambda: _fire(("writer", self)))
+            t.push(lambda: (t.join_side(), _fire(("writer", self))))
             proj = T_.linear(t, h, P(self.rep_projector.mlp[0].weight), P(self.rep_projector.mlp[0].bias), act=ELU,
                              out_ld=(E if E % 4 == 0 else (E + 3) // 4 * 4))
             x = T_.tuple_gather(t, proj, pack, self.level_id, pe, F, E)
@@ -629,10 +630,28 @@ class WriteParameters(nn.Module):
                                                       wrong_symmetry, torsion_cutoff)
 
     def forward(self, g):
-        g = self.bond_writer(g)
-        g = self.angle_writer(g)
-        g = self.proper_writer(g)
-        g = self.improper_writer(g)
+        writers = (self.proper_writer, self.angle_writer, self.bond_writer, self.improper_writer)   # largest first
+        h = g.nodes["n1"].data.get("h")
+        if h is None or not h.is_cuda or not T_.concurrency():
+            for w in (self.bond_writer, self.angle_writer, self.proper_writer, self.improper_writer):
+                g = w(g)
+            return g
+        # The four writers are independent (the reference runs them one after the other, see its note at
+        # interaction_parameters.py:126-128): each one gets its own stream, so their kernels -- most of which cannot
+        # fill 148 SMs alone -- overlap; autograd replays each writer's backward on the same stream.
+        main = torch.cuda.current_stream()
+        start = torch.cuda.Event()
+        start.record(main)
+        done = []
+        for w, st in zip(writers, T_.helper_streams(len(writers), "writer")):
+            st.wait_event(start)
+            with torch.cuda.stream(st):
+                g = w(g)
+                ev = torch.cuda.Event()
+                ev.record(st)
+            done.append(ev)
+        for ev in done:
+            main.wait_event(ev)
         return g
 
 

@@ -30,6 +30,20 @@ def get_matmul_precision() -> str:
     return "fp32" if _precision == FP32 else "tf32"
 
 
+_rng_offset = None     # device uint64 counter mixed into every dropout seed (None = static seeds)
+
+
+def set_rng_offset(t):
+    """Register a 1-element device int64 tensor whose value is added to every dropout seed at RUN time.
+    A captured CUDA graph then draws fresh masks on each replay once the counter is advanced (`tick`)."""
+    global _rng_offset
+    _rng_offset = t
+
+
+def _rng_ptr() -> int:
+    return 0 if _rng_offset is None else _rng_offset.data_ptr()
+
+
 _gemm_profile = None   # list collecting (flops, start_event, stop_event, kernel) when profiling is on
 
 
@@ -50,14 +64,21 @@ def _s() -> int:
 _ws_cache = {}
 
 
-def workspace(nbytes: int, device, tag: str = "ws") -> torch.Tensor:
-    """A reusable scratch buffer per (device, stream, tag); grows monotonically."""
+def workspace(nbytes: int, device, tag: str = "ws", zero: bool = False) -> torch.Tensor:
+    """A reusable scratch buffer per (device, stream, tag); grows monotonically.  `zero`: zero-filled when created
+    (kernels that keep self-resetting counters in it)."""
     key = (device, torch.cuda.current_stream().cuda_stream, tag)
     t = _ws_cache.get(key)
     if t is None or t.numel() * 4 < nbytes:
-        t = torch.empty(max((nbytes + 3) // 4, 1 << 20), dtype=torch.float32, device=device)
+        n = max((nbytes + 3) // 4, 1 << 20)
+        t = (torch.zeros if zero else torch.empty)(n, dtype=torch.float32, device=device)
         _ws_cache[key] = t
     return t
+
+
+def drop_workspaces():
+    """Forget cached scratch buffers (they are re-created on demand)."""
+    _ws_cache.clear()
 
 
 def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a=False, trans_b=False, bias=None, act=0, mul_elu_out=None,
@@ -84,6 +105,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a=False, trans_b=False, bias
     g.ldm = mul_elu_out.stride(0) if mul_elu_out is not None else 0
     g.dropout_p = float(dropout_p)
     g.dropout_seed = int(dropout_seed) & 0xFFFFFFFFFFFFFFFF
+    g.dropout_offset = _rng_ptr() if dropout_p > 0.0 else 0
     g.residual = _p(residual)
     g.ldr = residual.stride(0) if residual is not None else 0
     g.accumulate = int(accumulate)
@@ -141,7 +163,7 @@ def col_reduce(dy, out_sum=None, x=None, mean=None, rstd=None, out_xhat=None, ac
                 out_xhat.zero_()
         return out_sum, out_xhat
     nb = lib.grappa_b200_col_reduce_workspace(rows, cols)
-    ws = workspace(nb, dy.device, "colred")
+    ws = workspace(nb, dy.device, "colred", zero=True)
     _lib.check(lib.grappa_b200_col_reduce(dy.data_ptr(), dy.stride(0), _p(x), _p(mean), _p(rstd), out_sum.data_ptr(),
                                           _p(out_xhat), ws.data_ptr(), rows, cols, int(accumulate), _s()), "col_reduce")
     return out_sum, out_xhat
@@ -270,7 +292,8 @@ def dropout(x, p, seed, out=None):
     lib = _lib.lib()
     if out is None:
         out = torch.empty_like(x)
-    _lib.check(lib.grappa_b200_dropout(_p(x), _p(out), x.numel(), float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, _s()), "dropout")
+    _lib.check(lib.grappa_b200_dropout(_p(x), _p(out), x.numel(), float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, _rng_ptr(),
+                                       _s()), "dropout")
     return out
 
 
@@ -278,7 +301,8 @@ def act_dropout_bwd(dy, act_out, p, seed):
     lib = _lib.lib()
     dx = torch.empty_like(dy)
     _lib.check(lib.grappa_b200_act_dropout_bwd(_p(dy), _p(act_out), _p(dx), dy.numel(), float(p),
-                                               int(seed) & 0xFFFFFFFFFFFFFFFF, _s()), "act_dropout_bwd")
+                                               int(seed) & 0xFFFFFFFFFFFFFFFF, _rng_ptr() if p > 0.0 else 0, _s()),
+               "act_dropout_bwd")
     return dx
 
 
@@ -298,3 +322,17 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, gnorm_sq=None, clip=0.0, 
     lib = _lib.lib()
     _lib.check(lib.grappa_b200_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2,
                                          eps, step, _p(gnorm_sq), float(clip), float(grad_scale), _s()), "adam_step")
+
+
+def adam_step_dev(p, g, m, v, lr_dev, beta1, beta2, eps, step_dev, gnorm_sq=None, clip=0.0, grad_scale=1.0):
+    """Adam with learning rate / step count read from device tensors (CUDA-graph friendly)."""
+    lib = _lib.lib()
+    _lib.check(lib.grappa_b200_adam_step_dev(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(),
+                                             lr_dev.data_ptr(), beta1, beta2, eps, step_dev.data_ptr(), _p(gnorm_sq),
+                                             float(clip), float(grad_scale), _s()), "adam_step_dev")
+
+
+def tick(counters):
+    """counters[:] += 1 on the device (int64 tensor of <= 32 elements)."""
+    lib = _lib.lib()
+    _lib.check(lib.grappa_b200_tick(counters.data_ptr(), counters.numel(), _s()), "tick")

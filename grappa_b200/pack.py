@@ -112,6 +112,7 @@ class PackedBatch:
     def _materialise(self, device):
         self.device = torch.device(device)
         flat = self._stage.to(self.device, non_blocking=True)
+        self._flat = flat
         off = 0
         self._dev = {}
         for k, s in zip(self._names, self._sizes):
@@ -124,6 +125,20 @@ class PackedBatch:
         p = _copy.copy(self)
         p._materialise(device)
         return p
+
+    def signature(self):
+        """Everything the host bakes into kernel arguments / grids: two packs with equal signatures can share a
+        captured CUDA graph (training.Trainer)."""
+        return (self.n_atoms, self.n_mols, self.n_edges, tuple(self.n_tuples), self.max_atoms_per_mol, self.max_degree,
+                tuple(self._sizes))
+
+    def copy_from(self, other: "PackedBatch"):
+        """Overwrite the device tables in place with another pack of the same signature (one async H2D copy)."""
+        if other.signature() != self.signature():
+            raise ValueError("PackedBatch.copy_from: signatures differ")
+        src = other._stage if other._flat.device != self._flat.device else other._flat
+        self._flat.copy_(src, non_blocking=True)
+        self.host = other.host
 
     def __getitem__(self, k) -> torch.Tensor:
         return self._dev[k]

@@ -13,11 +13,41 @@ where possible (`residual=` existing gradient) instead of separate add kernels.
 """
 from __future__ import annotations
 
+import contextlib
 from typing import Callable, Dict, List, Optional
 
 import torch
 
 from . import ops
+
+# Weight / bias gradient kernels do not feed the backward chain, so they are issued on a per-stream helper
+# stream and overlap with the dgrad kernels (inside a captured CUDA graph this becomes a parallel branch).
+_CONCURRENT = True
+_side_streams: Dict[tuple, "torch.cuda.Stream"] = {}
+
+
+def set_concurrency(on: bool):
+    """Enable / disable multi-stream overlap (weight-gradient branch, concurrent writers)."""
+    global _CONCURRENT
+    _CONCURRENT = bool(on)
+
+
+def concurrency() -> bool:
+    return _CONCURRENT
+
+
+def helper_streams(n: int, tag: str):
+    """`n` cached helper streams tied to the current stream (one set per (device, current stream, tag))."""
+    cur = torch.cuda.current_stream()
+    out = []
+    for i in range(n):
+        key = (cur.device, cur.cuda_stream, tag, i)
+        st = _side_streams.get(key)
+        if st is None:
+            st = torch.cuda.Stream(device=cur.device)
+            _side_streams[key] = st
+        out.append(st)
+    return out
 
 
 class Var:
@@ -42,6 +72,9 @@ class Tape:
         self.pgrads: Dict[int, torch.Tensor] = {}   # id(param tensor) -> grad
         self.sinks: Dict[int, torch.Tensor] = {}    # id(param tensor) -> preallocated gradient buffer (flat-buffer view)
         self._sink_written = set()
+        self._side = None          # helper stream of the weight-gradient branch (created on first use)
+        self._side_dirty = False
+        self._keep: List[torch.Tensor] = []   # tensors the helper stream still reads (released at the next join)
 
     def next_seed(self) -> int:
         self._n += 1
@@ -55,6 +88,33 @@ class Tape:
         for fn in reversed(self.fns):
             fn()
         self.fns = []
+        self.join_side()
+
+    @contextlib.contextmanager
+    def side_branch(self, *tensors):
+        """Run the enclosed kernel launches on the helper stream, ordered after everything enqueued so far on the
+        current stream.  `tensors` (allocated on the current stream) stay referenced until `join_side`."""
+        if not _CONCURRENT or not tensors[0].is_cuda:
+            yield
+            return
+        if self._side is None:
+            self._side = helper_streams(1, "wgrad")[0]
+        ev = torch.cuda.Event()
+        ev.record()
+        self._side.wait_event(ev)
+        self._keep.extend(tensors)
+        self._side_dirty = True
+        with torch.cuda.stream(self._side):
+            yield
+
+    def join_side(self):
+        """Make the current stream wait for the weight-gradient branch (before gradients are consumed)."""
+        if self._side_dirty:
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+            torch.cuda.current_stream().wait_event(ev)
+            self._side_dirty = False
+        self._keep = []
 
     def grad_target(self, p: torch.Tensor):
         """(buffer, accumulate) if the parameter's gradient is written in place by the kernels, else (None, False)."""
@@ -127,19 +187,20 @@ def linear(t: Tape, x: Var, W: torch.Tensor, b: Optional[torch.Tensor], *, act: 
         else:
             dpre_full = dy_full
         dpre = dpre_full[:, :N] if dpre_full.shape[1] != N else dpre_full
-        # weight / bias gradients
-        tgt, acc = t.grad_target(W)
-        if tgt is None:
-            t.add_pgrad(W, ops.gemm(dpre, xv, trans_a=True, trans_b=True, m=N, n=K, k=M))
-        else:
-            ops.gemm(dpre, xv, trans_a=True, trans_b=True, m=N, n=K, k=M, out=tgt, accumulate=acc)
-        if b is not None:
-            tgt, acc = t.grad_target(b)
+        # weight / bias gradients (parallel branch)
+        with t.side_branch(dpre_full, xv):
+            tgt, acc = t.grad_target(W)
             if tgt is None:
-                db, _ = ops.col_reduce(dpre, cols=N)
-                t.add_pgrad(b, db)
+                t.add_pgrad(W, ops.gemm(dpre, xv, trans_a=True, trans_b=True, m=N, n=K, k=M))
             else:
-                ops.col_reduce(dpre, out_sum=tgt, cols=N, accumulate=acc)
+                ops.gemm(dpre, xv, trans_a=True, trans_b=True, m=N, n=K, k=M, out=tgt, accumulate=acc)
+            if b is not None:
+                tgt, acc = t.grad_target(b)
+                if tgt is None:
+                    db, _ = ops.col_reduce(dpre, cols=N)
+                    t.add_pgrad(b, db)
+                else:
+                    ops.col_reduce(dpre, out_sum=tgt, cols=N, accumulate=acc)
         if x.needs:
             fuse = x.elu_fusable and x.g is None
             if K == xv.shape[1]:
@@ -164,14 +225,15 @@ def layernorm(t: Tape, x: Var, gamma: torch.Tensor, beta: torch.Tensor) -> Var:
         dy = y.g
         if dy is None:
             return
-        tg, acc = t.grad_target(gamma)
-        tb, _ = t.grad_target(beta)
-        if tg is None or tb is None:
-            dbeta, dgamma = ops.col_reduce(dy, x=x.v, mean=mean, rstd=rstd)
-            t.add_pgrad(gamma, dgamma)
-            t.add_pgrad(beta, dbeta)
-        else:
-            ops.col_reduce(dy, out_sum=tb, x=x.v, mean=mean, rstd=rstd, out_xhat=tg, accumulate=acc)
+        with t.side_branch(dy, x.v, mean, rstd):
+            tg, acc = t.grad_target(gamma)
+            tb, _ = t.grad_target(beta)
+            if tg is None or tb is None:
+                dbeta, dgamma = ops.col_reduce(dy, x=x.v, mean=mean, rstd=rstd)
+                t.add_pgrad(gamma, dgamma)
+                t.add_pgrad(beta, dbeta)
+            else:
+                ops.col_reduce(dy, out_sum=tb, x=x.v, mean=mean, rstd=rstd, out_xhat=tg, accumulate=acc)
         if x.needs:
             add_grad(x, ops.layernorm_bwd(dy, x.v, mean, rstd, gamma))
 

@@ -65,20 +65,51 @@ class FlatParams:
         return self.offsets[idx[0]], self.offsets[last] + (self.params[last].numel() + 3) // 4 * 4
 
 
+class _Captured:
+    """One captured training step: static input graph + CUDA graph + static loss."""
+    __slots__ = ("graph", "g_static", "pack", "loss", "keys")
+
+
 class Trainer:
-    """forward -> loss -> backward -> (bucketed all-reduce) -> clip + Adam, all on the GPU."""
+    """forward -> loss -> backward -> (bucketed all-reduce) -> clip + Adam, all on the GPU.
+
+    `use_cuda_graph=True` (default on CUDA): the whole step -- ~900 kernel launches, the NCCL bucket
+    all-reduces on the side stream, clip + Adam -- is captured once per batch *shape signature*
+    (`PackedBatch.signature()` + conformation count) and replayed with a single launch.  The step count,
+    the learning rate and the dropout RNG offset live in device memory so that replays stay correct:
+    `counters[0]` = completed steps (Adam bias correction), `counters[1]` = offset added to every dropout
+    seed; a `tick` kernel at the end of the step advances both.  The first step of a new signature runs
+    eagerly (it also performs the one-off kernel attribute set-up), the second one is captured.
+    """
+
+    INPUT_KEYS = ("xyz", "energy_ref", "gradient_ref", "partial_charge")
 
     def __init__(self, model: models.GrappaModel, energy, loss_fn, lr: float = 1.5e-5, clip: float = 10.0,
-                 betas=(0.9, 0.999), eps: float = 1e-8, device="cuda", distributed: Optional[bool] = None):
+                 betas=(0.9, 0.999), eps: float = 1e-8, device="cuda", distributed: Optional[bool] = None,
+                 use_cuda_graph: Optional[bool] = None, max_graphs: int = 8):
         self.model, self.energy, self.loss_fn = model, energy, loss_fn
-        self.lr, self.clip, self.betas, self.eps = lr, clip, betas, eps
+        self.clip, self.betas, self.eps = clip, betas, eps
         self.device = torch.device(device)
         model.to(self.device)
         self.fp = FlatParams(model, self.device)
-        self.step_count = 0
         self.distributed = dist.is_available() and dist.is_initialized() if distributed is None else distributed
         self.world = dist.get_world_size() if self.distributed else 1
         self.gnorm_sq = torch.zeros(1, device=self.device, dtype=torch.float32)
+        self.counters = torch.zeros(2, device=self.device, dtype=torch.int64)
+        self.lr_dev = torch.full((1,), float(lr), device=self.device, dtype=torch.float32)
+        self._lr = float(lr)
+        self._host_steps = 0
+        if self.device.type == "cuda":
+            ops.set_rng_offset(self.counters[1:2])
+        self.use_cuda_graph = (self.device.type == "cuda") if use_cuda_graph is None else use_cuda_graph
+        # every step (eager or replayed) is enqueued on the trainer's own stream: autograd binds its per-parameter
+        # bookkeeping nodes to the stream they were first used on, and a stream capture may only depend on work of
+        # the capturing stream -- so eager warm-up steps and the capture must share one non-default stream
+        self.stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+        self.max_graphs = max_graphs
+        self._captured = {}
+        self._seen = {}
+        self.last_graph = None
         # buckets in the order their gradients become available during backward
         w = model.parameter_writer
         g = model.gnn
@@ -91,6 +122,21 @@ class Trainer:
         self._pending: List = []
         if self.distributed:
             models.set_backward_hook(self._on_stage_backward)
+
+    # ---- learning rate / step count (device-resident) ------------------------------------------
+    @property
+    def lr(self) -> float:
+        return self._lr
+
+    @lr.setter
+    def lr(self, value: float):
+        if float(value) != self._lr:
+            self._lr = float(value)
+            self.lr_dev.fill_(self._lr)
+
+    @property
+    def step_count(self) -> int:
+        return self._host_steps
 
     # ---- gradient exchange ---------------------------------------------------------------------
     def _launch_allreduce(self, start: int, end: int):
@@ -135,6 +181,14 @@ class Trainer:
 
     # ---- one optimisation step -----------------------------------------------------------------
     def forward_backward(self, g) -> torch.Tensor:
+        from .pack import get_pack
+        pack = get_pack(g)
+        for (name, _), lvl in zip(self.buckets, (3, 2, 1, 0)):
+            if pack.n_tuples[lvl] == 0:      # writer unused by this batch: its gradient is zero, not stale
+                s, e = self._bucket_spans[name]
+                self.fp.grad[s:e].zero_()
+                if self.distributed:
+                    self._launch_allreduce(s, e)
         g = self.model(g)
         g = self.energy(g)
         loss = self.loss_fn(g)
@@ -143,16 +197,105 @@ class Trainer:
 
     def optimizer_step(self):
         self._wait_comm()
-        self.step_count += 1
         self.gnorm_sq.zero_()
         ops.sumsq(self.fp.grad, self.gnorm_sq)
-        ops.adam_step(self.fp.flat, self.fp.grad, self.fp.m, self.fp.v, self.lr, self.betas[0], self.betas[1], self.eps,
-                      self.step_count, gnorm_sq=self.gnorm_sq, clip=self.clip, grad_scale=1.0 / self.world)
+        ops.adam_step_dev(self.fp.flat, self.fp.grad, self.fp.m, self.fp.v, self.lr_dev, self.betas[0], self.betas[1],
+                          self.eps, self.counters[0:1], gnorm_sq=self.gnorm_sq, clip=self.clip, grad_scale=1.0 / self.world)
+        ops.tick(self.counters)
 
-    def step(self, g) -> torch.Tensor:
+    def _eager_step(self, g) -> torch.Tensor:
         loss = self.forward_backward(g)
         self.optimizer_step()
         return loss
+
+    # ---- CUDA-graph path ------------------------------------------------------------------------
+    def _input_keys(self, g):
+        names = set(self.INPUT_KEYS) | set(self.model.gnn.in_feat_name)
+        keys = []
+        for nt in g.ntypes:
+            for k in g.nodes[nt].data.keys():
+                if k in names or k.endswith("_ref"):
+                    keys.append((nt, k))
+        return keys
+
+    def _signature(self, g):
+        from .pack import get_pack
+        xyz = g.nodes["n1"].data.get("xyz")
+        keys = tuple((nt, k, tuple(g.nodes[nt].data[k].shape)) for nt, k in self._input_keys(g))
+        return (get_pack(g).signature(), None if xyz is None else tuple(xyz.shape), keys)
+
+    def _refresh_inputs(self, cap: _Captured, g):
+        from .pack import get_pack
+        for nt, k in cap.keys:
+            cap.g_static.nodes[nt].data[k].copy_(g.nodes[nt].data[k], non_blocking=True)
+        cap.pack.copy_from(get_pack(g))
+
+    def h2d_bytes(self, g) -> int:
+        """Bytes `step(g)` copies host->device for a host-resident batch (inputs + index tables)."""
+        from .pack import get_pack
+        n = sum(g.nodes[nt].data[k].numel() * g.nodes[nt].data[k].element_size() for nt, k in self._input_keys(g))
+        return n + get_pack(g).bytes
+
+    def _capture(self, g) -> _Captured:
+        from .pack import get_pack
+        cap = _Captured()
+        cap.keys = self._input_keys(g)
+        gs = g.to(self.device)
+        if g.device.type == "cuda":      # never alias the caller's tensors
+            for nt, k in cap.keys:
+                gs.nodes[nt].data[k] = g.nodes[nt].data[k].clone()
+        for nt in gs.ntypes:             # stale outputs of an earlier eager pass are not inputs
+            for k in list(gs.nodes[nt].data.keys()):
+                if (nt, k) not in cap.keys and k != "idxs":
+                    del gs.nodes[nt].data[k]
+        cap.pack = get_pack(gs)
+        if cap.pack is getattr(g, "_pack_cache", None):
+            cap.pack = cap.pack.to(self.device)
+            gs._pack_cache = cap.pack
+        cap.g_static = gs
+        torch.cuda.synchronize(self.device)
+        cap.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(cap.graph, stream=self.stream):
+            cap.loss = self._eager_step(gs)
+        ops.drop_workspaces()            # scratch allocated while capturing belongs to the graph's pool
+        return cap
+
+    def step(self, g) -> torch.Tensor:
+        """One optimisation step on batch `g` (host or device resident); returns the (device) loss."""
+        self._host_steps += 1
+        if self.stream is None:
+            self.last_graph = g
+            return self._eager_step(g)
+        caller = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(caller)
+        with torch.cuda.stream(self.stream):
+            loss = self._step_on_stream(g)
+        caller.wait_stream(self.stream)
+        return loss
+
+    def _step_on_stream(self, g) -> torch.Tensor:
+        if not self.use_cuda_graph:
+            if g.device.type != "cuda":
+                g = g.to(self.device, non_blocking=True)
+            self.last_graph = g
+            return self._eager_step(g)
+        sig = self._signature(g)
+        cap = self._captured.get(sig)
+        if cap is None:
+            n = self._seen.get(sig, 0)
+            self._seen[sig] = n + 1
+            if n == 0 or len(self._captured) >= self.max_graphs:
+                if g.device.type != "cuda":
+                    g = g.to(self.device, non_blocking=True)
+                self.last_graph = g
+                return self._eager_step(g)
+            cap = self._capture(g)
+            self._captured[sig] = cap
+        else:
+            self._refresh_inputs(cap, g)
+        cap.graph.replay()
+        self.last_graph = cap.g_static
+        return cap.loss
 
 
 def init_distributed(backend: Optional[str] = None) -> Tuple[int, int, int]:

@@ -107,7 +107,7 @@ int grappa_b200_energy_bwd(const gb_energy_bwd_args* a, void* stream);
  *
  *   acc[m,n] = sum_k opA(A)[m,k] * opB(B)[n,k]
  *   v = acc + bias[n]; v = act(v); [act_out[m,n] = v;] v *= elu'(y = mul_elu_out[m,n]);
- *   v *= dropout_mask(seed, m*N+n)/(1-p);
+ *   v *= dropout_mask(seed + *dropout_offset, m*N+n)/(1-p);
  *   v += residual[m,n];  C[m,n] = accumulate ? C[m,n] + v : v
  *
  * trans_a = 0: A is [M,K] row-major (lda >= K);  1: A is stored [K,M] row-major (lda >= M)
@@ -136,6 +136,8 @@ typedef struct {
   int64_t workspace_bytes;
   float* act_out;             /* optional [M,N] (ld = ldact): value after bias+activation, before dropout/residual */
   int32_t ldact;
+  const uint64_t* dropout_offset; /* optional DEVICE counter added to dropout_seed at run time: lets a captured CUDA
+                                     graph draw a fresh mask on every replay (see grappa_b200_tick) */
 } gb_gemm_args;
 
 int grappa_b200_gemm(const gb_gemm_args* a, void* stream);
@@ -149,10 +151,13 @@ int grappa_b200_layernorm_fwd(const float* x, const float* gamma, const float* b
 /* dx only; parameter gradients come from grappa_b200_col_reduce below */
 int grappa_b200_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
                               const float* gamma, float* dx, int32_t rows, int32_t cols, void* stream);
-/* Column reductions over rows (deterministic two-stage):
+/* Column reductions over rows (deterministic):
  *   out_sum[c]  = sum_r dy[r,c]                                  (bias gradients, LayerNorm beta)
  *   out_xhat[c] = sum_r dy[r,c] * (x[r,c] - mean[r]) * rstd[r]   (LayerNorm gamma; skipped if x NULL)
- * workspace: >= grappa_b200_col_reduce_workspace(rows, cols) bytes. accumulate: add to outputs. */
+ * One launch: the last block of every column group folds the partial sums in a fixed order.
+ * workspace: >= grappa_b200_col_reduce_workspace(rows, cols) bytes whose first 256 bytes (ticket counters) are ZERO
+ * when first used; the kernel leaves them zero, so the buffer can be reused by later launches on the same stream.
+ * accumulate: add to outputs. */
 int64_t grappa_b200_col_reduce_workspace(int32_t rows, int32_t cols);
 int grappa_b200_col_reduce(const float* dy, int32_t ld, const float* x, const float* mean, const float* rstd,
                            float* out_sum, float* out_xhat, float* workspace, int32_t rows, int32_t cols,
@@ -242,11 +247,13 @@ int grappa_b200_head_output_bwd(const gb_head_out_args* a, const float* scores, 
 /* ---------------------------------------------------------------------------------------------
  * Small fused elementwise kernels.
  * ------------------------------------------------------------------------------------------- */
-/* y[i] = x[i] * keep(seed, i) / (1 - p)   (same call regenerates the mask in the backward pass) */
-int grappa_b200_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, void* stream);
+/* y[i] = x[i] * keep(seed + *seed_offset, i) / (1 - p)   (same call regenerates the mask in the backward pass;
+ * seed_offset: optional device counter, NULL = 0) */
+int grappa_b200_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, const uint64_t* seed_offset,
+                        void* stream);
 /* dx[i] = dy[i] * keep(seed, i)/(1-p) * elu'(act_out[i])   (act_out NULL: no activation; p = 0: no mask) */
 int grappa_b200_act_dropout_bwd(const float* dy, const float* act_out, float* dx, int64_t n, float p, uint64_t seed,
-                                void* stream);
+                                const uint64_t* seed_offset, void* stream);
 /* y = a*x + b*y */
 int grappa_b200_axpby(const float* x, float* y, int64_t n, float a, float b, void* stream);
 /* out[0] += sum x^2  (out must be zeroed by the caller; deterministic two-stage when ws given) */
@@ -255,6 +262,13 @@ int grappa_b200_sumsq(const float* x, int64_t n, float* out, void* stream);
  * min(1, clip / (sqrt(*gnorm_sq) + 1e-6)) * grad_scale -- gnorm_sq is a device scalar or NULL. */
 int grappa_b200_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                           float eps, int32_t step, const float* gnorm_sq, float clip, float grad_scale, void* stream);
+/* Same, with the learning rate and the step count read from DEVICE memory (CUDA-graph replays: the host updates
+ * *lr_dev with a copy, grappa_b200_tick advances *step_dev).  *step_dev counts completed steps (0 on the first call). */
+int grappa_b200_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_dev, float beta1,
+                              float beta2, float eps, const uint64_t* step_dev, const float* gnorm_sq, float clip,
+                              float grad_scale, void* stream);
+/* counters[i] += 1 for i < n  (device-side step / RNG counters advanced inside a captured graph) */
+int grappa_b200_tick(uint64_t* counters, int32_t n, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Molecule-wise loss (reference training/loss.py:45-167, terms active in grappa-1.2 training):
