@@ -88,7 +88,7 @@ def lib():
         except OSError as e:  # pragma: no cover
             raise GrappaB200Error(f"cannot load {LIB_PATH}: {e}") from e
         _declare(l)
-        if l.grappa_b200_abi_version() != 1:
+        if l.grappa_b200_abi_version() != 2:
             raise GrappaB200Error("libgrappa_b200.so ABI version mismatch; rebuild")
         _lib = l
     return _lib

@@ -25,7 +25,7 @@ extern "C" {
 #define GB_ERR_INVALID (-1) /* bad argument / unsupported shape */
 #define GB_ERR_CUDA (-2)    /* CUDA runtime / launch failure     */
 
-#define GB_ABI_VERSION 1
+#define GB_ABI_VERSION 2
 
 const char* grappa_b200_last_error(void);
 int grappa_b200_abi_version(void);
