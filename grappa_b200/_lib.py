@@ -39,6 +39,9 @@ class EnergyArgs(C.Structure):
         ("grad", c_f32p),
         ("x", c_f32p * 4),
         ("tuple_energy", c_f32p * 4),
+        ("sched", c_i32p * 4),
+        ("round_off", c_i32p * 4),
+        ("sched_groups", C.c_int32),
     ]
 
 
@@ -67,6 +70,9 @@ def _declare(lib):
     lib.grappa_b200_tuples_build.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.grappa_b200_torsions_classify.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int,
                                                   C.c_void_p, i64p, C.c_void_p, i64p]
+    lib.grappa_b200_conflict_free_rounds.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                                     C.c_void_p, C.c_int64]
+    lib.grappa_b200_conflict_free_rounds.restype = C.c_int64
     lib.grappa_b200_energy_fwd.argtypes = [C.POINTER(EnergyArgs), C.c_int, C.c_void_p]
     lib.grappa_b200_energy_bwd.argtypes = [C.POINTER(EnergyBwdArgs), C.c_void_p]
     lib.grappa_b200_energy_bwd_workspace.argtypes = [C.POINTER(EnergyArgs)]

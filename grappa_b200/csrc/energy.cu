@@ -22,6 +22,7 @@
 namespace gb {
 
 static __device__ __forceinline__ V3 ld3(const float* p) { return v3(p[0], p[1], p[2]); }
+static __device__ __forceinline__ V3 ld3g(const float* p) { return v3(__ldg(p), __ldg(p + 1), __ldg(p + 2)); }
 
 // molecule that owns tuple t (off has n_mols+1 monotone entries)
 static __device__ __forceinline__ int find_segment(const int32_t* __restrict__ off, int n, int t) {
@@ -186,6 +187,330 @@ __global__ void __launch_bounds__(512) energy_tiled_kernel(gb_energy_args a, int
     }
     if (a.energy) a.energy[(size_t)b * C + c0 + tid] = tot;
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// round-scheduled tiled forward (default when the pack carries a conflict-free schedule)
+//
+// CTA = (molecule, tile of <= 32 conformations); 32 lanes = conformations, G warps = tuple slots of a round.
+// The host packs the tuples of every molecule/level into rounds of <= G tuples that share no atom
+// (grappa_b200_conflict_free_rounds), so inside a round the G warps update DISJOINT rows of the shared force
+// tile: plain read-modify-write instead of float shared atomics (which are CAS loops in SASS), one
+// __syncthreads between rounds, and a fixed summation order -> bit-reproducible forces.  The molecule's
+// coordinates are staged once in shared memory as [atom][xyz][32] (bank-conflict-free columns).
+// ---------------------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(32 * G, 4) energy_rounds_kernel(gb_energy_args a, int n_tiles, int wtile) {
+  extern __shared__ float smem[];
+  constexpr int W = 32;
+  const int b = blockIdx.x / n_tiles;
+  const int tile = blockIdx.x - b * n_tiles;
+  const int a0 = __ldg(a.atom_off + b);
+  const int n_at = __ldg(a.atom_off + b + 1) - a0;
+  const int C = a.n_confs;
+  const int c0 = tile * wtile;
+  const int wc = min(wtile, C - c0);       // valid conformations in this tile (<= 32)
+  float* xs = smem;                        // [n_at][3][W]
+  float* gs = smem + (size_t)n_at * 3 * W; // [n_at][3][W]
+  const int tid = threadIdx.x;
+  constexpr int nthr = 32 * G;
+  const int cl = tid & 31, grp = tid >> 5;
+
+  for (int i = tid; i < n_at * 3 * W; i += nthr) {
+    const int at = i / (3 * W), rem = i - at * 3 * W;
+    const int cc = rem / 3, comp = rem - cc * 3;
+    float v = 0.f;
+    if (cc < wc) v = __ldg(a.xyz + ((size_t)(a0 + at) * C + c0) * 3 + rem);
+    xs[(at * 3 + comp) * W + cc] = v;
+    gs[(at * 3 + comp) * W + cc] = 0.f;
+  }
+  __syncthreads();
+
+  const bool active = cl < wc;
+  const int c = c0 + cl;
+  const bool want_grad = a.grad != nullptr;
+  float e_lvl[4] = {0.f, 0.f, 0.f, 0.f};
+#define XS(at) v3(xs[((at) * 3 + 0) * W + cl], xs[((at) * 3 + 1) * W + cl], xs[((at) * 3 + 2) * W + cl])
+#define GADD(at, vec)                         \
+  do {                                        \
+    float* g_ = gs + ((at) * 3) * W + cl;     \
+    g_[0] += (vec).x;                         \
+    g_[W] += (vec).y;                         \
+    g_[2 * W] += (vec).z;                     \
+  } while (0)
+  // ---- bonds
+  if ((a.level_mask & 1) && a.n_tuples[0] > 0) {
+    const int r1 = __ldg(a.round_off[0] + b + 1);
+    for (int r = __ldg(a.round_off[0] + b); r < r1; ++r) {
+      const int t = __ldg(a.sched[0] + (size_t)r * G + grp);            // warp-uniform
+      if (t >= 0 && active) {
+        const int i0 = __ldg(a.idx[0] + 2 * t) - a0, i1 = __ldg(a.idx[0] + 2 * t + 1) - a0;
+        const float k = __ldg(a.k[0] + t), eq = __ldg(a.eq[0] + t);
+        BondGeom g = bond_geom(XS(i0), XS(i1));
+        const float d = g.r - eq;
+        const float e = 0.5f * k * d * d;
+        e_lvl[0] += e;
+        if (a.x[0]) a.x[0][(size_t)t * C + c] = g.r;
+        if (a.tuple_energy[0]) a.tuple_energy[0][(size_t)t * C + c] = e;
+        if (want_grad) {
+          V3 f = (k * d) * g.d0;
+          GADD(i0, f);
+          GADD(i1, v3(-f.x, -f.y, -f.z));
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // ---- angles
+  if ((a.level_mask & 2) && a.n_tuples[1] > 0) {
+    const int r1 = __ldg(a.round_off[1] + b + 1);
+    for (int r = __ldg(a.round_off[1] + b); r < r1; ++r) {
+      const int t = __ldg(a.sched[1] + (size_t)r * G + grp);
+      if (t >= 0 && active) {
+        const int i0 = __ldg(a.idx[1] + 3 * t) - a0, i1 = __ldg(a.idx[1] + 3 * t + 1) - a0,
+                  i2 = __ldg(a.idx[1] + 3 * t + 2) - a0;
+        const float k = __ldg(a.k[1] + t), eq = __ldg(a.eq[1] + t);
+        AngleGeom g = angle_geom(XS(i0), XS(i1), XS(i2));
+        const float d = g.theta - eq;
+        const float e = 0.5f * k * d * d;
+        e_lvl[1] += e;
+        if (a.x[1]) a.x[1][(size_t)t * C + c] = g.theta;
+        if (a.tuple_energy[1]) a.tuple_energy[1][(size_t)t * C + c] = e;
+        if (want_grad) {
+          const float s = k * d;
+          V3 f0 = s * g.d0, f2 = s * g.d2;
+          GADD(i0, f0);
+          GADD(i2, f2);
+          GADD(i1, v3(-f0.x - f2.x, -f0.y - f2.y, -f0.z - f2.z));
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // ---- torsions (propers, then impropers): one instantiation of the loop body for both levels
+#pragma unroll 1
+  for (int lv = 2; lv < 4; ++lv) {
+    if (!((a.level_mask >> lv) & 1) || a.n_tuples[lv] == 0) continue;   // uniform
+    const int nper = a.n_per[lv - 2];
+    const int32_t* __restrict__ sched = a.sched[lv];
+    const int32_t* __restrict__ idx = a.idx[lv];
+    const float* __restrict__ kp = a.k[lv];
+    float* __restrict__ xo = a.x[lv];
+    float* __restrict__ teo = a.tuple_energy[lv];
+    const int r1 = __ldg(a.round_off[lv] + b + 1);
+    float e_acc = 0.f;
+    for (int r = __ldg(a.round_off[lv] + b); r < r1; ++r) {
+      const int t = __ldg(sched + (size_t)r * G + grp);
+      if (t >= 0 && active) {
+        const int32_t* ip = idx + 4 * t;
+        const int i0 = __ldg(ip) - a0, i1 = __ldg(ip + 1) - a0, i2 = __ldg(ip + 2) - a0, i3 = __ldg(ip + 3) - a0;
+        TorsionGeom g = torsion_geom(XS(i0), XS(i1), XS(i2), XS(i3));
+        float e, dedphi;
+        float kk[GB_MAX_PERIODICITY];
+        if (nper == 3) {
+          kk[0] = __ldg(kp + 3 * t); kk[1] = __ldg(kp + 3 * t + 1); kk[2] = __ldg(kp + 3 * t + 2);
+          kk[3] = kk[4] = kk[5] = 0.f;
+          torsion_series<3>(kk, g.cphi, g.sphi, e, dedphi, nullptr, nullptr);
+        } else {
+#pragma unroll
+          for (int n = 0; n < GB_MAX_PERIODICITY; ++n) kk[n] = n < nper ? __ldg(kp + (size_t)t * nper + n) : 0.f;
+          torsion_series<GB_MAX_PERIODICITY>(kk, g.cphi, g.sphi, e, dedphi, nullptr, nullptr);
+        }
+        if (a.offset_torsion) {
+#pragma unroll
+          for (int n = 0; n < GB_MAX_PERIODICITY; ++n) e += fabsf(kk[n]);
+        }
+        e_acc += e;
+        if (xo) xo[(size_t)t * C + c] = atan2f(g.sphi, g.cphi);
+        if (teo) teo[(size_t)t * C + c] = e;
+        if (want_grad) {
+          GADD(i0, dedphi * g.d0);
+          GADD(i1, dedphi * g.d1);
+          GADD(i2, dedphi * g.d2);
+          GADD(i3, dedphi * g.d3);
+        }
+      }
+      __syncthreads();
+    }
+    if (lv == 2) e_lvl[2] = e_acc; else e_lvl[3] = e_acc;
+  }
+#undef XS
+#undef GADD
+  // forces back to global, coalesced (the last round ended with a barrier)
+  if (want_grad) {
+    for (int i = tid; i < n_at * 3 * W; i += nthr) {
+      const int at = i / (3 * W), rem = i - at * 3 * W;
+      const int cc = rem / 3, comp = rem - cc * 3;
+      if (cc < wc) a.grad[((size_t)(a0 + at) * C + c0) * 3 + rem] = gs[(at * 3 + comp) * W + cc];
+    }
+  }
+  __syncthreads();
+  float* red = xs;  // [4][G][W]
+#pragma unroll
+  for (int lv = 0; lv < 4; ++lv) red[(lv * G + grp) * W + cl] = active ? e_lvl[lv] : 0.f;
+  __syncthreads();
+  if (tid < wc) {
+    float tot = 0.f;
+#pragma unroll
+    for (int lv = 0; lv < 4; ++lv) {
+      float s2 = 0.f;
+#pragma unroll
+      for (int g2 = 0; g2 < G; ++g2) s2 += red[(lv * G + g2) * W + tid];
+      if (a.term_energy[lv]) a.term_energy[lv][(size_t)b * C + c0 + tid] = s2;
+      tot += s2;
+    }
+    if (a.energy) a.energy[(size_t)b * C + c0 + tid] = tot;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// conformation-per-thread forward (default for molecules up to a few hundred atoms)
+//
+// One CTA = (molecule, tile of blockDim.x conformations); a thread owns ONE conformation and walks the
+// molecule's whole tuple list, so
+//   * the force accumulator column gs[atom][xyz][thread] in shared memory is private to the thread: plain
+//     read-modify-write, no atomics (float shared atomics are CAS loops in SASS), no __syncthreads, and the
+//     summation order is the tuple order -> bit-reproducible forces and energies;
+//   * per-level energies never leave registers (no cross-thread reduction at all);
+//   * tuple indices / parameters are warp-uniform loads (one transaction per warp);
+//   * coordinates come straight from global memory through L1 (lanes = consecutive conformations of one atom =
+//     384 contiguous bytes per warp); runs of consecutive tuples that share their central atom (angles) or
+//     central bond (torsions) -- the order the reference's tuple builder emits -- keep those positions and
+//     force accumulators in registers, halving the L1/shared traffic of the torsion loop.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) energy_conf_kernel(gb_energy_args a, int n_tiles) {
+  extern __shared__ float gs[];            // [n_at * 3][W]
+  const int W = blockDim.x, tid = threadIdx.x;
+  const int b = blockIdx.x / n_tiles;
+  const int tile = blockIdx.x - b * n_tiles;
+  const int a0 = __ldg(a.atom_off + b);
+  const int n_at = __ldg(a.atom_off + b + 1) - a0;
+  const int C = a.n_confs;
+  const int c = tile * W + tid;
+  if (c >= C) return;                      // threads are independent: no barrier below
+  const bool want_grad = a.grad != nullptr;
+  if (want_grad)
+    for (int i = 0; i < n_at * 3; ++i) gs[i * W + tid] = 0.f;
+  const float* __restrict__ xp = a.xyz + ((size_t)a0 * C + c) * 3;
+  const size_t astride = (size_t)C * 3;
+#define XG(i) ld3g(xp + (size_t)(i) * astride)
+#define GADD(i, vec)                         \
+  do {                                       \
+    float* g_ = gs + ((i) * 3) * W + tid;    \
+    g_[0] += (vec).x;                        \
+    g_[W] += (vec).y;                        \
+    g_[2 * W] += (vec).z;                    \
+  } while (0)
+  float e_lvl[4] = {0.f, 0.f, 0.f, 0.f};
+
+  // ---- bonds
+  if ((a.level_mask & 1) && a.n_tuples[0] > 0) {
+    const int t1 = __ldg(a.tup_off[0] + b + 1);
+    for (int t = __ldg(a.tup_off[0] + b); t < t1; ++t) {
+      const int i0 = __ldg(a.idx[0] + 2 * t) - a0, i1 = __ldg(a.idx[0] + 2 * t + 1) - a0;
+      const float k = __ldg(a.k[0] + t), eq = __ldg(a.eq[0] + t);
+      BondGeom g = bond_geom(XG(i0), XG(i1));
+      const float d = g.r - eq;
+      const float e = 0.5f * k * d * d;
+      e_lvl[0] += e;
+      if (a.x[0]) a.x[0][(size_t)t * C + c] = g.r;
+      if (a.tuple_energy[0]) a.tuple_energy[0][(size_t)t * C + c] = e;
+      if (want_grad) {
+        V3 f = (k * d) * g.d0;
+        GADD(i0, f);
+        GADD(i1, v3(-f.x, -f.y, -f.z));
+      }
+    }
+  }
+  // ---- angles: the central atom's position and force stay in registers across a run
+  if ((a.level_mask & 2) && a.n_tuples[1] > 0) {
+    const int t1 = __ldg(a.tup_off[1] + b + 1);
+    int cur = -1;
+    V3 xc = v3(0.f, 0.f, 0.f), fc = v3(0.f, 0.f, 0.f);
+    for (int t = __ldg(a.tup_off[1] + b); t < t1; ++t) {
+      const int i0 = __ldg(a.idx[1] + 3 * t) - a0, i1 = __ldg(a.idx[1] + 3 * t + 1) - a0,
+                i2 = __ldg(a.idx[1] + 3 * t + 2) - a0;
+      const float k = __ldg(a.k[1] + t), eq = __ldg(a.eq[1] + t);
+      if (i1 != cur) {                      // warp-uniform
+        if (cur >= 0 && want_grad) GADD(cur, fc);
+        cur = i1;
+        xc = XG(i1);
+        fc = v3(0.f, 0.f, 0.f);
+      }
+      AngleGeom g = angle_geom(XG(i0), xc, XG(i2));
+      const float d = g.theta - eq;
+      const float e = 0.5f * k * d * d;
+      e_lvl[1] += e;
+      if (a.x[1]) a.x[1][(size_t)t * C + c] = g.theta;
+      if (a.tuple_energy[1]) a.tuple_energy[1][(size_t)t * C + c] = e;
+      if (want_grad) {
+        const float s = k * d;
+        V3 f0 = s * g.d0, f2 = s * g.d2;
+        GADD(i0, f0);
+        GADD(i2, f2);
+        fc = v3(fc.x - f0.x - f2.x, fc.y - f0.y - f2.y, fc.z - f0.z - f2.z);
+      }
+    }
+    if (cur >= 0 && want_grad) GADD(cur, fc);
+  }
+  // ---- torsions (propers, impropers): the central bond's two atoms stay in registers across a run
+#pragma unroll
+  for (int lv = 2; lv < 4; ++lv) {
+    if (!((a.level_mask >> lv) & 1) || a.n_tuples[lv] == 0) continue;
+    const int nper = a.n_per[lv - 2];
+    const int t1 = __ldg(a.tup_off[lv] + b + 1);
+    int c1 = -1, c2 = -1;
+    V3 x1 = v3(0.f, 0.f, 0.f), x2 = x1, f1 = x1, f2 = x1;
+    for (int t = __ldg(a.tup_off[lv] + b); t < t1; ++t) {
+      const int32_t* ip = a.idx[lv] + 4 * t;
+      const int i0 = __ldg(ip) - a0, i1 = __ldg(ip + 1) - a0, i2 = __ldg(ip + 2) - a0, i3 = __ldg(ip + 3) - a0;
+      float kk[GB_MAX_PERIODICITY];
+#pragma unroll
+      for (int n = 0; n < GB_MAX_PERIODICITY; ++n) kk[n] = n < nper ? __ldg(a.k[lv] + (size_t)t * nper + n) : 0.f;
+      if (i1 != c1 || i2 != c2) {           // warp-uniform
+        if (c1 >= 0 && want_grad) { GADD(c1, f1); GADD(c2, f2); }
+        c1 = i1; c2 = i2;
+        x1 = XG(i1); x2 = XG(i2);
+        f1 = v3(0.f, 0.f, 0.f); f2 = f1;
+      }
+      TorsionGeom g = torsion_geom(XG(i0), x1, x2, XG(i3));
+      float e, dedphi;
+      if (nper == 3) torsion_series<3>(kk, g.cphi, g.sphi, e, dedphi, nullptr, nullptr);
+      else torsion_series_dyn(nper, kk, g.cphi, g.sphi, e, dedphi, nullptr, nullptr);
+      if (a.offset_torsion) {
+#pragma unroll
+        for (int n = 0; n < GB_MAX_PERIODICITY; ++n) e += fabsf(kk[n]);
+      }
+      e_lvl[lv] += e;
+      if (a.x[lv]) a.x[lv][(size_t)t * C + c] = atan2f(g.sphi, g.cphi);
+      if (a.tuple_energy[lv]) a.tuple_energy[lv][(size_t)t * C + c] = e;
+      if (want_grad) {
+        GADD(i0, dedphi * g.d0);
+        GADD(i3, dedphi * g.d3);
+        f1 = f1 + dedphi * g.d1;
+        f2 = f2 + dedphi * g.d2;
+      }
+    }
+    if (c1 >= 0 && want_grad) { GADD(c1, f1); GADD(c2, f2); }
+  }
+#undef XG
+#undef GADD
+  if (want_grad) {
+    float* gp = a.grad + ((size_t)a0 * C + c) * 3;
+    for (int i = 0; i < n_at; ++i) {
+      float* q = gp + (size_t)i * astride;
+      q[0] = gs[(i * 3 + 0) * W + tid];
+      q[1] = gs[(i * 3 + 1) * W + tid];
+      q[2] = gs[(i * 3 + 2) * W + tid];
+    }
+  }
+  float tot = 0.f;
+#pragma unroll
+  for (int lv = 0; lv < 4; ++lv) {
+    if (a.term_energy[lv]) a.term_energy[lv][(size_t)b * C + c] = e_lvl[lv];
+    tot += e_lvl[lv];
+  }
+  if (a.energy) a.energy[(size_t)b * C + c] = tot;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -392,6 +717,47 @@ extern "C" int grappa_b200_energy_fwd(const gb_energy_args* a, int variant, void
   const size_t smem = smem_floats * sizeof(float);
   const bool tile_ok = max_atoms > 0 && smem <= 200 * 1024;
   GB_REQUIRE(mode != 2 || tile_ok, "energy: tiled variant requested but max_atoms=%d does not fit", max_atoms);
+  // round-scheduled kernel: needs the host schedule and the molecule tile (xyz + forces, 32 conformations) in smem
+  {
+    bool have = a->sched_groups == 8;
+    for (int l = 0; l < 4 && have; ++l)
+      if (a->n_tuples[l] > 0 && ((a->level_mask >> l) & 1)) have = a->sched[l] && a->round_off[l];
+    size_t smem_r = (size_t)max_atoms * 3 * 32 * 2 * sizeof(float);
+    if (smem_r < (size_t)4 * 8 * 32 * sizeof(float)) smem_r = (size_t)4 * 8 * 32 * sizeof(float);
+    const bool fits = max_atoms > 0 && smem_r <= 200 * 1024;
+    GB_REQUIRE(mode != 4 || (have && fits), "energy: round-scheduled variant needs sched/round_off with sched_groups == 8 "
+               "and a molecule tile that fits in shared memory (max_atoms=%d)", max_atoms);
+    if (mode == 4 || (mode == 0 && have && fits)) {
+      static bool configured = false;
+      if (!configured) {
+        GB_CHECK_CUDA(cudaFuncSetAttribute(energy_rounds_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+      }
+      const int nt = (C + 31) / 32;
+      const int wtile = (C + nt - 1) / nt;          // balanced tiles of <= 32 conformations
+      energy_rounds_kernel<8><<<B * nt, 256, smem_r, stream>>>(*a, nt, wtile);
+      GB_CHECK_LAUNCH();
+      return GB_OK;
+    }
+  }
+  // conformation-per-thread kernel: force columns of one tile must leave room for >= 2 CTAs per SM
+  {
+    const int Wc = C <= 32 ? 32 : 64;
+    const size_t smem_c = (size_t)max_atoms * 3 * Wc * sizeof(float);
+    const bool conf_ok = max_atoms > 0 && smem_c <= 100 * 1024;
+    GB_REQUIRE(mode != 3 || conf_ok, "energy: conformation-per-thread variant requested but max_atoms=%d does not fit", max_atoms);
+    if (mode == 3) {
+      static bool configured = false;
+      if (!configured) {
+        GB_CHECK_CUDA(cudaFuncSetAttribute(energy_conf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        configured = true;
+      }
+      const int nt = (C + Wc - 1) / Wc;
+      energy_conf_kernel<<<B * nt, Wc, smem_c, stream>>>(*a, nt);
+      GB_CHECK_LAUNCH();
+      return GB_OK;
+    }
+  }
   const bool tiled = (mode == 2) || (mode == 0 && tile_ok);
   if (tiled) {
     auto kern = G > 1 ? energy_tiled_kernel<true> : energy_tiled_kernel<false>;

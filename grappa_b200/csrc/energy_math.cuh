@@ -37,9 +37,21 @@ GB_HD V3 cross(V3 a, V3 b) {
 }
 GB_HD float inv_sqrt(float x) {
 #ifdef __CUDA_ARCH__
-  return rsqrtf(x);
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));   // one MUFU.RSQ (2 ulp); geometry never produces denormals
+  return r;
 #else
   return 1.0f / sqrtf(x);
+#endif
+}
+// reciprocal: one MUFU.RCP on the device (<= 1 ulp), exact division on the host build
+GB_HD float recip(float x) {
+#ifdef __CUDA_ARCH__
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return 1.0f / x;
 #endif
 }
 
@@ -68,10 +80,11 @@ struct AngleGeom {
 GB_HD AngleGeom angle_geom(V3 x0, V3 x1, V3 x2) {
   V3 a = x0 - x1, b = x2 - x1;
   V3 n = cross(a, b);
-  float s = sqrtf(dot(n, n));     // |a||b| sin(theta)
+  float s2 = dot(n, n);
+  float is = inv_sqrt(s2);
+  float s = s2 * is;              // |a||b| sin(theta)
   float c = dot(a, b);            // |a||b| cos(theta)
-  float ia2 = 1.0f / dot(a, a), ib2 = 1.0f / dot(b, b);
-  float is = 1.0f / s;
+  float ia2 = recip(dot(a, a)), ib2 = recip(dot(b, b));
   AngleGeom g;
   g.theta = atan2f(s, c);
   // dtheta/da = (c/|a|^2 a - b) / s ,  dtheta/db = (c/|b|^2 b - a) / s
@@ -91,11 +104,12 @@ GB_HD TorsionGeom torsion_geom(V3 x0, V3 x1, V3 x2, V3 x3) {
   float A2 = dot(A, A), B2 = dot(B, B), G2 = dot(G, G);
   float iG = inv_sqrt(G2);
   float gl = G2 * iG;                      // |G|
+  float iA2 = recip(A2), iB2 = recip(B2);
   float iAB = inv_sqrt(A2 * B2);
   TorsionGeom t;
   t.cphi = dot(A, B) * iAB;
-  t.sphi = dot(cross(A, B), G) * iG * iAB;
-  float iA2 = 1.0f / A2, iB2 = 1.0f / B2;
+  // (A x B).G = ((F x G) x (H x G)).G = -[F,G,H] |G|^2 = -(A.H) |G|^2   (vector quadruple product)
+  t.sphi = -dot(A, H) * gl * iAB;
   float fg = dot(F, G) * iG, hg = dot(H, G) * iG;
   t.d0 = (gl * iA2) * A;
   t.d3 = (-gl * iB2) * B;

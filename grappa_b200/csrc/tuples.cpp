@@ -190,3 +190,74 @@ extern "C" int grappa_b200_torsions_classify(const int64_t* bonds, int64_t n_bon
   *n_impropers_out = ni;
   return GB_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// Conflict-free rounds for the energy kernel (see include/grappa_b200.h)
+// ---------------------------------------------------------------------------------------------
+extern "C" int64_t grappa_b200_conflict_free_rounds(const int32_t* idx, const int32_t* tup_off, int32_t n_mols, int32_t L,
+                                                    int32_t groups, int32_t* round_off, int32_t* sched,
+                                                    int64_t capacity_rounds) {
+  if (!tup_off || n_mols < 0 || L < 1 || L > 4 || groups < 1 || groups > 32) {
+    gb::set_error("conflict_free_rounds: bad arguments (n_mols=%d L=%d groups=%d)", n_mols, L, groups);
+    return GB_ERR_INVALID;
+  }
+  int64_t total = 0;
+  std::unordered_map<int32_t, std::vector<uint64_t>> busy;   // atom -> bitset over this molecule's rounds
+  std::vector<uint64_t> full, tmp;                           // rounds that already hold `groups` tuples
+  std::vector<int32_t> fill;                                 // tuples per round
+  for (int32_t b = 0; b < n_mols; ++b) {
+    const int32_t t0 = tup_off[b], t1 = tup_off[b + 1];
+    if (t1 < t0) {
+      gb::set_error("conflict_free_rounds: tup_off is not monotone at molecule %d", b);
+      return GB_ERR_INVALID;
+    }
+    if (t1 > t0 && !idx) {
+      gb::set_error("conflict_free_rounds: idx is NULL");
+      return GB_ERR_INVALID;
+    }
+    if (round_off) round_off[b] = (int32_t)total;
+    busy.clear();
+    full.clear();
+    fill.clear();
+    for (int32_t t = t0; t < t1; ++t) {
+      tmp = full;
+      for (int j = 0; j < L; ++j) {
+        auto it = busy.find(idx[(int64_t)t * L + j]);
+        if (it == busy.end()) continue;
+        if (it->second.size() > tmp.size()) tmp.resize(it->second.size(), 0);
+        for (size_t w = 0; w < it->second.size(); ++w) tmp[w] |= it->second[w];
+      }
+      int64_t r = -1;
+      for (size_t w = 0; w < tmp.size() && r < 0; ++w)
+        if (~tmp[w]) r = (int64_t)w * 64 + __builtin_ctzll(~tmp[w]);
+      if (r < 0) r = (int64_t)tmp.size() * 64;
+      if (r > (int64_t)fill.size()) r = (int64_t)fill.size();   // first never-used round
+      if (r == (int64_t)fill.size()) fill.push_back(0);
+      const size_t w = (size_t)r / 64;
+      const uint64_t bit = 1ull << (r % 64);
+      for (int j = 0; j < L; ++j) {
+        auto& v = busy[idx[(int64_t)t * L + j]];
+        if (v.size() <= w) v.resize(w + 1, 0);
+        v[w] |= bit;
+      }
+      if (sched) {
+        if (total + r >= capacity_rounds) {
+          gb::set_error("conflict_free_rounds: schedule buffer too small");
+          return GB_ERR_INVALID;
+        }
+        sched[(total + r) * groups + fill[r]] = t;
+      }
+      if (++fill[r] == groups) {
+        if (full.size() <= w) full.resize(w + 1, 0);
+        full[w] |= bit;
+      }
+    }
+    if (sched)
+      for (size_t r = 0; r < fill.size(); ++r)
+        for (int g = fill[r]; g < groups; ++g) sched[(total + (int64_t)r) * groups + g] = -1;
+    total += (int64_t)fill.size();
+  }
+  if (round_off) round_off[n_mols] = (int32_t)total;
+  return total;
+}

@@ -47,6 +47,11 @@ def _fill_common(a: _lib.EnergyArgs, pack, xyz, ks, eqs, n_per, level_mask, offs
     a.n_per[0], a.n_per[1] = n_per
     a.level_mask = level_mask
     a.offset_torsion = int(offset_torsion)
+    if getattr(pack, "sched_groups", 0):
+        a.sched_groups = pack.sched_groups
+        for l in range(4):
+            a.sched[l] = pack.ptr(f"sched{l}")
+            a.round_off[l] = pack.ptr(f"round_off{l}")
 
 
 class _EnergyFn(torch.autograd.Function):

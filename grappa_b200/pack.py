@@ -26,6 +26,31 @@ LEVELS = ("n2", "n3", "n4", "n4_improper")
 TUPLE_LEN = (2, 3, 4, 4)
 
 
+ENERGY_SCHED_GROUPS = 8   # tuples per round = warps per CTA of energy_rounds_kernel
+
+
+def conflict_free_rounds(idx: np.ndarray, tup_off: np.ndarray, n_mols: int, L: int, groups: int):
+    """(round_off[n_mols+1], sched[n_rounds, groups]) -- see grappa_b200_conflict_free_rounds."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.lib()
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    tup_off = np.ascontiguousarray(tup_off, dtype=np.int32)
+    ro = np.zeros(n_mols + 1, dtype=np.int32)
+    ip = idx.ctypes.data_as(C.c_void_p) if idx.size else None
+    n = lib.grappa_b200_conflict_free_rounds(ip, tup_off.ctypes.data_as(C.c_void_p), n_mols, L, groups,
+                                             ro.ctypes.data_as(C.c_void_p), None, 0)
+    if n < 0:
+        _lib.check(int(n), "conflict_free_rounds")
+    sc = np.full((max(int(n), 0), groups), -1, dtype=np.int32)
+    if n > 0:
+        n2 = lib.grappa_b200_conflict_free_rounds(ip, tup_off.ctypes.data_as(C.c_void_p), n_mols, L, groups,
+                                                  ro.ctypes.data_as(C.c_void_p), sc.ctypes.data_as(C.c_void_p), int(n))
+        if n2 != n:
+            _lib.check(int(n2) if n2 < 0 else -1, "conflict_free_rounds")
+    return ro, sc
+
+
 def _offsets(counts) -> np.ndarray:
     out = np.zeros(len(counts) + 1, dtype=np.int32)
     np.cumsum(np.asarray(counts, dtype=np.int64), out=out[1:])
@@ -68,6 +93,11 @@ class PackedBatch:
             order = np.argsort(flat, kind="stable").astype(np.int32)
             host[f"inv_ptr{l}"] = _offsets(np.bincount(flat, minlength=n_atoms)) if n_atoms else np.zeros(1, np.int32)
             host[f"inv_ent{l}"] = order
+        # conflict-free rounds for the energy kernel (host C++, include/grappa_b200.h)
+        self.sched_groups = ENERGY_SCHED_GROUPS
+        for l, L in enumerate(TUPLE_LEN):
+            ro, sc = conflict_free_rounds(host[f"idx{l}"], host[f"tup_off{l}"], self.n_mols, L, self.sched_groups)
+            host[f"round_off{l}"], host[f"sched{l}"] = ro, sc
         # bonded graph CSR by destination
         src, dst = g.edges(etype="n1_edge")
         src = src.detach().cpu().numpy().astype(np.int64)

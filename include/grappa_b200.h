@@ -80,10 +80,26 @@ typedef struct {
   float* grad;               /* [n_atoms, n_confs, 3] = +dE/dxyz ('gradient', not force)             */
   float* x[4];               /* [T_l, n_confs] internal coordinate (r, theta, phi)                   */
   float* tuple_energy[4];    /* [T_l, n_confs] per-tuple energy                                      */
+  /* optional conflict-free schedule (grappa_b200_conflict_free_rounds): enables the atomics-free kernel      */
+  const int32_t* sched[4];     /* [n_rounds_l, sched_groups] tuple index or -1                         */
+  const int32_t* round_off[4]; /* [n_mols+1] first round of each molecule at level l                   */
+  int32_t sched_groups;        /* tuples per round (0 = no schedule)                                   */
 } gb_energy_args;
 
-/* Zeroes and fills every non-NULL output.  variant: 0 = auto, 1 = global-atomics kernel,
- * 2 = shared-memory tiled kernel (one CTA per molecule x conformation tile). */
+/* Conflict-free processing order for K13 (host code).  Within one molecule and level, tuples are packed first-fit
+ * into rounds of at most `groups` tuples that share no atom, so `groups` threads can add forces of one round into a
+ * shared accumulator with plain read-modify-write (no atomics) and a barrier between rounds.
+ *   idx [T, L] int32 global atom indices, tup_off [n_mols+1].  round_off [n_mols+1] receives the first round of every
+ *   molecule; sched [capacity_rounds * groups] receives tuple indices (-1 = idle slot).
+ * Returns the total number of rounds (call with sched == NULL to size the buffer) or a negative error code. */
+int64_t grappa_b200_conflict_free_rounds(const int32_t* idx, const int32_t* tup_off, int32_t n_mols, int32_t L,
+                                         int32_t groups, int32_t* round_off, int32_t* sched, int64_t capacity_rounds);
+
+/* Zeroes and fills every non-NULL output.  variant: 0 = auto, 1 = global-atomics kernel (any molecule size),
+ * 2 = shared-memory tiled kernel (CTA per molecule x conformation tile, tuple groups, shared atomics),
+ * 3 = conformation-per-thread kernel (no atomics; latency-bound, kept for cross-checks),
+ * 4 = round-scheduled tiled kernel (needs sched/round_off: no atomics, bit-reproducible; what `auto` picks when a
+ *     schedule is given and the molecule tile fits in shared memory). */
 int grappa_b200_energy_fwd(const gb_energy_args* a, int variant, void* stream);
 
 typedef struct {

@@ -28,7 +28,7 @@ def _graph_with_params(z, dev, requires_grad=False):
     return g, leaves
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 def test_energy_forward_matches_reference_fixture(variant):
     from grappa_b200.energy import Energy
     z = load_golden("energy_mixed_batch.npz")
