@@ -60,6 +60,57 @@ __global__ void __launch_bounds__(256) tuple_gather_bwd_kernel(const float* __re
   }
 }
 
+// vectorised variant: one CTA per atom, one float4 column group per thread, incidence loop unrolled by 4 so
+// that several 16-byte loads are in flight per thread (needs E % 4 == 0, ldp % 4 == 0, 16-byte aligned bases)
+__global__ void __launch_bounds__(128) tuple_gather_bwd_vec_kernel(const float* __restrict__ dx, const int* __restrict__ inv_ptr,
+                                                                   const int* __restrict__ inv_ent, float* __restrict__ dp,
+                                                                   int ldp, int T, int L, int F, int E, int accumulate) {
+  const int n = blockIdx.x;
+  const int j0 = __ldg(inv_ptr + n), j1 = __ldg(inv_ptr + n + 1);
+  const int nv = ldp >> 2, ev = E >> 2;
+  const float4* dx4 = reinterpret_cast<const float4*>(dx);
+  for (int c = threadIdx.x; c < nv; c += blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c * 4 < F) {
+      int j = j0;
+      for (; j + 3 < j1; j += 4) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int ent = __ldg(inv_ent + j + u);
+          const int t = ent / L, l = ent - t * L;
+          v[u] = __ldg(dx4 + ((size_t)l * T + t) * ev + c);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+      }
+      for (; j < j1; ++j) {
+        const int ent = __ldg(inv_ent + j);
+        const int t = ent / L, l = ent - t * L;
+        const float4 v = __ldg(dx4 + ((size_t)l * T + t) * ev + c);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      // columns >= F of the last group carry the positional encoding (not a function of p): zero gradient
+      if (c * 4 + 3 >= F) {
+        if (c * 4 + 1 >= F) acc.y = 0.f;
+        if (c * 4 + 2 >= F) acc.z = 0.f;
+        acc.w = 0.f;
+      }
+    }
+    float4* o = reinterpret_cast<float4*>(dp + (size_t)n * ldp) + c;
+    if (accumulate) {
+      const float4 old = *o;
+      // padding columns (>= F) are zeroed, as in the scalar kernel
+      acc.x += old.x;
+      acc.y = (c * 4 + 1 < F) ? acc.y + old.y : 0.f;
+      acc.z = (c * 4 + 2 < F) ? acc.z + old.z : 0.f;
+      acc.w = (c * 4 + 3 < F) ? acc.w + old.w : 0.f;
+      if (c * 4 >= F) acc.x = 0.f;
+    }
+    *o = acc;
+  }
+}
+
 __global__ void __launch_bounds__(256) perm_concat_fwd_kernel(const float* __restrict__ x, float* __restrict__ s,
                                                               gb_perms perms, int T, int L, int E) {
   // one thread per float4 of the output [n_perm*T, L*E]
@@ -119,8 +170,12 @@ extern "C" int grappa_b200_tuple_gather_bwd(const float* dx, const int32_t* inv_
   GB_REQUIRE(T >= 0 && L >= 1 && L <= 4 && F >= 0 && F <= E && ldp >= F, "tuple_gather_bwd: bad shape");
   if (n_atoms == 0) return GB_OK;
   GB_REQUIRE(inv_ptr && dp && (T == 0 || (dx && inv_ent)), "tuple_gather_bwd: NULL pointer");
-  tuple_gather_bwd_kernel<<<(n_atoms + 7) / 8, 256, 0, (cudaStream_t)stream_>>>(dx, inv_ptr, inv_ent, dp, ldp, n_atoms, T, L,
-                                                                               F, E, accumulate);
+  const bool vec = (E % 4 == 0) && (ldp % 4 == 0) && (((uintptr_t)dx & 15) == 0) && (((uintptr_t)dp & 15) == 0);
+  if (vec)
+    tuple_gather_bwd_vec_kernel<<<n_atoms, 128, 0, (cudaStream_t)stream_>>>(dx, inv_ptr, inv_ent, dp, ldp, T, L, F, E, accumulate);
+  else
+    tuple_gather_bwd_kernel<<<(n_atoms + 7) / 8, 256, 0, (cudaStream_t)stream_>>>(dx, inv_ptr, inv_ent, dp, ldp, n_atoms, T, L,
+                                                                                 F, E, accumulate);
   GB_CHECK_LAUNCH();
   return GB_OK;
 }

@@ -20,6 +20,7 @@
 //                           (TMA SWIZZLE_128B_ATOM_32B, UMMA layout SWIZZLE_128B_BASE32B, atoms of 4 k-rows)
 // Rows / K tails are handled by TMA out-of-bounds zero fill and predicated stores.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "gemm_epilogue.cuh"
@@ -124,7 +125,7 @@ struct TcCfg {
   static constexpr int A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
   static constexpr int B_BYTES = BN * TC_BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN == 128 ? 5 : 7;      // 160-168 KB of operand ring
+  static constexpr int STAGES = BN == 256 ? 3 : (BN == 128 ? 5 : 7);   // 144-168 KB of operand ring
   static constexpr int EPI_LD = 36;                     // floats per staged row (float4-aligned, conflict-free)
   static constexpr int EPI_BYTES = 8 * 32 * EPI_LD * 4; // one 32x32 transpose patch per epilogue warp
   static_assert(STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256 <= 232448, "shared memory budget");
@@ -393,7 +394,21 @@ int gemm_tcgen05(const gb_gemm_args* a, cudaStream_t stream, bool* handled) {
   // legality: 16-byte aligned bases and row pitches (TMA), enough work to fill a tile
   if (((uintptr_t)a->A & 15) || ((uintptr_t)a->B & 15) || (a->lda & 3) || (a->ldb & 3)) return GB_OK;
   if (K < 8 || N < 16 || M < 1) return GB_OK;
-  const int BN = (N <= 64 || ((N + 127) / 128) * ((M + 127) / 128) < sm_count() / 2) ? 64 : 128;
+  // tile width.  Without split-K: 256 when the 128x256 grid still covers every SM (25 % less L2->SM operand traffic
+  // per FLOP than 128x128, which is what bounds the large token GEMMs), 64 when even 128x128 tiles cannot fill half
+  // the machine.  With split-K available (weight gradients: small output, very long K) the SMs are filled by K
+  // slices instead, so the widest tile that divides N is always the cheapest in operand traffic.
+  const int tiles_m = (M + TC_BM - 1) / TC_BM;
+  const int sms_ = sm_count();
+  const bool can_split = a->workspace != nullptr && (K + TC_BK - 1) / TC_BK >= 16;
+  int BN = 128;
+  if (can_split && ((N + 127) / 128) * tiles_m * 2 <= sms_) BN = (N % 256 == 0) ? 256 : (N >= 128 ? 128 : 64);
+  else if (N <= 64 || ((N + 127) / 128) * tiles_m < sms_ / 2) BN = 64;
+  else if (N % 256 == 0 && (N / 256) * tiles_m >= sms_) BN = 256;
+  {
+    static const int forced = [] { const char* e = getenv("GRAPPA_B200_GEMM_BN"); return e ? atoi(e) : 0; }();   // tuning aid
+    if ((forced == 64 || forced == 128 || forced == 256) && (forced != 256 || N % 256 == 0)) BN = forced;
+  }
   CUtensorMap ma, mb;
   bool ok = a->trans_a ? make_map(&ma, a->A, K, M, a->lda, TC_BK, true) : make_map(&ma, a->A, M, K, a->lda, TC_BM, false);
   ok = ok && (a->trans_b ? make_map(&mb, a->B, K, N, a->ldb, TC_BK, true) : make_map(&mb, a->B, N, K, a->ldb, BN, false));
@@ -408,7 +423,7 @@ int gemm_tcgen05(const gb_gemm_args* a, cudaStream_t stream, bool* handled) {
   const int sms = sm_count();
   if (a->workspace && gx * gy * 2 <= sms && total_kb >= 16) {
     splits = sms / (gx * gy);
-    if (splits > total_kb / 8) splits = total_kb / 8;
+    if (splits > total_kb / 4) splits = total_kb / 4;
     long long by_ws = a->workspace_bytes / ((long long)M * N * 4);
     if (splits > by_ws) splits = (int)by_ws;
     if (splits < 1) splits = 1;
@@ -423,7 +438,12 @@ int gemm_tcgen05(const gb_gemm_args* a, cudaStream_t stream, bool* handled) {
   const int grid = n_items < sms ? n_items : sms;
   int rc;
 #define GB_TC(BN_, TA_, TB_) rc = launch<BN_, TA_, TB_>(ma, mb, p, grid, stream)
-  if (BN == 128) {
+  if (BN == 256) {
+    if (!a->trans_a && !a->trans_b) GB_TC(256, 0, 0);
+    else if (!a->trans_a && a->trans_b) GB_TC(256, 0, 1);
+    else if (a->trans_a && !a->trans_b) GB_TC(256, 1, 0);
+    else GB_TC(256, 1, 1);
+  } else if (BN == 128) {
     if (!a->trans_a && !a->trans_b) GB_TC(128, 0, 0);
     else if (!a->trans_a && a->trans_b) GB_TC(128, 0, 1);
     else if (a->trans_a && !a->trans_b) GB_TC(128, 1, 0);
