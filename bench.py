@@ -242,17 +242,27 @@ def main():
     e2e_value = world * B * K / (ms_e2e * 1e-3)
 
     # ---- (3) roofline of the dominant kernel family (GEMMs), CUDA events around every launch ------
-    trainer.use_cuda_graph = False     # per-launch CUDA events need eager launches
+    # A second capture of the same step with (a) helper-stream concurrency off, so that a GEMM runs alone between its
+    # two events, and (b) a pair of timing events recorded around every GEMM launch as graph nodes; the instrumented
+    # graph is replayed and the events are read after each replay.
+    from grappa_b200 import tape as gb_tape
+    gb_tape.set_concurrency(False)
+    trainer.reset_graphs()
     prof = []
     ops.set_gemm_profiler(prof)
+    step_resident()                      # captures (the shape was seen before) and replays once
+    ops.set_gemm_profiler(None)
     n_prof_steps = 3
+    gemm_ms = 0.0
     for _ in range(n_prof_steps):
         step_resident()
-    torch.cuda.synchronize()
-    ops.set_gemm_profiler(None)
-    gemm_ms = sum(e0.elapsed_time(e1) for _, e0, e1, _ in prof)
-    gemm_flops = sum(f for f, _, _, _ in prof)
-    gemm_launches = len(prof) // n_prof_steps
+        torch.cuda.synchronize()
+        gemm_ms += sum(e0.elapsed_time(e1) for _, e0, e1, _ in prof)
+    ms_serial = timed(step_resident, 5) / 5
+    gemm_flops = sum(f for f, _, _, _ in prof) * n_prof_steps
+    gemm_launches = len(prof)
+    gb_tape.set_concurrency(True)
+    trainer.reset_graphs()
     achieved_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     tensor_path = args.precision == "tf32"
     roofline = {"bound": "tensor", "kernel": "gemm_tf32_kernel (tcgen05 + TMA)" if tensor_path else "sgemm_kernel (fp32 FFMA)",
@@ -260,8 +270,10 @@ def main():
                 "frac": achieved_tf / peaks["tflops_sustained"], "traffic": None,
                 "peak_source": peaks["source"] + " dense bf16, sustained (kernel timed inside a long step); TF32 runs at half the bf16 rate",
                 "how": f"sum of 2*M*N*K over the {gemm_launches} GEMM launches of one step / sum of their CUDA-event durations "
-                       f"({n_prof_steps} instrumented steps after the timed region)",
-                "gemm_ms_per_step": gemm_ms / n_prof_steps, "gemm_share_of_step": (gemm_ms / n_prof_steps) / (ms / K)}
+                       f"(events recorded as graph nodes around every GEMM of a single-stream capture of the step, "
+                       f"{n_prof_steps} replays)",
+                "gemm_ms_per_step": gemm_ms / n_prof_steps, "serial_step_ms": ms_serial,
+                "gemm_share_of_serial_step": (gemm_ms / n_prof_steps) / ms_serial}
 
     # ---- (4) energy + force evaluation throughput (K13), configs[3] slice, HBM roofline -----------
     energy_eval = None
@@ -334,8 +346,14 @@ def main():
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        # Leave without tearing NCCL down: destroy_process_group() can block for minutes while captured CUDA graphs
+        # still reference the communicator; every rank has finished its work once the barrier returns.
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

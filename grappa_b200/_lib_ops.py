@@ -32,6 +32,17 @@ class GemmArgs(C.Structure):
     ]
 
 
+COLSUM_MAX = 96
+
+
+class ColsumDesc(C.Structure):
+    _fields_ = [("partial", vp), ("out", vp), ("n_part", i32), ("stride", i32), ("cols", i32), ("accumulate", i32)]
+
+
+class ColsumBatch(C.Structure):
+    _fields_ = [("n", i32), ("pad_", i32), ("desc", ColsumDesc * COLSUM_MAX)]
+
+
 class Perms(C.Structure):
     _fields_ = [("n_perm", i32), ("perm", (i32 * 4) * 6)]
 
@@ -85,12 +96,16 @@ def declare(lib):
     lib.grappa_b200_act_dropout_bwd.argtypes = [vp, vp, vp, i64, f32, u64, vp, vp]
     lib.grappa_b200_axpby.argtypes = [vp, vp, i64, f32, f32, vp]
     lib.grappa_b200_sumsq.argtypes = [vp, i64, vp, vp]
+    lib.grappa_b200_sumsq_det.argtypes = [vp, i64, vp, vp, vp]
     lib.grappa_b200_adam_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, vp, f32, f32, vp]
     lib.grappa_b200_adam_step_dev.argtypes = [vp, vp, vp, vp, i64, vp, f32, f32, f32, vp, vp, f32, f32, vp]
     lib.grappa_b200_tick.argtypes = [vp, i32, vp]
+    lib.grappa_b200_layernorm_bwd_fused.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]
+    lib.grappa_b200_act_dropout_bwd_fused.argtypes = [vp, vp, vp, vp, i32, i32, i32, f32, u64, vp, vp]
+    lib.grappa_b200_finalize_colsums.argtypes = [C.POINTER(ColsumBatch), vp]
     lib.grappa_b200_molwise_loss.argtypes = [P(LossArgs), vp]
     for name in ("gemm", "layernorm_fwd", "layernorm_bwd", "col_reduce", "edge_attention_fwd", "edge_attention_bwd",
                  "tuple_attention_fwd", "tuple_attention_bwd", "tuple_gather_fwd", "tuple_gather_bwd",
                  "perm_concat_fwd", "perm_concat_bwd", "featurize", "head_output_fwd", "head_output_bwd", "dropout",
-                 "act_dropout_bwd", "axpby", "sumsq", "adam_step", "adam_step_dev", "tick", "molwise_loss"):
+                 "act_dropout_bwd", "axpby", "sumsq", "sumsq_det", "adam_step", "adam_step_dev", "tick", "layernorm_bwd_fused", "act_dropout_bwd_fused", "finalize_colsums", "molwise_loss"):
         getattr(lib, "grappa_b200_" + name).restype = C.c_int

@@ -368,6 +368,59 @@ extern "C" int grappa_b200_axpby(const float* x, float* y, int64_t n, float a, f
   return GB_OK;
 }
 
+// deterministic variant: fixed grid, per-block partials, the last block (ticket) adds them in block order
+__global__ void __launch_bounds__(256) sumsq_det_kernel(const float* __restrict__ x, long long n, float* __restrict__ out,
+                                                        unsigned int* __restrict__ ticket, float* __restrict__ partial) {
+  __shared__ float sh[8];
+  __shared__ bool last;
+  float s = 0.f;
+  const long long n4 = n >> 2;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(x4 + i);
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    s += x[i] * x[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += sh[i];
+    __stcg(partial + blockIdx.x, t);
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float t = 0.f;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += 256) t += __ldcg(partial + i);   // fixed assignment -> fixed order
+  t = warp_sum(t);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float r = 0.f;
+    for (int i = 0; i < 8; ++i) r += sh[i];
+    *out = r;
+    *ticket = 0u;
+  }
+}
+
+extern "C" int grappa_b200_sumsq_det(const float* x, int64_t n, float* out, float* workspace, void* stream_) {
+  GB_REQUIRE(x && out && workspace, "sumsq_det: NULL pointer");
+  GB_REQUIRE(((uintptr_t)x & 15) == 0, "sumsq_det: x must be 16-byte aligned");
+  int blocks = sm_count() * 4;
+  if (blocks > 1000) blocks = 1000;
+  long long need = (n / 4 + 255) / 256;
+  if (need < 1) need = 1;
+  if (blocks > need) blocks = (int)need;
+  sumsq_det_kernel<<<blocks, 256, 0, (cudaStream_t)stream_>>>(x, n, out, reinterpret_cast<unsigned int*>(workspace), workspace + 4);
+  GB_CHECK_LAUNCH();
+  return GB_OK;
+}
+
 extern "C" int grappa_b200_sumsq(const float* x, int64_t n, float* out, void* stream_) {
   if (n == 0) return GB_OK;
   GB_REQUIRE(x && out, "sumsq: NULL pointer");

@@ -122,11 +122,41 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
   }
 }
 
+// float4 variant (N % 4 == 0 and a 16-byte aligned epilogue): 4 slices in flight per thread, fixed summation order
+__global__ void __launch_bounds__(256) splitk_reduce_vec_kernel(const float4* __restrict__ partial, int splits, int M, int N,
+                                                                Epilogue ep) {
+  const int nv = N >> 2;
+  const size_t total = (size_t)M * nv;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    int z = 0;
+    for (; z + 3 < splits; z += 4) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldcs(partial + (size_t)(z + u) * total + i);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
+    }
+    for (; z < splits; ++z) {
+      const float4 v = __ldcs(partial + (size_t)z * total + i);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    const int row = (int)(i / nv), col = (int)(i - (size_t)row * nv) * 4;
+    ep.template store4<false>(s, row, col);
+  }
+}
+
 int launch_splitk_reduce(const float* partial, int splits, int M, int N, const Epilogue& ep, cudaStream_t stream) {
-  size_t total = (size_t)M * N;
+  const bool vec = (N % 4 == 0) && (((uintptr_t)partial & 15) == 0) && (((uintptr_t)ep.bias | (uintptr_t)ep.mul_elu_out |
+                    (uintptr_t)ep.residual | (uintptr_t)ep.C | (uintptr_t)ep.act_out) & 15) == 0 &&
+                   ((ep.ldc | (ep.mul_elu_out ? ep.ldm : 0) | (ep.residual ? ep.ldr : 0) | (ep.act_out ? ep.ldact : 0)) & 3) == 0;
+  size_t total = (size_t)M * N / (vec ? 4 : 1);
   int blocks = (int)((total + 255) / 256);
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-  splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(partial, splits, M, N, ep);
+  if (vec)
+    splitk_reduce_vec_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(partial), splits, M, N, ep);
+  else
+    splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(partial, splits, M, N, ep);
   GB_CHECK_LAUNCH();
   return GB_OK;
 }

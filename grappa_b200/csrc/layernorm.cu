@@ -182,6 +182,145 @@ __global__ void __launch_bounds__(256) col_reduce_kernel(const float* __restrict
   if (threadIdx.x == 0) tickets[blockIdx.x] = 0u;   // ready for the next launch on this workspace
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fused backward kernels that also emit per-CTA column partial sums (parameter gradients), finalised later
+// by ONE finalize_colsums launch per stage (deterministic: fixed row->CTA assignment, partials added in CTA order).
+// ------------------------------------------------------------------------------------------------
+// LayerNorm: dx as layernorm_bwd_kernel + partial[b][0][c] = sum_rows dy, partial[b][1][c] = sum_rows dy * xhat
+template <int VPT>
+__global__ void __launch_bounds__(256) layernorm_bwd_fused_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                                  const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                  const float* __restrict__ gamma, float* __restrict__ dx,
+                                                                  float* __restrict__ partial, int rows, int cols,
+                                                                  int rows_per_cta) {
+  extern __shared__ float sm[];   // [8 warps][2][cols]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nvec = cols >> 2;
+  const int r_begin = blockIdx.x * rows_per_cta;
+  const int r_end = min(rows, r_begin + rows_per_cta);
+  float4 pb[VPT], pg[VPT];
+  float4 gm[VPT];
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    pb[i] = pg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int c = lane + i * 32;
+    gm[i] = c < nvec ? __ldg(reinterpret_cast<const float4*>(gamma) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int row = r_begin + warp; row < r_end; row += 8) {
+    const float mu = __ldg(mean + row), rs = __ldg(rstd + row);
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * cols);
+    const float4* dr = reinterpret_cast<const float4*>(dy + (size_t)row * cols);
+    float4 xh[VPT], g[VPT];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int c = lane + i * 32;
+      if (c < nvec) {
+        const float4 xv = __ldg(xr + c), dv = __ldg(dr + c);
+        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        g[i] = make_float4(dv.x * gm[i].x, dv.y * gm[i].y, dv.z * gm[i].z, dv.w * gm[i].w);
+        s1 += g[i].x + g[i].y + g[i].z + g[i].w;
+        s2 += g[i].x * xh[i].x + g[i].y * xh[i].y + g[i].z * xh[i].z + g[i].w * xh[i].w;
+        pb[i].x += dv.x; pb[i].y += dv.y; pb[i].z += dv.z; pb[i].w += dv.w;
+        pg[i].x += dv.x * xh[i].x; pg[i].y += dv.y * xh[i].y; pg[i].z += dv.z * xh[i].z; pg[i].w += dv.w * xh[i].w;
+      } else {
+        xh[i] = g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    s1 = warp_sum(s1) / cols;
+    s2 = warp_sum(s2) / cols;
+    float4* o = reinterpret_cast<float4*>(dx + (size_t)row * cols);
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int c = lane + i * 32;
+      if (c < nvec)
+        o[c] = make_float4(rs * (g[i].x - s1 - xh[i].x * s2), rs * (g[i].y - s1 - xh[i].y * s2),
+                           rs * (g[i].z - s1 - xh[i].z * s2), rs * (g[i].w - s1 - xh[i].w * s2));
+    }
+  }
+  float4* smv = reinterpret_cast<float4*>(sm);
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      smv[(warp * 2 + 0) * nvec + c] = pb[i];
+      smv[(warp * 2 + 1) * nvec + c] = pg[i];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * cols; i += 256) {     // i = set * cols + c
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) a += sm[(size_t)w * 2 * cols + i];
+    partial[(size_t)blockIdx.x * 2 * cols + i] = a;
+  }
+}
+
+// dx = dy * keep/(1-p) * elu'(act_out) (as act_dropout_bwd_kernel) + partial[b][c] = sum over the CTA's rows of dx
+__global__ void __launch_bounds__(256) act_dropout_bwd_fused_kernel(const float* __restrict__ dy, const float* __restrict__ act_out,
+                                                                    float* __restrict__ dx, float* __restrict__ partial,
+                                                                    int rows, int cols, int rows_per_cta, uint32_t thresh,
+                                                                    float inv_keep, uint64_t seed0,
+                                                                    const uint64_t* __restrict__ seed_off) {
+  __shared__ float4 sh[256];
+  const uint64_t seed = seed_with_offset(seed0, seed_off);
+  const int ncg = cols >> 2;                 // float4 column groups (<= 256)
+  const int nrl = 256 / ncg;                 // row lanes
+  const int cg = threadIdx.x % ncg, rl = threadIdx.x / ncg;
+  const int r_begin = blockIdx.x * rows_per_cta;
+  const int r_end = min(rows, r_begin + rows_per_cta);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (rl < nrl) {
+    for (int row = r_begin + rl; row < r_end; row += nrl) {
+      const size_t i4 = (size_t)row * ncg + cg;
+      float4 v = __ldg(reinterpret_cast<const float4*>(dy) + i4);
+      if (thresh) {
+        const uint64_t base = (uint64_t)i4 * 4ull;
+        v.x *= dropout_scale(seed, base, thresh, inv_keep);
+        v.y *= dropout_scale(seed, base + 1, thresh, inv_keep);
+        v.z *= dropout_scale(seed, base + 2, thresh, inv_keep);
+        v.w *= dropout_scale(seed, base + 3, thresh, inv_keep);
+      }
+      if (act_out) {
+        const float4 y = __ldg(reinterpret_cast<const float4*>(act_out) + i4);
+        v.x *= elu1_grad_from_out(y.x); v.y *= elu1_grad_from_out(y.y);
+        v.z *= elu1_grad_from_out(y.z); v.w *= elu1_grad_from_out(y.w);
+      }
+      reinterpret_cast<float4*>(dx)[i4] = v;
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x < ncg) {
+    float4 a = sh[threadIdx.x];
+    for (int l = 1; l < nrl; ++l) {
+      const float4 o = sh[l * ncg + threadIdx.x];
+      a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+    }
+    reinterpret_cast<float4*>(partial)[(size_t)blockIdx.x * ncg + threadIdx.x] = a;
+  }
+}
+
+// out[c] (+)= sum_{p < n_part} partial[p * stride + c]   for every descriptor; grid = (column chunks of 256, n_desc)
+__global__ void __launch_bounds__(256) finalize_colsums_kernel(gb_colsum_batch batch) {
+  const gb_colsum_desc d = batch.desc[blockIdx.y];
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= d.cols) return;
+  const float* p = d.partial + c;
+  float acc = 0.f;
+  int i = 0;
+  for (; i + 7 < d.n_part; i += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldg(p + (size_t)(i + u) * d.stride);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc += v[u];
+  }
+  for (; i < d.n_part; ++i) acc += __ldg(p + (size_t)i * d.stride);
+  d.out[c] = d.accumulate ? d.out[c] + acc : acc;
+}
+
 static int col_slices(int rows) {
   int s = (rows + 63) / 64;
   if (s > 64) s = 64;
@@ -255,6 +394,58 @@ extern "C" int grappa_b200_col_reduce(const float* dy, int32_t ld, const float* 
   float* px = x ? ps + (size_t)slices * cols : nullptr;
   dim3 grid((cols + 31) / 32, slices);
   col_reduce_kernel<<<grid, 256, 0, stream>>>(dy, ld, x, mean, rstd, ps, px, tickets, out_sum, out_xhat, rows, cols, accumulate);
+  GB_CHECK_LAUNCH();
+  return GB_OK;
+}
+
+
+extern "C" int grappa_b200_layernorm_bwd_fused(const float* dy, const float* x, const float* mean, const float* rstd,
+                                               const float* gamma, float* dx, float* partial, int32_t n_cta, int32_t rows,
+                                               int32_t cols, void* stream_) {
+  GB_REQUIRE(rows > 0 && cols > 0 && cols % 4 == 0 && cols <= 512, "layernorm_bwd_fused: cols must be a multiple of 4 and <= 512 (got %d x %d)", rows, cols);
+  GB_REQUIRE(n_cta >= 1, "layernorm_bwd_fused: n_cta must be >= 1");
+  GB_REQUIRE(dy && x && mean && rstd && gamma && dx && partial, "layernorm_bwd_fused: NULL pointer");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int rpc = (rows + n_cta - 1) / n_cta;
+  const size_t smem = (size_t)8 * 2 * cols * sizeof(float);
+  const int nvec = cols / 4;
+  if (nvec <= 32) layernorm_bwd_fused_kernel<1><<<n_cta, 256, smem, stream>>>(dy, x, mean, rstd, gamma, dx, partial, rows, cols, rpc);
+  else if (nvec <= 64) layernorm_bwd_fused_kernel<2><<<n_cta, 256, smem, stream>>>(dy, x, mean, rstd, gamma, dx, partial, rows, cols, rpc);
+  else layernorm_bwd_fused_kernel<4><<<n_cta, 256, smem, stream>>>(dy, x, mean, rstd, gamma, dx, partial, rows, cols, rpc);
+  GB_CHECK_LAUNCH();
+  return GB_OK;
+}
+
+extern "C" int grappa_b200_act_dropout_bwd_fused(const float* dy, const float* act_out, float* dx, float* partial,
+                                                 int32_t n_cta, int32_t rows, int32_t cols, float p, uint64_t seed,
+                                                 const uint64_t* seed_offset, void* stream_) {
+  GB_REQUIRE(p >= 0.f && p < 1.f, "act_dropout_bwd_fused: p must be in [0,1)");
+  GB_REQUIRE(rows > 0 && cols >= 4 && cols % 4 == 0 && cols <= 1024, "act_dropout_bwd_fused: cols must be a multiple of 4 and <= 1024 (got %d x %d)", rows, cols);
+  GB_REQUIRE(n_cta >= 1 && dy && dx && partial, "act_dropout_bwd_fused: bad arguments");
+  uint32_t thresh = 0;
+  if (p > 0.f) {
+    double t = (double)p * 4294967296.0;
+    thresh = t >= 4294967295.0 ? 0xffffffffu : (uint32_t)t;
+    if (thresh == 0) thresh = 1;
+  }
+  const int rpc = (rows + n_cta - 1) / n_cta;
+  act_dropout_bwd_fused_kernel<<<n_cta, 256, 0, (cudaStream_t)stream_>>>(dy, act_out, dx, partial, rows, cols, rpc, thresh,
+                                                                         1.f / (1.f - p), seed, seed_offset);
+  GB_CHECK_LAUNCH();
+  return GB_OK;
+}
+
+extern "C" int grappa_b200_finalize_colsums(const gb_colsum_batch* batch, void* stream_) {
+  GB_REQUIRE(batch != nullptr && batch->n >= 0 && batch->n <= GB_COLSUM_MAX, "finalize_colsums: bad batch");
+  if (batch->n == 0) return GB_OK;
+  int max_cols = 0;
+  for (int i = 0; i < batch->n; ++i) {
+    const gb_colsum_desc& d = batch->desc[i];
+    GB_REQUIRE(d.partial && d.out && d.cols > 0 && d.n_part > 0 && d.stride >= d.cols, "finalize_colsums: bad descriptor %d", i);
+    if (d.cols > max_cols) max_cols = d.cols;
+  }
+  dim3 grid((max_cols + 255) / 256, batch->n);
+  finalize_colsums_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(*batch);
   GB_CHECK_LAUNCH();
   return GB_OK;
 }

@@ -12,7 +12,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib_ops import FeaturizeArgs, GemmArgs, HeadOutArgs, LossArgs, Perms
+from ._lib_ops import COLSUM_MAX, ColsumBatch, FeaturizeArgs, GemmArgs, HeadOutArgs, LossArgs, Perms
 
 FP32, TF32, AUTO = 0, 1, 2
 _precision = FP32
@@ -116,7 +116,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a=False, trans_b=False, bias
         ws = workspace(64 << 20, a.device, "splitk")
         g.workspace, g.workspace_bytes = ws.data_ptr(), ws.numel() * 4
     if _gemm_profile is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # inside a stream capture the events become graph nodes that are re-recorded by every replay
+        ext = torch.cuda.is_current_stream_capturing()
+        e0, e1 = torch.cuda.Event(enable_timing=True, external=ext), torch.cuda.Event(enable_timing=True, external=ext)
         e0.record()
         _lib.check(lib.grappa_b200_gemm(C.byref(g), _s()), "gemm")
         e1.record()
@@ -318,6 +320,13 @@ def sumsq(x, out):
     return out
 
 
+def sumsq_det(x, out, ws):
+    """out[0] = sum x^2, bit-reproducible; ws: zero-initialised fp32 scratch of >= 1024 elements (reusable)."""
+    lib = _lib.lib()
+    _lib.check(lib.grappa_b200_sumsq_det(_p(x), x.numel(), out.data_ptr(), ws.data_ptr(), _s()), "sumsq_det")
+    return out
+
+
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, gnorm_sq=None, clip=0.0, grad_scale=1.0):
     lib = _lib.lib()
     _lib.check(lib.grappa_b200_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2,
@@ -336,3 +345,67 @@ def tick(counters):
     """counters[:] += 1 on the device (int64 tensor of <= 32 elements)."""
     lib = _lib.lib()
     _lib.check(lib.grappa_b200_tick(counters.data_ptr(), counters.numel(), _s()), "tick")
+
+
+def _n_cta(rows: int) -> int:
+    """CTAs of the fused backward kernels: every CTA gets >= 8 rows, at most one CTA per SM."""
+    return max(1, min(_lib.lib().grappa_b200_sm_count() if _SMS[0] is None else _SMS[0], (rows + 7) // 8))
+
+
+_SMS = [None]
+
+
+def layernorm_bwd_fused(dy, x, mean, rstd, gamma):
+    """dx plus per-CTA partial sums [n_cta, 2, cols] (set 0: beta gradient, set 1: gamma gradient); see `ColumnSums`."""
+    lib = _lib.lib()
+    if _SMS[0] is None:
+        _SMS[0] = lib.grappa_b200_sm_count()
+    rows, cols = x.shape
+    n = _n_cta(rows)
+    dx = torch.empty_like(x)
+    partial = torch.empty((n, 2, cols), device=x.device, dtype=torch.float32)
+    _lib.check(lib.grappa_b200_layernorm_bwd_fused(dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                                   gamma.data_ptr(), dx.data_ptr(), partial.data_ptr(), n, rows, cols, _s()),
+               "layernorm_bwd_fused")
+    return dx, partial
+
+
+def act_dropout_bwd_fused(dy, act_out, p, seed):
+    """dx = dy * mask * elu'(act_out) plus per-CTA column sums of dx [n_cta, cols] (bias gradient partials)."""
+    lib = _lib.lib()
+    if _SMS[0] is None:
+        _SMS[0] = lib.grappa_b200_sm_count()
+    rows, cols = dy.shape
+    n = _n_cta(rows)
+    dx = torch.empty_like(dy)
+    partial = torch.empty((n, cols), device=dy.device, dtype=torch.float32)
+    _lib.check(lib.grappa_b200_act_dropout_bwd_fused(_p(dy), _p(act_out), _p(dx), partial.data_ptr(), n, rows, cols, float(p),
+                                                     int(seed) & 0xFFFFFFFFFFFFFFFF, _rng_ptr() if p > 0.0 else 0, _s()),
+               "act_dropout_bwd_fused")
+    return dx, partial
+
+
+class ColumnSums:
+    """Collects deferred column reductions (partial rows -> out vector) and folds them with one launch per
+    COLSUM_MAX entries (`flush`).  Partial buffers are kept alive until the flush has been enqueued."""
+
+    def __init__(self):
+        self.items = []
+
+    def add(self, partial, n_part, stride, cols, out, accumulate):
+        self.items.append((partial, int(n_part), int(stride), int(cols), out, bool(accumulate)))
+
+    def flush(self):
+        if not self.items:
+            return
+        lib = _lib.lib()
+        for i0 in range(0, len(self.items), COLSUM_MAX):
+            chunk = self.items[i0:i0 + COLSUM_MAX]
+            b = ColsumBatch()
+            b.n = len(chunk)
+            for j, (partial, n_part, stride, cols, out, acc) in enumerate(chunk):
+                d = b.desc[j]
+                d.partial, d.out = partial.data_ptr(), out.data_ptr()
+                d.n_part, d.stride, d.cols, d.accumulate = n_part, stride, cols, int(acc)
+            _lib.check(lib.grappa_b200_finalize_colsums(C.byref(b), _s()), "finalize_colsums")
+        self.items = []

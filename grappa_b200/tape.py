@@ -75,6 +75,7 @@ class Tape:
         self._side = None          # helper stream of the weight-gradient branch (created on first use)
         self._side_dirty = False
         self._keep: List[torch.Tensor] = []   # tensors the helper stream still reads (released at the next join)
+        self.colsums = ops.ColumnSums()       # deferred bias / LayerNorm parameter-gradient reductions
 
     def next_seed(self) -> int:
         self._n += 1
@@ -108,7 +109,9 @@ class Tape:
             yield
 
     def join_side(self):
-        """Make the current stream wait for the weight-gradient branch (before gradients are consumed)."""
+        """Fold the deferred column sums and make the current stream wait for the weight-gradient branch (before
+        parameter gradients are consumed)."""
+        self.colsums.flush()
         if self._side_dirty:
             ev = torch.cuda.Event()
             ev.record(self._side)
@@ -124,6 +127,19 @@ class Tape:
         acc = id(p) in self._sink_written
         self._sink_written.add(id(p))
         return s, acc
+
+    def deferred_target(self, p: torch.Tensor):
+        """(buffer, accumulate) for a parameter gradient that a later `colsums.flush()` writes: the flat-buffer view if
+        the trainer installed one, else a tensor handed to autograd (created here on first use)."""
+        tgt, acc = self.grad_target(p)
+        if tgt is not None:
+            return tgt, acc
+        k = id(p)
+        if k in self.pgrads:
+            return self.pgrads[k], True
+        g = torch.empty_like(p)
+        self.pgrads[k] = g
+        return g, False
 
     def add_pgrad(self, p: torch.Tensor, g: torch.Tensor):
         k = id(p)
@@ -179,11 +195,17 @@ def linear(t: Tape, x: Var, W: torch.Tensor, b: Optional[torch.Tensor], *, act: 
         if residual is not None:
             add_grad(residual, dy_full)
         # elementwise part on the full (possibly padded, contiguous) buffers; padded columns carry zeros
+        bias_partial = None
         if y.g_is_pre:
             dpre_full = dy_full
         elif act != 0 or p > 0.0:
             saved = act_out if need_act_out else (y.v if act != 0 else None)
-            dpre_full = ops.act_dropout_bwd(dy_full.contiguous(), saved, p, seed)
+            dyc = dy_full.contiguous()
+            if b is not None and dyc.shape[1] == N and N % 4 == 0 and N <= 1024 and M > 0:
+                # one pass: dpre and the per-CTA partial sums of the bias gradient (folded later by tape.colsums)
+                dpre_full, bias_partial = ops.act_dropout_bwd_fused(dyc, saved, p, seed)
+            else:
+                dpre_full = ops.act_dropout_bwd(dyc, saved, p, seed)
         else:
             dpre_full = dy_full
         dpre = dpre_full[:, :N] if dpre_full.shape[1] != N else dpre_full
@@ -194,13 +216,16 @@ def linear(t: Tape, x: Var, W: torch.Tensor, b: Optional[torch.Tensor], *, act: 
                 t.add_pgrad(W, ops.gemm(dpre, xv, trans_a=True, trans_b=True, m=N, n=K, k=M))
             else:
                 ops.gemm(dpre, xv, trans_a=True, trans_b=True, m=N, n=K, k=M, out=tgt, accumulate=acc)
-            if b is not None:
+            if b is not None and bias_partial is None:
                 tgt, acc = t.grad_target(b)
                 if tgt is None:
                     db, _ = ops.col_reduce(dpre, cols=N)
                     t.add_pgrad(b, db)
                 else:
                     ops.col_reduce(dpre, out_sum=tgt, cols=N, accumulate=acc)
+        if bias_partial is not None:
+            tgt, acc = t.deferred_target(b)
+            t.colsums.add(bias_partial, bias_partial.shape[0], N, N, tgt, acc)
         if x.needs:
             fuse = x.elu_fusable and x.g is None
             if K == xv.shape[1]:
@@ -224,6 +249,17 @@ def layernorm(t: Tape, x: Var, gamma: torch.Tensor, beta: torch.Tensor) -> Var:
     def bwd():
         dy = y.g
         if dy is None:
+            return
+        cols = x.v.shape[1]
+        if x.needs and cols <= 512 and cols % 4 == 0 and x.v.shape[0] > 0:
+            # one pass over dy / x: dx and per-CTA partials of the gamma / beta gradients
+            dx, partial = ops.layernorm_bwd_fused(dy.contiguous(), x.v, mean, rstd, gamma)
+            tg, acc_g = t.deferred_target(gamma)
+            tb, acc_b = t.deferred_target(beta)
+            n = partial.shape[0]
+            t.colsums.add(partial, n, 2 * cols, cols, tb, acc_b)
+            t.colsums.add(partial[0, 1], n, 2 * cols, cols, tg, acc_g)
+            add_grad(x, dx)
             return
         with t.side_branch(dy, x.v, mean, rstd):
             tg, acc = t.grad_target(gamma)

@@ -95,6 +95,7 @@ class Trainer:
         self.distributed = dist.is_available() and dist.is_initialized() if distributed is None else distributed
         self.world = dist.get_world_size() if self.distributed else 1
         self.gnorm_sq = torch.zeros(1, device=self.device, dtype=torch.float32)
+        self._norm_ws = torch.zeros(1024, device=self.device, dtype=torch.float32)
         self.counters = torch.zeros(2, device=self.device, dtype=torch.int64)
         self.lr_dev = torch.full((1,), float(lr), device=self.device, dtype=torch.float32)
         self._lr = float(lr)
@@ -193,12 +194,18 @@ class Trainer:
         g = self.energy(g)
         loss = self.loss_fn(g)
         loss.backward()
+        # the outputs left on the graph (h, k, eq, energy, gradient ...) must not keep the autograd graph -- and with
+        # it per-parameter autograd nodes bound to this step's streams -- alive beyond the step
+        for nt in g.ntypes:
+            d = g.nodes[nt].data
+            for k in list(d.keys()):
+                if d[k].grad_fn is not None:
+                    d[k] = d[k].detach()
         return loss.detach()
 
     def optimizer_step(self):
         self._wait_comm()
-        self.gnorm_sq.zero_()
-        ops.sumsq(self.fp.grad, self.gnorm_sq)
+        ops.sumsq_det(self.fp.grad, self.gnorm_sq, self._norm_ws)
         ops.adam_step_dev(self.fp.flat, self.fp.grad, self.fp.m, self.fp.v, self.lr_dev, self.betas[0], self.betas[1],
                           self.eps, self.counters[0:1], gnorm_sq=self.gnorm_sq, clip=self.clip, grad_scale=1.0 / self.world)
         ops.tick(self.counters)
@@ -229,6 +236,11 @@ class Trainer:
         for nt, k in cap.keys:
             cap.g_static.nodes[nt].data[k].copy_(g.nodes[nt].data[k], non_blocking=True)
         cap.pack.copy_from(get_pack(g))
+
+    def reset_graphs(self):
+        """Drop every captured step (the next step of a known shape is captured again)."""
+        self._captured.clear()
+        self.last_graph = None
 
     def h2d_bytes(self, g) -> int:
         """Bytes `step(g)` copies host->device for a host-resident batch (inputs + index tables)."""

@@ -179,6 +179,32 @@ int grappa_b200_col_reduce(const float* dy, int32_t ld, const float* x, const fl
                            float* out_sum, float* out_xhat, float* workspace, int32_t rows, int32_t cols,
                            int32_t accumulate, void* stream);
 
+/* Fused backward kernels with DEFERRED column sums.  They write dx and, per CTA, the column sums over the CTA's rows
+ * into `partial` ([n_cta, 2, cols] for LayerNorm: set 0 = sum dy (beta), set 1 = sum dy * xhat (gamma);
+ * [n_cta, cols] for act_dropout_bwd: sum dx = bias gradient).  grappa_b200_finalize_colsums then folds the partials
+ * of up to GB_COLSUM_MAX reductions in ONE launch (fixed order: deterministic).  cols <= 512 / <= 1024. */
+int grappa_b200_layernorm_bwd_fused(const float* dy, const float* x, const float* mean, const float* rstd,
+                                    const float* gamma, float* dx, float* partial, int32_t n_cta, int32_t rows,
+                                    int32_t cols, void* stream);
+int grappa_b200_act_dropout_bwd_fused(const float* dy, const float* act_out, float* dx, float* partial, int32_t n_cta,
+                                      int32_t rows, int32_t cols, float p, uint64_t seed, const uint64_t* seed_offset,
+                                      void* stream);
+#define GB_COLSUM_MAX 96
+typedef struct {
+  const float* partial;   /* first partial row                                   */
+  float* out;             /* [cols]                                              */
+  int32_t n_part;         /* number of partial rows                              */
+  int32_t stride;         /* floats between consecutive partial rows             */
+  int32_t cols;
+  int32_t accumulate;     /* 1: out += sum                                       */
+} gb_colsum_desc;
+typedef struct {
+  int32_t n;
+  int32_t pad_;
+  gb_colsum_desc desc[GB_COLSUM_MAX];
+} gb_colsum_batch;
+int grappa_b200_finalize_colsums(const gb_colsum_batch* batch, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Graph attention over bonded neighbours (DGL DotGatConv body: u_dot_v / sqrt(d) -> edge softmax over
  * the in-edges of each destination -> u_mul_e + sum; call site reference models/graph_attention.py:283).
@@ -274,6 +300,9 @@ int grappa_b200_act_dropout_bwd(const float* dy, const float* act_out, float* dx
 int grappa_b200_axpby(const float* x, float* y, int64_t n, float a, float b, void* stream);
 /* out[0] += sum x^2  (out must be zeroed by the caller; deterministic two-stage when ws given) */
 int grappa_b200_sumsq(const float* x, int64_t n, float* out, void* stream);
+/* out[0] = sum x^2, bit-reproducible (fixed grid, partials folded in block order by the last block).
+ * workspace: >= 4096 bytes, ZERO on first use (the kernel leaves its ticket counter zero). */
+int grappa_b200_sumsq_det(const float* x, int64_t n, float* out, float* workspace, void* stream);
 /* Adam (torch.optim.Adam semantics, weight_decay = 0) with the gradient pre-scaled by
  * min(1, clip / (sqrt(*gnorm_sq) + 1e-6)) * grad_scale -- gnorm_sq is a device scalar or NULL. */
 int grappa_b200_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
