@@ -302,23 +302,32 @@ __global__ void __launch_bounds__(256) act_dropout_bwd_fused_kernel(const float*
   }
 }
 
-// out[c] (+)= sum_{p < n_part} partial[p * stride + c]   for every descriptor; grid = (column chunks of 256, n_desc)
+// out[c] (+)= sum_{p < n_part} partial[p * stride + c]   for every descriptor; grid = (column chunks of 64, n_desc).
+// 4 lanes share a column (partial rows p = lane, lane + 4, ...), combined in a fixed order.
 __global__ void __launch_bounds__(256) finalize_colsums_kernel(gb_colsum_batch batch) {
   const gb_colsum_desc d = batch.desc[blockIdx.y];
-  const int c = blockIdx.x * 256 + threadIdx.x;
-  if (c >= d.cols) return;
-  const float* p = d.partial + c;
+  const int c = blockIdx.x * 64 + (threadIdx.x >> 2);
+  const int sub = threadIdx.x & 3;
   float acc = 0.f;
-  int i = 0;
-  for (; i + 7 < d.n_part; i += 8) {
-    float v[8];
+  if (c < d.cols) {
+    const float* p = d.partial + c;
+    int i = sub;
+    for (; i + 12 < d.n_part; i += 16) {
+      float v[4];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = __ldg(p + (size_t)(i + u) * d.stride);
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(p + (size_t)(i + 4 * u) * d.stride);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) acc += v[u];
+      for (int u = 0; u < 4; ++u) acc += v[u];
+    }
+    for (; i < d.n_part; i += 4) acc += __ldg(p + (size_t)i * d.stride);
   }
-  for (; i < d.n_part; ++i) acc += __ldg(p + (size_t)i * d.stride);
-  d.out[c] = d.accumulate ? d.out[c] + acc : acc;
+  const float a1 = __shfl_down_sync(0xffffffffu, acc, 1);
+  const float a2 = __shfl_down_sync(0xffffffffu, acc, 2);
+  const float a3 = __shfl_down_sync(0xffffffffu, acc, 3);
+  if (sub == 0 && c < d.cols) {
+    const float tot = ((acc + a1) + a2) + a3;
+    d.out[c] = d.accumulate ? d.out[c] + tot : tot;
+  }
 }
 
 static int col_slices(int rows) {
@@ -444,7 +453,7 @@ extern "C" int grappa_b200_finalize_colsums(const gb_colsum_batch* batch, void* 
     GB_REQUIRE(d.partial && d.out && d.cols > 0 && d.n_part > 0 && d.stride >= d.cols, "finalize_colsums: bad descriptor %d", i);
     if (d.cols > max_cols) max_cols = d.cols;
   }
-  dim3 grid((max_cols + 255) / 256, batch->n);
+  dim3 grid((max_cols + 63) / 64, batch->n);
   finalize_colsums_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(*batch);
   GB_CHECK_LAUNCH();
   return GB_OK;

@@ -348,8 +348,9 @@ def tick(counters):
 
 
 def _n_cta(rows: int) -> int:
-    """CTAs of the fused backward kernels: every CTA gets >= 8 rows, at most one CTA per SM."""
-    return max(1, min(_lib.lib().grappa_b200_sm_count() if _SMS[0] is None else _SMS[0], (rows + 7) // 8))
+    """CTAs of the fused backward kernels: every CTA gets >= 8 rows, at most two CTAs per SM."""
+    sms = _lib.lib().grappa_b200_sm_count() if _SMS[0] is None else _SMS[0]
+    return max(1, min(2 * sms, (rows + 7) // 8))
 
 
 _SMS = [None]

@@ -1,0 +1,172 @@
+"""BASELINE.json configs at their FULL sizes on the GPU (configs[0] is tests/test_model_gpu.py's dipeptide fixture).
+
+configs[1]  32 peptides x 52 atoms x 50 conformations, grappa-1.2: training forward vs the CPU oracle (live)
+configs[2]  1502-atom protein parametrisation, grappa-1.2, fp32 GEMMs vs the CPU oracle (live)
+configs[3]  energy+force sweep 1000 molecules x 100 conformations: size-independent properties (sharding
+            invariance, rigid-motion invariance, forces = finite-difference gradient of the energy, kernel variants)
+configs[4]  Espaloma-shaped mix (small molecules / peptides / RNA-like): loss and its gradients vs the oracle
+"""
+import numpy as np
+import pytest
+import torch
+
+from util import LEVELS, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(cfg, seed):
+    from grappa_b200 import models, synthetic
+    m = models.model_from_config(dict(cfg))
+    m.load_state_dict(synthetic.deterministic_state_dict(m.state_dict(), seed=seed))
+    return m
+
+
+def _oracle_forward(model, g, cfg, gradients=True):
+    import grappa_oracle as orc
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    return orc.path_forward(sd, g, cfg, gradients=gradients)
+
+
+def test_config1_training_batch_forward_matches_oracle():
+    import grappa_oracle as orc
+    from grappa_b200 import ops, synthetic
+    from grappa_b200.energy import Energy
+    cfg = orc.grappa_1_2_model_config()
+    model = _model(cfg, seed=11).eval()
+    g = synthetic.peptide_batch(seed=100, batch_size=32, n_res=4, n_confs=50)
+    assert g.num_nodes("n1") == 32 * 52 and g.nodes["n1"].data["xyz"].shape == (1664, 50, 3)
+    h, params, en = _oracle_forward(model, g, cfg)
+    model = model.cuda()
+    for prec, tol, tol_k4 in (("fp32", 1e-5, 1e-5), ("tf32", 1e-3, 5e-3)):
+        ops.set_matmul_precision(prec)
+        try:
+            with torch.no_grad():
+                gd = torch.nn.Sequential(model, Energy(write_tuple_terms=False))(g.to("cuda"))
+            assert rel_err(gd.nodes["g"].data["energy"].cpu().numpy(), en["energy"].detach().numpy()) < tol
+            assert rel_err(gd.nodes["n1"].data["gradient"].cpu().numpy(), en["gradient"].detach().numpy()) < tol
+            for l in LEVELS:
+                lim = tol_k4 if l in ("n4", "n4_improper") else tol
+                assert rel_err(gd.nodes[l].data["k"].cpu().numpy(), params[l]["k"].detach().numpy()) < lim, (prec, l)
+        finally:
+            ops.set_matmul_precision("fp32")
+
+
+def test_config2_protein_1502_atoms_parametrisation_matches_oracle():
+    import grappa_oracle as orc
+    from grappa_b200 import ops, synthetic
+    cfg = orc.grappa_1_2_model_config()
+    model = _model(cfg, seed=12).eval()
+    g = synthetic.protein(seed=0)
+    assert [g.num_nodes(t) for t in ("n1", "n2", "n3", "n4", "n4_improper")] == [1502, 1501, 2700, 3741, 900]
+    import grappa_oracle as orc2
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    h, params = orc2.model_forward(sd, g, cfg)
+    ops.set_matmul_precision("fp32")
+    model = model.cuda()
+    with torch.no_grad():
+        gd = model(g.to("cuda"))
+    assert rel_err(gd.nodes["n1"].data["h"].cpu().numpy(), h.detach().numpy()) < 1e-5
+    for l in LEVELS:
+        assert rel_err(gd.nodes[l].data["k"].cpu().numpy(), params[l]["k"].detach().numpy()) < 1e-5, l
+        if l in ("n2", "n3"):
+            assert rel_err(gd.nodes[l].data["eq"].cpu().numpy(), params[l]["eq"].detach().numpy()) < 1e-5, l
+    # params are written to the graph with the reference's shapes
+    assert gd.nodes["n2"].data["k"].shape == (1501,) and gd.nodes["n4"].data["k"].shape == (3741, 3)
+    assert gd.nodes["n4_improper"].data["k"].shape == (900, 3)
+
+
+def _sweep_graph(n_mols, n_confs, seed=7):
+    from grappa_b200 import graph as gbg, synthetic
+    base = synthetic.peptide_batch(seed=seed, batch_size=8, n_res=4, n_confs=n_confs)
+    g = gbg.batch([base] * (n_mols // 8))
+    gen = torch.Generator().manual_seed(1)
+    for l in LEVELS:
+        T = g.num_nodes(l)
+        if l in ("n2", "n3"):
+            g.nodes[l].data["k"] = 100 + 300 * torch.rand(T, generator=gen)
+            g.nodes[l].data["eq"] = (1.0 if l == "n2" else 1.6) + 0.5 * torch.rand(T, generator=gen)
+        else:
+            g.nodes[l].data["k"] = torch.randn(T, 3, generator=gen)
+    return g
+
+
+def test_config3_energy_sweep_full_size_properties():
+    from grappa_b200 import graph as gbg
+    from grappa_b200.energy import Energy
+    from grappa_b200.training import shard_molecules
+    n_mols, n_confs = 1000, 100
+    g = _sweep_graph(n_mols, n_confs)
+    en = Energy(write_tuple_terms=False)
+    with torch.no_grad():
+        gd = en(g.to("cuda"))
+    E = gd.nodes["g"].data["energy"].clone()
+    F = gd.nodes["n1"].data["gradient"].clone()
+    assert E.shape == (n_mols, n_confs) and F.shape == (n_mols * 52, n_confs, 3)
+    assert torch.isfinite(E).all() and torch.isfinite(F).all()
+    # (a) bit-reproducible and identical across kernel variants up to rounding
+    with torch.no_grad():
+        gd2 = en(g.to("cuda"))
+    assert torch.equal(gd2.nodes["g"].data["energy"], E) and torch.equal(gd2.nodes["n1"].data["gradient"], F)
+    en_atomic = Energy(write_tuple_terms=False)
+    en_atomic.kernel_variant = 2
+    with torch.no_grad():
+        gd3 = en_atomic(g.to("cuda"))
+    assert rel_err(gd3.nodes["g"].data["energy"].cpu().numpy(), E.cpu().numpy()) < 1e-5
+    assert rel_err(gd3.nodes["n1"].data["gradient"].cpu().numpy(), F.cpu().numpy()) < 1e-5
+    # (b) sharding invariance: molecules i = rank (mod world) evaluated alone give the same rows (no communication)
+    mols = gbg.unbatch(g)
+    world = 8
+    for rank in (0, 5):
+        ids = list(shard_molecules(n_mols, rank, world))
+        with torch.no_grad():
+            gs = en(gbg.batch([mols[i] for i in ids]).to("cuda"))
+        assert torch.equal(gs.nodes["g"].data["energy"], E[ids])
+    # (c) rigid motion invariance of E; forces rotate with the frame
+    c, s = np.cos(0.7), np.sin(0.7)
+    R = torch.tensor([[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]], dtype=torch.float32)
+    g2 = g.to("cpu")
+    g2.nodes["n1"].data["xyz"] = g.nodes["n1"].data["xyz"] @ R.T + torch.tensor([1.0, -2.0, 0.5])
+    with torch.no_grad():
+        gr = en(g2.to("cuda"))
+    assert rel_err(gr.nodes["g"].data["energy"].cpu().numpy(), E.cpu().numpy()) < 2e-5
+    assert rel_err(gr.nodes["n1"].data["gradient"].cpu().numpy(), (F.cpu() @ R.T).numpy()) < 2e-4
+    # (d) gradient = dE/dxyz: fp64 central differences on the CPU oracle for one molecule / 3 conformations
+    import grappa_oracle as orc
+    m = mols[3]
+    idxs = {l: m.nodes[l].data["idxs"] for l in LEVELS}
+    params = {l: {k: m.nodes[l].data[k].double() for k in ("k", "eq") if k in m.nodes[l].data} for l in LEVELS}
+    counts = {l: [m.num_nodes(l)] for l in LEVELS}
+    ref = orc.energy_forward(m.nodes["n1"].data["xyz"][:, :3].double(), idxs, params, counts, gradients=True)
+    assert rel_err(F[3 * 52:4 * 52, :3].cpu().numpy(), ref["gradient"].detach().numpy()) < 1e-5
+    assert rel_err(E[3, :3].cpu().numpy(), ref["energy"][0].detach().numpy()) < 1e-5
+
+
+def test_config4_espaloma_mix_loss_and_gradients_match_oracle():
+    import grappa_oracle as orc
+    from grappa_b200 import ops, synthetic
+    from grappa_b200.energy import Energy
+    from grappa_b200.loss import MolwiseLoss
+    cfg = orc.small_model_config()
+    model = _model(cfg, seed=13).eval()
+    g = synthetic.espaloma_mix_batch(seed=4, batch_size=32, n_confs=32)
+    counts = g.batch_num_nodes("n1").tolist()
+    assert len(counts) == 32 and min(counts) < 20 and max(counts) > 80      # small molecules and RNA-like graphs mixed
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point() and v.dim() > 0) for k, v in model.state_dict().items()}
+    h, params, en = orc.path_forward(sd, g, cfg, create_graph=True)
+    ref_loss = orc.molwise_loss(en, params, g)
+    names = ["gnn.att_blocks.1.self_interaction.0.weight", "parameter_writer.proper_writer.torsion_model.symmetriser.mlp.0.linear1.weight",
+             "parameter_writer.bond_writer.bond_model.grappa_transformer.transformer.0.attn.in_proj_weight",
+             "parameter_writer.angle_writer.rep_projector.mlp.0.bias", "gnn.pre_dense.0.weight"]
+    ref_grads = torch.autograd.grad(ref_loss, [sd[n] for n in names])
+    ops.set_matmul_precision("fp32")
+    model = model.cuda()
+    gd = torch.nn.Sequential(model, Energy(write_tuple_terms=False))(g.to("cuda"))
+    loss = MolwiseLoss(gradient_weight=0.8, energy_weight=1.0, param_weight=0.0, proper_regularisation=1e-3,
+                       improper_regularisation=1e-3)(gd)
+    assert abs(loss.item() - float(ref_loss)) < 1e-5 * abs(float(ref_loss))
+    loss.backward()
+    named = dict(model.named_parameters())
+    for n, rg in zip(names, ref_grads):
+        assert rel_err(named[n].grad.cpu().numpy(), rg.numpy()) < 1e-4, n
