@@ -259,6 +259,16 @@ def main():
         torch.cuda.synchronize()
         gemm_ms += sum(e0.elapsed_time(e1) for _, e0, e1, _ in prof)
     ms_serial = timed(step_resident, 5) / 5
+    if os.environ.get("GRAPPA_B200_GEMM_TABLE") and rank == 0:
+        # tuning aid: per-shape totals of the last instrumented replay -> a small text table
+        agg = {}
+        for f, e0, e1, shp in prof:
+            a = agg.setdefault(shp, [0, 0.0, 0.0])
+            a[0] += 1; a[1] += e0.elapsed_time(e1); a[2] += f
+        with open(os.environ["GRAPPA_B200_GEMM_TABLE"], "w") as fh:
+            for shp, (c, t, f) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                fh.write(f"M={shp[0]:6d} N={shp[1]:5d} K={shp[2]:6d} ta={shp[3]} tb={shp[4]}  x{c:3d}  {t * 1e3:9.1f} us total  "
+                         f"{t * 1e3 / c:7.1f} us each  {f / t / 1e9:7.1f} TFLOP/s\n")
     gemm_flops = sum(f for f, _, _, _ in prof) * n_prof_steps
     gemm_launches = len(prof)
     gb_tape.set_concurrency(True)

@@ -69,7 +69,16 @@ class LossArgs(C.Structure):
         ("B", i32), ("C", i32), ("n_per_p", i32), ("n_per_i", i32),
         ("w_energy", f32), ("w_grad", f32), ("w_proper", f32), ("w_improper", f32),
         ("loss", vp), ("mol_loss", vp), ("g_energy", vp), ("g_grad", vp), ("g_k_proper", vp), ("g_k_improper", vp),
-        ("grad_scale", vp),
+        ("grad_scale", vp), ("extra_mol_loss", vp),
+    ]
+
+
+class ParamLossArgs(C.Structure):
+    _fields_ = [
+        ("n_terms", i32), ("B", i32),
+        ("pred", vp * 5), ("ref", vp * 5), ("off", vp * 5),
+        ("width", i32 * 5), ("ref_width", i32 * 5), ("fac", f32 * 5),
+        ("mol_weight", vp), ("mol_loss", vp), ("g_pred", vp * 5), ("grad_scale", vp),
     ]
 
 
@@ -104,6 +113,8 @@ def declare(lib):
     lib.grappa_b200_act_dropout_bwd_fused.argtypes = [vp, vp, vp, vp, i32, i32, i32, f32, u64, vp, vp]
     lib.grappa_b200_finalize_colsums.argtypes = [C.POINTER(ColsumBatch), vp]
     lib.grappa_b200_molwise_loss.argtypes = [P(LossArgs), vp]
+    lib.grappa_b200_param_loss.argtypes = [P(ParamLossArgs), vp]
+    lib.grappa_b200_param_loss.restype = C.c_int
     for name in ("gemm", "layernorm_fwd", "layernorm_bwd", "col_reduce", "edge_attention_fwd", "edge_attention_bwd",
                  "tuple_attention_fwd", "tuple_attention_bwd", "tuple_gather_fwd", "tuple_gather_bwd",
                  "perm_concat_fwd", "perm_concat_bwd", "featurize", "head_output_fwd", "head_output_bwd", "dropout",

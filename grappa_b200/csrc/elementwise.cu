@@ -254,7 +254,34 @@ __global__ void __launch_bounds__(256) molwise_loss_kernel(gb_loss_args a) {
     }
     term += w * block_sum(q, sh) / (float)(i1 - i0);
   }
-  if (tid == 0) a.mol_loss[b] = term * invB_loss;
+  if (tid == 0) a.mol_loss[b] = (term + (a.extra_mol_loss ? a.extra_mol_loss[b] : 0.f)) * invB_loss;
+}
+
+// classical-parameter MSE, one block per molecule (see gb_param_loss_args)
+__global__ void __launch_bounds__(256) param_loss_kernel(gb_param_loss_args a) {
+  __shared__ float sh[8];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  long long total = 0;
+  for (int i = 0; i < a.n_terms; ++i) total += (long long)(a.off[i][b + 1] - a.off[i][b]) * a.width[i];
+  const float w = a.mol_weight[b];
+  const float inv_total = total > 0 ? 1.f / (float)total : 0.f;
+  const float gsc = (a.grad_scale ? __ldg(a.grad_scale) : 1.f) / a.B * w * 2.f * inv_total;
+  float q = 0.f;
+  for (int i = 0; i < a.n_terms; ++i) {
+    const int wd = a.width[i], rw = a.ref_width[i];
+    const long long e0 = (long long)a.off[i][b] * wd, e1 = (long long)a.off[i][b + 1] * wd;
+    const float fac = a.fac[i];
+    for (long long e = e0 + tid; e < e1; e += blockDim.x) {
+      const long long t = e / wd;
+      const int j = (int)(e - t * wd);
+      const float r = j < rw ? a.ref[i][t * rw + j] : 0.f;
+      const float d = (r != r) ? 0.f : fac * (a.pred[i][e] - r);
+      q += d * d;
+      if (a.g_pred[i]) a.g_pred[i][e] = gsc * fac * d;
+    }
+  }
+  q = block_sum(q, sh);
+  if (tid == 0) a.mol_loss[b] = w * q * inv_total;
 }
 
 __global__ void __launch_bounds__(256) loss_final_kernel(const float* __restrict__ mol_loss, int B, float* loss) {
@@ -503,6 +530,20 @@ extern "C" int grappa_b200_adam_step_dev(float* p, const float* g, float* m, flo
 extern "C" int grappa_b200_tick(uint64_t* counters, int32_t n, void* stream_) {
   GB_REQUIRE(counters && n >= 1 && n <= 32, "tick: need 1..32 counters");
   tick_kernel<<<1, 32, 0, (cudaStream_t)stream_>>>(counters, n);
+  GB_CHECK_LAUNCH();
+  return GB_OK;
+}
+
+extern "C" int grappa_b200_param_loss(const gb_param_loss_args* a, void* stream_) {
+  GB_REQUIRE(a != nullptr, "param_loss: args is NULL");
+  GB_REQUIRE(a->B > 0, "param_loss: empty batch");
+  GB_REQUIRE(a->n_terms >= 0 && a->n_terms <= GB_PARAM_LOSS_MAX_TERMS, "param_loss: at most %d terms", GB_PARAM_LOSS_MAX_TERMS);
+  GB_REQUIRE(a->mol_weight && a->mol_loss, "param_loss: NULL pointer");
+  for (int i = 0; i < a->n_terms; ++i) {
+    GB_REQUIRE(a->pred[i] && a->ref[i] && a->off[i], "param_loss: term %d has a NULL pointer", i);
+    GB_REQUIRE(a->width[i] > 0 && a->ref_width[i] >= 0, "param_loss: term %d has a bad width", i);
+  }
+  param_loss_kernel<<<a->B, 256, 0, (cudaStream_t)stream_>>>(*a);
   GB_CHECK_LAUNCH();
   return GB_OK;
 }

@@ -55,14 +55,43 @@ struct Epilogue {
     }
     if (drop_thresh) {
       const uint64_t base = (uint64_t)m * (uint64_t)N + (uint64_t)n;
-      const uint64_t sd = seed();
+      if ((N & 3) == 0) {   // aligned group of four: one key, two finalisers
+        const float4 d = dropout_scale4(seed(), base, drop_thresh, drop_inv_keep);
+        v[0] *= d.x; v[1] *= d.y; v[2] *= d.z; v[3] *= d.w;
+      } else {
+        const uint64_t sd = seed();
 #pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] *= dropout_scale(sd, base + i, drop_thresh, drop_inv_keep);
+        for (int i = 0; i < 4; ++i) v[i] *= dropout_scale(sd, base + i, drop_thresh, drop_inv_keep);
+      }
     }
     if (residual) {
       const float4 r = __ldg(reinterpret_cast<const float4*>(residual + (size_t)m * ldr + n));
       v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
     }
+    float4* c = reinterpret_cast<float4*>(C + (size_t)m * ldc + n);
+    if (accumulate) {
+      const float4 o = *c;
+      v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;
+    }
+    *c = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  // tensor-core path: bias already added, residual / saved-activation values already loaded by the caller
+  __device__ __forceinline__ void store4_pre(float4 acc, int m, int n, const float4& res, const float4& y) const {
+    float v[4] = {acc.x, acc.y, acc.z, acc.w};
+    if (act == 1) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = v[i] > 0.f ? v[i] : __expf(v[i]) - 1.f;
+    }
+    if (act_out) *reinterpret_cast<float4*>(act_out + (size_t)m * ldact + n) = make_float4(v[0], v[1], v[2], v[3]);
+    if (mul_elu_out) {
+      v[0] *= elu1_grad_from_out(y.x); v[1] *= elu1_grad_from_out(y.y);
+      v[2] *= elu1_grad_from_out(y.z); v[3] *= elu1_grad_from_out(y.w);
+    }
+    if (drop_thresh) {
+      const float4 d = dropout_scale4(seed(), (uint64_t)m * (uint64_t)N + (uint64_t)n, drop_thresh, drop_inv_keep);
+      v[0] *= d.x; v[1] *= d.y; v[2] *= d.z; v[3] *= d.w;
+    }
+    if (residual) { v[0] += res.x; v[1] += res.y; v[2] += res.z; v[3] += res.w; }
     float4* c = reinterpret_cast<float4*>(C + (size_t)m * ldc + n);
     if (accumulate) {
       const float4 o = *c;

@@ -161,9 +161,138 @@ int launch_splitk_reduce(const float* partial, int splits, int M, int N, const E
   return GB_OK;
 }
 
+
+// ---- skinny shapes ---------------------------------------------------------------------------------
+// The last symmetriser layer has 2 (bond / angle) or 6 (gated torsion) outputs: its forward GEMM has N <= 8, its
+// input gradient K <= 8 and its weight gradient M <= 8.  A 128x128 tile wastes > 90 % of its work on them (45-60 us per
+// launch, measured); these three kernels stream the one large operand exactly once instead.
+constexpr int SK_MAX = 8;
+
+// C[m, n] = sum_k A[m, k] * B[n, k]   (N <= 8): one warp per row, B staged in shared memory
+__global__ void __launch_bounds__(256) skinny_n_kernel(const float* __restrict__ A, const float* __restrict__ B, int M, int N,
+                                                       int K, int lda, int ldb, Epilogue ep) {
+  extern __shared__ float sB[];   // [N][K]
+  for (int i = threadIdx.x; i < N * K; i += blockDim.x) sB[i] = __ldg(B + (size_t)(i / K) * ldb + (i % K));
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; m < M; m += warps) {
+    float acc[SK_MAX];
+#pragma unroll
+    for (int n = 0; n < SK_MAX; ++n) acc[n] = 0.f;
+    const float* a = A + (size_t)m * lda;
+    for (int k = lane; k < K; k += 32) {
+      const float av = __ldg(a + k);
+#pragma unroll
+      for (int n = 0; n < SK_MAX; ++n)
+        if (n < N) acc[n] = fmaf(av, sB[n * K + k], acc[n]);
+    }
+#pragma unroll
+    for (int n = 0; n < SK_MAX; ++n)
+      if (n < N) acc[n] = warp_sum(acc[n]);
+    if (lane == 0) {
+#pragma unroll
+      for (int n = 0; n < SK_MAX; ++n)
+        if (n < N) ep.store(acc[n], m, n);
+    }
+  }
+}
+
+// C[m, n] = sum_{k < K} A[m, k] * B[k, n]   (K <= 8, B row-major [K, N]): one thread per output element
+__global__ void __launch_bounds__(256) skinny_k_kernel(const float* __restrict__ A, const float* __restrict__ B, int M, int N,
+                                                       int K, int lda, int ldb, Epilogue ep) {
+  const size_t total = (size_t)M * N;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int m = (int)(i / N), n = (int)(i - (size_t)m * N);
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < SK_MAX; ++k)
+      if (k < K) acc = fmaf(__ldg(A + (size_t)m * lda + k), __ldg(B + (size_t)k * ldb + n), acc);
+    ep.store(acc, m, n);
+  }
+}
+
+// C[i, n] = sum_k A[k, i] * B[k, n]   (M <= 8; A is [K, M], B is [K, N]): column sums over K in two deterministic stages.
+// Stage 1: CTA (chunk, column block) accumulates its K rows; stage 2: chunks are folded in order and the epilogue runs.
+__global__ void __launch_bounds__(256) skinny_m_stage1_kernel(const float* __restrict__ A, const float* __restrict__ B, int M,
+                                                              int N, int K, int lda, int ldb, int rows_per_chunk,
+                                                              float* __restrict__ partial) {
+  __shared__ float sA[64][SK_MAX];
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k0 = blockIdx.y * rows_per_chunk, k1 = min(K, k0 + rows_per_chunk);
+  float acc[SK_MAX];
+#pragma unroll
+  for (int i = 0; i < SK_MAX; ++i) acc[i] = 0.f;
+  for (int kb = k0; kb < k1; kb += 64) {
+    const int nk = min(64, k1 - kb);
+    __syncthreads();
+    for (int t = threadIdx.x; t < nk * M; t += blockDim.x) sA[t / M][t % M] = __ldg(A + (size_t)(kb + t / M) * lda + (t % M));
+    __syncthreads();
+    if (n < N) {
+      for (int kk = 0; kk < nk; ++kk) {
+        const float b = __ldg(B + (size_t)(kb + kk) * ldb + n);
+#pragma unroll
+        for (int i = 0; i < SK_MAX; ++i)
+          if (i < M) acc[i] = fmaf(sA[kk][i], b, acc[i]);
+      }
+    }
+  }
+  if (n < N) {
+#pragma unroll
+    for (int i = 0; i < SK_MAX; ++i)
+      if (i < M) partial[((size_t)blockIdx.y * M + i) * N + n] = acc[i];
+  }
+}
+
+static bool skinny_gemm(const gb_gemm_args* a, const Epilogue& ep, cudaStream_t stream, int* rc) {
+  const int M = a->M, N = a->N, K = a->K;
+  *rc = GB_OK;
+  if (K == 0) return false;
+  if (!a->trans_a && !a->trans_b && N <= SK_MAX && (size_t)N * K * 4 <= 32768 && M >= 64) {
+    int blocks = (M + 7) / 8;
+    if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+    skinny_n_kernel<<<blocks, 256, (size_t)N * K * 4, stream>>>(a->A, a->B, M, N, K, a->lda, a->ldb, ep);
+    count_launch();
+    return true;
+  }
+  if (!a->trans_a && a->trans_b && K <= SK_MAX && M >= 64) {
+    size_t total = (size_t)M * N;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > sm_count() * 16) blocks = sm_count() * 16;
+    skinny_k_kernel<<<blocks, 256, 0, stream>>>(a->A, a->B, M, N, K, a->lda, a->ldb, ep);
+    count_launch();
+    return true;
+  }
+  if (a->trans_a && a->trans_b && M <= SK_MAX && a->workspace && K >= 256) {
+    const int col_blocks = (N + 255) / 256;
+    int chunks = (2 * sm_count()) / col_blocks;
+    if (chunks > (K + 63) / 64) chunks = (K + 63) / 64;
+    const long long by_ws = a->workspace_bytes / ((long long)M * N * 4);
+    if (chunks > by_ws) chunks = (int)by_ws;
+    if (chunks < 1) return false;
+    const int rows_per_chunk = ((K + chunks - 1) / chunks + 63) / 64 * 64;
+    chunks = (K + rows_per_chunk - 1) / rows_per_chunk;
+    skinny_m_stage1_kernel<<<dim3(col_blocks, chunks), 256, 0, stream>>>(a->A, a->B, M, N, K, a->lda, a->ldb, rows_per_chunk,
+                                                                       a->workspace);
+    count_launch();
+    *rc = launch_splitk_reduce(a->workspace, chunks, M, N, ep, stream);
+    return true;
+  }
+  return false;
+}
+
 int gemm_simt(const gb_gemm_args* a, cudaStream_t stream) {
   Epilogue ep = make_epilogue(a);
   const int M = a->M, N = a->N, K = a->K;
+  {
+    int rc;
+    if (skinny_gemm(a, ep, stream, &rc)) {
+      if (rc) return rc;
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) { set_error("skinny gemm launch -> %s", cudaGetErrorString(e)); return GB_ERR_CUDA; }
+      return GB_OK;
+    }
+  }
   const int gx = (N + BN - 1) / BN, gy = (M + BM - 1) / BM;
   // split-K when the output grid cannot fill the machine and K is long (weight gradients)
   int splits = 1;

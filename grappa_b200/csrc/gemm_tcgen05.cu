@@ -268,11 +268,30 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const int z = rest / p.tiles_m;
       const int m0 = mb * TC_BM + q * 32, n0 = nb * BN + half * (BN / 2);
       const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
-      mbar_wait(&acc_full[as], aph);
-      tc_fence_after();
       const uint32_t t_addr = tmem_base + as * BN + half * (BN / 2) + ((uint32_t)(q * 32) << 16);
+      const bool side_inputs = !p.partial && vec_ok && (p.ep.residual != nullptr || p.ep.mul_elu_out != nullptr);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN / 2; c0 += 32) {
+        const int col = n0 + c0 + sub_c;
+        // Side inputs of this 32x32 patch (residual / saved activation) are requested BEFORE the accumulator is
+        // touched: 8 independent 16-byte loads per lane are in flight while the MMAs finish, the TMEM read and the
+        // transpose run.  (Loading them one row at a time inside the store loop made a residual epilogue
+        // latency-bound: 60 us instead of 28 us for M=14848, N=K=512.)
+        float4 res4[8], elu4[8];
+        if (side_inputs && col < p.N) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = m0 + sub_r + 4 * i;
+            if (r < p.M) {
+              if (p.ep.residual) res4[i] = __ldg(reinterpret_cast<const float4*>(p.ep.residual + (size_t)r * p.ep.ldr + col));
+              if (p.ep.mul_elu_out) elu4[i] = __ldg(reinterpret_cast<const float4*>(p.ep.mul_elu_out + (size_t)r * p.ep.ldm + col));
+            }
+          }
+        }
+        if (c0 == 0) {
+          mbar_wait(&acc_full[as], aph);
+          tc_fence_after();
+        }
         float v[32];
         tc_ld16(t_addr + (uint32_t)c0, v);
         tc_ld16(t_addr + (uint32_t)c0 + 16u, v + 16);
@@ -286,7 +305,6 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         for (int j = 0; j < 8; ++j)
           *reinterpret_cast<float4*>(patch + lane * Cfg::EPI_LD + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         __syncwarp();
-        const int col = n0 + c0 + sub_c;
         if (col < p.N) {
           if (p.partial) {
             float* dst0 = p.partial + ((size_t)z * p.M + m0) * p.N + col;
@@ -306,13 +324,14 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
           } else if (vec_ok) {
             const float4 b4 = p.ep.bias ? __ldg(reinterpret_cast<const float4*>(p.ep.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 2
+#pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int r = sub_r + 4 * i;
-              if (m0 + r >= p.M) break;
-              float4 acc = *reinterpret_cast<const float4*>(patch + r * Cfg::EPI_LD + sub_c);
-              acc.x += b4.x; acc.y += b4.y; acc.z += b4.z; acc.w += b4.w;
-              p.ep.template store4<true>(acc, m0 + r, col);
+              if (m0 + r < p.M) {
+                float4 acc = *reinterpret_cast<const float4*>(patch + r * Cfg::EPI_LD + sub_c);
+                acc.x += b4.x; acc.y += b4.y; acc.z += b4.z; acc.w += b4.w;
+                p.ep.store4_pre(acc, m0 + r, col, res4[i], elu4[i]);
+              }
             }
           } else {
 #pragma unroll 1

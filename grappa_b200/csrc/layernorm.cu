@@ -276,10 +276,8 @@ __global__ void __launch_bounds__(256) act_dropout_bwd_fused_kernel(const float*
       float4 v = __ldg(reinterpret_cast<const float4*>(dy) + i4);
       if (thresh) {
         const uint64_t base = (uint64_t)i4 * 4ull;
-        v.x *= dropout_scale(seed, base, thresh, inv_keep);
-        v.y *= dropout_scale(seed, base + 1, thresh, inv_keep);
-        v.z *= dropout_scale(seed, base + 2, thresh, inv_keep);
-        v.w *= dropout_scale(seed, base + 3, thresh, inv_keep);
+        const float4 d = dropout_scale4(seed, base, thresh, inv_keep);
+        v.x *= d.x; v.y *= d.y; v.z *= d.z; v.w *= d.w;
       }
       if (act_out) {
         const float4 y = __ldg(reinterpret_cast<const float4*>(act_out) + i4);

@@ -10,8 +10,11 @@ dL/d(energy), dL/d(gradient), dL/d(k_torsion) directly (they feed kernel K14).
 Deviations, both documented in SURVEY.md appendix A.7:
   * the improper regulariser enters twice in the reference (loss.py:127-132); we use weight 2x for
     molecules with impropers and 0 (instead of NaN) for molecules without any.
-  * the classical-parameter MSE term (`param_weight`, needs `*_ref` parameters on the graph) is not
-    fused yet: graphs carrying `k_ref` raise NotImplementedError unless param_weight == 0.
+
+The classical-parameter MSE term (`param_weight`, reference loss.py:70-113; graphs carrying `k_ref` /
+`eq_ref`) is a second one-block-per-molecule kernel (`grappa_b200_param_loss`) whose per-molecule
+results are folded into the same mean; NaN references are masked and torsion references are
+padded / truncated to the model's periodicity exactly as `correct_torsion_shape` does.
 """
 from __future__ import annotations
 
@@ -21,7 +24,7 @@ from typing import Dict, List
 import torch
 
 from . import _lib
-from ._lib_ops import LossArgs
+from ._lib_ops import LossArgs, ParamLossArgs
 from .pack import get_pack
 
 
@@ -31,29 +34,55 @@ def _p(t):
 
 class _LossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pack, weights, energy, energy_ref, grad, grad_ref, k_proper, k_improper):
-        ctx.pack, ctx.weights = pack, weights
+    def forward(ctx, pack, weights, pterms, energy, energy_ref, grad, grad_ref, k_proper, k_improper, *ppred):
+        ctx.pack, ctx.weights, ctx.pterms = pack, weights, pterms
         tens = [None if t is None else t.detach().contiguous().float() for t in
                 (energy, energy_ref, grad, grad_ref, k_proper, k_improper)]
-        ctx.save_for_backward(*[t if t is not None else torch.empty(0) for t in tens])
+        ppred = [t.detach().contiguous().float() for t in ppred]
+        ctx.save_for_backward(*[t if t is not None else torch.empty(0) for t in tens], *ppred)
         ctx.present = [t is not None for t in tens]
-        loss = _LossFn._launch(pack, weights, tens, None, False)[0]
+        loss = _LossFn._launch(pack, weights, tens, None, False, pterms, ppred)[0]
         return loss.reshape(())
 
     @staticmethod
-    def _launch(pack, weights, tens, scale, want_grads):
+    def _param_terms(pack, pterms, ppred, scale, want_grads):
+        """grappa_b200_param_loss: per-molecule classical-parameter MSE -> [B] (and gradients w.r.t. the predictions)."""
+        B = pack.n_mols
+        mol = torch.empty(B, device=pack.device, dtype=torch.float32)
+        a = ParamLossArgs()
+        a.n_terms, a.B = len(pterms["terms"]), B
+        outs = []
+        for i, ((level_id, ref, fac), pred) in enumerate(zip(pterms["terms"], ppred)):
+            a.pred[i], a.ref[i], a.off[i] = pred.data_ptr(), ref.data_ptr(), pack.ptr(f"tup_off{level_id}")
+            a.width[i] = pred.shape[1] if pred.dim() == 2 else 1
+            a.ref_width[i] = ref.shape[1] if ref.dim() == 2 else 1
+            a.fac[i] = fac
+            if want_grads:
+                outs.append(torch.empty_like(pred))
+                a.g_pred[i] = outs[-1].data_ptr()
+        a.mol_weight, a.mol_loss = pterms["mol_weight"].data_ptr(), mol.data_ptr()
+        a.grad_scale = _p(scale) if want_grads else 0
+        _lib.check(_lib.lib().grappa_b200_param_loss(C.byref(a), torch.cuda.current_stream().cuda_stream), "param_loss")
+        return mol, outs
+
+    @staticmethod
+    def _launch(pack, weights, tens, scale, want_grads, pterms=None, ppred=()):
         energy, energy_ref, grad, grad_ref, kp, ki = tens
         dev = pack.device
         B = pack.n_mols
         loss = torch.empty(1, device=dev, dtype=torch.float32)
         mol = torch.empty(B, device=dev, dtype=torch.float32)
         a = LossArgs()
+        extra, pgrads = None, []
+        if pterms is not None and len(pterms["terms"]) > 0:
+            extra, pgrads = _LossFn._param_terms(pack, pterms, ppred, scale, want_grads)
+            a.extra_mol_loss = extra.data_ptr()
         a.energy, a.energy_ref, a.grad, a.grad_ref = _p(energy), _p(energy_ref), _p(grad), _p(grad_ref)
         a.atom_off = pack.ptr("atom_off")
         a.k_proper, a.k_improper = _p(kp), _p(ki)
         a.proper_off, a.improper_off = pack.ptr("tup_off2"), pack.ptr("tup_off3")
         a.B = B
-        a.C = energy.shape[1] if energy is not None else grad.shape[1]
+        a.C = energy.shape[1] if energy is not None else (grad.shape[1] if grad is not None else 1)
         a.n_per_p = kp.shape[1] if kp is not None and kp.dim() == 2 else 0
         a.n_per_i = ki.shape[1] if ki is not None and ki.dim() == 2 else 0
         a.w_energy, a.w_grad, a.w_proper, a.w_improper = weights
@@ -64,17 +93,18 @@ class _LossFn(torch.autograd.Function):
             a.g_energy, a.g_grad, a.g_k_proper, a.g_k_improper = [_p(t) for t in outs]
             a.grad_scale = _p(scale)
         _lib.check(_lib.lib().grappa_b200_molwise_loss(C.byref(a), torch.cuda.current_stream().cuda_stream), "molwise_loss")
-        return loss, outs
+        return loss, outs, pgrads
 
     @staticmethod
     def backward(ctx, go):
         saved = list(ctx.saved_tensors)
-        tens = [t if p else None for t, p in zip(saved, ctx.present)]
+        tens = [t if p else None for t, p in zip(saved[:6], ctx.present)]
+        ppred = saved[6:]
         scale = go.detach().reshape(1).float().contiguous()
-        _, (ge, gg, gkp, gki) = _LossFn._launch(ctx.pack, ctx.weights, tens, scale, True)
+        _, (ge, gg, gkp, gki), pgrads = _LossFn._launch(ctx.pack, ctx.weights, tens, scale, True, ctx.pterms, ppred)
         if gki is not None and gki.numel() == 0:
             gki = torch.zeros_like(tens[5])
-        return None, None, ge, None, gg, None, gkp, gki
+        return (None, None, None, ge, None, gg, None, gkp, gki, *pgrads)
 
 
 class MolwiseLoss(torch.nn.Module):
@@ -93,18 +123,42 @@ class MolwiseLoss(torch.nn.Module):
         assert not (self.gradient_weight == 0 and self.energy_weight == 0 and self.param_weight == 0), \
             "At least one of the weights must be non-zero."
         assert self.tuplewise_weight == 0., f"Tuplewise loss not implemented yet., but weight is {self.tuplewise_weight}."
-        if self.param_weight != 0. and "k_ref" in g.nodes["n2"].data.keys():
-            raise NotImplementedError("classical-parameter loss (graphs with *_ref parameters) is not fused yet; "
-                                      "set param_weight=0")
-        if "k_ref" not in g.nodes["n2"].data.keys() and not self.skip_params_if_not_present and self.param_weight != 0.:
+        has_ref = "k_ref" in g.nodes["n2"].data.keys()
+        if not has_ref and not self.skip_params_if_not_present and self.param_weight != 0.:
             raise KeyError("k_ref")
         gd, nd = g.nodes["g"].data, g.nodes["n1"].data
         energy = gd["energy"] if self.energy_weight != 0. else None
         grad = nd["gradient"] if self.gradient_weight != 0. else None
         _lib.require_cuda(energy, grad)
+        pack = get_pack(g)
         kp = g.nodes["n4"].data["k"] if self.proper_regularisation > 0. and "n4" in g.ntypes else None
         ki = g.nodes["n4_improper"].data["k"] if self.improper_regularisation > 0. and "n4_improper" in g.ntypes else None
         weights = (float(self.energy_weight), float(self.gradient_weight), float(self.proper_regularisation),
                    2.0 * float(self.improper_regularisation))
-        return _LossFn.apply(get_pack(g), weights, energy, gd["energy_ref"] if energy is not None else None, grad,
-                             nd["gradient_ref"] if grad is not None else None, kp, ki)
+        pterms, ppred = None, []
+        use_params = has_ref and (self.param_weight != 0. or (dsnames is not None and len(self.param_weights_by_dataset) > 0))
+        if use_params:
+            # reference order BONDED_CONTRIBUTIONS minus impropers (loss.py:88-92): n2_k, n2_eq, n3_k, n3_eq, n4_k
+            terms = []
+            for level_id, lvl, name in ((0, "n2", "k"), (0, "n2", "eq"), (1, "n3", "k"), (1, "n3", "eq"), (2, "n4", "k")):
+                if lvl not in g.ntypes or name + "_ref" not in g.nodes[lvl].data.keys():
+                    continue
+                pred, ref = g.nodes[lvl].data[name], g.nodes[lvl].data[name + "_ref"]
+                _lib.require_cuda(pred, ref)
+                if lvl != "n4" and tuple(pred.shape) != tuple(ref.shape):
+                    raise ValueError(f"Shape of parameters {lvl}_{name} and {lvl}_{name}_ref do not match: "
+                                     f"{tuple(pred.shape)} vs {tuple(ref.shape)}")
+                terms.append((level_id, ref.detach().contiguous().float(), float(self.weights.get(f"{lvl}_{name}", 1.))))
+                ppred.append(pred)
+            w = [float(self.param_weight)] * pack.n_mols
+            if dsnames is not None:
+                w = [float(self.param_weights_by_dataset.get(d, self.param_weight)) for d in dsnames]
+                assert len(w) == pack.n_mols, "dsnames must hold one entry per molecule"
+            key = tuple(w)
+            cache = getattr(self, "_mol_weight_cache", None)
+            if cache is None or cache[0] != key or cache[1].device != pack.device:
+                cache = (key, torch.tensor(w, dtype=torch.float32, device=pack.device))
+                self._mol_weight_cache = cache
+            pterms = {"terms": terms, "mol_weight": cache[1]}
+        return _LossFn.apply(pack, weights, pterms, energy, gd["energy_ref"] if energy is not None else None, grad,
+                             nd["gradient_ref"] if grad is not None else None, kp, ki, *ppred)

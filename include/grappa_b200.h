@@ -340,8 +340,32 @@ typedef struct {
   float* g_k_proper;        /* like k_proper         or NULL */
   float* g_k_improper;      /* like k_improper       or NULL */
   const float* grad_scale;  /* device scalar multiplied into every g_* output (upstream dL), or NULL = 1 */
+  const float* extra_mol_loss; /* [B] or NULL: per-molecule terms computed elsewhere (grappa_b200_param_loss),
+                                  added to each molecule's term before the mean over molecules */
 } gb_loss_args;
 int grappa_b200_molwise_loss(const gb_loss_args* a, void* stream);
+
+/* Classical-parameter term of MolwiseLoss (reference training/loss.py:70-113): per molecule b,
+ *   mol_loss[b] = mol_weight[b] * mean over all elements of the concatenated terms of ( fac_i * (p - p_ref) )^2
+ * where elements whose reference is NaN count as zero difference (loss.py:101-103) but still count in the mean,
+ * and a torsion reference with a different number of periodicities is zero-padded / truncated to the model's
+ * (correct_torsion_shape, loss.py:170-182).  Terms in reference order: n2_k, n2_eq, n3_k, n3_eq, n4_k
+ * (impropers are excluded, loss.py:91-92).  With g_pred set, also writes
+ *   g_pred_i = grad_scale / B * dmol_loss[b]/dp.                                                     */
+#define GB_PARAM_LOSS_MAX_TERMS 5
+typedef struct {
+  int32_t n_terms, B;
+  const float* pred[GB_PARAM_LOSS_MAX_TERMS];   /* [T_i, width_i] contiguous */
+  const float* ref[GB_PARAM_LOSS_MAX_TERMS];    /* [T_i, ref_width_i] contiguous, NaN = no reference */
+  const int32_t* off[GB_PARAM_LOSS_MAX_TERMS];  /* [B+1] tuple offsets of the term's level */
+  int32_t width[GB_PARAM_LOSS_MAX_TERMS], ref_width[GB_PARAM_LOSS_MAX_TERMS];
+  float fac[GB_PARAM_LOSS_MAX_TERMS];
+  const float* mol_weight;                      /* [B] param_weight per molecule */
+  float* mol_loss;                              /* [B] (overwritten) */
+  float* g_pred[GB_PARAM_LOSS_MAX_TERMS];       /* like pred, or NULL */
+  const float* grad_scale;                      /* device scalar or NULL = 1 */
+} gb_param_loss_args;
+int grappa_b200_param_loss(const gb_param_loss_args* a, void* stream);
 
 #ifdef __cplusplus
 }

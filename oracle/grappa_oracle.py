@@ -329,3 +329,40 @@ def molwise_loss(en, params, g, energy_weight=1.0, gradient_weight=0.8, proper_r
         loss = loss + term / nb
         a0 += a_counts[b]; p0 += p_counts[b]; i0 += i_counts[b]
     return loss
+
+
+def param_loss(params, params_ref, counts, param_weight=1e-3, mol_weights=None,
+               weights={"n2_k": 1e-3, "n3_k": 1e-2, "n4_k": 1e-4}):
+    """Classical-parameter term of MolwiseLoss.forward (training/loss.py:70-113), mean over molecules:
+    per molecule, the concatenation (reference key order n2_k, n2_eq, n3_k, n3_eq, n4_k; impropers skipped, :91-92) of
+    fac * parameter with NaN references zeroed on both sides (:101-103), torsion references padded / cut to the model's
+    periodicity (correct_torsion_shape, :170-182), mean of squared differences times the molecule's weight.
+    `params[lvl][name]`, `params_ref[lvl][name]`: tensors; `counts[lvl]`: tuples per molecule."""
+    nb = len(counts["n2"])
+    off = {l: [0] * (nb + 1) for l in counts}
+    for l in counts:
+        for b in range(nb):
+            off[l][b + 1] = off[l][b] + counts[l][b]
+    loss = 0.0
+    for b in range(nb):
+        pt, rt = [], []
+        for lvl, name in (("n2", "k"), ("n2", "eq"), ("n3", "k"), ("n3", "eq"), ("n4", "k")):
+            if lvl not in params_ref or name not in params_ref[lvl]:
+                continue
+            p = params[lvl][name][off[lvl][b]:off[lvl][b + 1]]
+            r = params_ref[lvl][name][off[lvl][b]:off[lvl][b + 1]].to(p.dtype)
+            if lvl == "n4":
+                if r.shape[1] < p.shape[1]:
+                    r = torch.cat([r, torch.zeros_like(r[:, :(p.shape[1] - r.shape[1])])], dim=1)
+                elif r.shape[1] > p.shape[1]:
+                    r = r[:, :p.shape[1]]
+            nan = torch.isnan(r)
+            p = torch.where(nan, torch.zeros_like(p), p)
+            r = torch.where(nan, torch.zeros_like(r), r)
+            fac = weights.get(f"{lvl}_{name}", 1.0)
+            pt.append(p.flatten() * fac)
+            rt.append(r.flatten() * fac)
+        if pt:
+            w = param_weight if mol_weights is None else mol_weights[b]
+            loss = loss + w * torch.mean((torch.cat(pt) - torch.cat(rt)) ** 2) / nb
+    return loss

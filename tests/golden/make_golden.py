@@ -83,9 +83,58 @@ def run_reference(ns, cfg, g, seed, with_loss):
     return out, sd
 
 
+def param_loss_case(ns):
+    """case 5: the classical-parameter term of MolwiseLoss (training/loss.py:70-113) from the reference itself:
+    predicted parameters as leaves, references with NaN holes, a torsion reference with MORE periodicities than the
+    model (correct_torsion_shape truncates) -- and a second variant with fewer (zero padding) --, per-dataset weights."""
+    rng = np.random.default_rng(17)
+    mols = [synthetic.make_molecule(rng, "peptide", n_confs=4, n_res=1), synthetic.make_molecule(rng, "small", n_confs=4, n_atoms=17),
+            synthetic.make_molecule(rng, "peptide", n_confs=4, n_res=2), synthetic.make_molecule(rng, "rna", n_confs=4)]
+    mols = [m for m in mols if m.num_nodes("n4_improper") > 0]
+    g = gbgraph.batch(mols)
+    gen = torch.Generator().manual_seed(33)
+    out = {}
+    for variant, ref_per in (("a", 6), ("b", 2)):
+        dg = to_reference_graph(ns, g)
+        leaves = {}
+        for lvl in LEVELS:
+            T = g.num_nodes(lvl)
+            names = ("k", "eq") if lvl in ("n2", "n3") else ("k",)
+            for name in names:
+                shape = (T,) if lvl in ("n2", "n3") else (T, 3)
+                v = torch.randn(shape, generator=gen) * (50.0 if name == "k" and lvl in ("n2", "n3") else 1.0)
+                v.requires_grad_(True)
+                dg.nodes[lvl].data[name] = v
+                leaves[f"{lvl}.{name}"] = v
+                rshape = shape if lvl in ("n2", "n3") else (T, ref_per if lvl == "n4" else 3)
+                r = torch.randn(rshape, generator=gen) * (50.0 if name == "k" and lvl in ("n2", "n3") else 1.0)
+                r[torch.rand(rshape, generator=gen) < 0.15] = float("nan")
+                dg.nodes[lvl].data[name + "_ref"] = r
+                out[f"{variant}.ref.{lvl}.{name}"] = r.numpy()
+                out[f"{variant}.in.{lvl}.{name}"] = v.detach().numpy()
+        # energies / gradients are not part of this case, but unbatch() needs consistent graph-level data
+        dsnames = ["spice", "other", "spice", "rna"][:len(mols)]
+        loss_fn = ns.loss.MolwiseLoss(gradient_weight=0., energy_weight=0., param_weight=1e-3,
+                                      param_weights_by_dataset={"spice": 0.5, "rna": 2.0})
+        loss = loss_fn(dg, dsnames=dsnames)
+        keys = [k for k in sorted(leaves) if "improper" not in k]
+        grads = torch.autograd.grad(loss, [leaves[k] for k in keys])
+        out[f"{variant}.loss"] = np.array(loss.item(), dtype=np.float64)
+        for k, gr in zip(keys, grads):
+            out[f"{variant}.grad.{k}"] = gr.numpy()
+        loss2 = ns.loss.MolwiseLoss(gradient_weight=0., energy_weight=0., param_weight=1e-3)(dg)
+        out[f"{variant}.loss_uniform"] = np.array(loss2.item(), dtype=np.float64)
+    out["meta.dsnames"] = np.array(dsnames)
+    np.savez_compressed(os.path.join(OUT, "param_loss.npz"), **graph_inputs(g), **out)
+    print("param_loss: loss a/b =", out["a.loss"], out["b.loss"], "mols =", len(mols))
+
+
 def main():
     ns = import_reference()
     torch.set_num_threads(8)
+    if "--only-param-loss" in sys.argv:
+        return param_loss_case(ns)
+    param_loss_case(ns)
 
     # ---- case 1: BASELINE config 1 -- grappa-1.2 architecture, capped dipeptide, 50 conformations
     g = synthetic.dipeptide(seed=11, n_confs=50)

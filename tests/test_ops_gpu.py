@@ -361,3 +361,31 @@ def test_gemm_tcgen05_rejects_unaligned_and_auto_falls_back():
         ops.gemm(A, B, precision=ops.TF32)
     out = ops.gemm(A, B, precision=ops.AUTO)     # same call, automatic kernel choice: FFMA path
     assert R(out, A.double() @ B.double().T) < 1e-5
+
+
+def test_param_loss_term_matches_reference_fixture():
+    """Classical-parameter MSE of MolwiseLoss (reference training/loss.py:70-113): value and gradients against the
+    fixture the reference's own MolwiseLoss produced (NaN masks, torsion width correction, per-dataset weights)."""
+    from grappa_b200.loss import MolwiseLoss
+    from util import LEVELS, graph_from_fixture, load_golden
+    z = load_golden("param_loss.npz")
+    dsnames = [str(d) for d in z["meta.dsnames"]]
+    for v in ("a", "b"):
+        g = graph_from_fixture(z).to("cuda")
+        leaves = {}
+        for l in LEVELS:
+            for n in ("k", "eq"):
+                if f"{v}.in.{l}.{n}" in z.files:
+                    t = torch.from_numpy(z[f"{v}.in.{l}.{n}"]).cuda().requires_grad_(True)
+                    g.nodes[l].data[n] = t
+                    g.nodes[l].data[n + "_ref"] = torch.from_numpy(z[f"{v}.ref.{l}.{n}"]).cuda()
+                    leaves[f"{l}.{n}"] = t
+        loss = MolwiseLoss(gradient_weight=0., energy_weight=0., param_weight=1e-3,
+                           param_weights_by_dataset={"spice": 0.5, "rna": 2.0})(g, dsnames=dsnames)
+        assert abs(loss.item() - float(z[f"{v}.loss"])) < 1e-5 * abs(float(z[f"{v}.loss"]))
+        keys = [k[len(v) + 6:] for k in z.files if k.startswith(f"{v}.grad.")]
+        grads = torch.autograd.grad(loss, [leaves[k] for k in keys])
+        for k, gr in zip(keys, grads):
+            assert R(gr, torch.from_numpy(z[f"{v}.grad.{k}"])) < 1e-5, k
+        uni = MolwiseLoss(gradient_weight=0., energy_weight=0., param_weight=1e-3)(g)
+        assert abs(uni.item() - float(z[f"{v}.loss_uniform"])) < 1e-5 * abs(float(z[f"{v}.loss_uniform"]))

@@ -103,3 +103,24 @@ def test_oracle_vs_live_reference_on_fresh_inputs():
     assert rel_err(en["gradient"].numpy(), dg.nodes["n1"].data["gradient"].detach().numpy()) < 1e-5
     for l in LEVELS:
         assert rel_err(params[l]["k"].detach().numpy(), dg.nodes[l].data["k"].detach().numpy()) < 2e-5
+
+
+def test_oracle_param_loss_vs_reference_fixture():
+    """Classical-parameter loss term: oracle restatement vs values / gradients the reference's MolwiseLoss produced."""
+    z = load_golden("param_loss.npz")
+    g = graph_from_fixture(z)
+    counts = {l: g.batch_num_nodes(l).tolist() for l in LEVELS}
+    dsw = {"spice": 0.5, "rna": 2.0}
+    mw = [dsw.get(str(d), 1e-3) for d in z["meta.dsnames"]]
+    for v in ("a", "b"):
+        prm = {l: {n: torch.from_numpy(z[f"{v}.in.{l}.{n}"]).double().requires_grad_(True)
+                   for n in ("k", "eq") if f"{v}.in.{l}.{n}" in z.files} for l in LEVELS}
+        ref = {l: {n: torch.from_numpy(z[f"{v}.ref.{l}.{n}"]) for n in ("k", "eq") if f"{v}.ref.{l}.{n}" in z.files} for l in LEVELS}
+        loss = orc.param_loss(prm, ref, counts, mol_weights=mw)
+        assert abs(float(loss) - float(z[f"{v}.loss"])) < 1e-6 * abs(float(z[f"{v}.loss"]))
+        uni = orc.param_loss(prm, ref, counts, param_weight=1e-3)
+        assert abs(float(uni) - float(z[f"{v}.loss_uniform"])) < 1e-6 * abs(float(z[f"{v}.loss_uniform"]))
+        keys = [k[len(v) + 6:] for k in z.files if k.startswith(f"{v}.grad.")]
+        grads = torch.autograd.grad(loss, [prm[k.split(".")[0]][k.split(".")[1]] for k in keys])
+        for k, gr in zip(keys, grads):
+            assert rel_err(gr.numpy(), z[f"{v}.grad.{k}"]) < 1e-5, k
