@@ -99,6 +99,47 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// ---- CTA-pair (cta_group::2) helpers ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t cta_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// data lands in THIS CTA's shared memory, the transaction bytes complete on the barrier at `mbar_cluster_addr`
+// (the leader CTA's full barrier): what cute::SM100_TMA_2SM_LOAD does
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t mbar_cluster_addr, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(mbar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+// arrive on the barrier at the same offset in every CTA of `mask` once all prior MMAs of this thread retire
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
 // 64-bit shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 128-byte swizzle, version 1
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
                                                    uint32_t layout_type) {
@@ -120,12 +161,16 @@ struct TcParams {
   Epilogue ep;
 };
 
-template <int BN>
+// CTAS = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) computes a 256 x BN tile; each CTA stages its own 128 rows
+// of A but only HALF of the B tile, so a pair moves 32 KB per k-block and CTA where two independent 128 x 256 CTAs move
+// 48 KB for the same FLOPs -- the kernel is bound by exactly that L2 -> SM operand traffic (profiles/r1_summary.md).
+template <int BN, int CTAS = 1>
 struct TcCfg {
   static constexpr int A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
-  static constexpr int B_BYTES = BN * TC_BK * 4;
+  static constexpr int B_ROWS = BN / CTAS;            // rows of the B tile this CTA stages
+  static constexpr int B_BYTES = B_ROWS * TC_BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN == 256 ? 3 : (BN == 128 ? 5 : 7);   // 144-168 KB of operand ring
+  static constexpr int STAGES = CTAS == 2 ? (BN == 256 ? 5 : 7) : (BN == 256 ? 3 : (BN == 128 ? 5 : 7));   // 144-168 KB of operand ring
   static constexpr int EPI_LD = 36;                     // floats per staged row (float4-aligned, conflict-free)
   static constexpr int EPI_BYTES = 8 * 32 * EPI_LD * 4; // one 32x32 transpose patch per epilogue warp
   static_assert(STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256 <= 232448, "shared memory budget");
@@ -134,11 +179,16 @@ struct TcCfg {
 
 // Persistent kernel: grid = min(#work items, #SMs); work item = (split-K slice, m tile, n tile), n fastest.
 // Two TMEM accumulator stages: the epilogue of item i overlaps the mainloop of item i+1.
-template <int BN, int TA, int TB>
+template <int BN, int TA, int TB, int CTAS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, CTAS>;
+  constexpr bool PAIR = CTAS == 2;
+  constexpr int B_ROWS = Cfg::B_ROWS;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;      // 0 = leader (issues the MMAs)
+  const int first_item = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int item_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   constexpr int A_BYTES = Cfg::A_BYTES;
   constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
   constexpr int STAGES = Cfg::STAGES;
@@ -163,16 +213,22 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 8);   // one arrival per epilogue warp
+      mbar_init(&acc_empty[s], 8 * CTAS);   // one arrival per epilogue warp (of both CTAs of a pair, on the leader)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {   // TMEM: 2 accumulator stages of BN fp32 columns
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * BN)));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (warp == 1) {   // TMEM: 2 accumulator stages of BN fp32 columns (pair: one collective allocation, same address in both)
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * BN)));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * BN)));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's barriers must be initialised before anything is signalled on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -180,12 +236,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // ===================== TMA producer =====================
     if (elect_one()) {
       uint32_t it = 0;   // running k-block counter across work items (ring position)
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      for (int item = first_item; item < n_items; item += item_stride) {
         const int nb = item % p.tiles_n;
         const int rest = item / p.tiles_n;
         const int mb = rest % p.tiles_m;
         const int z = rest / p.tiles_m;
-        const int m0 = mb * TC_BM, n0 = nb * BN;
+        const int m0 = mb * (TC_BM * CTAS) + (int)rank * TC_BM, n0 = nb * BN + (int)rank * B_ROWS;
         const int kb0 = z * p.k_blocks_per_split;
         const int num_kb = min(total_kb, kb0 + p.k_blocks_per_split) - kb0;
         for (int i = 0; i < num_kb; ++i, ++it) {
@@ -194,32 +250,50 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
-          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
           const int k = (kb0 + i) * TC_BK;
-          if (TA == 0) {
-            tma_load_2d(&map_a, &full_bar[s], sa, k, m0);                     // box {32 k, 128 rows}
-          } else {
+          if (PAIR) {
+            // both CTAs' bytes are counted on the LEADER's full barrier (the leader's MMA reads both shared memories)
+            if (rank == 0) mbar_expect_tx(&full_bar[s], CTAS * STAGE_BYTES);
+            const uint32_t fb = mapa_rank(smem_u32(&full_bar[s]), 0);
+            if (TA == 0) {
+              tma_load_2d_pair(&map_a, fb, sa, k, m0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < TC_BM / 32; ++j)                              // boxes {32 rows, 32 k}
-              tma_load_2d(&map_a, &full_bar[s], sa + j * (TC_BK * 128), m0 + j * 32, k);
-          }
-          if (TB == 0) {
-            tma_load_2d(&map_b, &full_bar[s], sb, k, n0);
-          } else {
+              for (int j = 0; j < TC_BM / 32; ++j) tma_load_2d_pair(&map_a, fb, sa + j * (TC_BK * 128), m0 + j * 32, k);
+            }
+            if (TB == 0) {
+              tma_load_2d_pair(&map_b, fb, sb, k, n0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 32; ++j)
-              tma_load_2d(&map_b, &full_bar[s], sb + j * (TC_BK * 128), n0 + j * 32, k);
+              for (int j = 0; j < B_ROWS / 32; ++j) tma_load_2d_pair(&map_b, fb, sb + j * (TC_BK * 128), n0 + j * 32, k);
+            }
+          } else {
+            mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+            if (TA == 0) {
+              tma_load_2d(&map_a, &full_bar[s], sa, k, m0);                     // box {32 k, 128 rows}
+            } else {
+#pragma unroll
+              for (int j = 0; j < TC_BM / 32; ++j)                              // boxes {32 rows, 32 k}
+                tma_load_2d(&map_a, &full_bar[s], sa + j * (TC_BK * 128), m0 + j * 32, k);
+            }
+            if (TB == 0) {
+              tma_load_2d(&map_b, &full_bar[s], sb, k, n0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 32; ++j)
+                tma_load_2d(&map_b, &full_bar[s], sb + j * (TC_BK * 128), n0 + j * 32, k);
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+    // ===================== MMA issuer (pair: the leader CTA only) =====================
     // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, majors, N >> 3, M >> 4
     constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)TA << 15) | ((uint32_t)TB << 16) |
-                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((TC_BM * CTAS) >> 4) << 24);
     uint32_t it = 0, lt = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++lt) {
+    for (int item = first_item; item < n_items && rank == 0; item += item_stride, ++lt) {
       const int z = item / (p.tiles_n * p.tiles_m);
       const int kb0 = z * p.k_blocks_per_split;
       const int num_kb = min(total_kb, kb0 + p.k_blocks_per_split) - kb0;
@@ -242,10 +316,16 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             //           UMMA_K = 8 step, LBO = box size between 32-wide MN chunks; k step = 1024 B
             const uint64_t da = TA == 0 ? make_smem_desc(sa + kk * 32, 16, 1024, 2) : make_smem_desc(sa + kk * 1024, TC_BK * 128, 512, 1);
             const uint64_t db = TB == 0 ? make_smem_desc(sb + kk * 32, 16, 1024, 2) : make_smem_desc(sb + kk * 1024, TC_BK * 128, 512, 1);
-            tc_mma_tf32(d_tmem, da, db, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+            if (PAIR) tc_mma_tf32_pair(d_tmem, da, db, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+            else tc_mma_tf32(d_tmem, da, db, idesc, (i > 0 || kk > 0) ? 1u : 0u);
           }
-          tc_commit(&empty_bar[s]);                       // frees the smem stage when these MMAs retire
-          if (i == num_kb - 1) tc_commit(&acc_full[as]);  // accumulator complete
+          if (PAIR) {
+            tc_commit_pair(&empty_bar[s], 3);                       // frees this stage in BOTH CTAs
+            if (i == num_kb - 1) tc_commit_pair(&acc_full[as], 3);  // accumulator complete (both halves)
+          } else {
+            tc_commit(&empty_bar[s]);                       // frees the smem stage when these MMAs retire
+            if (i == num_kb - 1) tc_commit(&acc_full[as]);  // accumulator complete
+          }
         }
         __syncwarp();
       }
@@ -260,13 +340,14 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     float* patch = epi + (warp - 2) * (32 * Cfg::EPI_LD);
     const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
     const bool vec_ok = p.partial ? ((p.N & 3) == 0) : p.ep.vec_ok();
+    const uint32_t acc_empty_remote = PAIR ? mapa_rank(smem_u32(&acc_empty[0]), 0) : 0u;   // leader's acc_empty[0]
     uint32_t lt = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++lt) {
+    for (int item = first_item; item < n_items; item += item_stride, ++lt) {
       const int nb = item % p.tiles_n;
       const int rest = item / p.tiles_n;
       const int mb = rest % p.tiles_m;
       const int z = rest / p.tiles_m;
-      const int m0 = mb * TC_BM + q * 32, n0 = nb * BN + half * (BN / 2);
+      const int m0 = mb * (TC_BM * CTAS) + (int)rank * TC_BM + q * 32, n0 = nb * BN + half * (BN / 2);
       const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
       const uint32_t t_addr = tmem_base + as * BN + half * (BN / 2) + ((uint32_t)(q * 32) << 16);
       const bool side_inputs = !p.partial && vec_ok && (p.ep.residual != nullptr || p.ep.mul_elu_out != nullptr);
@@ -298,7 +379,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (c0 + 32 >= BN / 2) {   // accumulator fully read: hand the TMEM stage back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[as]);
+          if (lane == 0) {
+            if (PAIR && rank != 0) mbar_arrive_cluster(acc_empty_remote + as * 8u);
+            else mbar_arrive(&acc_empty[as]);
+          }
         }
         if (n0 + c0 >= p.N) continue;   // warp-uniform
 #pragma unroll
@@ -351,9 +435,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // neither CTA may release shared / tensor memory while the pair still uses it
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)));
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)));
   }
 }
 
@@ -392,15 +478,31 @@ static bool make_map(CUtensorMap* map, const float* base, int rows, int cols, in
   return r == CUDA_SUCCESS;
 }
 
-template <int BN, int TA, int TB>
+template <int BN, int TA, int TB, int CTAS>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int grid, cudaStream_t stream) {
-  constexpr int smem = TcCfg<BN>::SMEM;
+  constexpr int smem = TcCfg<BN, CTAS>::SMEM;
   static bool configured = false;
   if (!configured) {
-    GB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN, TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    GB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN, TA, TB, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  gemm_tf32_kernel<BN, TA, TB><<<grid, TC_THREADS, smem, stream>>>(ma, mb, p);
+  if (CTAS == 1) {
+    gemm_tf32_kernel<BN, TA, TB, CTAS><<<grid, TC_THREADS, smem, stream>>>(ma, mb, p);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3(TC_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CTAS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    GB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BN, TA, TB, CTAS>, ma, mb, p));
+  }
   GB_CHECK_LAUNCH();
   return GB_OK;
 }
@@ -413,36 +515,52 @@ int gemm_tcgen05(const gb_gemm_args* a, cudaStream_t stream, bool* handled) {
   // legality: 16-byte aligned bases and row pitches (TMA), enough work to fill a tile
   if (((uintptr_t)a->A & 15) || ((uintptr_t)a->B & 15) || (a->lda & 3) || (a->ldb & 3)) return GB_OK;
   if (K < 8 || N < 16 || M < 1) return GB_OK;
-  // tile width.  Without split-K: 256 when the 128x256 grid still covers every SM (25 % less L2->SM operand traffic
-  // per FLOP than 128x128, which is what bounds the large token GEMMs), 64 when even 128x128 tiles cannot fill half
-  // the machine.  With split-K available (weight gradients: small output, very long K) the SMs are filled by K
-  // slices instead, so the widest tile that divides N is always the cheapest in operand traffic.
-  const int tiles_m = (M + TC_BM - 1) / TC_BM;
+  // tile shape.  pair = a cluster of two CTAs computes 256 x BN (cta_group::2), each staging half of B.  Measured on
+  // B200 (tools/gemm_one.py): 16384 x 4096 x 4096 runs at 526 / 626 TFLOP/s with single-CTA 128 x 128 / 128 x 256 tiles
+  // and at 764 TFLOP/s with 256 x 256 pair tiles (the cuBLAS-measured TF32-equivalent peak), so the pair wins whenever
+  // the K loop is long enough for the steady state to matter (K >= 1024: in_proj dgrad / every weight gradient,
+  // -10..-17 %); with K = 512 a tile is 16 k-blocks, fill / drain dominate and the variants tie.
+  // Width without split-K: 256 when the grid still covers every SM, 64 (single CTA) when even 128-wide tiles cannot
+  // fill half the machine.  With split-K available (weight gradients: small output, very long K) the SMs are filled
+  // by K slices instead, so the widest tile that divides N is always the cheapest in operand traffic.
   const int sms_ = sm_count();
+  static const int forced_pair = [] { const char* e = getenv("GRAPPA_B200_GEMM_PAIR"); return e ? atoi(e) : -1; }();   // tuning aid
   const bool can_split = a->workspace != nullptr && (K + TC_BK - 1) / TC_BK >= 16;
-  int BN = 128;
-  if (can_split && ((N + 127) / 128) * tiles_m * 2 <= sms_) BN = (N % 256 == 0) ? 256 : (N >= 128 ? 128 : 64);
-  else if (N <= 64 || ((N + 127) / 128) * tiles_m < sms_ / 2) BN = 64;
-  else if (N % 256 == 0 && (N / 256) * tiles_m >= sms_) BN = 256;
-  {
+  bool pair = M > TC_BM && N >= 128 && forced_pair != 0 && (K >= 1024 || forced_pair == 1);
+  int units = 0, tiles_m = 0, BN = 128;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    const int bm = pair ? 2 * TC_BM : TC_BM;
+    units = pair ? sms_ / 2 : sms_;          // concurrently resident tiles
+    tiles_m = (M + bm - 1) / bm;
+    BN = 128;
+    if (can_split && ((N + 127) / 128) * tiles_m * 2 <= units) BN = (N % 256 == 0) ? 256 : (N >= 128 ? 128 : 64);
+    else if (N <= 64 || ((N + 127) / 128) * tiles_m < units / 2) BN = 64;
+    else if (N % 256 == 0 && (N / 256) * tiles_m >= units) BN = 256;
     static const int forced = [] { const char* e = getenv("GRAPPA_B200_GEMM_BN"); return e ? atoi(e) : 0; }();   // tuning aid
     if ((forced == 64 || forced == 128 || forced == 256) && (forced != 256 || N % 256 == 0)) BN = forced;
+    if (pair && BN == 64) {
+      if (forced_pair == 1) { BN = 128; break; }
+      pair = false;   // too little work for 256-row tiles: single CTAs with 128 x 64 tiles
+      continue;
+    }
+    break;
   }
+  const int b_rows = pair ? BN / 2 : BN;
   CUtensorMap ma, mb;
   bool ok = a->trans_a ? make_map(&ma, a->A, K, M, a->lda, TC_BK, true) : make_map(&ma, a->A, M, K, a->lda, TC_BM, false);
-  ok = ok && (a->trans_b ? make_map(&mb, a->B, K, N, a->ldb, TC_BK, true) : make_map(&mb, a->B, N, K, a->ldb, BN, false));
+  ok = ok && (a->trans_b ? make_map(&mb, a->B, K, N, a->ldb, TC_BK, true) : make_map(&mb, a->B, N, K, a->ldb, b_rows, false));
   if (!ok) return GB_OK;   // descriptor could not be encoded (e.g. no driver): let the FFMA path handle it
 
   TcParams p;
   p.M = M; p.N = N; p.K = K;
   p.ep = make_epilogue(a);
-  const int gx = (N + BN - 1) / BN, gy = (M + TC_BM - 1) / TC_BM;
+  const int gx = (N + BN - 1) / BN, gy = tiles_m;
   const int total_kb = (K + TC_BK - 1) / TC_BK;
   int splits = 1;
-  const int sms = sm_count();
-  if (a->workspace && gx * gy * 2 <= sms && total_kb >= 16) {
-    splits = sms / (gx * gy);
-    if (splits > total_kb / 4) splits = total_kb / 4;
+  if (a->workspace && gx * gy * 2 <= units && total_kb >= 16) {
+    static const int min_kb = [] { const char* e = getenv("GRAPPA_B200_GEMM_MINKB"); return e ? atoi(e) : 4; }();   // tuning aid
+    splits = units / (gx * gy);
+    if (splits > total_kb / min_kb) splits = total_kb / min_kb;
     long long by_ws = a->workspace_bytes / ((long long)M * N * 4);
     if (splits > by_ws) splits = (int)by_ws;
     if (splits < 1) splits = 1;
@@ -454,25 +572,27 @@ int gemm_tcgen05(const gb_gemm_args* a, cudaStream_t stream, bool* handled) {
   p.tiles_n = gx;
   p.partial = splits > 1 ? a->workspace : nullptr;
   const int n_items = gx * gy * splits;
-  const int grid = n_items < sms ? n_items : sms;
+  const int grid = pair ? 2 * (n_items < units ? n_items : units) : (n_items < units ? n_items : units);
   int rc;
-#define GB_TC(BN_, TA_, TB_) rc = launch<BN_, TA_, TB_>(ma, mb, p, grid, stream)
-  if (BN == 256) {
-    if (!a->trans_a && !a->trans_b) GB_TC(256, 0, 0);
-    else if (!a->trans_a && a->trans_b) GB_TC(256, 0, 1);
-    else if (a->trans_a && !a->trans_b) GB_TC(256, 1, 0);
-    else GB_TC(256, 1, 1);
+#define GB_TC(BN_, TA_, TB_, C_) rc = launch<BN_, TA_, TB_, C_>(ma, mb, p, grid, stream)
+#define GB_TC4(BN_, C_)                                       \
+  do {                                                        \
+    if (!a->trans_a && !a->trans_b) GB_TC(BN_, 0, 0, C_);     \
+    else if (!a->trans_a && a->trans_b) GB_TC(BN_, 0, 1, C_); \
+    else if (a->trans_a && !a->trans_b) GB_TC(BN_, 1, 0, C_); \
+    else GB_TC(BN_, 1, 1, C_);                                \
+  } while (0)
+  if (pair) {
+    if (BN == 256) GB_TC4(256, 2);
+    else GB_TC4(128, 2);
+  } else if (BN == 256) {
+    GB_TC4(256, 1);
   } else if (BN == 128) {
-    if (!a->trans_a && !a->trans_b) GB_TC(128, 0, 0);
-    else if (!a->trans_a && a->trans_b) GB_TC(128, 0, 1);
-    else if (a->trans_a && !a->trans_b) GB_TC(128, 1, 0);
-    else GB_TC(128, 1, 1);
+    GB_TC4(128, 1);
   } else {
-    if (!a->trans_a && !a->trans_b) GB_TC(64, 0, 0);
-    else if (!a->trans_a && a->trans_b) GB_TC(64, 0, 1);
-    else if (a->trans_a && !a->trans_b) GB_TC(64, 1, 0);
-    else GB_TC(64, 1, 1);
+    GB_TC4(64, 1);
   }
+#undef GB_TC4
 #undef GB_TC
   if (rc) return rc;
   if (splits > 1) {

@@ -28,6 +28,15 @@ SHAPES = [  # (M, N, K, trans_a, trans_b, tag)
     (1536, 512, 14848, 1, 1, "proper in_proj wgrad"),
     (2048, 512, 1664, 1, 1, "gnn ff1 wgrad"),
     (256, 2048, 7424, 1, 1, "symmetriser l1 wgrad"),
+    (512, 512, 1664, 1, 1, "gnn 512 wgrad"),
+    (512, 512, 3264, 1, 1, "bond wgrad"),
+    (512, 512, 8640, 1, 1, "angle wgrad"),
+    (256, 256, 7424, 1, 1, "symmetriser 256 wgrad"),
+    (256, 256, 1920, 1, 1, "improper symmetriser 256 wgrad"),
+    (3264, 512, 512, 0, 0, "bond tokens fwd"),
+    (3840, 512, 512, 0, 1, "improper dgrad"),
+    (8640, 512, 512, 0, 1, "angle dgrad"),
+    (1664, 2048, 512, 0, 1, "gnn ff2 dgrad"),
 ]
 
 
@@ -36,18 +45,21 @@ def main():
     ap.add_argument("--precision", default="tf32")
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--only", default="", help="substring filter on the shape tag")
     args = ap.parse_args()
     ops.set_matmul_precision(args.precision)
     dev = torch.device("cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     tot_ms, tot_fl = 0.0, 0.0
     for M, N, K, ta, tb, tag in SHAPES:
+        if args.only and args.only not in tag:
+            continue
         a = torch.randn((K, M) if ta else (M, K), device=dev)
         b = torch.randn((K, N) if tb else (N, K), device=dev)
         bias = torch.randn(N, device=dev)
         out = torch.empty(M, N, device=dev)
         def call():
-            ops.gemm(a, b, trans_a=bool(ta), trans_b=bool(tb), bias=bias, act=1, out=out)
+            ops.gemm(a, b, trans_a=bool(ta), trans_b=bool(tb), bias=None if ta else bias, act=0 if ta else 1, out=out)
         for _ in range(3):
             call()
         torch.cuda.synchronize()

@@ -11,6 +11,9 @@ from grappa_b200.pack import get_pack
 from grappa_b200.training import Trainer
 
 eager = "--eager" in sys.argv
+if "--serial" in sys.argv:      # one stream: every kernel alone on the GPU -> clean per-kernel durations
+    from grappa_b200 import tape as _tape
+    _tape.set_concurrency(False)
 ops.set_matmul_precision("tf32")
 dev = torch.device("cuda")
 torch.manual_seed(0)
@@ -58,7 +61,7 @@ agg = collections.defaultdict(lambda: [0, 0.0])
 for e in step:
     n = e["name"].split("(")[0].replace("void ", "")[:60]
     agg[n][0] += 1; agg[n][1] += e["dur"]
-for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:25]:
+for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
     print(f"{t:9.1f} us {c:5d}  {t / c:7.1f} us/launch  {n}")
 # phases on the main timeline: coarse 0.5 ms buckets of concurrency (sum of durations / bucket width)
 B = 500.0
