@@ -267,8 +267,9 @@ def main():
             a[0] += 1; a[1] += e0.elapsed_time(e1); a[2] += f
         with open(os.environ["GRAPPA_B200_GEMM_TABLE"], "w") as fh:
             for shp, (c, t, f) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-                fh.write(f"M={shp[0]:6d} N={shp[1]:5d} K={shp[2]:6d} ta={shp[3]} tb={shp[4]}  x{c:3d}  {t * 1e3:9.1f} us total  "
-                         f"{t * 1e3 / c:7.1f} us each  {f / t / 1e9:7.1f} TFLOP/s\n")
+                tag = (f"M={shp[0]:6d} N={shp[1]:5d} K={shp[2]:6d} ta={shp[3]} tb={shp[4]}" if shp[0] != "grouped"
+                       else "grouped " + " ".join("x".join(map(str, q)) for q in shp[1:]))
+                fh.write(f"{tag}  x{c:3d}  {t * 1e3:9.1f} us total  {t * 1e3 / c:7.1f} us each  {f / t / 1e9:7.1f} TFLOP/s\n")
     gemm_flops = sum(f for f, _, _, _ in prof) * n_prof_steps
     gemm_launches = len(prof)
     gb_tape.set_concurrency(True)

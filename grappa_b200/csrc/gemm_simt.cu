@@ -146,6 +146,83 @@ __global__ void __launch_bounds__(256) splitk_reduce_vec_kernel(const float4* __
   }
 }
 
+// one launch for the partials of a grouped GEMM: blockIdx.y = problem
+struct ReduceGroup {
+  int n;
+  const float4* partial[4];
+  int splits[4], M[4], N[4];
+  Epilogue ep[4];
+};
+__global__ void __launch_bounds__(256) splitk_reduce_grouped_kernel(const __grid_constant__ ReduceGroup g) {
+  const int pi = blockIdx.y;
+  const float4* __restrict__ partial = g.partial[pi];
+  const int splits = g.splits[pi], N = g.N[pi];
+  if (splits <= 1) return;
+  const int nv = N >> 2;
+  const size_t total = (size_t)g.M[pi] * nv;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    int z = 0;
+    for (; z + 3 < splits; z += 4) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldcs(partial + (size_t)(z + u) * total + i);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
+    }
+    for (; z < splits; ++z) {
+      const float4 v = __ldcs(partial + (size_t)z * total + i);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    const int row = (int)(i / nv), col = (int)(i - (size_t)row * nv) * 4;
+    g.ep[pi].template store4<false>(s, row, col);
+  }
+}
+
+static bool reduce_vec_ok(const float* partial, int N, const Epilogue& ep) {
+  return (N % 4 == 0) && (((uintptr_t)partial & 15) == 0) && (((uintptr_t)ep.bias | (uintptr_t)ep.mul_elu_out |
+          (uintptr_t)ep.residual | (uintptr_t)ep.C | (uintptr_t)ep.act_out) & 15) == 0 &&
+         ((ep.ldc | (ep.mul_elu_out ? ep.ldm : 0) | (ep.residual ? ep.ldr : 0) | (ep.act_out ? ep.ldact : 0)) & 3) == 0;
+}
+
+int launch_splitk_reduce(const float* partial, int splits, int M, int N, const Epilogue& ep, cudaStream_t stream);
+
+int launch_splitk_reduce_grouped(int n, const float* const* partial, const int* splits, const int* Ms, const int* Ns,
+                                 const Epilogue* eps, cudaStream_t stream) {
+  bool vec = n <= 4;
+  size_t max_total = 0;
+  for (int i = 0; i < n && vec; ++i) {
+    if (splits[i] <= 1) continue;
+    vec = reduce_vec_ok(partial[i], Ns[i], eps[i]);
+    const size_t t = (size_t)Ms[i] * Ns[i] / 4;
+    max_total = t > max_total ? t : max_total;
+  }
+  if (!vec) {
+    for (int i = 0; i < n; ++i)
+      if (splits[i] > 1) {
+        int rc = launch_splitk_reduce(partial[i], splits[i], Ms[i], Ns[i], eps[i], stream);
+        if (rc) return rc;
+      }
+    return GB_OK;
+  }
+  ReduceGroup g;
+  g.n = n;
+  for (int i = 0; i < 4; ++i) {
+    g.partial[i] = i < n ? reinterpret_cast<const float4*>(partial[i]) : nullptr;
+    g.splits[i] = i < n ? splits[i] : 0;
+    g.M[i] = i < n ? Ms[i] : 0;
+    g.N[i] = i < n ? Ns[i] : 0;
+    if (i < n) g.ep[i] = eps[i]; else g.ep[i] = eps[0];
+  }
+  int bx = (int)((max_total + 255) / 256);
+  const int cap = sm_count() * 8 / n > 1 ? sm_count() * 8 / n : 1;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  splitk_reduce_grouped_kernel<<<dim3(bx, n), 256, 0, stream>>>(g);
+  GB_CHECK_LAUNCH();
+  return GB_OK;
+}
+
 int launch_splitk_reduce(const float* partial, int splits, int M, int N, const Epilogue& ep, cudaStream_t stream) {
   const bool vec = (N % 4 == 0) && (((uintptr_t)partial & 15) == 0) && (((uintptr_t)ep.bias | (uintptr_t)ep.mul_elu_out |
                     (uintptr_t)ep.residual | (uintptr_t)ep.C | (uintptr_t)ep.act_out) & 15) == 0 &&
@@ -326,8 +403,33 @@ int gemm_simt(const gb_gemm_args* a, cudaStream_t stream) {
 }
 
 int gemm_tcgen05(const gb_gemm_args* a, cudaStream_t stream, bool* handled);
+int gemm_tcgen05_grouped(const gb_gemm_args* list, int n, cudaStream_t stream, bool* handled);
 
 }  // namespace gb
+
+extern "C" int grappa_b200_gemm(const gb_gemm_args* a, void* stream_);
+
+extern "C" int grappa_b200_gemm_grouped(const gb_gemm_args* list, int32_t n, void* stream_) {
+  GB_REQUIRE(list != nullptr || n == 0, "gemm_grouped: list is NULL");
+  GB_REQUIRE(n >= 0, "gemm_grouped: negative count");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int i = 0;
+  while (i < n) {
+    // longest run (<= 4) of non-empty tensor-core problems that one persistent launch can serve
+    int j = i;
+    while (j < n && j - i < 4 && list[j].M > 0 && list[j].N > 0 && (list[j].precision == 1 || list[j].precision == 2)) ++j;
+    if (j - i >= 2) {
+      bool handled = false;
+      int rc = gb::gemm_tcgen05_grouped(list + i, j - i, stream, &handled);
+      if (rc != GB_OK) return rc;
+      if (handled) { i = j; continue; }
+    }
+    int rc = grappa_b200_gemm(list + i, stream_);
+    if (rc != GB_OK) return rc;
+    ++i;
+  }
+  return GB_OK;
+}
 
 extern "C" int grappa_b200_gemm(const gb_gemm_args* a, void* stream_) {
   GB_REQUIRE(a != nullptr, "gemm: args is NULL");

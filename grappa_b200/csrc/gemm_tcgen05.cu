@@ -152,14 +152,33 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 
-struct TcParams {
+// One launch serves up to TC_MAX_GROUP independent problems that share the tile configuration (grouped GEMM: the four
+// weight gradients of a transformer layer run as ONE persistent kernel, so a work item's K slice is 3-4x longer and the
+// split-K partials 3-4x fewer than with one launch per GEMM).  Work items are numbered problem by problem.
+constexpr int TC_MAX_GROUP = 4;
+struct TcProblem {
   int M, N, K;
   int k_blocks_per_split;   // K blocks (of TC_BK) handled by one split-K slice
   int splits;               // number of split-K slices (1 = none)
   int tiles_m, tiles_n;     // output tile grid
+  int item_begin;           // first work item of this problem
   float* partial;           // split-K workspace or NULL
   Epilogue ep;
 };
+struct TcParams {
+  int n_problems, n_items;
+  TcProblem pr[TC_MAX_GROUP];
+};
+struct TcMaps {
+  CUtensorMap a[TC_MAX_GROUP], b[TC_MAX_GROUP];
+};
+__device__ __forceinline__ int find_problem(const TcParams& p, int item) {
+  int g = 0;
+#pragma unroll
+  for (int i = 1; i < TC_MAX_GROUP; ++i)
+    if (i < p.n_problems && item >= p.pr[i].item_begin) g = i;
+  return g;
+}
 
 // CTAS = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) computes a 256 x BN tile; each CTA stages its own 128 rows
 // of A but only HALF of the B tile, so a pair moves 32 KB per k-block and CTA where two independent 128 x 256 CTAs move
@@ -179,9 +198,10 @@ struct TcCfg {
 
 // Persistent kernel: grid = min(#work items, #SMs); work item = (split-K slice, m tile, n tile), n fastest.
 // Two TMEM accumulator stages: the epilogue of item i overlaps the mainloop of item i+1.
-template <int BN, int TA, int TB, int CTAS>
+// GROUPED = false: exactly one problem, indexed statically (its fields stay immediate constant-bank operands).
+template <int BN, int TA, int TB, int CTAS, bool GROUPED>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcParams p) {
+gemm_tf32_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   using Cfg = TcCfg<BN, CTAS>;
   constexpr bool PAIR = CTAS == 2;
@@ -201,12 +221,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_kb = (p.K + TC_BK - 1) / TC_BK;
-  const int n_items = p.tiles_m * p.tiles_n * p.splits;
+  const int n_items = p.n_items;
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_b) : "memory");
+    for (int g = 0; g < (GROUPED ? p.n_problems : 1); ++g) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&maps.a[g]) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&maps.b[g]) : "memory");
+    }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -237,13 +258,19 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (elect_one()) {
       uint32_t it = 0;   // running k-block counter across work items (ring position)
       for (int item = first_item; item < n_items; item += item_stride) {
-        const int nb = item % p.tiles_n;
-        const int rest = item / p.tiles_n;
-        const int mb = rest % p.tiles_m;
-        const int z = rest / p.tiles_m;
+        const int gi = GROUPED ? find_problem(p, item) : 0;
+        const TcProblem& q = p.pr[gi];
+        const CUtensorMap& map_a = maps.a[gi];
+        const CUtensorMap& map_b = maps.b[gi];
+        const int local = item - q.item_begin;
+        const int nb = local % q.tiles_n;
+        const int rest = local / q.tiles_n;
+        const int mb = rest % q.tiles_m;
+        const int z = rest / q.tiles_m;
         const int m0 = mb * (TC_BM * CTAS) + (int)rank * TC_BM, n0 = nb * BN + (int)rank * B_ROWS;
-        const int kb0 = z * p.k_blocks_per_split;
-        const int num_kb = min(total_kb, kb0 + p.k_blocks_per_split) - kb0;
+        const int total_kb = (q.K + TC_BK - 1) / TC_BK;
+        const int kb0 = z * q.k_blocks_per_split;
+        const int num_kb = min(total_kb, kb0 + q.k_blocks_per_split) - kb0;
         for (int i = 0; i < num_kb; ++i, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
@@ -294,9 +321,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((TC_BM * CTAS) >> 4) << 24);
     uint32_t it = 0, lt = 0;
     for (int item = first_item; item < n_items && rank == 0; item += item_stride, ++lt) {
-      const int z = item / (p.tiles_n * p.tiles_m);
-      const int kb0 = z * p.k_blocks_per_split;
-      const int num_kb = min(total_kb, kb0 + p.k_blocks_per_split) - kb0;
+      const TcProblem& q = p.pr[GROUPED ? find_problem(p, item) : 0];
+      const int z = (item - q.item_begin) / (q.tiles_n * q.tiles_m);
+      const int total_kb = (q.K + TC_BK - 1) / TC_BK;
+      const int kb0 = z * q.k_blocks_per_split;
+      const int num_kb = min(total_kb, kb0 + q.k_blocks_per_split) - kb0;
       const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
       mbar_wait(&acc_empty[as], aph ^ 1);               // epilogue has drained this accumulator stage
       tc_fence_after();
@@ -339,18 +368,20 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int half = (warp - 2) >> 2;                  // which half of the tile's columns
     float* patch = epi + (warp - 2) * (32 * Cfg::EPI_LD);
     const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
-    const bool vec_ok = p.partial ? ((p.N & 3) == 0) : p.ep.vec_ok();
     const uint32_t acc_empty_remote = PAIR ? mapa_rank(smem_u32(&acc_empty[0]), 0) : 0u;   // leader's acc_empty[0]
     uint32_t lt = 0;
     for (int item = first_item; item < n_items; item += item_stride, ++lt) {
-      const int nb = item % p.tiles_n;
-      const int rest = item / p.tiles_n;
-      const int mb = rest % p.tiles_m;
-      const int z = rest / p.tiles_m;
+      const TcProblem& pq = p.pr[GROUPED ? find_problem(p, item) : 0];
+      const bool vec_ok = pq.partial ? ((pq.N & 3) == 0) : pq.ep.vec_ok();
+      const int local = item - pq.item_begin;
+      const int nb = local % pq.tiles_n;
+      const int rest = local / pq.tiles_n;
+      const int mb = rest % pq.tiles_m;
+      const int z = rest / pq.tiles_m;
       const int m0 = mb * (TC_BM * CTAS) + (int)rank * TC_BM + q * 32, n0 = nb * BN + half * (BN / 2);
       const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
       const uint32_t t_addr = tmem_base + as * BN + half * (BN / 2) + ((uint32_t)(q * 32) << 16);
-      const bool side_inputs = !p.partial && vec_ok && (p.ep.residual != nullptr || p.ep.mul_elu_out != nullptr);
+      const bool side_inputs = !pq.partial && vec_ok && (pq.ep.residual != nullptr || pq.ep.mul_elu_out != nullptr);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN / 2; c0 += 32) {
         const int col = n0 + c0 + sub_c;
@@ -359,13 +390,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // transpose run.  (Loading them one row at a time inside the store loop made a residual epilogue
         // latency-bound: 60 us instead of 28 us for M=14848, N=K=512.)
         float4 res4[8], elu4[8];
-        if (side_inputs && col < p.N) {
+        if (side_inputs && col < pq.N) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int r = m0 + sub_r + 4 * i;
-            if (r < p.M) {
-              if (p.ep.residual) res4[i] = __ldg(reinterpret_cast<const float4*>(p.ep.residual + (size_t)r * p.ep.ldr + col));
-              if (p.ep.mul_elu_out) elu4[i] = __ldg(reinterpret_cast<const float4*>(p.ep.mul_elu_out + (size_t)r * p.ep.ldm + col));
+            if (r < pq.M) {
+              if (pq.ep.residual) res4[i] = __ldg(reinterpret_cast<const float4*>(pq.ep.residual + (size_t)r * pq.ep.ldr + col));
+              if (pq.ep.mul_elu_out) elu4[i] = __ldg(reinterpret_cast<const float4*>(pq.ep.mul_elu_out + (size_t)r * pq.ep.ldm + col));
             }
           }
         }
@@ -384,48 +415,48 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             else mbar_arrive(&acc_empty[as]);
           }
         }
-        if (n0 + c0 >= p.N) continue;   // warp-uniform
+        if (n0 + c0 >= pq.N) continue;   // warp-uniform
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           *reinterpret_cast<float4*>(patch + lane * Cfg::EPI_LD + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         __syncwarp();
-        if (col < p.N) {
-          if (p.partial) {
-            float* dst0 = p.partial + ((size_t)z * p.M + m0) * p.N + col;
+        if (col < pq.N) {
+          if (pq.partial) {
+            float* dst0 = pq.partial + ((size_t)z * pq.M + m0) * pq.N + col;
 #pragma unroll 2
             for (int i = 0; i < 8; ++i) {
               const int r = sub_r + 4 * i;
-              if (m0 + r >= p.M) break;
+              if (m0 + r >= pq.M) break;
               const float4 acc = *reinterpret_cast<const float4*>(patch + r * Cfg::EPI_LD + sub_c);
-              float* dst = dst0 + (size_t)r * p.N;
+              float* dst = dst0 + (size_t)r * pq.N;
               if (vec_ok) {
                 *reinterpret_cast<float4*>(dst) = acc;
               } else {
                 const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
                 for (int e = 0; e < 4; ++e)
-                  if (col + e < p.N) dst[e] = a4[e];
+                  if (col + e < pq.N) dst[e] = a4[e];
               }
             }
           } else if (vec_ok) {
-            const float4 b4 = p.ep.bias ? __ldg(reinterpret_cast<const float4*>(p.ep.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 b4 = pq.ep.bias ? __ldg(reinterpret_cast<const float4*>(pq.ep.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int r = sub_r + 4 * i;
-              if (m0 + r < p.M) {
+              if (m0 + r < pq.M) {
                 float4 acc = *reinterpret_cast<const float4*>(patch + r * Cfg::EPI_LD + sub_c);
                 acc.x += b4.x; acc.y += b4.y; acc.z += b4.z; acc.w += b4.w;
-                p.ep.store4_pre(acc, m0 + r, col, res4[i], elu4[i]);
+                pq.ep.store4_pre(acc, m0 + r, col, res4[i], elu4[i]);
               }
             }
           } else {
 #pragma unroll 1
             for (int i = 0; i < 8; ++i) {
               const int r = sub_r + 4 * i;
-              if (m0 + r >= p.M) break;
+              if (m0 + r >= pq.M) break;
               const float4 acc = *reinterpret_cast<const float4*>(patch + r * Cfg::EPI_LD + sub_c);
               const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
               for (int e = 0; e < 4; ++e)
-                if (col + e < p.N) p.ep.store(a4[e], m0 + r, col + e);
+                if (col + e < pq.N) pq.ep.store(a4[e], m0 + r, col + e);
             }
           }
         }
@@ -478,16 +509,16 @@ static bool make_map(CUtensorMap* map, const float* base, int rows, int cols, in
   return r == CUDA_SUCCESS;
 }
 
-template <int BN, int TA, int TB, int CTAS>
-static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int grid, cudaStream_t stream) {
+template <int BN, int TA, int TB, int CTAS, bool GROUPED>
+static int launch(const TcMaps& maps, const TcParams& p, int grid, cudaStream_t stream) {
   constexpr int smem = TcCfg<BN, CTAS>::SMEM;
   static bool configured = false;
   if (!configured) {
-    GB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN, TA, TB, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    GB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN, TA, TB, CTAS, GROUPED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   if (CTAS == 1) {
-    gemm_tf32_kernel<BN, TA, TB, CTAS><<<grid, TC_THREADS, smem, stream>>>(ma, mb, p);
+    gemm_tf32_kernel<BN, TA, TB, CTAS, GROUPED><<<grid, TC_THREADS, smem, stream>>>(maps, p);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid, 1, 1);
@@ -501,20 +532,60 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    GB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BN, TA, TB, CTAS>, ma, mb, p));
+    GB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BN, TA, TB, CTAS, GROUPED>, maps, p));
   }
   GB_CHECK_LAUNCH();
   return GB_OK;
 }
 
+static int dispatch(int BN, bool pair, int ta, int tb, const TcMaps& maps, const TcParams& p, int grid, cudaStream_t stream) {
+  int rc = GB_OK;
+  if (p.n_problems > 1) {   // grouped launches exist for weight gradients only (both operands MN-major)
+    if (!(ta && tb) || BN == 64) { set_error("gemm: grouped launch needs trans_a = trans_b = 1 and 128/256-wide tiles"); return GB_ERR_INVALID; }
+    if (pair) rc = BN == 256 ? launch<256, 1, 1, 2, true>(maps, p, grid, stream) : launch<128, 1, 1, 2, true>(maps, p, grid, stream);
+    else rc = BN == 256 ? launch<256, 1, 1, 1, true>(maps, p, grid, stream) : launch<128, 1, 1, 1, true>(maps, p, grid, stream);
+    return rc;
+  }
+#define GB_TC(BN_, TA_, TB_, C_) rc = launch<BN_, TA_, TB_, C_, false>(maps, p, grid, stream)
+#define GB_TC4(BN_, C_)                     \
+  do {                                      \
+    if (!ta && !tb) GB_TC(BN_, 0, 0, C_);   \
+    else if (!ta && tb) GB_TC(BN_, 0, 1, C_); \
+    else if (ta && !tb) GB_TC(BN_, 1, 0, C_); \
+    else GB_TC(BN_, 1, 1, C_);              \
+  } while (0)
+  if (pair) {
+    if (BN == 256) GB_TC4(256, 2);
+    else GB_TC4(128, 2);
+  } else if (BN == 256) {
+    GB_TC4(256, 1);
+  } else if (BN == 128) {
+    GB_TC4(128, 1);
+  } else {
+    GB_TC4(64, 1);
+  }
+#undef GB_TC4
+#undef GB_TC
+  return rc;
+}
+
 int launch_splitk_reduce(const float* partial, int splits, int M, int N, const Epilogue& ep, cudaStream_t stream);
+
+static bool tma_legal(const gb_gemm_args* a) {
+  // 16-byte aligned bases and row pitches (TMA), enough work to fill a tile
+  if (((uintptr_t)a->A & 15) || ((uintptr_t)a->B & 15) || (a->lda & 3) || (a->ldb & 3)) return false;
+  return a->K >= 8 && a->N >= 16 && a->M >= 1;
+}
+
+static bool make_maps(const gb_gemm_args* a, int b_rows, CUtensorMap* ma, CUtensorMap* mb) {
+  bool ok = a->trans_a ? make_map(ma, a->A, a->K, a->M, a->lda, TC_BK, true) : make_map(ma, a->A, a->M, a->K, a->lda, TC_BM, false);
+  return ok && (a->trans_b ? make_map(mb, a->B, a->K, a->N, a->ldb, TC_BK, true) : make_map(mb, a->B, a->N, a->K, a->ldb, b_rows, false));
+}
 
 int gemm_tcgen05(const gb_gemm_args* a, cudaStream_t stream, bool* handled) {
   *handled = false;
   const int M = a->M, N = a->N, K = a->K;
-  // legality: 16-byte aligned bases and row pitches (TMA), enough work to fill a tile
-  if (((uintptr_t)a->A & 15) || ((uintptr_t)a->B & 15) || (a->lda & 3) || (a->ldb & 3)) return GB_OK;
-  if (K < 8 || N < 16 || M < 1) return GB_OK;
+  if (!tma_legal(a)) return GB_OK;
   // tile shape.  pair = a cluster of two CTAs computes 256 x BN (cta_group::2), each staging half of B.  Measured on
   // B200 (tools/gemm_one.py): 16384 x 4096 x 4096 runs at 526 / 626 TFLOP/s with single-CTA 128 x 128 / 128 x 256 tiles
   // and at 764 TFLOP/s with 256 x 256 pair tiles (the cuBLAS-measured TF32-equivalent peak), so the pair wins whenever
@@ -545,15 +616,14 @@ int gemm_tcgen05(const gb_gemm_args* a, cudaStream_t stream, bool* handled) {
     }
     break;
   }
-  const int b_rows = pair ? BN / 2 : BN;
-  CUtensorMap ma, mb;
-  bool ok = a->trans_a ? make_map(&ma, a->A, K, M, a->lda, TC_BK, true) : make_map(&ma, a->A, M, K, a->lda, TC_BM, false);
-  ok = ok && (a->trans_b ? make_map(&mb, a->B, K, N, a->ldb, TC_BK, true) : make_map(&mb, a->B, N, K, a->ldb, b_rows, false));
-  if (!ok) return GB_OK;   // descriptor could not be encoded (e.g. no driver): let the FFMA path handle it
+  TcMaps maps;
+  if (!make_maps(a, pair ? BN / 2 : BN, &maps.a[0], &maps.b[0])) return GB_OK;   // no driver entry point: FFMA path
 
   TcParams p;
-  p.M = M; p.N = N; p.K = K;
-  p.ep = make_epilogue(a);
+  p.n_problems = 1;
+  TcProblem& q = p.pr[0];
+  q.M = M; q.N = N; q.K = K;
+  q.ep = make_epilogue(a);
   const int gx = (N + BN - 1) / BN, gy = tiles_m;
   const int total_kb = (K + TC_BK - 1) / TC_BK;
   int splits = 1;
@@ -565,38 +635,113 @@ int gemm_tcgen05(const gb_gemm_args* a, cudaStream_t stream, bool* handled) {
     if (splits > by_ws) splits = (int)by_ws;
     if (splits < 1) splits = 1;
   }
-  p.k_blocks_per_split = (total_kb + splits - 1) / splits;
-  splits = (total_kb + p.k_blocks_per_split - 1) / p.k_blocks_per_split;
-  p.splits = splits;
-  p.tiles_m = gy;
-  p.tiles_n = gx;
-  p.partial = splits > 1 ? a->workspace : nullptr;
+  q.k_blocks_per_split = (total_kb + splits - 1) / splits;
+  splits = (total_kb + q.k_blocks_per_split - 1) / q.k_blocks_per_split;
+  q.splits = splits;
+  q.tiles_m = gy;
+  q.tiles_n = gx;
+  q.item_begin = 0;
+  q.partial = splits > 1 ? a->workspace : nullptr;
   const int n_items = gx * gy * splits;
+  p.n_items = n_items;
   const int grid = pair ? 2 * (n_items < units ? n_items : units) : (n_items < units ? n_items : units);
-  int rc;
-#define GB_TC(BN_, TA_, TB_, C_) rc = launch<BN_, TA_, TB_, C_>(ma, mb, p, grid, stream)
-#define GB_TC4(BN_, C_)                                       \
-  do {                                                        \
-    if (!a->trans_a && !a->trans_b) GB_TC(BN_, 0, 0, C_);     \
-    else if (!a->trans_a && a->trans_b) GB_TC(BN_, 0, 1, C_); \
-    else if (a->trans_a && !a->trans_b) GB_TC(BN_, 1, 0, C_); \
-    else GB_TC(BN_, 1, 1, C_);                                \
-  } while (0)
-  if (pair) {
-    if (BN == 256) GB_TC4(256, 2);
-    else GB_TC4(128, 2);
-  } else if (BN == 256) {
-    GB_TC4(256, 1);
-  } else if (BN == 128) {
-    GB_TC4(128, 1);
-  } else {
-    GB_TC4(64, 1);
-  }
-#undef GB_TC4
-#undef GB_TC
+  int rc = dispatch(BN, pair, a->trans_a, a->trans_b, maps, p, grid, stream);
   if (rc) return rc;
   if (splits > 1) {
-    rc = launch_splitk_reduce(p.partial, splits, M, N, p.ep, stream);
+    rc = launch_splitk_reduce(q.partial, splits, M, N, q.ep, stream);
+    if (rc) return rc;
+  }
+  *handled = true;
+  return GB_OK;
+}
+
+// Grouped launch: n <= TC_MAX_GROUP problems with the same operand layouts, all TMA-legal, one shared workspace.
+// Splits are chosen so that ALL problems' work items together fill the machine exactly once (one wave of equally long
+// K slices) -- the weight gradients of one transformer layer: 4 launches + 4 reduces become 1 + (0 or 1).
+int launch_splitk_reduce_grouped(int n, const float* const* partial, const int* splits, const int* Ms, const int* Ns,
+                                 const Epilogue* eps, cudaStream_t stream);
+
+int gemm_tcgen05_grouped(const gb_gemm_args* list, int n, cudaStream_t stream, bool* handled) {
+  *handled = false;
+  if (n < 1 || n > TC_MAX_GROUP) return GB_OK;
+  const int ta = list[0].trans_a, tb = list[0].trans_b;
+  if (!(ta && tb)) return GB_OK;
+  bool all256 = true, all128 = true, big_m = true, long_k = true;
+  for (int i = 0; i < n; ++i) {
+    const gb_gemm_args* a = &list[i];
+    if (!tma_legal(a) || a->trans_a != ta || a->trans_b != tb) return GB_OK;
+    if (a->workspace != list[0].workspace || a->workspace_bytes != list[0].workspace_bytes) return GB_OK;
+    all256 = all256 && (a->N % 256 == 0);
+    all128 = all128 && (a->N >= 128);
+    big_m = big_m && (a->M > TC_BM);
+    long_k = long_k && (a->K >= 1024);
+  }
+  if (!all128) return GB_OK;
+  static const int forced_pair = [] { const char* e = getenv("GRAPPA_B200_GEMM_PAIR"); return e ? atoi(e) : -1; }();
+  const bool pair = big_m && long_k && forced_pair != 0;
+  const int BN = all256 ? 256 : 128;
+  const int bm = pair ? 2 * TC_BM : TC_BM;
+  const int units = pair ? sm_count() / 2 : sm_count();
+  TcMaps maps;
+  TcParams p;
+  p.n_problems = n;
+  int total_tiles = 0;
+  for (int i = 0; i < n; ++i) {
+    const gb_gemm_args* a = &list[i];
+    if (!make_maps(a, pair ? BN / 2 : BN, &maps.a[i], &maps.b[i])) return GB_OK;
+    TcProblem& q = p.pr[i];
+    q.M = a->M; q.N = a->N; q.K = a->K;
+    q.ep = make_epilogue(a);
+    q.tiles_m = (a->M + bm - 1) / bm;
+    q.tiles_n = (a->N + BN - 1) / BN;
+    total_tiles += q.tiles_m * q.tiles_n;
+  }
+  // slices per tile: minimise rounds x (k-blocks per item + fill/drain allowance) + reduce cost over S = 1..16
+  int max_kb = 0;
+  for (int i = 0; i < n; ++i) max_kb = max_kb > (list[i].K + TC_BK - 1) / TC_BK ? max_kb : (list[i].K + TC_BK - 1) / TC_BK;
+  int S = 1;
+  if (list[0].workspace) {
+    long long best = -1;
+    for (int s_try = 1; s_try <= 16; ++s_try) {
+      const int kb = (max_kb + s_try - 1) / s_try;
+      if (s_try > 1 && kb < 4) break;
+      const long long rounds = ((long long)total_tiles * s_try + units - 1) / units;
+      const long long cost = rounds * (kb + 8) + (s_try > 1 ? 4 + s_try : 0);
+      if (best < 0 || cost < best) { best = cost; S = s_try; }
+    }
+  }
+  const int kb_target = (max_kb + S - 1) / S > 4 ? (max_kb + S - 1) / S : 4;
+  long long ws_used = 0;
+  int items = 0, any_split = 0;
+  const float* partials[TC_MAX_GROUP];
+  int splits_v[TC_MAX_GROUP], Ms[TC_MAX_GROUP], Ns[TC_MAX_GROUP];
+  Epilogue eps[TC_MAX_GROUP];
+  for (int i = 0; i < n; ++i) {
+    TcProblem& q = p.pr[i];
+    const int total_kb = (q.K + TC_BK - 1) / TC_BK;
+    int splits = (total_kb + kb_target - 1) / kb_target;
+    const long long bytes_per_split = (long long)q.M * q.N * 4;
+    if (splits > 1 && ws_used + (long long)splits * bytes_per_split > list[0].workspace_bytes) splits = 1;
+    q.k_blocks_per_split = (total_kb + splits - 1) / splits;
+    splits = (total_kb + q.k_blocks_per_split - 1) / q.k_blocks_per_split;
+    q.splits = splits;
+    q.item_begin = items;
+    items += q.tiles_m * q.tiles_n * splits;
+    q.partial = nullptr;
+    if (splits > 1) {
+      q.partial = list[0].workspace + ws_used / 4;
+      ws_used += (long long)splits * bytes_per_split;
+      ws_used = (ws_used + 255) / 256 * 256;
+      any_split = 1;
+    }
+    partials[i] = q.partial; splits_v[i] = splits; Ms[i] = q.M; Ns[i] = q.N; eps[i] = q.ep;
+  }
+  p.n_items = items;
+  const int grid = pair ? 2 * (items < units ? items : units) : (items < units ? items : units);
+  int rc = dispatch(BN, pair, ta, tb, maps, p, grid, stream);
+  if (rc) return rc;
+  if (any_split) {
+    rc = launch_splitk_reduce_grouped(n, partials, splits_v, Ms, Ns, eps, stream);
     if (rc) return rc;
   }
   *handled = true;

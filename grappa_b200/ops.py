@@ -81,12 +81,10 @@ def drop_workspaces():
     _ws_cache.clear()
 
 
-def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a=False, trans_b=False, bias=None, act=0, mul_elu_out=None,
-         dropout_p=0.0, dropout_seed=0, residual=None, out=None, accumulate=False, m=None, n=None, k=None,
-         precision=None, act_out=None) -> torch.Tensor:
-    """C[M,N] = opA(a) opB(b)^T (+ fused epilogue), see gb_gemm_args.  a/b may be column-sliced views
-    (last-dim stride 1); leading dimensions are taken from the row strides."""
-    lib = _lib.lib()
+def _gemm_args(a: torch.Tensor, b: torch.Tensor, *, trans_a=False, trans_b=False, bias=None, act=0, mul_elu_out=None,
+               dropout_p=0.0, dropout_seed=0, residual=None, out=None, accumulate=False, m=None, n=None, k=None,
+               precision=None, act_out=None):
+    """Fill a gb_gemm_args for C[M,N] = opA(a) opB(b)^T (+ fused epilogue); returns (args, out)."""
     _lib.require_cuda(a, b)
     assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
     M = m if m is not None else (a.shape[1] if trans_a else a.shape[0])
@@ -115,6 +113,14 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a=False, trans_b=False, bias
     if trans_a and M * N <= (1 << 22) and K >= 1024:
         ws = workspace(64 << 20, a.device, "splitk")
         g.workspace, g.workspace_bytes = ws.data_ptr(), ws.numel() * 4
+    return g, out
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, **kw) -> torch.Tensor:
+    """C[M,N] = opA(a) opB(b)^T (+ fused epilogue), see gb_gemm_args.  a/b may be column-sliced views
+    (last-dim stride 1); leading dimensions are taken from the row strides."""
+    lib = _lib.lib()
+    g, out = _gemm_args(a, b, **kw)
     if _gemm_profile is not None:
         # inside a stream capture the events become graph nodes that are re-recorded by every replay
         ext = torch.cuda.is_current_stream_capturing()
@@ -122,10 +128,34 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a=False, trans_b=False, bias
         e0.record()
         _lib.check(lib.grappa_b200_gemm(C.byref(g), _s()), "gemm")
         e1.record()
-        _gemm_profile.append((2.0 * M * N * K, e0, e1, (M, N, K, int(trans_a), int(trans_b))))
+        _gemm_profile.append((2.0 * g.M * g.N * g.K, e0, e1, (g.M, g.N, g.K, int(g.trans_a), int(g.trans_b))))
         return out
     _lib.check(lib.grappa_b200_gemm(C.byref(g), _s()), "gemm")
     return out
+
+
+def gemm_grouped(problems) -> None:
+    """`problems`: list of (a, b, kwargs) as for `gemm` with `out=` given.  Independent GEMMs issued through
+    grappa_b200_gemm_grouped: runs of up to four tensor-core problems share one persistent launch."""
+    if not problems:
+        return
+    lib = _lib.lib()
+    arr = (GemmArgs * len(problems))()
+    flops, shapes = 0.0, []
+    for i, (a, b, kw) in enumerate(problems):
+        g, _ = _gemm_args(a, b, **kw)
+        arr[i] = g
+        flops += 2.0 * g.M * g.N * g.K
+        shapes.append((g.M, g.N, g.K))
+    if _gemm_profile is not None:
+        ext = torch.cuda.is_current_stream_capturing()
+        e0, e1 = torch.cuda.Event(enable_timing=True, external=ext), torch.cuda.Event(enable_timing=True, external=ext)
+        e0.record()
+        _lib.check(lib.grappa_b200_gemm_grouped(arr, len(problems), _s()), "gemm_grouped")
+        e1.record()
+        _gemm_profile.append((flops, e0, e1, ("grouped",) + tuple(shapes)))
+        return
+    _lib.check(lib.grappa_b200_gemm_grouped(arr, len(problems), _s()), "gemm_grouped")
 
 
 def layernorm_fwd(x, gamma, beta, eps=1e-5):

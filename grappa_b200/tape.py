@@ -76,6 +76,7 @@ class Tape:
         self._side_dirty = False
         self._keep: List[torch.Tensor] = []   # tensors the helper stream still reads (released at the next join)
         self.colsums = ops.ColumnSums()       # deferred bias / LayerNorm parameter-gradient reductions
+        self._wgrads: List[tuple] = []        # deferred weight-gradient GEMMs (a, b, kwargs): issued in groups of <= 4
 
     def next_seed(self) -> int:
         self._n += 1
@@ -108,9 +109,29 @@ class Tape:
         with torch.cuda.stream(self._side):
             yield
 
+    def defer_wgrad(self, dpre: torch.Tensor, x: torch.Tensor, out: torch.Tensor, accumulate: bool, **kw):
+        """Queue dW = dpre^T x for a grouped launch.  The weight gradients of consecutive layers of one stage are
+        independent of the backward chain and of each other, so four of them share ONE persistent kernel whose work
+        items are sized to fill the SMs once (grappa_b200_gemm_grouped): fewer, longer K slices, fewer partials, a
+        quarter of the launches.  A second write to a buffer that is already queued flushes first (ordering)."""
+        if any(o.data_ptr() == out.data_ptr() for _, _, o, _ in self._wgrads):
+            self.flush_wgrads()
+        self._wgrads.append((dpre, x, out, dict(trans_a=True, trans_b=True, out=out, accumulate=accumulate, **kw)))
+        if len(self._wgrads) >= 4:
+            self.flush_wgrads()
+
+    def flush_wgrads(self):
+        if not self._wgrads:
+            return
+        batch, self._wgrads = self._wgrads, []
+        tensors = [t for d, x, _, _ in batch for t in (d, x)]
+        with self.side_branch(*tensors):
+            ops.gemm_grouped([(d, x, kw) for d, x, _, kw in batch])
+
     def join_side(self):
         """Fold the deferred column sums and make the current stream wait for the weight-gradient branch (before
         parameter gradients are consumed)."""
+        self.flush_wgrads()
         self.colsums.flush()
         if self._side_dirty:
             ev = torch.cuda.Event()
@@ -209,13 +230,20 @@ def linear(t: Tape, x: Var, W: torch.Tensor, b: Optional[torch.Tensor], *, act: 
         else:
             dpre_full = dy_full
         dpre = dpre_full[:, :N] if dpre_full.shape[1] != N else dpre_full
-        # weight / bias gradients (parallel branch)
-        with t.side_branch(dpre_full, xv):
-            tgt, acc = t.grad_target(W)
-            if tgt is None:
-                t.add_pgrad(W, ops.gemm(dpre, xv, trans_a=True, trans_b=True, m=N, n=K, k=M))
+        # weight / bias gradients (parallel branch; the GEMMs are queued and issued four at a time)
+        tgt, acc = t.grad_target(W)
+        if tgt is None:
+            if id(W) in t.pgrads:       # second use of a weight inside one stage: keep the simple ordered path
+                t.flush_wgrads()
+                with t.side_branch(dpre_full, xv):
+                    t.add_pgrad(W, ops.gemm(dpre, xv, trans_a=True, trans_b=True, m=N, n=K, k=M))
             else:
-                ops.gemm(dpre, xv, trans_a=True, trans_b=True, m=N, n=K, k=M, out=tgt, accumulate=acc)
+                gw = torch.empty((N, K), device=xv.device, dtype=torch.float32)
+                t.pgrads[id(W)] = gw
+                t.defer_wgrad(dpre, xv, gw, False, m=N, n=K, k=M)
+        else:
+            t.defer_wgrad(dpre, xv, tgt, acc, m=N, n=K, k=M)
+        with t.side_branch(dpre_full, xv) if (b is not None and bias_partial is None) else contextlib.nullcontext():
             if b is not None and bias_partial is None:
                 tgt, acc = t.grad_target(b)
                 if tgt is None:

@@ -157,6 +157,13 @@ typedef struct {
 } gb_gemm_args;
 
 int grappa_b200_gemm(const gb_gemm_args* a, void* stream);
+/* n independent GEMMs in as few launches as possible: runs of up to 4 tensor-core problems with the same operand
+ * layouts, tile configuration and workspace share ONE persistent kernel (work items numbered problem by problem, split-K
+ * slices sized so that all problems together fill the SMs once) and one reduce launch; everything else falls back to
+ * grappa_b200_gemm per problem.  Results are identical to n separate grappa_b200_gemm calls up to the summation
+ * order of split-K slices.  Used for the weight gradients of a layer (reference: torch autograd's per-Linear
+ * weight.grad accumulation, e.g. models/network_utils.py:44-54 backward). */
+int grappa_b200_gemm_grouped(const gb_gemm_args* list, int32_t n, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * LayerNorm over the last dimension (eps, affine, biased variance = torch.nn.LayerNorm defaults;

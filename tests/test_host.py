@@ -49,7 +49,9 @@ def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(GemmArgs) % 8 == 0 and ctypes.sizeof(EnergyArgs) % 8 == 0
     assert ctypes.sizeof(EnergyBwdArgs) > ctypes.sizeof(EnergyArgs)
     assert ctypes.sizeof(HeadOutArgs) == 6 * 4 + 8 * 4 + 12 * 4 + 4
-    assert ctypes.sizeof(LossArgs) == 9 * 8 + 4 * 4 + 4 * 4 + 7 * 8
+    assert ctypes.sizeof(LossArgs) == 9 * 8 + 4 * 4 + 4 * 4 + 8 * 8
+    from grappa_b200._lib_ops import ParamLossArgs
+    assert ctypes.sizeof(ParamLossArgs) == 2 * 4 + 3 * 5 * 8 + 3 * 5 * 4 + 4 + 2 * 8 + 5 * 8 + 8   # 4 bytes of padding after fac[5]
 
 
 @pytest.mark.parametrize("name", ["dipeptide", "peptide4", "tree", "rna", "protein30"])
