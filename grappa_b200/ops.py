@@ -47,6 +47,30 @@ def _rng_ptr() -> int:
 _gemm_profile = None   # list collecting (flops, start_event, stop_event, kernel) when profiling is on
 
 
+_gemm_record = None    # list collecting every GEMM call (argument structs + the tensors they point to) of a step
+
+
+def set_gemm_recorder(sink):
+    """bench.py: pass a list to record every GEMM call (the exact gb_gemm_args, tensors kept alive); None = off.
+    `replay_gemms(sink)` re-issues them back to back, so the GEMM family can be timed without anything in between."""
+    global _gemm_record
+    _gemm_record = sink
+
+
+def replay_gemms(records) -> float:
+    """Issue the recorded GEMM calls on the current stream; returns the FLOPs issued."""
+    lib = _lib.lib()
+    flops = 0.0
+    for kind, arr, n, _keep in records:
+        if kind == "single":
+            _lib.check(lib.grappa_b200_gemm(C.byref(arr), _s()), "gemm")
+            flops += 2.0 * arr.M * arr.N * arr.K
+        else:
+            _lib.check(lib.grappa_b200_gemm_grouped(arr, n, _s()), "gemm_grouped")
+            flops += sum(2.0 * arr[i].M * arr[i].N * arr[i].K for i in range(n))
+    return flops
+
+
 def set_gemm_profiler(sink):
     """bench.py: pass a list to time every GEMM launch with CUDA events on the launching stream; None = off."""
     global _gemm_profile
@@ -121,6 +145,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, **kw) -> torch.Tensor:
     (last-dim stride 1); leading dimensions are taken from the row strides."""
     lib = _lib.lib()
     g, out = _gemm_args(a, b, **kw)
+    if _gemm_record is not None:
+        _gemm_record.append(("single", g, 1, (a, b, out, kw)))
     if _gemm_profile is not None:
         # inside a stream capture the events become graph nodes that are re-recorded by every replay
         ext = torch.cuda.is_current_stream_capturing()
@@ -147,6 +173,8 @@ def gemm_grouped(problems) -> None:
         arr[i] = g
         flops += 2.0 * g.M * g.N * g.K
         shapes.append((g.M, g.N, g.K))
+    if _gemm_record is not None:
+        _gemm_record.append(("grouped", arr, len(problems), problems))
     if _gemm_profile is not None:
         ext = torch.cuda.is_current_stream_capturing()
         e0, e1 = torch.cuda.Event(enable_timing=True, external=ext), torch.cuda.Event(enable_timing=True, external=ext)
