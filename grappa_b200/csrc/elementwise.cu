@@ -142,6 +142,17 @@ __global__ void __launch_bounds__(256) act_dropout_bwd_kernel(const float* __res
   }
 }
 
+// out[r, c] = c < cols ? in[r, c] : 0   (row pitch ld_in -> ld_out): a weight whose rows are not 16-byte multiples
+// (pre_dense: 85 input features) gets a TMA-legal padded copy so its GEMM can run on the tensor cores
+__global__ void __launch_bounds__(256) pad_rows_kernel(const float* __restrict__ in, int rows, int cols, int ld_in,
+                                                       float* __restrict__ out, int ld_out) {
+  const long long total = (long long)rows * ld_out;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / ld_out), c = (int)(i - (long long)r * ld_out);
+    out[i] = c < cols ? __ldg(in + (size_t)r * ld_in + c) : 0.f;
+  }
+}
+
 __global__ void __launch_bounds__(256) axpby_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float a,
                                                     float b) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -383,6 +394,16 @@ extern "C" int grappa_b200_act_dropout_bwd(const float* dy, const float* act_out
   }
   act_dropout_bwd_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream_>>>(dy, act_out, dx, n, thresh, 1.f / (1.f - p), seed,
                                                                                  seed_offset);
+  GB_CHECK_LAUNCH();
+  return GB_OK;
+}
+
+extern "C" int grappa_b200_pad_rows(const float* in, int32_t rows, int32_t cols, int32_t ld_in, float* out, int32_t ld_out,
+                                    void* stream_) {
+  if (rows == 0) return GB_OK;
+  GB_REQUIRE(in && out, "pad_rows: NULL pointer");
+  GB_REQUIRE(cols >= 0 && ld_in >= cols && ld_out >= cols, "pad_rows: pitch smaller than the row length");
+  pad_rows_kernel<<<grid_for((long long)rows * ld_out), 256, 0, (cudaStream_t)stream_>>>(in, rows, cols, ld_in, out, ld_out);
   GB_CHECK_LAUNCH();
   return GB_OK;
 }

@@ -191,7 +191,7 @@ class GrappaGNN(nn.Module):
             x = ins[0]
             t.push(lambda: (t.join_side(), _fire(("gnn_rest", None))))          # runs last in backward
             h = T_.linear(t, x, P(self.pre_dense[0].weight), P(self.pre_dense[0].bias), act=ELU,
-                          dropout_p=self.p_initial, k=self.in_feats)
+                          dropout_p=self.p_initial, k=self.in_feats, x_pad_is_zero=True)   # featurize zero-fills the pad
             if not self.no_convs:
                 for i, blk in enumerate(self.att_blocks):
                     if _BACKWARD_HOOK is not None:               # runs after block i's backward ops

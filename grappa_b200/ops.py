@@ -134,7 +134,9 @@ def _gemm_args(a: torch.Tensor, b: torch.Tensor, *, trans_a=False, trans_b=False
     g.act_out = _p(act_out)
     g.ldact = act_out.stride(0) if act_out is not None else 0
     g.precision = _precision if precision is None else precision
-    if trans_a and M * N <= (1 << 22) and K >= 1024:
+    if (trans_a and M * N <= (1 << 22) and K >= 1024) or (M * N <= (1 << 20) and K >= 2048):
+        # weight gradients (tiny output, very long K) and the 2048-deep feed-forward GEMMs of the GNN (13 row tiles):
+        # split-K slices fill the SMs, a reduce kernel applies the epilogue
         ws = workspace(64 << 20, a.device, "splitk")
         g.workspace, g.workspace_bytes = ws.data_ptr(), ws.numel() * 4
     return g, out
@@ -184,6 +186,18 @@ def gemm_grouped(problems) -> None:
         _gemm_profile.append((flops, e0, e1, ("grouped",) + tuple(shapes)))
         return
     _lib.check(lib.grappa_b200_gemm_grouped(arr, len(problems), _s()), "gemm_grouped")
+
+
+def pad_rows(w: torch.Tensor, ld: int) -> torch.Tensor:
+    """Zero-padded copy [rows, ld] of a 2-D matrix (rows made 16-byte multiples for TMA)."""
+    lib = _lib.lib()
+    out = torch.empty((w.shape[0], ld), device=w.device, dtype=torch.float32)
+    _lib.check(lib.grappa_b200_pad_rows(w.data_ptr(), w.shape[0], w.shape[1], w.stride(0), out.data_ptr(), ld, _s()), "pad_rows")
+    return out
+
+
+def matmul_precision() -> int:
+    return _precision
 
 
 def layernorm_fwd(x, gamma, beta, eps=1e-5):

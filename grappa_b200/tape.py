@@ -186,8 +186,9 @@ def add_grad(var: Var, g: torch.Tensor):
 # --------------------------------------------------------------------------------------------------
 def linear(t: Tape, x: Var, W: torch.Tensor, b: Optional[torch.Tensor], *, act: int = 0, dropout_p: float = 0.0,
            residual: Optional[Var] = None, k: Optional[int] = None, out_ld: Optional[int] = None,
-           fuse_elu_into_consumer: bool = False) -> Var:
-    """y = dropout(act(x[:, :k] W^T + b)) + residual.  `out_ld` > N gives a padded output buffer."""
+           fuse_elu_into_consumer: bool = False, x_pad_is_zero: bool = False) -> Var:
+    """y = dropout(act(x[:, :k] W^T + b)) + residual.  `out_ld` > N gives a padded output buffer.  `x_pad_is_zero`:
+    the columns of x beyond k (up to the next multiple of 4) hold zeros."""
     xv = x.v
     N = W.shape[0]
     K = k if k is not None else W.shape[1]
@@ -203,8 +204,15 @@ def linear(t: Tape, x: Var, W: torch.Tensor, b: Optional[torch.Tensor], *, act: 
         buf = torch.empty((M, N), device=xv.device, dtype=torch.float32)
         out = buf
     act_out = torch.empty((M, N), device=xv.device, dtype=torch.float32) if need_act_out else None
-    ops.gemm(xv, W, bias=b, act=act, dropout_p=p, dropout_seed=seed, residual=None if residual is None else residual.v,
-             out=out, k=K, m=M, n=N, act_out=act_out)
+    Wf, Kf = W, K
+    K4 = (K + 3) // 4 * 4
+    if (x_pad_is_zero and W.stride(0) % 4 != 0 and ops.matmul_precision() != ops.FP32 and xv.shape[1] >= K4
+            and xv.stride(0) % 4 == 0 and M >= 128):
+        # rows of W are not 16-byte multiples (pre_dense: 85 features): the tensor-core path needs a zero-padded copy;
+        # the activation buffer already carries zero pad columns (featurize), so the product is unchanged
+        Wf, Kf = ops.pad_rows(W, K4), K4
+    ops.gemm(xv, Wf, bias=b, act=act, dropout_p=p, dropout_seed=seed, residual=None if residual is None else residual.v,
+             out=out, k=Kf, m=M, n=N, act_out=act_out)
     y = Var(buf)
     if act != 0 and p == 0.0 and residual is None and fuse_elu_into_consumer:
         y.elu_fusable = True

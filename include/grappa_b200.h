@@ -305,6 +305,10 @@ int grappa_b200_act_dropout_bwd(const float* dy, const float* act_out, float* dx
                                 const uint64_t* seed_offset, void* stream);
 /* y = a*x + b*y */
 int grappa_b200_axpby(const float* x, float* y, int64_t n, float a, float b, void* stream);
+/* out[r, c] = c < cols ? in[r, c] : 0 for c < ld_out: zero-padded copy of a matrix whose row pitch is not a 16-byte
+ * multiple (GrappaGNN.pre_dense, 85 input features, reference models/graph_attention.py:166) so that its GEMM is
+ * TMA-legal */
+int grappa_b200_pad_rows(const float* in, int32_t rows, int32_t cols, int32_t ld_in, float* out, int32_t ld_out, void* stream);
 /* out[0] += sum x^2  (out must be zeroed by the caller; deterministic two-stage when ws given) */
 int grappa_b200_sumsq(const float* x, int64_t n, float* out, void* stream);
 /* out[0] = sum x^2, bit-reproducible (fixed grid, partials folded in block order by the last block).
