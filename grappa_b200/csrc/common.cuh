@@ -42,6 +42,15 @@ void count_launch();  // bumps the process-wide kernel launch counter (grappa_b2
 int sm_count();  // cached multiprocessor count of the current device (148 on B200)
 
 #ifdef __CUDACC__
+// Programmatic dependent launch (PDL).  Every kernel calls pdl_trigger() first thing: once all CTAs of a grid have done
+// so (or exited), a following kernel that was launched with the programmatic-stream-serialization attribute may start
+// its CTAs -- they run their prologue (barrier init, TMEM allocation, descriptor prefetch) while this grid's tail is
+// still executing -- and must call pdl_wait() before touching global memory: it returns when the preceding grid has
+// completed and its writes are visible.  Only the tensor-core GEMM is launched with the attribute (heaviest prologue,
+// 230 launches per step); for kernels launched normally both calls are no-ops.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -21,6 +21,7 @@ __device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a
 __global__ void __launch_bounds__(256) edge_attn_fwd_kernel(const float* __restrict__ ft, const int* __restrict__ indptr,
                                                             const int* __restrict__ esrc, float* __restrict__ out,
                                                             float* __restrict__ alpha, int n_nodes, int H, int D) {
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (v >= n_nodes) return;
@@ -63,6 +64,7 @@ __global__ void __launch_bounds__(256) edge_attn_bwd1_kernel(const float* __rest
                                                              const float* __restrict__ dout, const int* __restrict__ indptr,
                                                              const int* __restrict__ esrc, float* __restrict__ ds,
                                                              int n_nodes, int H, int D) {
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (v >= n_nodes) return;
@@ -99,6 +101,7 @@ __global__ void __launch_bounds__(256) edge_attn_bwd2_kernel(const float* __rest
                                                              const int* __restrict__ indptr, const int* __restrict__ esrc,
                                                              const int* __restrict__ erev, float* __restrict__ dft,
                                                              int n_nodes, int H, int D) {
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (u >= n_nodes) return;

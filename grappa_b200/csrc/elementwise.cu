@@ -9,6 +9,7 @@ namespace gb {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) featurize_kernel(gb_featurize_args a, float* __restrict__ out, int n, int ld,
                                                         int width_total) {
+  pdl_trigger();
   const long long total = (long long)n * ld;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int row = (int)(i / ld);
@@ -44,6 +45,7 @@ __device__ __forceinline__ float to_positive_grad(float x, float mos, float sd) 
 
 __global__ void __launch_bounds__(256) head_output_fwd_kernel(gb_head_out_args a, const float* __restrict__ scores,
                                                               float* __restrict__ k, float* __restrict__ eq) {
+  pdl_trigger();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= a.T) return;
   float c[12];
@@ -74,6 +76,7 @@ __global__ void __launch_bounds__(256) head_output_fwd_kernel(gb_head_out_args a
 __global__ void __launch_bounds__(256) head_output_bwd_kernel(gb_head_out_args a, const float* __restrict__ scores,
                                                               const float* __restrict__ dk, const float* __restrict__ deq,
                                                               float* __restrict__ dscores) {
+  pdl_trigger();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= a.T) return;
   float c[12], d[12];
@@ -124,6 +127,7 @@ __global__ void __launch_bounds__(256) head_output_bwd_kernel(gb_head_out_args a
 __global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ x, float* __restrict__ y, long long n,
                                                       uint32_t thresh, float inv_keep, uint64_t seed0,
                                                       const uint64_t* __restrict__ seed_off) {
+  pdl_trigger();
   const uint64_t seed = seed_with_offset(seed0, seed_off);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = x[i] * dropout_scale(seed, (uint64_t)i, thresh, inv_keep);
@@ -133,6 +137,7 @@ __global__ void __launch_bounds__(256) act_dropout_bwd_kernel(const float* __res
                                                               float* __restrict__ dx, long long n, uint32_t thresh,
                                                               float inv_keep, uint64_t seed0,
                                                               const uint64_t* __restrict__ seed_off) {
+  pdl_trigger();
   const uint64_t seed = seed_with_offset(seed0, seed_off);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float v = dy[i];
@@ -146,6 +151,7 @@ __global__ void __launch_bounds__(256) act_dropout_bwd_kernel(const float* __res
 // (pre_dense: 85 input features) gets a TMA-legal padded copy so its GEMM can run on the tensor cores
 __global__ void __launch_bounds__(256) pad_rows_kernel(const float* __restrict__ in, int rows, int cols, int ld_in,
                                                        float* __restrict__ out, int ld_out) {
+  pdl_trigger();
   const long long total = (long long)rows * ld_out;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / ld_out), c = (int)(i - (long long)r * ld_out);
@@ -155,11 +161,13 @@ __global__ void __launch_bounds__(256) pad_rows_kernel(const float* __restrict__
 
 __global__ void __launch_bounds__(256) axpby_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float a,
                                                     float b) {
+  pdl_trigger();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = b == 0.f ? a * x[i] : a * x[i] + b * y[i];
 }
 
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, long long n, float* out) {
+  pdl_trigger();
   __shared__ float sh[8];
   float s = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -178,6 +186,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                    float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
                                                    float bc1, float bc2_sqrt, const float* __restrict__ gnorm_sq, float clip,
                                                    float grad_scale) {
+  pdl_trigger();
   float coef = grad_scale;
   if (gnorm_sq && clip > 0.f) {
     // the norm was accumulated on UNSCALED gradients: total norm of the scaled gradient = scale * sqrt(sumsq)
@@ -208,6 +217,7 @@ __device__ float block_sum(float v, float* sh) {
 }
 
 __global__ void __launch_bounds__(256) molwise_loss_kernel(gb_loss_args a) {
+  pdl_trigger();
   __shared__ float sh[8];
   const int b = blockIdx.x, tid = threadIdx.x, C = a.C;
   const float invB = (a.grad_scale ? __ldg(a.grad_scale) : 1.f) / a.B;
@@ -270,6 +280,7 @@ __global__ void __launch_bounds__(256) molwise_loss_kernel(gb_loss_args a) {
 
 // classical-parameter MSE, one block per molecule (see gb_param_loss_args)
 __global__ void __launch_bounds__(256) param_loss_kernel(gb_param_loss_args a) {
+  pdl_trigger();
   __shared__ float sh[8];
   const int b = blockIdx.x, tid = threadIdx.x;
   long long total = 0;
@@ -296,6 +307,7 @@ __global__ void __launch_bounds__(256) param_loss_kernel(gb_param_loss_args a) {
 }
 
 __global__ void __launch_bounds__(256) loss_final_kernel(const float* __restrict__ mol_loss, int B, float* loss) {
+  pdl_trigger();
   __shared__ float sh[8];
   float s = 0.f;
   for (int i = threadIdx.x; i < B; i += blockDim.x) s += mol_loss[i];
@@ -392,8 +404,7 @@ extern "C" int grappa_b200_act_dropout_bwd(const float* dy, const float* act_out
     thresh = t >= 4294967295.0 ? 0xffffffffu : (uint32_t)t;
     if (thresh == 0) thresh = 1;
   }
-  act_dropout_bwd_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream_>>>(dy, act_out, dx, n, thresh, 1.f / (1.f - p), seed,
-                                                                                 seed_offset);
+  act_dropout_bwd_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream_>>>(dy, act_out, dx, n, thresh, 1.f / (1.f - p), seed, seed_offset);
   GB_CHECK_LAUNCH();
   return GB_OK;
 }
@@ -419,6 +430,7 @@ extern "C" int grappa_b200_axpby(const float* x, float* y, int64_t n, float a, f
 // deterministic variant: fixed grid, per-block partials, the last block (ticket) adds them in block order
 __global__ void __launch_bounds__(256) sumsq_det_kernel(const float* __restrict__ x, long long n, float* __restrict__ out,
                                                         unsigned int* __restrict__ ticket, float* __restrict__ partial) {
+  pdl_trigger();
   __shared__ float sh[8];
   __shared__ bool last;
   float s = 0.f;
@@ -485,8 +497,7 @@ extern "C" int grappa_b200_adam_step(float* p, const float* g, float* m, float* 
   GB_REQUIRE(step >= 1, "adam_step: step counts from 1");
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
-  adam_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream_>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2s, gnorm_sq, clip,
-                                                             grad_scale);
+  adam_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream_>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2s, gnorm_sq, clip, grad_scale);
   GB_CHECK_LAUNCH();
   return GB_OK;
 }
@@ -495,6 +506,7 @@ __global__ void __launch_bounds__(256) adam_dev_kernel(float* __restrict__ p, co
                                                        float* __restrict__ v, long long n, const float* __restrict__ lr_dev,
                                                        float b1, float b2, float eps, const uint64_t* __restrict__ step_dev,
                                                        const float* __restrict__ gnorm_sq, float clip, float grad_scale) {
+  pdl_trigger();
   const float step = (float)(__ldg(reinterpret_cast<const unsigned long long*>(step_dev)) + 1ull);
   const float lr = __ldg(lr_dev);
   const float bc1 = 1.f - powf(b1, step);
@@ -533,6 +545,7 @@ __global__ void __launch_bounds__(256) adam_dev_kernel(float* __restrict__ p, co
 }
 
 __global__ void tick_kernel(uint64_t* counters, int n) {
+  pdl_trigger();
   if ((int)threadIdx.x < n) counters[threadIdx.x] += 1ull;
 }
 
@@ -542,8 +555,7 @@ extern "C" int grappa_b200_adam_step_dev(float* p, const float* g, float* m, flo
   if (n == 0) return GB_OK;
   GB_REQUIRE(p && g && m && v && lr_dev && step_dev, "adam_step_dev: NULL pointer");
   GB_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "adam_step_dev: buffers must be 16-byte aligned");
-  adam_dev_kernel<<<grid_for(n / 4 + 1), 256, 0, (cudaStream_t)stream_>>>(p, g, m, v, n, lr_dev, beta1, beta2, eps, step_dev,
-                                                                         gnorm_sq, clip, grad_scale);
+  adam_dev_kernel<<<grid_for(n / 4 + 1), 256, 0, (cudaStream_t)stream_>>>(p, g, m, v, n, lr_dev, beta1, beta2, eps, step_dev, gnorm_sq, clip, grad_scale);
   GB_CHECK_LAUNCH();
   return GB_OK;
 }

@@ -44,6 +44,7 @@ static __device__ __forceinline__ void sm_add(float* p, float v) {
 
 template <bool ATOMIC>
 __global__ void __launch_bounds__(512) energy_tiled_kernel(gb_energy_args a, int W, int G, int n_tiles) {
+  pdl_trigger();
   extern __shared__ float smem[];
   const int b = blockIdx.x / n_tiles;
   const int tile = blockIdx.x % n_tiles;
@@ -201,6 +202,7 @@ __global__ void __launch_bounds__(512) energy_tiled_kernel(gb_energy_args a, int
 // ---------------------------------------------------------------------------------------------
 template <int G>
 __global__ void __launch_bounds__(32 * G, 4) energy_rounds_kernel(gb_energy_args a, int n_tiles, int wtile) {
+  pdl_trigger();
   extern __shared__ float smem[];
   constexpr int W = 32;
   const int b = blockIdx.x / n_tiles;
@@ -379,6 +381,7 @@ __global__ void __launch_bounds__(32 * G, 4) energy_rounds_kernel(gb_energy_args
 //     force accumulators in registers, halving the L1/shared traffic of the torsion loop.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) energy_conf_kernel(gb_energy_args a, int n_tiles) {
+  pdl_trigger();
   extern __shared__ float gs[];            // [n_at * 3][W]
   const int W = blockDim.x, tid = threadIdx.x;
   const int b = blockIdx.x / n_tiles;
@@ -518,6 +521,7 @@ __global__ void __launch_bounds__(128) energy_conf_kernel(gb_energy_args a, int 
 // ---------------------------------------------------------------------------------------------
 template <int LV>
 __global__ void __launch_bounds__(256) energy_global_kernel(gb_energy_args a) {
+  pdl_trigger();
   const int C = a.n_confs;
   const long long n_items = (long long)a.n_tuples[LV] * C;
   const bool want_grad = a.grad != nullptr;
@@ -591,6 +595,7 @@ __global__ void __launch_bounds__(256) energy_global_kernel(gb_energy_args a) {
 // ---------------------------------------------------------------------------------------------
 template <int LV>
 __global__ void __launch_bounds__(256) energy_bwd_kernel(gb_energy_bwd_args ba) {
+  pdl_trigger();
   const gb_energy_args& a = ba.fwd;
   const int C = a.n_confs;
   constexpr int L = LV == 0 ? 2 : (LV == 1 ? 3 : 4);

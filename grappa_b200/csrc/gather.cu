@@ -10,6 +10,7 @@ namespace gb {
 __global__ void __launch_bounds__(256) tuple_gather_fwd_kernel(const float* __restrict__ p, int ldp,
                                                                const int* __restrict__ idx, const float* __restrict__ pe,
                                                                float* __restrict__ x, int T, int L, int F, int E) {
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= (long long)L * T) return;
@@ -42,6 +43,7 @@ __global__ void __launch_bounds__(256) tuple_gather_bwd_kernel(const float* __re
                                                                const int* __restrict__ inv_ent, float* __restrict__ dp,
                                                                int ldp, int n_atoms, int T, int L, int F, int E,
                                                                int accumulate) {
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (n >= n_atoms) return;
@@ -65,6 +67,7 @@ __global__ void __launch_bounds__(256) tuple_gather_bwd_kernel(const float* __re
 __global__ void __launch_bounds__(128) tuple_gather_bwd_vec_kernel(const float* __restrict__ dx, const int* __restrict__ inv_ptr,
                                                                    const int* __restrict__ inv_ent, float* __restrict__ dp,
                                                                    int ldp, int T, int L, int F, int E, int accumulate) {
+  pdl_trigger();
   const int n = blockIdx.x;
   const int j0 = __ldg(inv_ptr + n), j1 = __ldg(inv_ptr + n + 1);
   const int nv = ldp >> 2, ev = E >> 2;
@@ -113,6 +116,7 @@ __global__ void __launch_bounds__(128) tuple_gather_bwd_vec_kernel(const float* 
 
 __global__ void __launch_bounds__(256) perm_concat_fwd_kernel(const float* __restrict__ x, float* __restrict__ s,
                                                               gb_perms perms, int T, int L, int E) {
+  pdl_trigger();
   // one thread per float4 of the output [n_perm*T, L*E]
   const int nv = E >> 2;
   const long long total = (long long)perms.n_perm * T * L * nv;
@@ -129,6 +133,7 @@ __global__ void __launch_bounds__(256) perm_concat_fwd_kernel(const float* __res
 
 __global__ void __launch_bounds__(256) perm_concat_bwd_kernel(const float* __restrict__ ds, float* __restrict__ dx,
                                                               gb_perms perms, int T, int L, int E) {
+  pdl_trigger();
   // one thread per float4 of dx [L*T, E]: sum over permutations of the slot that read position l
   const int nv = E >> 2;
   const long long total = (long long)L * T * nv;
@@ -174,8 +179,7 @@ extern "C" int grappa_b200_tuple_gather_bwd(const float* dx, const int32_t* inv_
   if (vec)
     tuple_gather_bwd_vec_kernel<<<n_atoms, 128, 0, (cudaStream_t)stream_>>>(dx, inv_ptr, inv_ent, dp, ldp, T, L, F, E, accumulate);
   else
-    tuple_gather_bwd_kernel<<<(n_atoms + 7) / 8, 256, 0, (cudaStream_t)stream_>>>(dx, inv_ptr, inv_ent, dp, ldp, n_atoms, T, L,
-                                                                                 F, E, accumulate);
+    tuple_gather_bwd_kernel<<<(n_atoms + 7) / 8, 256, 0, (cudaStream_t)stream_>>>(dx, inv_ptr, inv_ent, dp, ldp, n_atoms, T, L, F, E, accumulate);
   GB_CHECK_LAUNCH();
   return GB_OK;
 }

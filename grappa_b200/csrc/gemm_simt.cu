@@ -51,6 +51,7 @@ template <int TA, int TB>
 __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, const float* __restrict__ B, int M,
                                                     int N, int K, int lda, int ldb, bool vec_a, bool vec_b,
                                                     int k_chunk, float* __restrict__ partial, Epilogue ep) {
+  pdl_trigger();
   __shared__ __align__(16) float As[2][BK][BM + PAD];
   __shared__ __align__(16) float Bs[2][BK][BN + PAD];
   const int tid = threadIdx.x;
@@ -114,6 +115,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
 
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N,
                                                             Epilogue ep) {
+  pdl_trigger();
   const size_t total = (size_t)M * N;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     float s = 0.f;
@@ -125,6 +127,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
 // float4 variant (N % 4 == 0 and a 16-byte aligned epilogue): 4 slices in flight per thread, fixed summation order
 __global__ void __launch_bounds__(256) splitk_reduce_vec_kernel(const float4* __restrict__ partial, int splits, int M, int N,
                                                                 Epilogue ep) {
+  pdl_trigger();
   const int nv = N >> 2;
   const size_t total = (size_t)M * nv;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -154,6 +157,7 @@ struct ReduceGroup {
   Epilogue ep[4];
 };
 __global__ void __launch_bounds__(256) splitk_reduce_grouped_kernel(const __grid_constant__ ReduceGroup g) {
+  pdl_trigger();
   const int pi = blockIdx.y;
   const float4* __restrict__ partial = g.partial[pi];
   const int splits = g.splits[pi], N = g.N[pi];
@@ -248,6 +252,7 @@ constexpr int SK_MAX = 8;
 // C[m, n] = sum_k A[m, k] * B[n, k]   (N <= 8): one warp per row, B staged in shared memory
 __global__ void __launch_bounds__(256) skinny_n_kernel(const float* __restrict__ A, const float* __restrict__ B, int M, int N,
                                                        int K, int lda, int ldb, Epilogue ep) {
+  pdl_trigger();
   extern __shared__ float sB[];   // [N][K]
   for (int i = threadIdx.x; i < N * K; i += blockDim.x) sB[i] = __ldg(B + (size_t)(i / K) * ldb + (i % K));
   __syncthreads();
@@ -278,6 +283,7 @@ __global__ void __launch_bounds__(256) skinny_n_kernel(const float* __restrict__
 // C[m, n] = sum_{k < K} A[m, k] * B[k, n]   (K <= 8, B row-major [K, N]): one thread per output element
 __global__ void __launch_bounds__(256) skinny_k_kernel(const float* __restrict__ A, const float* __restrict__ B, int M, int N,
                                                        int K, int lda, int ldb, Epilogue ep) {
+  pdl_trigger();
   const size_t total = (size_t)M * N;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int m = (int)(i / N), n = (int)(i - (size_t)m * N);
@@ -294,6 +300,7 @@ __global__ void __launch_bounds__(256) skinny_k_kernel(const float* __restrict__
 __global__ void __launch_bounds__(256) skinny_m_stage1_kernel(const float* __restrict__ A, const float* __restrict__ B, int M,
                                                               int N, int K, int lda, int ldb, int rows_per_chunk,
                                                               float* __restrict__ partial) {
+  pdl_trigger();
   __shared__ float sA[64][SK_MAX];
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int k0 = blockIdx.y * rows_per_chunk, k1 = min(K, k0 + rows_per_chunk);
@@ -349,8 +356,7 @@ static bool skinny_gemm(const gb_gemm_args* a, const Epilogue& ep, cudaStream_t 
     if (chunks < 1) return false;
     const int rows_per_chunk = ((K + chunks - 1) / chunks + 63) / 64 * 64;
     chunks = (K + rows_per_chunk - 1) / rows_per_chunk;
-    skinny_m_stage1_kernel<<<dim3(col_blocks, chunks), 256, 0, stream>>>(a->A, a->B, M, N, K, a->lda, a->ldb, rows_per_chunk,
-                                                                       a->workspace);
+    skinny_m_stage1_kernel<<<dim3(col_blocks, chunks), 256, 0, stream>>>(a->A, a->B, M, N, K, a->lda, a->ldb, rows_per_chunk, a->workspace);
     count_launch();
     *rc = launch_splitk_reduce(a->workspace, chunks, M, N, ep, stream);
     return true;

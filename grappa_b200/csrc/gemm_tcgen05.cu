@@ -223,6 +223,7 @@ gemm_tf32_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Tc
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items = p.n_items;
 
+  if (threadIdx.x == 0) pdl_trigger();   // the next kernel's CTAs may start their prologue as SMs free up
   if (warp == 0 && lane == 0) {
     for (int g = 0; g < (GROUPED ? p.n_problems : 1); ++g) {
       asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&maps.a[g]) : "memory");
@@ -256,6 +257,7 @@ gemm_tf32_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Tc
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
+      pdl_wait();        // operands are written by the preceding kernel(s)
       uint32_t it = 0;   // running k-block counter across work items (ring position)
       for (int item = first_item; item < n_items; item += item_stride) {
         const int gi = GROUPED ? find_problem(p, item) : 0;
@@ -369,6 +371,7 @@ gemm_tf32_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Tc
     float* patch = epi + (warp - 2) * (32 * Cfg::EPI_LD);
     const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
     const uint32_t acc_empty_remote = PAIR ? mapa_rank(smem_u32(&acc_empty[0]), 0) : 0u;   // leader's acc_empty[0]
+    pdl_wait();          // side inputs are read and C / the split-K workspace written only after the preceding grid is done
     uint32_t lt = 0;
     for (int item = first_item; item < n_items; item += item_stride, ++lt) {
       const TcProblem& pq = p.pr[GROUPED ? find_problem(p, item) : 0];
@@ -517,23 +520,29 @@ static int launch(const TcMaps& maps, const TcParams& p, int grid, cudaStream_t 
     GB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN, TA, TB, CTAS, GROUPED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  if (CTAS == 1) {
-    gemm_tf32_kernel<BN, TA, TB, CTAS, GROUPED><<<grid, TC_THREADS, smem, stream>>>(maps, p);
-  } else {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid, 1, 1);
-    cfg.blockDim = dim3(TC_THREADS, 1, 1);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CTAS;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    GB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BN, TA, TB, CTAS, GROUPED>, maps, p));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(TC_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int n_attr = 0;
+  static const bool use_pdl = [] { const char* e = getenv("GRAPPA_B200_PDL"); return e ? atoi(e) != 0 : true; }();
+  if (use_pdl) {   // start while the preceding kernel of this stream drains (see pdl_trigger / pdl_wait in common.cuh)
+    attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+    ++n_attr;
   }
+  if (CTAS > 1) {
+    attr[n_attr].id = cudaLaunchAttributeClusterDimension;
+    attr[n_attr].val.clusterDim.x = CTAS;
+    attr[n_attr].val.clusterDim.y = 1;
+    attr[n_attr].val.clusterDim.z = 1;
+    ++n_attr;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n_attr;
+  GB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BN, TA, TB, CTAS, GROUPED>, maps, p));
   GB_CHECK_LAUNCH();
   return GB_OK;
 }

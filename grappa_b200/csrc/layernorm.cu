@@ -12,6 +12,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
                                                             const float* __restrict__ beta, float* __restrict__ y,
                                                             float* __restrict__ mean, float* __restrict__ rstd, int rows,
                                                             int cols, float eps) {
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -63,6 +64,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
                                                             const float* __restrict__ gamma, float* __restrict__ dx,
                                                             int rows, int cols) {
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -106,6 +108,7 @@ __global__ void __launch_bounds__(256) col_reduce_kernel(const float* __restrict
                                                          float* __restrict__ part_sum, float* __restrict__ part_xhat,
                                                          unsigned int* __restrict__ tickets, float* __restrict__ out_sum,
                                                          float* __restrict__ out_xhat, int rows, int cols, int accumulate) {
+  pdl_trigger();
   __shared__ float sh[2][8][33];
   __shared__ bool is_last;
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
@@ -193,6 +196,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_fused_kernel(const float* _
                                                                   const float* __restrict__ gamma, float* __restrict__ dx,
                                                                   float* __restrict__ partial, int rows, int cols,
                                                                   int rows_per_cta) {
+  pdl_trigger();
   extern __shared__ float sm[];   // [8 warps][2][cols]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nvec = cols >> 2;
@@ -262,6 +266,7 @@ __global__ void __launch_bounds__(256) act_dropout_bwd_fused_kernel(const float*
                                                                     int rows, int cols, int rows_per_cta, uint32_t thresh,
                                                                     float inv_keep, uint64_t seed0,
                                                                     const uint64_t* __restrict__ seed_off) {
+  pdl_trigger();
   __shared__ float4 sh[256];
   const uint64_t seed = seed_with_offset(seed0, seed_off);
   const int ncg = cols >> 2;                 // float4 column groups (<= 256)
@@ -303,6 +308,7 @@ __global__ void __launch_bounds__(256) act_dropout_bwd_fused_kernel(const float*
 // out[c] (+)= sum_{p < n_part} partial[p * stride + c]   for every descriptor; grid = (column chunks of 64, n_desc).
 // 4 lanes share a column (partial rows p = lane, lane + 4, ...), combined in a fixed order.
 __global__ void __launch_bounds__(256) finalize_colsums_kernel(gb_colsum_batch batch) {
+  pdl_trigger();
   const gb_colsum_desc d = batch.desc[blockIdx.y];
   const int c = blockIdx.x * 64 + (threadIdx.x >> 2);
   const int sub = threadIdx.x & 3;
@@ -436,8 +442,7 @@ extern "C" int grappa_b200_act_dropout_bwd_fused(const float* dy, const float* a
     if (thresh == 0) thresh = 1;
   }
   const int rpc = (rows + n_cta - 1) / n_cta;
-  act_dropout_bwd_fused_kernel<<<n_cta, 256, 0, (cudaStream_t)stream_>>>(dy, act_out, dx, partial, rows, cols, rpc, thresh,
-                                                                         1.f / (1.f - p), seed, seed_offset);
+  act_dropout_bwd_fused_kernel<<<n_cta, 256, 0, (cudaStream_t)stream_>>>(dy, act_out, dx, partial, rows, cols, rpc, thresh, 1.f / (1.f - p), seed, seed_offset);
   GB_CHECK_LAUNCH();
   return GB_OK;
 }

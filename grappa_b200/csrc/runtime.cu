@@ -1,4 +1,6 @@
 // Device-property cache and small runtime helpers shared by all kernels.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 #include <atomic>

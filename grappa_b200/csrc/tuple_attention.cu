@@ -22,6 +22,7 @@ __device__ __forceinline__ float4 fma4(float s, float4 a, float4 b) {
 template <int L>
 __global__ void __launch_bounds__(256) tuple_attn_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out, int T,
                                                              int heads, int HD) {
+  pdl_trigger();
   const int gs = HD >> 2;
   const int groups_per_warp = 32 / gs;
   const int lane = threadIdx.x & 31;
@@ -68,6 +69,7 @@ __global__ void __launch_bounds__(256) tuple_attn_fwd_kernel(const float* __rest
 template <int L>
 __global__ void __launch_bounds__(256) tuple_attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ dout,
                                                              float* __restrict__ dqkv, int T, int heads, int HD) {
+  pdl_trigger();
   const int gs = HD >> 2;
   const int groups_per_warp = 32 / gs;
   const int lane = threadIdx.x & 31;
