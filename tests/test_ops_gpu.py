@@ -389,3 +389,74 @@ def test_param_loss_term_matches_reference_fixture():
             assert R(gr, torch.from_numpy(z[f"{v}.grad.{k}"])) < 1e-5, k
         uni = MolwiseLoss(gradient_weight=0., energy_weight=0., param_weight=1e-3)(g)
         assert abs(uni.item() - float(z[f"{v}.loss_uniform"])) < 1e-5 * abs(float(z[f"{v}.loss_uniform"]))
+
+
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(1664, 512, 2048), (700, 256, 1024), (300, 1536, 1100)])
+def test_gemm_tf32_cta_pair_all_layouts(ta, tb, M, N, K):
+    """K >= 1024 selects the cta_group::2 kernel (a cluster of two CTAs per 256-row tile, ragged last pair)."""
+    from grappa_b200 import ops
+    dev = "cuda"
+    A = torch.randn((K, M) if ta else (M, K), device=dev)
+    B = torch.randn((K, N) if tb else (N, K), device=dev)
+    bias = torch.randn(N, device=dev)
+    res = torch.randn(M, N, device=dev)
+    ref = (A.double().T if ta else A.double()) @ (B.double() if tb else B.double().T) + bias.double() + res.double()
+    out = ops.gemm(A, B, trans_a=ta, trans_b=tb, bias=bias, residual=res, precision=ops.TF32)
+    assert R(out, ref) < 1e-3
+
+
+def test_gemm_grouped_matches_separate_launches():
+    """grappa_b200_gemm_grouped == the same problems through grappa_b200_gemm (weight gradients of one layer: different
+    output shapes and reduction lengths, split-K partials in one shared workspace, accumulate into an existing gradient)."""
+    from grappa_b200 import ops
+    dev = "cuda"
+    shapes = [(512, 512, 14848), (1536, 512, 14848), (512, 512, 3264), (256, 2048, 1920), (512, 256, 1664)]
+    probs, refs = [], []
+    for i, (M, N, K) in enumerate(shapes):
+        dY = torch.randn(K, M, device=dev)
+        X = torch.randn(K, N, device=dev)
+        out = torch.randn(M, N, device=dev)
+        acc = i % 2 == 1
+        ref = ops.gemm(dY, X, trans_a=True, trans_b=True, out=out.clone(), accumulate=acc, precision=ops.TF32)
+        exact = dY.double().T @ X.double() + (out.double() if acc else 0)
+        assert R(ref, exact) < 1e-3
+        probs.append((dY, X, dict(trans_a=True, trans_b=True, out=out, accumulate=acc, precision=ops.TF32)))
+        refs.append(exact)
+    ops.gemm_grouped(probs)
+    for (_, _, kw), exact in zip(probs, refs):
+        assert R(kw["out"], exact) < 1e-3
+    # fp32 requests fall back to one launch per problem inside the same entry point
+    probs32 = [(d, x, dict(kw, out=torch.empty_like(kw["out"]), accumulate=False, precision=ops.FP32)) for d, x, kw in probs[2:]]
+    ops.gemm_grouped(probs32)
+    for (d, x, kw) in probs32:
+        assert R(kw["out"], d.double().T @ x.double()) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,K,ta,tb", [(7424, 6, 256, False, False), (3264, 2, 256, False, False),
+                                         (7424, 256, 6, False, True), (5760, 256, 2, False, True),
+                                         (6, 256, 7424, True, True), (2, 256, 3264, True, True)])
+def test_skinny_gemm_kernels(M, N, K, ta, tb):
+    """Last symmetriser layer (2 / 6 outputs): forward N <= 8, input gradient K <= 8, weight gradient M <= 8."""
+    from grappa_b200 import ops
+    dev = "cuda"
+    A = torch.randn((K, M) if ta else (M, K), device=dev)
+    B = torch.randn((K, N) if tb else (N, K), device=dev)
+    bias = torch.randn(N, device=dev)
+    ref = (A.double().T if ta else A.double()) @ (B.double() if tb else B.double().T) + bias.double()
+    for prec in (ops.FP32, ops.AUTO):   # AUTO = what set_matmul_precision('tf32') selects
+        out = ops.gemm(A, B, trans_a=ta, trans_b=tb, bias=bias, precision=prec)
+        assert R(out, ref) < 1e-5      # these shapes always run on the fp32 streaming kernels
+
+
+def test_pad_rows_and_padded_pre_dense():
+    from grappa_b200 import ops
+    dev = "cuda"
+    W = torch.randn(512, 85, device=dev)
+    Wp = ops.pad_rows(W, 88)
+    assert Wp.shape == (512, 88) and torch.equal(Wp[:, :85], W) and Wp[:, 85:].abs().max() == 0
+    X = torch.zeros(1664, 88, device=dev)
+    X[:, :85] = torch.randn(1664, 85, device=dev)
+    ref = X[:, :85].double() @ W.double().T
+    got = ops.gemm(X, Wp, k=88, precision=ops.AUTO)
+    assert R(got, ref) < 1e-3
