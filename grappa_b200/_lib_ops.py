@@ -85,6 +85,8 @@ class ParamLossArgs(C.Structure):
 def declare(lib):
     P = C.POINTER
     lib.grappa_b200_gemm.argtypes = [P(GemmArgs), vp]
+    lib.grappa_b200_neighbor_mean.argtypes = [vp, i32, vp, vp, vp, i32, i32, i32, i32, vp]
+    lib.grappa_b200_neighbor_mean.restype = C.c_int
     lib.grappa_b200_pad_rows.argtypes = [vp, i32, i32, i32, vp, i32, vp]
     lib.grappa_b200_pad_rows.restype = C.c_int
     lib.grappa_b200_gemm_grouped.argtypes = [P(GemmArgs), i32, vp]

@@ -19,8 +19,10 @@ struct Epilogue {
   const uint64_t* drop_offset;   // device counter mixed into the seed (CUDA-graph replays), or NULL
 
   __device__ __forceinline__ uint64_t seed() const { return seed_with_offset(drop_seed, drop_offset); }
+  // accumulate == 2: the old C joins the accumulator BEFORE bias / activation (two Linear layers under one activation)
   __device__ __forceinline__ float apply(float acc, int m, int n) const {
     float v = acc;
+    if (accumulate == 2) v += C[(size_t)m * ldc + n];
     if (bias) v += __ldg(bias + n);
     if (act == 1) v = elu1(v);
     if (act_out) act_out[(size_t)m * ldact + n] = v;
@@ -39,6 +41,10 @@ struct Epilogue {
   template <bool FAST>
   __device__ __forceinline__ void store4(float4 acc, int m, int n) const {
     float v[4] = {acc.x, acc.y, acc.z, acc.w};
+    if (accumulate == 2) {
+      const float4 o = *reinterpret_cast<const float4*>(C + (size_t)m * ldc + n);
+      v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;
+    }
     if (!FAST && bias) {
       const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n));
       v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
@@ -69,7 +75,7 @@ struct Epilogue {
       v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
     }
     float4* c = reinterpret_cast<float4*>(C + (size_t)m * ldc + n);
-    if (accumulate) {
+    if (accumulate == 1) {
       const float4 o = *c;
       v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;
     }
@@ -78,6 +84,10 @@ struct Epilogue {
   // tensor-core path: bias already added, residual / saved-activation values already loaded by the caller
   __device__ __forceinline__ void store4_pre(float4 acc, int m, int n, const float4& res, const float4& y) const {
     float v[4] = {acc.x, acc.y, acc.z, acc.w};
+    if (accumulate == 2) {
+      const float4 o = *reinterpret_cast<const float4*>(C + (size_t)m * ldc + n);
+      v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;
+    }
     if (act == 1) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) v[i] = v[i] > 0.f ? v[i] : __expf(v[i]) - 1.f;
@@ -93,7 +103,7 @@ struct Epilogue {
     }
     if (residual) { v[0] += res.x; v[1] += res.y; v[2] += res.z; v[3] += res.w; }
     float4* c = reinterpret_cast<float4*>(C + (size_t)m * ldc + n);
-    if (accumulate) {
+    if (accumulate == 1) {
       const float4 o = *c;
       v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;
     }
@@ -102,7 +112,7 @@ struct Epilogue {
   __device__ __forceinline__ void store(float acc, int m, int n) const {
     float v = apply(acc, m, n);
     float* c = C + (size_t)m * ldc + n;
-    if (accumulate) v += *c;
+    if (accumulate == 1) v += *c;
     *c = v;
   }
 };

@@ -146,6 +146,51 @@ class ResidualAttentionBlock(nn.Module):
                          dropout_p=self.p2, residual=z)
 
 
+class SAGEConv(nn.Module):
+    """Parameters of dgl.nn.SAGEConv(in, out, 'mean') as the oracle's dgl shim restates it (DGL is unpinned and absent:
+    `fc_self` Linear with bias, bias-free `fc_neigh`; rst = fc_self(h) + fc_neigh(mean_{u in N(v)} h_u)).  DGL >= 1.1
+    keeps the bias as a separate `bias` parameter: such state_dicts are remapped on load."""
+
+    def __init__(self, in_feats, out_feats, aggregator_type="mean"):
+        super().__init__()
+        if aggregator_type != "mean":
+            raise NotImplementedError("only the 'mean' aggregator (the one grappa uses) is implemented")
+        self.fc_self = nn.Linear(in_feats, out_feats)
+        self.fc_neigh = nn.Linear(in_feats, out_feats, bias=False)
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        if prefix + "bias" in state_dict and prefix + "fc_self.bias" not in state_dict:
+            state_dict[prefix + "fc_self.bias"] = state_dict.pop(prefix + "bias")
+        return super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+
+class ResidualConvBlock(nn.Module):
+    """grappa-1.0 convolution block (reference models/graph_attention.py:314-415): u = LN(h);
+    y = dropout(ELU(SAGEConv(u))) + u; z = LN(y); out = dropout(ELU(W z + b)) + z."""
+
+    def __init__(self, in_feats, out_feats=None, self_interaction=True, layer_norm=True, dropout=0.0, skip_connection=True):
+        super().__init__()
+        out_feats = in_feats if out_feats is None else out_feats
+        if not (layer_norm and self_interaction and skip_connection and out_feats == in_feats):
+            raise NotImplementedError("grappa_b200 implements the grappa-1.0 block: layer_norm, self_interaction and "
+                                      "skip connection enabled, out_feats == in_feats")
+        self.in_feats, self.out_feats, self.p = in_feats, out_feats, dropout
+        self.graph_module = SAGEConv(in_feats, out_feats, "mean")
+        self.layer_norm = nn.LayerNorm(in_feats)
+        self.self_interaction = nn.Sequential(nn.Linear(out_feats, out_feats), nn.ELU())
+        self.interaction_norm = nn.LayerNorm(out_feats)
+
+    def tape_forward(self, t: Tape, pack, h: Var, P) -> Var:
+        u = T_.layernorm(t, h, P(self.layer_norm.weight), P(self.layer_norm.bias))
+        s_self = T_.linear(t, u, P(self.graph_module.fc_self.weight), None)
+        hn = T_.neighbor_mean(t, u, pack)
+        y = T_.linear(t, hn, P(self.graph_module.fc_neigh.weight), P(self.graph_module.fc_self.bias), act=ELU,
+                      dropout_p=self.p, residual=u, pre_add=s_self)
+        z = T_.layernorm(t, y, P(self.interaction_norm.weight), P(self.interaction_norm.bias))
+        return T_.linear(t, z, P(self.self_interaction[0].weight), P(self.self_interaction[0].bias), act=ELU,
+                         dropout_p=self.p, residual=z)
+
+
 class GrappaGNN(nn.Module):
     """Atom featurisation -> residual graph-attention blocks -> atom embedding g.nodes['n1'].data['h']."""
 
@@ -155,9 +200,6 @@ class GrappaGNN(nn.Module):
                  final_dropout: float = 0., initial_dropout: float = 0., layer_norm: bool = True,
                  self_interaction: bool = True, charge_encoding=True):
         super().__init__()
-        if n_conv != 0:
-            raise NotImplementedError("SAGEConv blocks (gnn_convolutions > 0) are only used by grappa-1.0 and are not "
-                                      "implemented in grappa_b200 (SURVEY.md section 8a, row a5)")
         self.charge_encoding = charge_encoding
         if not isinstance(in_feat_name, list):
             in_feat_name = [in_feat_name]
@@ -174,7 +216,8 @@ class GrappaGNN(nn.Module):
         self.pre_dense = nn.Sequential(nn.Linear(self.in_feats, node_feats), nn.ELU())
         self.no_convs = (n_conv + n_att) == 0
         if not self.no_convs:
-            self.conv_blocks = nn.ModuleList([])
+            self.conv_blocks = nn.ModuleList([
+                ResidualConvBlock(node_feats, node_feats, self_interaction, layer_norm, conv_dropout) for _ in range(n_conv)])
             self.att_blocks = nn.ModuleList([
                 ResidualAttentionBlock(node_feats, node_feats, n_heads, self_interaction, layer_norm, attention_dropout,
                                        attention_dropout, True) for _ in range(n_att)])
@@ -193,6 +236,8 @@ class GrappaGNN(nn.Module):
             h = T_.linear(t, x, P(self.pre_dense[0].weight), P(self.pre_dense[0].bias), act=ELU,
                           dropout_p=self.p_initial, k=self.in_feats, x_pad_is_zero=True)   # featurize zero-fills the pad
             if not self.no_convs:
+                for blk in self.conv_blocks:                     # grappa-1.0 only; their gradients are final with 'gnn_rest'
+                    h = blk.tape_forward(t, pack, h, P)
                 for i, blk in enumerate(self.att_blocks):
                     if _BACKWARD_HOOK is not None:               # runs after block i's backward ops
                         t.push(lambda i=i: (t.join_side(), _fire(("gnn_block", i))))

@@ -130,7 +130,7 @@ def _gemm_args(a: torch.Tensor, b: torch.Tensor, *, trans_a=False, trans_b=False
     g.dropout_offset = _rng_ptr() if dropout_p > 0.0 else 0
     g.residual = _p(residual)
     g.ldr = residual.stride(0) if residual is not None else 0
-    g.accumulate = int(accumulate)
+    g.accumulate = int(accumulate)          # 0 overwrite, 1 C += result, 2 old C added before bias / activation
     g.act_out = _p(act_out)
     g.ldact = act_out.stride(0) if act_out is not None else 0
     g.precision = _precision if precision is None else precision
@@ -186,6 +186,17 @@ def gemm_grouped(problems) -> None:
         _gemm_profile.append((flops, e0, e1, ("grouped",) + tuple(shapes)))
         return
     _lib.check(lib.grappa_b200_gemm_grouped(arr, len(problems), _s()), "gemm_grouped")
+
+
+def neighbor_mean(x: torch.Tensor, pack, transpose: bool = False) -> torch.Tensor:
+    """SAGEConv('mean') aggregation over the bonded graph (mode 0) or its transpose (backward, mode 1)."""
+    lib = _lib.lib()
+    _lib.require_cuda(x)
+    assert x.dim() == 2 and x.stride(1) == 1
+    out = torch.empty((x.shape[0], x.shape[1]), device=x.device, dtype=torch.float32)
+    _lib.check(lib.grappa_b200_neighbor_mean(x.data_ptr(), x.stride(0), pack.ptr("indptr"), pack.ptr("esrc"), out.data_ptr(),
+                                             out.stride(0), x.shape[0], x.shape[1], int(transpose), _s()), "neighbor_mean")
+    return out
 
 
 def pad_rows(w: torch.Tensor, ld: int) -> torch.Tensor:

@@ -186,9 +186,11 @@ def add_grad(var: Var, g: torch.Tensor):
 # --------------------------------------------------------------------------------------------------
 def linear(t: Tape, x: Var, W: torch.Tensor, b: Optional[torch.Tensor], *, act: int = 0, dropout_p: float = 0.0,
            residual: Optional[Var] = None, k: Optional[int] = None, out_ld: Optional[int] = None,
-           fuse_elu_into_consumer: bool = False, x_pad_is_zero: bool = False) -> Var:
-    """y = dropout(act(x[:, :k] W^T + b)) + residual.  `out_ld` > N gives a padded output buffer.  `x_pad_is_zero`:
-    the columns of x beyond k (up to the next multiple of 4) hold zeros."""
+           fuse_elu_into_consumer: bool = False, x_pad_is_zero: bool = False, pre_add: Optional[Var] = None) -> Var:
+    """y = dropout(act(x[:, :k] W^T + b + pre_add)) + residual.  `out_ld` > N gives a padded output buffer.
+    `x_pad_is_zero`: the columns of x beyond k (up to the next multiple of 4) hold zeros.  `pre_add`: a value added
+    under the activation (the output of another bias-free linear: SAGEConv's fc_self + fc_neigh); its buffer is reused
+    as the output, so it must have no other consumer."""
     xv = x.v
     N = W.shape[0]
     K = k if k is not None else W.shape[1]
@@ -200,6 +202,9 @@ def linear(t: Tape, x: Var, W: torch.Tensor, b: Optional[torch.Tensor], *, act: 
         buf = torch.zeros((M, out_ld), device=xv.device, dtype=torch.float32)
         out = buf[:, :N]
         assert p == 0.0, "dropout on a padded output is not supported"
+    elif pre_add is not None:
+        assert tuple(pre_add.v.shape) == (M, N) and pre_add.v.is_contiguous()
+        buf = out = pre_add.v
     else:
         buf = torch.empty((M, N), device=xv.device, dtype=torch.float32)
         out = buf
@@ -212,7 +217,7 @@ def linear(t: Tape, x: Var, W: torch.Tensor, b: Optional[torch.Tensor], *, act: 
         # the activation buffer already carries zero pad columns (featurize), so the product is unchanged
         Wf, Kf = ops.pad_rows(W, K4), K4
     ops.gemm(xv, Wf, bias=b, act=act, dropout_p=p, dropout_seed=seed, residual=None if residual is None else residual.v,
-             out=out, k=Kf, m=M, n=N, act_out=act_out)
+             out=out, k=Kf, m=M, n=N, act_out=act_out, accumulate=2 if pre_add is not None else False)
     y = Var(buf)
     if act != 0 and p == 0.0 and residual is None and fuse_elu_into_consumer:
         y.elu_fusable = True
@@ -238,6 +243,8 @@ def linear(t: Tape, x: Var, W: torch.Tensor, b: Optional[torch.Tensor], *, act: 
         else:
             dpre_full = dy_full
         dpre = dpre_full[:, :N] if dpre_full.shape[1] != N else dpre_full
+        if pre_add is not None:
+            add_grad(pre_add, dpre_full)
         # weight / bias gradients (parallel branch; the GEMMs are queued and issued four at a time)
         tgt, acc = t.grad_target(W)
         if tgt is None:
@@ -321,6 +328,19 @@ def edge_attention(t: Tape, ft: Var, pack, heads: int) -> Var:
         if y.g is None:
             return
         add_grad(ft, ops.edge_attention_bwd(ft.v, alpha, y.g, pack, heads))
+
+    t.push(bwd)
+    return y
+
+
+def neighbor_mean(t: Tape, x: Var, pack) -> Var:
+    """SAGEConv('mean') aggregation: y[v] = mean over bonded neighbours of x."""
+    y = Var(ops.neighbor_mean(x.v, pack))
+
+    def bwd():
+        if y.g is None:
+            return
+        add_grad(x, ops.neighbor_mean(y.g.contiguous(), pack, transpose=True))
 
     t.push(bwd)
     return y

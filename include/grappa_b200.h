@@ -156,7 +156,8 @@ typedef struct {
                                      graph draw a fresh mask on every replay (see grappa_b200_tick) */
 } gb_gemm_args;
 
-int grappa_b200_gemm(const gb_gemm_args* a, void* stream);
+int grappa_b200_gemm(const gb_gemm_args* a, void* stream);   /* accumulate: 0 = overwrite C, 1 = C += epilogue(acc), 2 = the old C is added to the
+                                                                * accumulator BEFORE bias / activation (sum of two Linear layers under one activation) */
 /* n independent GEMMs in as few launches as possible: runs of up to 4 tensor-core problems with the same operand
  * layouts, tile configuration and workspace share ONE persistent kernel (work items numbered problem by problem, split-K
  * slices sized so that all problems together fill the SMs once) and one reduce launch; everything else falls back to
@@ -218,6 +219,11 @@ int grappa_b200_finalize_colsums(const gb_colsum_batch* batch, void* stream);
  * CSR by destination: indptr[n+1], esrc[E]; erev[e] = position of the reverse edge.
  * ft/out/dout/dft: [n_nodes, heads*dim]; alpha, ds: [E, heads].
  * ------------------------------------------------------------------------------------------- */
+/* SAGEConv('mean') neighbour aggregation of grappa-1.0's ResidualConvBlock (reference models/graph_attention.py:314-415,
+ * dgl.nn.SAGEConv): mode 0: out[v] = mean_{u in N(v)} x[u];  mode 1 (backward; bonded graphs are symmetric):
+ * out[u] = sum_{v in N(u)} x[v] / deg(v).  CSR by destination as for edge attention; rows of `width` floats. */
+int grappa_b200_neighbor_mean(const float* x, int32_t ldx, const int32_t* indptr, const int32_t* esrc, float* out,
+                              int32_t ldo, int32_t n_nodes, int32_t width, int32_t mode, void* stream);
 int grappa_b200_edge_attention_fwd(const float* ft, const int32_t* indptr, const int32_t* esrc, float* out,
                                    float* alpha, int32_t n_nodes, int32_t heads, int32_t dim, void* stream);
 int grappa_b200_edge_attention_bwd(const float* ft, const float* alpha, const float* dout, const int32_t* indptr,

@@ -113,8 +113,22 @@ def gnn_forward(sd, g, cfg, prefix: str = "gnn.", dtype=torch.float32, taps: dic
     src, dst = g.edges(etype="n1_edge")
     src, dst = src.long(), dst.long()
     heads = cfg["gnn_attention_heads"]
+    n_conv = cfg.get("gnn_convolutions", 0)
+    for i in range(n_conv):
+        # ResidualConvBlock.forward (graph_attention.py:378-415) around dgl.nn.SAGEConv(in, out, 'mean') as restated in
+        # oracle/dgl_shim (fc_self with bias + bias-free fc_neigh on the mean over in-neighbours)
+        p = f"{prefix}conv_blocks.{i}."
+        u = layer_norm(sd, p + "layer_norm", h)
+        agg = torch.zeros_like(u).index_add(0, dst, u[src])
+        deg = torch.zeros(len(u), dtype=u.dtype).index_add(0, dst, torch.ones(len(dst), dtype=u.dtype)).clamp(min=1)
+        conv = linear(sd, p + "graph_module.fc_self", u) + F.linear(agg / deg[:, None], sd[p + "graph_module.fc_neigh.weight"].to(dtype))
+        y = F.elu(conv) + u
+        z = layer_norm(sd, p + "interaction_norm", y)
+        h = F.elu(linear(sd, p + "self_interaction.0", z)) + z
+        if taps is not None:
+            taps[f"conv{i}"] = h
     for i in range(cfg["gnn_attentional_layers"]):
-        p = f"{prefix}att_blocks.{i}."
+        p = f"{prefix}att_blocks.{i}."          # same parameters as blocks.{n_conv + i} (graph_attention.py:129)
         u = layer_norm(sd, p + "layer_norm", h)
         ft = F.linear(u, sd[p + "graph_module.fc.weight"].to(dtype)).view(len(u), heads, -1)
         m = dot_gat(ft, src, dst).flatten(1)

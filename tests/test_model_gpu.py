@@ -223,3 +223,38 @@ def test_product_path_has_no_cpu_fallback():
     model = models.model_from_config(orc.small_model_config())
     with pytest.raises(GrappaB200Error):
         model(synthetic.dipeptide(seed=0, n_confs=2))          # CPU graph -> loud failure
+
+
+def test_conv_block_model_matches_oracle_forward_and_gradients():
+    """GNN with SAGEConv('mean') convolution blocks (grappa-1.0 layout) -- forward and parameter
+    gradients against the CPU oracle (which tests/test_oracle.py pins against the live reference on the dgl shim)."""
+    import grappa_oracle as orc
+    from grappa_b200 import ops, synthetic
+    from grappa_b200.energy import Energy
+    from grappa_b200.loss import MolwiseLoss
+    ops.set_matmul_precision("fp32")
+    cfg = orc.small_model_config()
+    cfg.update(gnn_convolutions=2, gnn_attentional_layers=1)
+    model = _model(cfg, seed=11).eval()
+    g = synthetic.espaloma_mix_batch(seed=6, batch_size=4, n_confs=5)
+    sd = {k: v.detach().cpu().double().requires_grad_(v.is_floating_point() and "conv_blocks" in k)
+          for k, v in model.state_dict().items()}
+    h, params, en = orc.path_forward(sd, g, cfg, dtype=torch.float64, create_graph=True)
+    ref_loss = orc.molwise_loss(en, params, g)
+    leaves = {k: v for k, v in sd.items() if v.requires_grad}
+    ref_grads = dict(zip(leaves, torch.autograd.grad(ref_loss, list(leaves.values()))))
+    gd = torch.nn.Sequential(model, Energy(write_tuple_terms=False))(g.to("cuda"))
+    assert rel_err(gd.nodes["n1"].data["h"].detach().cpu().numpy(), h.detach().numpy()) < 1e-5
+    assert rel_err(gd.nodes["g"].data["energy"].detach().cpu().numpy(), en["energy"].detach().numpy()) < 1e-5
+    loss = MolwiseLoss(gradient_weight=0.8, energy_weight=1.0, param_weight=0.0, proper_regularisation=1e-3,
+                       improper_regularisation=1e-3)(gd)
+    assert abs(loss.item() - float(ref_loss)) < 1e-5 * abs(float(ref_loss))
+    model.zero_grad()
+    loss.backward()
+    named = dict(model.named_parameters())
+    checked = 0
+    for k, gr in ref_grads.items():
+        if k in named:      # `blocks.*` aliases of conv_blocks.* share the parameter
+            assert rel_err(named[k].grad.cpu().numpy(), gr.numpy()) < 1e-4, k
+            checked += 1
+    assert checked >= 16

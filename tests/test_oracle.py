@@ -124,3 +124,30 @@ def test_oracle_param_loss_vs_reference_fixture():
         grads = torch.autograd.grad(loss, [prm[k.split(".")[0]][k.split(".")[1]] for k in keys])
         for k, gr in zip(keys, grads):
             assert rel_err(gr.numpy(), z[f"{v}.grad.{k}"]) < 1e-5, k
+
+
+def test_oracle_conv_blocks_vs_live_reference():
+    """grappa-1.0 style GNN (gnn_convolutions > 0: ResidualConvBlock around SAGEConv('mean')):
+    oracle restatement vs the unmodified reference running on the dgl shim; also the state_dict key set."""
+    from ref_import import import_reference, no_dihedral_noise, reference_available, to_reference_graph
+    if not reference_available():
+        pytest.skip("/root/reference not mounted (GPU box)")
+    from grappa_b200 import models, synthetic
+    ns = import_reference()
+    cfg = orc.small_model_config()
+    cfg.update(gnn_convolutions=2, gnn_attentional_layers=1)
+    torch.manual_seed(0)
+    ref = ns.deploy.model_from_config(dict(cfg), param_statistics=ns.graph_utils.get_default_statistics()).eval()
+    sd = {k: v.clone() for k, v in ref.state_dict().items()}
+    ours = models.model_from_config(dict(cfg))
+    assert sorted(ours.state_dict().keys()) == sorted(sd.keys())
+    assert all(tuple(ours.state_dict()[k].shape) == tuple(v.shape) for k, v in sd.items())
+    g = synthetic.espaloma_mix_batch(seed=4, batch_size=3, n_confs=4)
+    dg = to_reference_graph(ns, g)
+    with no_dihedral_noise():
+        dg = torch.nn.Sequential(ref, ns.energy.Energy())(dg)
+    h, params, en = orc.path_forward(sd, g, cfg)
+    assert rel_err(h.detach().numpy(), dg.nodes["n1"].data["h"].detach().numpy()) < 2e-5
+    assert rel_err(en["energy"].detach().numpy(), dg.nodes["g"].data["energy"].detach().numpy()) < 1e-5
+    for l in LEVELS:
+        assert rel_err(params[l]["k"].detach().numpy(), dg.nodes[l].data["k"].detach().numpy()) < 2e-5
