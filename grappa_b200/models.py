@@ -582,10 +582,9 @@ class WriteTorsionParameters(_TupleWriter):
                  param_statistics=None, positional_encoding=True, gated: bool = False, learnable_statistics: bool = False,
                  wrong_symmetry: bool = False, cutoff=1e-4):
         super().__init__()
-        if wrong_symmetry:
-            raise NotImplementedError("wrong_symmetry=True (ablation only) is not supported by grappa_b200")
         if learnable_statistics:
             raise NotImplementedError("learnable_statistics=True is not supported by grappa_b200")
+        self.wrong_symmetry = wrong_symmetry
         EPS = 1e-1 if gated else 1e-2
         st = get_default_statistics() if param_statistics is None else param_statistics
         self.gated, self.improper, self.suffix = gated, improper, suffix
@@ -610,6 +609,11 @@ class WriteTorsionParameters(_TupleWriter):
         symmetriser_feats = between_feats if symmetriser_feats is None else symmetriser_feats
         attention_hidden_feats = 4 * between_feats if attention_hidden_feats is None else attention_hidden_feats
         perms = torch.tensor([[0, 1, 2, 3], [3, 1, 2, 0]] if improper else [[0, 1, 2, 3], [3, 2, 1, 0]], dtype=torch.int32)
+        if improper and wrong_symmetry:
+            # ablation (interaction_parameters.py:499-505): every permutation that keeps the central atom (index 2) fixed
+            perms = torch.tensor([[0, 1, 2, 3], [3, 1, 2, 0], [1, 3, 2, 0], [0, 3, 2, 1], [3, 0, 2, 1], [1, 0, 2, 3]], dtype=torch.int32)
+            positional_encoding = torch.tensor([[0], [0], [1], [0]], dtype=torch.float32)
+        self._n_perm = int(perms.shape[0])
         n_out = 2 * n_periodicity if gated else n_periodicity
         self.torsion_model = SymmetrisedTransformer(proj_feats, n_heads, attention_hidden_feats, n_att, n_out, perms,
                                                     layer_norm, dropout, dense_layers, symmetriser_feats,
@@ -618,7 +622,7 @@ class WriteTorsionParameters(_TupleWriter):
 
     def _head_args(self, T):
         n = self._n_per
-        a = HeadOutArgs(kind=2, T=T, n_perm=2, n_out=(2 * n if self.gated else n), n_per=n, gated=int(self.gated))
+        a = HeadOutArgs(kind=2, T=T, n_perm=self._n_perm, n_out=(2 * n if self.gated else n), n_per=n, gated=int(self.gated))
         std, mean = self._host("kstd", self.k_std), self._host("kmean", self.k_mean)
         for i in range(n):
             a.tk_std[i], a.tk_mean[i] = std[i], mean[i]

@@ -166,8 +166,13 @@ def writer_scores(sd, h, idxs, level, cfg, prefix="parameter_writer.", taps: dic
     proj = F.elu(linear(sd, p + "rep_projector.mlp.0", h))
     x = proj[idxs.long()].transpose(0, 1)                                  # (L, T, F)
     T = x.shape[1]
-    if POS_ENC[level] is not None and cfg.get("positional_encoding", True):
-        pe = torch.tensor(POS_ENC[level], dtype=x.dtype)[:, None, None].expand(L, T, 1)
+    perms, pos_enc = PERMS[level], POS_ENC[level]
+    if level == "n4_improper" and cfg.get("wrong_symmetry", False):
+        # ablation switch (interaction_parameters.py:499-505): all permutations that keep the central atom fixed
+        perms = [[0, 1, 2, 3], [3, 1, 2, 0], [1, 3, 2, 0], [0, 3, 2, 1], [3, 0, 2, 1], [1, 0, 2, 3]]
+        pos_enc = [0.0, 0.0, 1.0, 0.0]
+    if pos_enc is not None and cfg.get("positional_encoding", True):
+        pe = torch.tensor(pos_enc, dtype=x.dtype)[:, None, None].expand(L, T, 1)
         x = torch.cat([x, pe], dim=-1)
     n_heads = cfg[f"{short}_n_heads"]
     for i in range(cfg[f"{short}_transformer_depth"]):
@@ -180,7 +185,7 @@ def writer_scores(sd, h, idxs, level, cfg, prefix="parameter_writer.", taps: dic
             taps[f"{level}_layer{i}"] = x
     out = 0.0
     depth = cfg[f"{short}_symmetriser_depth"]
-    for perm in PERMS[level]:
+    for perm in perms:
         s = torch.cat([x[j] for j in perm], dim=-1)                        # (T, L*E)
         for i in range(depth):
             q = f"{p}{mname}.symmetriser.mlp.{i}."

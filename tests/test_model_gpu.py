@@ -234,7 +234,7 @@ def test_conv_block_model_matches_oracle_forward_and_gradients():
     from grappa_b200.loss import MolwiseLoss
     ops.set_matmul_precision("fp32")
     cfg = orc.small_model_config()
-    cfg.update(gnn_convolutions=2, gnn_attentional_layers=1)
+    cfg.update(gnn_convolutions=2, gnn_attentional_layers=1, wrong_symmetry=True)   # + the improper-symmetry ablation switch
     model = _model(cfg, seed=11).eval()
     g = synthetic.espaloma_mix_batch(seed=6, batch_size=4, n_confs=5)
     sd = {k: v.detach().cpu().double().requires_grad_(v.is_floating_point() and "conv_blocks" in k)
@@ -246,6 +246,8 @@ def test_conv_block_model_matches_oracle_forward_and_gradients():
     gd = torch.nn.Sequential(model, Energy(write_tuple_terms=False))(g.to("cuda"))
     assert rel_err(gd.nodes["n1"].data["h"].detach().cpu().numpy(), h.detach().numpy()) < 1e-5
     assert rel_err(gd.nodes["g"].data["energy"].detach().cpu().numpy(), en["energy"].detach().numpy()) < 1e-5
+    for l in LEVELS:
+        assert rel_err(gd.nodes[l].data["k"].detach().cpu().numpy(), params[l]["k"].detach().numpy()) < 1e-5, l
     loss = MolwiseLoss(gradient_weight=0.8, energy_weight=1.0, param_weight=0.0, proper_regularisation=1e-3,
                        improper_regularisation=1e-3)(gd)
     assert abs(loss.item() - float(ref_loss)) < 1e-5 * abs(float(ref_loss))

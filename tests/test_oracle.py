@@ -135,7 +135,7 @@ def test_oracle_conv_blocks_vs_live_reference():
     from grappa_b200 import models, synthetic
     ns = import_reference()
     cfg = orc.small_model_config()
-    cfg.update(gnn_convolutions=2, gnn_attentional_layers=1)
+    cfg.update(gnn_convolutions=2, gnn_attentional_layers=1, wrong_symmetry=True)   # + the improper-symmetry ablation switch
     torch.manual_seed(0)
     ref = ns.deploy.model_from_config(dict(cfg), param_statistics=ns.graph_utils.get_default_statistics()).eval()
     sd = {k: v.clone() for k, v in ref.state_dict().items()}
