@@ -69,7 +69,7 @@ class LossArgs(C.Structure):
         ("B", i32), ("C", i32), ("n_per_p", i32), ("n_per_i", i32),
         ("w_energy", f32), ("w_grad", f32), ("w_proper", f32), ("w_improper", f32),
         ("loss", vp), ("mol_loss", vp), ("g_energy", vp), ("g_grad", vp), ("g_k_proper", vp), ("g_k_improper", vp),
-        ("grad_scale", vp), ("extra_mol_loss", vp),
+        ("grad_scale", vp), ("extra_mol_loss", vp), ("n_valid", vp),
     ]
 
 

@@ -223,36 +223,45 @@ __global__ void __launch_bounds__(256) molwise_loss_kernel(gb_loss_args a) {
   const float invB = (a.grad_scale ? __ldg(a.grad_scale) : 1.f) / a.B;
   const float invB_loss = 1.f / a.B;
   float term = 0.f;
+  const int nv = a.n_valid ? min(max(a.n_valid[b], 0), C) : C;   // real (non-padding) conformations of this molecule
   // energies
-  if (a.w_energy != 0.f && a.energy) {
+  if (a.w_energy != 0.f && a.energy && nv > 0) {
     float s1 = 0.f, s2 = 0.f;
-    for (int c = tid; c < C; c += blockDim.x) {
+    for (int c = tid; c < nv; c += blockDim.x) {
       s1 += a.energy[(size_t)b * C + c];
       s2 += a.energy_ref[(size_t)b * C + c];
     }
-    const float me = block_sum(s1, sh) / C, mr = block_sum(s2, sh) / C;
+    const float me = block_sum(s1, sh) / nv, mr = block_sum(s2, sh) / nv;
     float q = 0.f;
     for (int c = tid; c < C; c += blockDim.x) {
-      const float d = (a.energy[(size_t)b * C + c] - me) - (a.energy_ref[(size_t)b * C + c] - mr);
-      q += d * d;
-      if (a.g_energy) a.g_energy[(size_t)b * C + c] = a.w_energy * invB * 2.f * d / C;
+      float d = 0.f;
+      if (c < nv) {
+        d = (a.energy[(size_t)b * C + c] - me) - (a.energy_ref[(size_t)b * C + c] - mr);
+        q += d * d;
+      }
+      if (a.g_energy) a.g_energy[(size_t)b * C + c] = a.w_energy * invB * 2.f * d / nv;
     }
-    term += a.w_energy * block_sum(q, sh) / C;
+    term += a.w_energy * block_sum(q, sh) / nv;
   } else if (a.g_energy) {
     for (int c = tid; c < C; c += blockDim.x) a.g_energy[(size_t)b * C + c] = 0.f;
   }
   // gradients
   const int a0 = a.atom_off[b], a1 = a.atom_off[b + 1];
   const long long n0 = (long long)a0 * C * 3, n1 = (long long)a1 * C * 3;
-  if (a.w_grad != 0.f && a.grad) {
+  if (a.w_grad != 0.f && a.grad && nv > 0 && a1 > a0) {
     float q = 0.f;
-    const float sc = a.w_grad * invB * 2.f / (float)(n1 - n0);
+    const float n_el = (float)(a1 - a0) * (float)nv * 3.f;
+    const float sc = a.w_grad * invB * 2.f / n_el;
+    const int row = C * 3, valid = nv * 3;               // per atom: C conformations x 3, the first nv x 3 are real
     for (long long i = n0 + tid; i < n1; i += blockDim.x) {
-      const float d = a.grad[i] - a.grad_ref[i];
-      q += d * d;
+      float d = 0.f;
+      if (nv == C || (int)((i - n0) % row) < valid) {
+        d = a.grad[i] - a.grad_ref[i];
+        q += d * d;
+      }
       if (a.g_grad) a.g_grad[i] = sc * d;
     }
-    term += a.w_grad * block_sum(q, sh) / (float)(n1 - n0);
+    term += a.w_grad * block_sum(q, sh) / n_el;
   } else if (a.g_grad) {
     for (long long i = n0 + tid; i < n1; i += blockDim.x) a.g_grad[i] = 0.f;
   }

@@ -1,0 +1,308 @@
+"""Packed dataset, collate and prefetching loader for the training hot path.
+
+What this replaces in the reference (host side, around `model(g)`):
+
+    data/Dataset.py:125             dgl.save_graphs storage: one pickled DGL graph per molecule
+    utils/dgl_utils.py:132-171      set_number_confs: random sub-sampling / padding ('is_dummy') of conformations
+    utils/dgl_utils.py:11-60        batch: deep copies + per-type concatenation + index offsets
+    data/GraphDataLoader.py:23-73   collate_fn: conf_strategy -> n_confs, set_number_confs per graph, batch
+
+At > 4,000 molecules/s per GPU the collate has ~6 ms per 32-molecule batch; per-graph Python objects and deep copies
+do not fit in that.  Here a dataset is a handful of flat arrays (concatenated per node type, plus offsets) that can be
+memory-mapped, a batch is assembled with a few slice-concatenations, the index tables of `pack.PackedBatch` are built in
+the same call, and `PrefetchLoader` runs collate + pinning on a worker thread so the step only sees the H2D copy.
+
+Semantics kept from the reference (checked against `tests/golden/ragged_confs.npz`, produced by the reference's own
+`set_number_confs` / `batch` / `MolwiseLoss`):
+  * n_confs of a batch: int -> min(int, max over the batch); 'min' | 'max' | 'all' | 'mean' (GraphDataLoader.py:52-66);
+  * a molecule with MORE conformations keeps a random subset, one with FEWER repeats its last conformation and the
+    padding is flagged in g.nodes['g'].data['is_dummy'] (B, n_confs) -- the loss ignores flagged conformations;
+  * per-type concatenation in batch order, `idxs` and edges shifted by the atom offset, per-molecule counts kept.
+The random subset is drawn from a numpy Generator (the reference uses torch.randperm on the global RNG): same
+distribution, different stream.
+"""
+from __future__ import annotations
+
+import json
+import os
+import queue
+import threading
+from typing import Dict, Iterable, Iterator, List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from .graph import LEVELS, NTYPES, MolGraph
+
+_CONF_FIELDS_G = ("energy",)        # substring match, as the reference does ('energy' in feat)
+_CONF_FIELDS_N1 = ("gradient",)
+
+
+def _n_confs_of(g: MolGraph) -> int:
+    return int(g.nodes["n1"].data["xyz"].shape[1]) if "xyz" in g.nodes["n1"].data else 0
+
+
+def batch_n_confs(confs: Sequence[int], conf_strategy: Union[str, int]) -> int:
+    """Number of conformations of a batch (reference data/GraphDataLoader.py:52-66)."""
+    if isinstance(conf_strategy, (int, np.integer)):
+        return int(min(int(conf_strategy), max(confs)))
+    if conf_strategy == "min":
+        return int(min(confs))
+    if conf_strategy in ("max", "all"):
+        return int(max(confs))
+    if conf_strategy == "mean":
+        return int(np.mean(confs))
+    raise ValueError(f"Unknown conf_strategy: {conf_strategy}")
+
+
+def conformation_indices(present: int, wanted: int, rng: Optional[np.random.Generator]) -> np.ndarray:
+    """Which stored conformations fill the `wanted` slots (reference utils/dgl_utils.py:146-160)."""
+    if present == wanted:
+        return np.arange(present)
+    if present > wanted:
+        rng = np.random.default_rng() if rng is None else rng
+        return rng.permutation(present)[:wanted]
+    return np.concatenate((np.arange(present), np.full(wanted - present, present - 1, dtype=np.int64)))
+
+
+def set_number_confs(g: MolGraph, num_confs: int, rng: Optional[np.random.Generator] = None) -> MolGraph:
+    """Shallow copy of a single-molecule graph with exactly `num_confs` conformations and `is_dummy` (1, num_confs)."""
+    present = _n_confs_of(g)
+    if present == 0:
+        return g
+    idx = torch.from_numpy(conformation_indices(present, num_confs, rng))
+    out = MolGraph({nt: g.num_nodes(nt) for nt in g.ntypes}, g._src, g._dst,
+                   {nt: g.batch_num_nodes(nt) for nt in g.ntypes})
+    for nt in g.ntypes:
+        for k, v in g.nodes[nt].data.items():
+            if nt == "n1" and (k == "xyz" or any(f in k for f in _CONF_FIELDS_N1)):
+                v = v[:, idx]
+            elif nt == "g" and any(f in k for f in _CONF_FIELDS_G):
+                v = v[:, idx]
+                if torch.isnan(v).any():
+                    raise RuntimeError(f"Found nan in {k} after setting number of conformations to {num_confs}")
+            out.nodes[nt].data[k] = v
+    dummy = torch.zeros((1, num_confs), dtype=torch.float32)
+    if present < num_confs:
+        dummy[0, present:] = 1.0
+    out.nodes["g"].data["is_dummy"] = dummy
+    return out
+
+
+def collate(graphs: Sequence[MolGraph], conf_strategy: Union[str, int] = "mean",
+            rng: Optional[np.random.Generator] = None, build_pack: bool = True) -> MolGraph:
+    """List of single-molecule graphs -> one batched graph (reference collate_fn), index tables attached."""
+    from .graph import batch
+    from .pack import get_pack
+    confs = [_n_confs_of(g) for g in graphs]
+    if any(confs):
+        n = batch_n_confs(confs, conf_strategy)
+        graphs = [set_number_confs(g, n, rng) for g in graphs]
+    bg = batch(graphs)
+    if "is_dummy" in bg.nodes["g"].data:
+        bg.nodes["g"].data["n_valid"] = (bg.nodes["g"].data["is_dummy"] == 0).sum(dim=1).to(torch.int32)
+    if build_pack:
+        get_pack(bg)
+    return bg
+
+
+# --------------------------------------------------------------------------------------------------
+# flat storage
+# --------------------------------------------------------------------------------------------------
+class PackedDataset:
+    """Many molecules as flat arrays: per node type and field one concatenated array plus element offsets.
+
+    Conformation-dependent fields (xyz, *energy*, *gradient*) have a molecule-dependent second dimension, so they are
+    stored flattened with their own offsets; everything else is concatenated along dim 0.  `save` writes one `.npy`
+    per array and an `index.json`; `load(..., mmap=True)` maps them read-only, so a training job touches only the pages
+    of the molecules it samples.
+    """
+
+    def __init__(self, arrays: Dict[str, np.ndarray], meta: dict):
+        self.arrays, self.meta = arrays, meta
+        self.n = int(meta["n_molecules"])
+
+    def __len__(self) -> int:
+        return self.n
+
+    # ---- construction ------------------------------------------------------------------------
+    @classmethod
+    def from_graphs(cls, graphs: Sequence[MolGraph], dsnames: Optional[Sequence[str]] = None) -> "PackedDataset":
+        n = len(graphs)
+        if n == 0:
+            raise ValueError("empty dataset")
+        arrays: Dict[str, np.ndarray] = {}
+        counts = {nt: np.array([g.num_nodes(nt) for g in graphs], dtype=np.int64) for nt in NTYPES}
+        for nt in NTYPES:
+            arrays[f"off.{nt}"] = np.concatenate(([0], np.cumsum(counts[nt]))).astype(np.int64)
+        arrays["confs"] = np.array([_n_confs_of(g) for g in graphs], dtype=np.int64)
+        ecounts = np.array([g.num_edges() for g in graphs], dtype=np.int64)
+        arrays["off.edges"] = np.concatenate(([0], np.cumsum(ecounts))).astype(np.int64)
+        arrays["edges.src"] = np.concatenate([g._src.numpy() for g in graphs]).astype(np.int32)
+        arrays["edges.dst"] = np.concatenate([g._dst.numpy() for g in graphs]).astype(np.int32)
+        fields = {nt: sorted(graphs[0].nodes[nt].data.keys()) for nt in NTYPES}
+        conf_fields = []
+        for nt in NTYPES:
+            for k in fields[nt]:
+                parts = [g.nodes[nt].data[k].numpy() for g in graphs]
+                if cls._is_conf_field(nt, k):
+                    conf_fields.append(f"{nt}.{k}")
+                    arrays[f"data.{nt}.{k}"] = np.concatenate([p.reshape(-1) for p in parts])
+                    arrays[f"foff.{nt}.{k}"] = np.concatenate(([0], np.cumsum([p.size for p in parts]))).astype(np.int64)
+                else:
+                    arrays[f"data.{nt}.{k}"] = np.concatenate(parts, axis=0)
+        meta = {"n_molecules": n, "fields": fields, "conf_fields": conf_fields,
+                "dsnames": list(dsnames) if dsnames is not None else [""] * n}
+        return cls(arrays, meta)
+
+    @staticmethod
+    def _is_conf_field(nt: str, k: str) -> bool:
+        return (nt == "n1" and (k == "xyz" or any(f in k for f in _CONF_FIELDS_N1))) or \
+               (nt == "g" and any(f in k for f in _CONF_FIELDS_G))
+
+    def save(self, path: str) -> None:
+        os.makedirs(path, exist_ok=True)
+        for name, a in self.arrays.items():
+            np.save(os.path.join(path, name + ".npy"), a)
+        with open(os.path.join(path, "index.json"), "w") as f:
+            json.dump({**self.meta, "arrays": sorted(self.arrays)}, f)
+
+    @classmethod
+    def load(cls, path: str, mmap: bool = True) -> "PackedDataset":
+        with open(os.path.join(path, "index.json")) as f:
+            meta = json.load(f)
+        arrays = {name: np.load(os.path.join(path, name + ".npy"), mmap_mode="r" if mmap else None)
+                  for name in meta.pop("arrays")}
+        return cls(arrays, meta)
+
+    # ---- access ------------------------------------------------------------------------------
+    def molecule(self, i: int) -> MolGraph:
+        """Molecule i as a single-molecule MolGraph (views into the flat arrays where possible)."""
+        return self.collate([i], conf_strategy="max", build_pack=False, keep_is_dummy=False)
+
+    def dsname(self, i: int) -> str:
+        return self.meta["dsnames"][i]
+
+    def collate(self, indices: Sequence[int], conf_strategy: Union[str, int] = "mean",
+                rng: Optional[np.random.Generator] = None, build_pack: bool = True, keep_is_dummy: bool = True) -> MolGraph:
+        """Batched graph of the molecules `indices` (same result as `collate([molecule(i) ...])`, without building
+        per-molecule objects): slices of the flat arrays are concatenated per field, `idxs` / edges get the atom offset of
+        the batch, conformations are sub-sampled / padded per molecule."""
+        from .pack import get_pack
+        A = self.arrays
+        idx = [int(i) for i in indices]
+        off = {nt: A[f"off.{nt}"] for nt in NTYPES}
+        counts = {nt: np.array([off[nt][i + 1] - off[nt][i] for i in idx], dtype=np.int64) for nt in NTYPES}
+        atom_shift = np.concatenate(([0], np.cumsum(counts["n1"])))[:-1]
+        confs = [int(A["confs"][i]) for i in idx]
+        n_confs = batch_n_confs(confs, conf_strategy) if any(confs) else 0
+        csel = [conformation_indices(c, n_confs, rng) if n_confs else None for c in confs]
+        eo = A["off.edges"]
+        src = np.concatenate([A["edges.src"][eo[i]:eo[i + 1]] + s for i, s in zip(idx, atom_shift)]).astype(np.int32)
+        dst = np.concatenate([A["edges.dst"][eo[i]:eo[i + 1]] + s for i, s in zip(idx, atom_shift)]).astype(np.int32)
+        g = MolGraph({nt: int(counts[nt].sum()) for nt in NTYPES}, torch.from_numpy(src), torch.from_numpy(dst),
+                     {nt: torch.from_numpy(counts[nt].copy()) for nt in NTYPES})
+        for nt in NTYPES:
+            for k in self.meta["fields"][nt]:
+                data = A[f"data.{nt}.{k}"]
+                if f"{nt}.{k}" in self.meta["conf_fields"]:
+                    fo = A[f"foff.{nt}.{k}"]
+                    parts = []
+                    for j, i in enumerate(idx):
+                        flat = np.asarray(data[fo[i]:fo[i + 1]])
+                        rows = int(counts[nt][j])
+                        p = flat.reshape((rows, confs[j]) + ((3,) if nt == "n1" else ()))
+                        parts.append(p[:, csel[j]])
+                    arr = np.concatenate(parts, axis=0)
+                else:
+                    parts = [np.asarray(data[off[nt][i]:off[nt][i + 1]]) for i in idx]
+                    if k == "idxs":
+                        parts = [p + s for p, s in zip(parts, atom_shift)]
+                    arr = np.concatenate(parts, axis=0)
+                g.nodes[nt].data[k] = torch.from_numpy(np.ascontiguousarray(arr))
+        if n_confs and keep_is_dummy:
+            dummy = np.zeros((len(idx), n_confs), dtype=np.float32)
+            for j, c in enumerate(confs):
+                dummy[j, min(c, n_confs):] = 1.0
+            g.nodes["g"].data["is_dummy"] = torch.from_numpy(dummy)
+            g.nodes["g"].data["n_valid"] = torch.from_numpy((dummy == 0).sum(axis=1).astype(np.int32))
+        if build_pack:
+            get_pack(g)
+        return g
+
+
+# --------------------------------------------------------------------------------------------------
+# loader
+# --------------------------------------------------------------------------------------------------
+class PrefetchLoader:
+    """Iterates batched, pinned host graphs built on a worker thread, `depth` batches ahead of the consumer.
+
+    `batches` yields index lists (a sampler); every rank of a data-parallel job passes its own shard
+    (`shard_indices(len(ds), rank, world)`).  The consumer hands each graph to `Trainer.step(host_graph)`, whose H2D copy
+    into the static device buffers is the only per-step host work left on the critical path.
+    """
+
+    def __init__(self, dataset: PackedDataset, batches: Iterable[Sequence[int]], conf_strategy: Union[str, int] = "mean",
+                 seed: int = 0, depth: int = 3, pin: bool = True, param_weight: Optional[float] = None,
+                 param_weights_by_dataset: Optional[Dict[str, float]] = None):
+        """`param_weight` / `param_weights_by_dataset`: MolwiseLoss's classical-parameter weights (reference
+        training/loss.py:72-76) resolved per molecule here and shipped as g.nodes['g'].data['param_weight'] (B,), an
+        ordinary input tensor (a captured step sees each batch's weights; dataset names never reach the device)."""
+        self.dataset, self.batches, self.conf_strategy = dataset, batches, conf_strategy
+        self.seed, self.depth, self.pin = seed, depth, pin and torch.cuda.is_available()
+        self.param_weight, self.param_weights_by_dataset = param_weight, dict(param_weights_by_dataset or {})
+
+    def __iter__(self) -> Iterator[MolGraph]:
+        q: "queue.Queue" = queue.Queue(maxsize=self.depth)
+        stop = threading.Event()
+        rng = np.random.default_rng(self.seed)
+
+        def work():
+            try:
+                for idx in self.batches:
+                    if stop.is_set():
+                        return
+                    g = self.dataset.collate(idx, self.conf_strategy, rng)
+                    if self.param_weight is not None:
+                        w = [self.param_weights_by_dataset.get(self.dataset.dsname(i), self.param_weight) for i in idx]
+                        g.nodes["g"].data["param_weight"] = torch.tensor(w, dtype=torch.float32)
+                    if self.pin:
+                        g = g.pin_memory()
+                    g.dsnames = [self.dataset.dsname(i) for i in idx]
+                    q.put(g)
+                q.put(None)
+            except BaseException as e:          # surface worker errors in the consumer
+                q.put(e)
+
+        th = threading.Thread(target=work, daemon=True)
+        th.start()
+        try:
+            while True:
+                item = q.get()
+                if item is None:
+                    return
+                if isinstance(item, BaseException):
+                    raise item
+                yield item
+        finally:
+            stop.set()
+            while not q.empty():
+                q.get_nowait()
+
+
+def shard_indices(n: int, rank: int, world: int) -> List[int]:
+    """Molecule i -> rank i mod world (independent molecules, no collective)."""
+    return list(range(rank, n, world))
+
+
+def batch_sampler(indices: Sequence[int], batch_size: int, rng: Optional[np.random.Generator] = None,
+                  drop_last: bool = True) -> Iterator[List[int]]:
+    """Shuffled fixed-size batches of `indices` (one epoch)."""
+    order = np.array(indices)
+    if rng is not None:
+        order = rng.permutation(order)
+    for s in range(0, len(order), batch_size):
+        b = order[s:s + batch_size].tolist()
+        if len(b) < batch_size and drop_last:
+            return
+        yield b

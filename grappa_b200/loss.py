@@ -7,6 +7,10 @@ reference unbatches the graph and loops over molecules in Python (deepcopy per g
 kernels each); here one kernel handles the whole batch and, in the backward pass, writes
 dL/d(energy), dL/d(gradient), dL/d(k_torsion) directly (they feed kernel K14).
 
+Padding conformations (`g.nodes['g'].data['is_dummy']`, written by `set_number_confs` / our `dataset.collate`) are ignored
+per molecule exactly as the reference's `unbatch()` drops them; they must be the trailing conformations (which is how
+the reference creates them).
+
 Deviations, both documented in SURVEY.md appendix A.7:
   * the improper regulariser enters twice in the reference (loss.py:127-132); we use weight 2x for
     molecules with impropers and 0 (instead of NaN) for molecules without any.
@@ -34,14 +38,14 @@ def _p(t):
 
 class _LossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pack, weights, pterms, energy, energy_ref, grad, grad_ref, k_proper, k_improper, *ppred):
-        ctx.pack, ctx.weights, ctx.pterms = pack, weights, pterms
+    def forward(ctx, pack, weights, pterms, n_valid, energy, energy_ref, grad, grad_ref, k_proper, k_improper, *ppred):
+        ctx.pack, ctx.weights, ctx.pterms, ctx.n_valid = pack, weights, pterms, n_valid
         tens = [None if t is None else t.detach().contiguous().float() for t in
                 (energy, energy_ref, grad, grad_ref, k_proper, k_improper)]
         ppred = [t.detach().contiguous().float() for t in ppred]
         ctx.save_for_backward(*[t if t is not None else torch.empty(0) for t in tens], *ppred)
         ctx.present = [t is not None for t in tens]
-        loss = _LossFn._launch(pack, weights, tens, None, False, pterms, ppred)[0]
+        loss = _LossFn._launch(pack, weights, tens, None, False, pterms, ppred, n_valid)[0]
         return loss.reshape(())
 
     @staticmethod
@@ -66,7 +70,7 @@ class _LossFn(torch.autograd.Function):
         return mol, outs
 
     @staticmethod
-    def _launch(pack, weights, tens, scale, want_grads, pterms=None, ppred=()):
+    def _launch(pack, weights, tens, scale, want_grads, pterms=None, ppred=(), n_valid=None):
         energy, energy_ref, grad, grad_ref, kp, ki = tens
         dev = pack.device
         B = pack.n_mols
@@ -87,6 +91,7 @@ class _LossFn(torch.autograd.Function):
         a.n_per_i = ki.shape[1] if ki is not None and ki.dim() == 2 else 0
         a.w_energy, a.w_grad, a.w_proper, a.w_improper = weights
         a.loss, a.mol_loss = loss.data_ptr(), mol.data_ptr()
+        a.n_valid = _p(n_valid)
         outs = [None] * 4
         if want_grads:
             outs = [torch.empty_like(t) if t is not None else None for t in (energy, grad, kp, ki)]
@@ -101,10 +106,11 @@ class _LossFn(torch.autograd.Function):
         tens = [t if p else None for t, p in zip(saved[:6], ctx.present)]
         ppred = saved[6:]
         scale = go.detach().reshape(1).float().contiguous()
-        _, (ge, gg, gkp, gki), pgrads = _LossFn._launch(ctx.pack, ctx.weights, tens, scale, True, ctx.pterms, ppred)
+        _, (ge, gg, gkp, gki), pgrads = _LossFn._launch(ctx.pack, ctx.weights, tens, scale, True, ctx.pterms, ppred,
+                                                        ctx.n_valid)
         if gki is not None and gki.numel() == 0:
             gki = torch.zeros_like(tens[5])
-        return (None, None, None, ge, None, gg, None, gkp, gki, *pgrads)
+        return (None, None, None, None, ge, None, gg, None, gkp, gki, *pgrads)
 
 
 class MolwiseLoss(torch.nn.Module):
@@ -136,7 +142,8 @@ class MolwiseLoss(torch.nn.Module):
         weights = (float(self.energy_weight), float(self.gradient_weight), float(self.proper_regularisation),
                    2.0 * float(self.improper_regularisation))
         pterms, ppred = None, []
-        use_params = has_ref and (self.param_weight != 0. or (dsnames is not None and len(self.param_weights_by_dataset) > 0))
+        use_params = has_ref and (self.param_weight != 0. or "param_weight" in g.nodes["g"].data.keys()
+                                  or (dsnames is not None and len(self.param_weights_by_dataset) > 0))
         if use_params:
             # reference order BONDED_CONTRIBUTIONS minus impropers (loss.py:88-92): n2_k, n2_eq, n3_k, n3_eq, n4_k
             terms = []
@@ -151,14 +158,28 @@ class MolwiseLoss(torch.nn.Module):
                 terms.append((level_id, ref.detach().contiguous().float(), float(self.weights.get(f"{lvl}_{name}", 1.))))
                 ppred.append(pred)
             w = [float(self.param_weight)] * pack.n_mols
-            if dsnames is not None:
+            if "param_weight" in gd.keys():
+                # per-molecule weights shipped as a graph field (dataset.PrefetchLoader): a plain input tensor, so a
+                # captured training step picks up each batch's weights when its static inputs are refreshed
+                pterms_w = gd["param_weight"].reshape(-1).float().contiguous()
+                _lib.require_cuda(pterms_w)
+                pterms = {"terms": terms, "mol_weight": pterms_w}
+            elif dsnames is not None:
                 w = [float(self.param_weights_by_dataset.get(d, self.param_weight)) for d in dsnames]
                 assert len(w) == pack.n_mols, "dsnames must hold one entry per molecule"
-            key = tuple(w)
-            cache = getattr(self, "_mol_weight_cache", None)
-            if cache is None or cache[0] != key or cache[1].device != pack.device:
-                cache = (key, torch.tensor(w, dtype=torch.float32, device=pack.device))
-                self._mol_weight_cache = cache
-            pterms = {"terms": terms, "mol_weight": cache[1]}
-        return _LossFn.apply(pack, weights, pterms, energy, gd["energy_ref"] if energy is not None else None, grad,
+            if pterms is None:
+                key = tuple(w)
+                cache = getattr(self, "_mol_weight_cache", None)
+                if cache is None or cache[0] != key or cache[1].device != pack.device:
+                    cache = (key, torch.tensor(w, dtype=torch.float32, device=pack.device))
+                    self._mol_weight_cache = cache
+                pterms = {"terms": terms, "mol_weight": cache[1]}
+        # padded conformations ('is_dummy', appended by set_number_confs when a molecule has fewer conformations than the
+        # batch) are dropped by the reference's unbatch() before any term is evaluated (utils/dgl_utils.py:63-118)
+        n_valid = None
+        if "n_valid" in gd.keys():
+            n_valid = gd["n_valid"].reshape(-1).to(torch.int32).contiguous()
+        elif "is_dummy" in gd.keys():
+            n_valid = (gd["is_dummy"] == 0).sum(dim=1).to(torch.int32).contiguous()
+        return _LossFn.apply(pack, weights, pterms, n_valid, energy, gd["energy_ref"] if energy is not None else None, grad,
                              nd["gradient_ref"] if grad is not None else None, kp, ki, *ppred)

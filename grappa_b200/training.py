@@ -267,7 +267,7 @@ class Trainer:
         cap.g_static = gs
         torch.cuda.synchronize(self.device)
         cap.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(cap.graph, stream=self.stream):
+        with torch.cuda.graph(cap.graph, stream=self.stream, capture_error_mode="thread_local"):   # a loader thread may pin memory meanwhile
             cap.loss = self._eager_step(gs)
         ops.drop_workspaces()            # scratch allocated while capturing belongs to the graph's pool
         return cap

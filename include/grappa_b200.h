@@ -359,6 +359,9 @@ typedef struct {
   const float* grad_scale;  /* device scalar multiplied into every g_* output (upstream dL), or NULL = 1 */
   const float* extra_mol_loss; /* [B] or NULL: per-molecule terms computed elsewhere (grappa_b200_param_loss),
                                   added to each molecule's term before the mean over molecules */
+  const int32_t* n_valid;      /* [B] or NULL: molecule b's first n_valid[b] conformations are real, the rest are the
+                                  padding set_number_confs appends ('is_dummy', reference utils/dgl_utils.py:132-171) and
+                                  are ignored exactly as unbatch() / delete_dummy_confs (:63-118) drops them */
 } gb_loss_args;
 int grappa_b200_molwise_loss(const gb_loss_args* a, void* stream);
 

@@ -322,7 +322,7 @@ def path_forward(sd, g, cfg, dtype=torch.float32, gradients=True, create_graph=F
     return h, params, en
 
 
-def molwise_loss(en, params, g, energy_weight=1.0, gradient_weight=0.8, proper_reg=1e-3, improper_reg=1e-3):
+def molwise_loss(en, params, g, energy_weight=1.0, gradient_weight=0.8, proper_reg=1e-3, improper_reg=1e-3, n_valid=None):
     """MolwiseLoss.forward (training/loss.py:45-167) restricted to the terms active in the grappa-1.2
     config with no reference parameters on the graph: centred-energy MSE + gradient MSE + torsion L2
     (the improper regulariser enters twice, loss.py:127-132).  Mean over molecules."""
@@ -335,10 +335,13 @@ def molwise_loss(en, params, g, energy_weight=1.0, gradient_weight=0.8, proper_r
     a0 = p0 = i0 = 0
     nb = len(a_counts)
     for b in range(nb):
-        eb = e[b] - e[b].mean()
-        rb = e_ref[b] - e_ref[b].mean()
+        # padding conformations (is_dummy) are removed per molecule by unbatch() -> delete_dummy_confs
+        # (utils/dgl_utils.py:63-118) before any term is evaluated; they are the trailing ones (:155-157)
+        nv = e.shape[1] if n_valid is None else int(n_valid[b])
+        eb = e[b, :nv] - e[b, :nv].mean()
+        rb = e_ref[b, :nv] - e_ref[b, :nv].mean()
         term = energy_weight * torch.mean((eb - rb) ** 2)
-        term = term + gradient_weight * torch.mean((gr[a0:a0 + a_counts[b]] - gr_ref[a0:a0 + a_counts[b]]) ** 2)
+        term = term + gradient_weight * torch.mean((gr[a0:a0 + a_counts[b], :nv] - gr_ref[a0:a0 + a_counts[b], :nv]) ** 2)
         kp = params["n4"]["k"][p0:p0 + p_counts[b]]
         if len(kp) > 0:
             term = term + proper_reg * torch.mean(kp ** 2)

@@ -129,12 +129,60 @@ def param_loss_case(ns):
     print("param_loss: loss a/b =", out["a.loss"], out["b.loss"], "mols =", len(mols))
 
 
+def ragged_conformations_case(ns):
+    """case 6: molecules with different numbers of conformations through the reference's own collate steps
+    (dgl_utils.set_number_confs -> padding + 'is_dummy', dgl_utils.batch) and MolwiseLoss, whose unbatch() drops the padding
+    again (utils/dgl_utils.py:63-118,132-171; data/GraphDataLoader.py:23-73).  Stores the single molecules, the batched
+    fields, loss and gradients w.r.t. energy / gradient / torsion amplitudes."""
+    rng = np.random.default_rng(23)
+    confs = [3, 7, 5, 7, 1]
+    kinds = [("peptide", dict(n_res=1)), ("small", dict(n_atoms=12)), ("peptide", dict(n_res=2)), ("rna", {}), ("small", dict(n_atoms=25))]
+    mols = [synthetic.make_molecule(rng, k, n_confs=c, **kw) for (k, kw), c in zip(kinds, confs)]
+    keep = [i for i, m in enumerate(mols) if m.num_nodes("n4_improper") > 0]
+    mols, confs = [mols[i] for i in keep], [confs[i] for i in keep]
+    n_confs = max(confs)                     # conf_strategy 'max' / int >= max: only padding, no random sub-sampling
+    graphs = [ns.dgl_utils.set_number_confs(to_reference_graph(ns, m), n_confs) for m in mols]
+    bg = ns.dgl_utils.batch(graphs, deep_copies_of_same_n_atoms=False)
+    gen = torch.Generator().manual_seed(5)
+    B, N = bg.num_nodes("g"), bg.num_nodes("n1")
+    e = (torch.randn(B, n_confs, generator=gen) * 3).requires_grad_(True)
+    gr = (torch.randn(N, n_confs, 3, generator=gen) * 5).requires_grad_(True)
+    kp = torch.randn(bg.num_nodes("n4"), 3, generator=gen).requires_grad_(True)
+    ki = torch.randn(bg.num_nodes("n4_improper"), 3, generator=gen).requires_grad_(True)
+    bg.nodes["g"].data["energy"] = e
+    bg.nodes["n1"].data["gradient"] = gr
+    bg.nodes["n4"].data["k"] = kp
+    bg.nodes["n4_improper"].data["k"] = ki
+    for lvl in ("n2", "n3"):
+        T = bg.num_nodes(lvl)
+        bg.nodes[lvl].data["k"] = torch.rand(T, generator=gen)
+        bg.nodes[lvl].data["eq"] = torch.rand(T, generator=gen)
+    loss = ns.loss.MolwiseLoss(gradient_weight=0.8, energy_weight=1.0, param_weight=0., proper_regularisation=1e-3,
+                               improper_regularisation=1e-3)(bg)
+    ge, gg, gkp, gki = torch.autograd.grad(loss, [e, gr, kp, ki])
+    out = {"meta.n_confs": np.array(confs), "meta.n_mols": np.array(len(mols)),
+           "batched.xyz": bg.nodes["n1"].data["xyz"].numpy(), "batched.is_dummy": bg.nodes["g"].data["is_dummy"].numpy(),
+           "batched.energy_ref": bg.nodes["g"].data["energy_ref"].numpy(),
+           "batched.gradient_ref": bg.nodes["n1"].data["gradient_ref"].numpy(),
+           "batched.n4.idxs": bg.nodes["n4"].data["idxs"].numpy(),
+           "in.energy": e.detach().numpy(), "in.gradient": gr.detach().numpy(), "in.k_proper": kp.detach().numpy(),
+           "in.k_improper": ki.detach().numpy(), "out.loss": np.array(loss.item(), dtype=np.float64),
+           "grad.energy": ge.numpy(), "grad.gradient": gg.numpy(), "grad.k_proper": gkp.numpy(), "grad.k_improper": gki.numpy()}
+    for i, m in enumerate(mols):
+        out.update(graph_inputs(m, prefix=f"mol{i}."))
+    np.savez_compressed(os.path.join(OUT, "ragged_confs.npz"), **out)
+    print("ragged_confs: loss =", out["out.loss"], "confs =", confs)
+
+
 def main():
     ns = import_reference()
     torch.set_num_threads(8)
     if "--only-param-loss" in sys.argv:
         return param_loss_case(ns)
+    if "--only-ragged" in sys.argv:
+        return ragged_conformations_case(ns)
     param_loss_case(ns)
+    ragged_conformations_case(ns)
 
     # ---- case 1: BASELINE config 1 -- grappa-1.2 architecture, capped dipeptide, 50 conformations
     g = synthetic.dipeptide(seed=11, n_confs=50)

@@ -49,7 +49,7 @@ def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(GemmArgs) % 8 == 0 and ctypes.sizeof(EnergyArgs) % 8 == 0
     assert ctypes.sizeof(EnergyBwdArgs) > ctypes.sizeof(EnergyArgs)
     assert ctypes.sizeof(HeadOutArgs) == 6 * 4 + 8 * 4 + 12 * 4 + 4
-    assert ctypes.sizeof(LossArgs) == 9 * 8 + 4 * 4 + 4 * 4 + 8 * 8
+    assert ctypes.sizeof(LossArgs) == 9 * 8 + 4 * 4 + 4 * 4 + 9 * 8
     from grappa_b200._lib_ops import ParamLossArgs
     assert ctypes.sizeof(ParamLossArgs) == 2 * 4 + 3 * 5 * 8 + 3 * 5 * 4 + 4 + 2 * 8 + 5 * 8 + 8   # 4 bytes of padding after fac[5]
 
@@ -159,8 +159,10 @@ def test_module_tree_state_dict_and_error_behaviour():
     assert m.field_of_view == 10 and sd["gnn.pre_dense.0.weight"].shape == (512, 85)
     # Lightning checkpoints prefix keys with 'model.0.' (training/lightning_model.py); stripping it must load
     m.load_state_dict({k: v for k, v in {("model.0." + k)[8:]: v for k, v in sd.items()}.items()})
+    gnn10 = models.GrappaGNN(n_conv=2, n_att=1, out_feats=32, node_feats=64, n_heads=4)     # grappa-1.0 layout
+    assert "conv_blocks.1.graph_module.fc_neigh.weight" in gnn10.state_dict() and len(gnn10.blocks) == 3
     with pytest.raises(NotImplementedError):
-        models.GrappaGNN(n_conv=2)
+        models.ToPositive(1.0, 1.0, learnable_statistics=True)
     g = synthetic.dipeptide(seed=0, n_confs=2)
     with pytest.raises(ValueError):
         Energy(terms="n2")

@@ -460,3 +460,29 @@ def test_pad_rows_and_padded_pre_dense():
     ref = X[:, :85].double() @ W.double().T
     got = ops.gemm(X, Wp, k=88, precision=ops.AUTO)
     assert R(got, ref) < 1e-3
+
+
+def test_loss_ignores_padding_conformations_like_the_reference():
+    """Molecules padded to the batch's conformation count ('is_dummy'): value and gradients of the fused loss against
+    the fixture produced by the reference's set_number_confs + batch + MolwiseLoss (tests/golden/ragged_confs.npz)."""
+    from grappa_b200 import dataset
+    from grappa_b200.loss import MolwiseLoss
+    from util import graph_from_fixture, load_golden
+    z = load_golden("ragged_confs.npz")
+    mols = [graph_from_fixture(z, prefix=f"mol{i}.") for i in range(int(z["meta.n_mols"]))]
+    for drop_n_valid in (False, True):          # with the collate's n_valid field, and from is_dummy alone
+        g = dataset.collate(mols, conf_strategy="max").to("cuda")
+        if drop_n_valid:
+            del g.nodes["g"].data["n_valid"]
+        leaves = {n: torch.from_numpy(z[f"in.{n}"]).cuda().requires_grad_(True) for n in ("energy", "gradient", "k_proper", "k_improper")}
+        g.nodes["g"].data["energy"], g.nodes["n1"].data["gradient"] = leaves["energy"], leaves["gradient"]
+        g.nodes["n4"].data["k"], g.nodes["n4_improper"].data["k"] = leaves["k_proper"], leaves["k_improper"]
+        loss = MolwiseLoss(gradient_weight=0.8, energy_weight=1.0, param_weight=0., proper_regularisation=1e-3,
+                           improper_regularisation=1e-3)(g)
+        assert abs(loss.item() - float(z["out.loss"])) < 1e-5 * abs(float(z["out.loss"]))
+        grads = torch.autograd.grad(loss, list(leaves.values()))
+        for n, gr in zip(leaves, grads):
+            assert R(gr, torch.from_numpy(z[f"grad.{n}"])) < 1e-5, n
+        # padding conformations receive exactly zero gradient
+        nv = z["meta.n_confs"].tolist()
+        assert all(float(grads[0][b, nv[b]:].abs().sum()) == 0.0 for b in range(len(nv)))

@@ -92,3 +92,27 @@ def test_adam_and_clip_match_torch():
     assert total.item() > 0.05, "the clip must be active for this test to mean something"
     opt.step()
     np.testing.assert_allclose(tr.fp.flat.cpu().numpy(), p.detach().cpu().numpy(), rtol=2e-6, atol=1e-9)
+
+
+def test_training_from_packed_dataset_through_the_prefetch_loader():
+    """dataset.PackedDataset -> PrefetchLoader (worker thread, pinned batches, ragged conformation counts) ->
+    Trainer.step on host graphs: losses stay finite, batches with a new shape run eagerly first and are captured later."""
+    import numpy as np
+    from grappa_b200 import dataset, synthetic
+    from grappa_b200.training import Trainer
+    model, energy, loss = _setup(0.1)
+    tr = Trainer(model, energy, loss, lr=1e-3, clip=10.0, device="cuda", use_cuda_graph=True)
+    rng = np.random.default_rng(0)
+    mols = []
+    for i in range(12):
+        m = synthetic.make_molecule(rng, "peptide", n_confs=int(rng.integers(2, 7)), n_res=1 + i % 2)
+        if m.num_nodes("n4_improper") > 0:
+            mols.append(m)
+    ds = dataset.PackedDataset.from_graphs(mols, dsnames=["a", "b"] * (len(mols) // 2) + ["a"] * (len(mols) % 2))
+    losses = []
+    for epoch in range(3):
+        batches = list(dataset.batch_sampler(range(len(ds)), 4, np.random.default_rng(epoch)))
+        for g in dataset.PrefetchLoader(ds, batches, conf_strategy=4, seed=epoch, depth=2):
+            assert g.nodes["g"].data["is_dummy"].shape == (4, g.nodes["n1"].data["xyz"].shape[1])
+            losses.append(tr.step(g).item())
+    assert len(losses) == 3 * (len(ds) // 4) and all(np.isfinite(losses))
