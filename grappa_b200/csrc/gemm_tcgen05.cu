@@ -152,6 +152,30 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 
+// Rows sub_r, sub_r + 4, ... of one transposed 32 x 32 accumulator patch: bias, feature-specialised epilogue, 16-byte stores.
+template <int MASK, int EPI_LD>
+__device__ __forceinline__ void epi_patch_rows(const Epilogue& ep, const float* __restrict__ patch, int sub_r, int sub_c, int m0,
+                                               int M, int col, const float4* res4, const float4* elu4) {
+  const float4 b4 = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const uint64_t sd = (MASK & 4) ? ep.seed() : 0ull;
+  float* crow = ep.C + (size_t)(m0 + sub_r) * ep.ldc + col;
+  float* arow = ((MASK & 1) && ep.act_out) ? ep.act_out + (size_t)(m0 + sub_r) * ep.ldact + col : nullptr;
+  uint64_t didx = (uint64_t)(m0 + sub_r) * (uint64_t)ep.N + (uint64_t)col;
+  const size_t cstep = (size_t)4 * ep.ldc, astep = (size_t)4 * ep.ldact;
+  const uint64_t dstep = (uint64_t)4 * (uint64_t)ep.N;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (m0 + sub_r + 4 * i < M) {
+      float4 acc = *reinterpret_cast<const float4*>(patch + (sub_r + 4 * i) * EPI_LD + sub_c);
+      acc.x += b4.x; acc.y += b4.y; acc.z += b4.z; acc.w += b4.w;
+      ep.template store4_masked<MASK>(acc, crow, arow, didx, sd, res4[i], elu4[i]);
+    }
+    crow += cstep;
+    if ((MASK & 1) && arow) arow += astep;
+    didx += dstep;
+  }
+}
+
 // One launch serves up to TC_MAX_GROUP independent problems that share the tile configuration (grouped GEMM: the four
 // weight gradients of a transformer layer run as ONE persistent kernel, so a work item's K slice is 3-4x longer and the
 // split-K partials 3-4x fewer than with one launch per GEMM).  Work items are numbered problem by problem.
@@ -385,6 +409,7 @@ gemm_tf32_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Tc
       const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
       const uint32_t t_addr = tmem_base + as * BN + half * (BN / 2) + ((uint32_t)(q * 32) << 16);
       const bool side_inputs = !pq.partial && vec_ok && (pq.ep.residual != nullptr || pq.ep.mul_elu_out != nullptr);
+      const int fmask = pq.ep.feature_mask();      // warp-uniform: selects one specialised row loop per tile
 #pragma unroll 1
       for (int c0 = 0; c0 < BN / 2; c0 += 32) {
         const int col = n0 + c0 + sub_c;
@@ -426,31 +451,33 @@ gemm_tf32_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Tc
         if (col < pq.N) {
           if (pq.partial) {
             float* dst0 = pq.partial + ((size_t)z * pq.M + m0) * pq.N + col;
-#pragma unroll 2
-            for (int i = 0; i < 8; ++i) {
-              const int r = sub_r + 4 * i;
-              if (m0 + r >= pq.M) break;
-              const float4 acc = *reinterpret_cast<const float4*>(patch + r * Cfg::EPI_LD + sub_c);
-              float* dst = dst0 + (size_t)r * pq.N;
-              if (vec_ok) {
-                *reinterpret_cast<float4*>(dst) = acc;
-              } else {
+            if (vec_ok) {
+              float* dst = dst0 + (size_t)sub_r * pq.N;
+              const size_t step = (size_t)4 * pq.N;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (m0 + sub_r + 4 * i < pq.M)
+                  *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(patch + (sub_r + 4 * i) * Cfg::EPI_LD + sub_c);
+                dst += step;
+              }
+            } else {
+#pragma unroll 1
+              for (int i = 0; i < 8; ++i) {
+                const int r = sub_r + 4 * i;
+                if (m0 + r >= pq.M) break;
+                const float4 acc = *reinterpret_cast<const float4*>(patch + r * Cfg::EPI_LD + sub_c);
+                float* dst = dst0 + (size_t)r * pq.N;
                 const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
                 for (int e = 0; e < 4; ++e)
                   if (col + e < pq.N) dst[e] = a4[e];
               }
             }
           } else if (vec_ok) {
-            const float4 b4 = pq.ep.bias ? __ldg(reinterpret_cast<const float4*>(pq.ep.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int r = sub_r + 4 * i;
-              if (m0 + r < pq.M) {
-                float4 acc = *reinterpret_cast<const float4*>(patch + r * Cfg::EPI_LD + sub_c);
-                acc.x += b4.x; acc.y += b4.y; acc.z += b4.z; acc.w += b4.w;
-                pq.ep.store4_pre(acc, m0 + r, col, res4[i], elu4[i]);
-              }
-            }
+            if (fmask == 0) epi_patch_rows<0, Cfg::EPI_LD>(pq.ep, patch, sub_r, sub_c, m0, pq.M, col, res4, elu4);
+            else if (fmask == 1) epi_patch_rows<1, Cfg::EPI_LD>(pq.ep, patch, sub_r, sub_c, m0, pq.M, col, res4, elu4);
+            else if (fmask == 12) epi_patch_rows<12, Cfg::EPI_LD>(pq.ep, patch, sub_r, sub_c, m0, pq.M, col, res4, elu4);
+            else if (fmask == 10) epi_patch_rows<10, Cfg::EPI_LD>(pq.ep, patch, sub_r, sub_c, m0, pq.M, col, res4, elu4);
+            else epi_patch_rows<31, Cfg::EPI_LD>(pq.ep, patch, sub_r, sub_c, m0, pq.M, col, res4, elu4);
           } else {
 #pragma unroll 1
             for (int i = 0; i < 8; ++i) {

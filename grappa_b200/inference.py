@@ -185,9 +185,10 @@ class Grappa:
                 cap.g_static = gs
                 torch.cuda.synchronize(self.device)
                 cap.graph = torch.cuda.CUDAGraph()
+                from . import ops as _ops
+                _ops.drop_workspaces()           # cached scratch of eager launches must not be baked into the graph
                 with torch.cuda.graph(cap.graph, stream=self._stream, capture_error_mode="thread_local"):
                     self.model(gs)
-                from . import ops as _ops
                 _ops.drop_workspaces()           # scratch allocated while capturing belongs to the graph's pool
                 self._captured[sig] = cap
             else:

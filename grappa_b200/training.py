@@ -267,6 +267,10 @@ class Trainer:
         cap.g_static = gs
         torch.cuda.synchronize(self.device)
         cap.graph = torch.cuda.CUDAGraph()
+        # Scratch buffers cached by earlier eager launches must not be baked into the graph: they live in the regular
+        # allocator pool, would be freed by the drop below and unmapped by the empty_cache() of the next capture while this
+        # graph still writes to them.  Dropping the cache first makes the capture allocate its scratch in its own pool.
+        ops.drop_workspaces()
         with torch.cuda.graph(cap.graph, stream=self.stream, capture_error_mode="thread_local"):   # a loader thread may pin memory meanwhile
             cap.loss = self._eager_step(gs)
         ops.drop_workspaces()            # scratch allocated while capturing belongs to the graph's pool

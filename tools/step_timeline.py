@@ -15,7 +15,10 @@ if "--serial" in sys.argv:      # one stream: every kernel alone on the GPU -> c
     from grappa_b200 import tape as _tape
     _tape.set_concurrency(False)
 ops.set_matmul_precision("tf32")
-dev = torch.device("cuda")
+from grappa_b200.training import init_distributed
+rank, local, world = init_distributed()
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
 torch.manual_seed(0)
 model = models.model_from_config(models.grappa_1_2_model_config()).train()
 tr = Trainer(model, Energy(write_tuple_terms=False), MolwiseLoss(gradient_weight=0.8, energy_weight=1.0, param_weight=0.0,
@@ -30,6 +33,11 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(3):
         tr.step(g)
     torch.cuda.synchronize()
+if rank != 0:
+    torch.cuda.synchronize()
+    import torch.distributed as dist
+    dist.barrier()
+    os._exit(0)
 out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "step_trace.json")
 prof.export_chrome_trace(out)
 ev = json.load(open(out))["traceEvents"]
@@ -73,3 +81,10 @@ for e in step:
         b = int(s / B); take = min(d, (b + 1) * B - s)
         occ[b] += take; s += take; d -= take
 print("avg concurrent kernels per 0.5 ms bucket:", [round(o / B, 2) for o in occ])
+nccl = [e for e in step if "nccl" in e["name"].lower()]
+if nccl:
+    print("NCCL kernels of the step (start us, duration us):", [(round(e["ts"] - t0), round(e["dur"])) for e in nccl])
+if world > 1:
+    import torch.distributed as dist
+    dist.barrier()
+    os._exit(0)
