@@ -633,7 +633,9 @@ int gemm_tcgen05(const gb_gemm_args* a, cudaStream_t stream, bool* handled) {
   const int sms_ = sm_count();
   static const int forced_pair = [] { const char* e = getenv("GRAPPA_B200_GEMM_PAIR"); return e ? atoi(e) : -1; }();   // tuning aid
   const bool can_split = a->workspace != nullptr && (K + TC_BK - 1) / TC_BK >= 16;
-  bool pair = M > TC_BM && N >= 128 && forced_pair != 0 && (K >= 1024 || forced_pair == 1);
+  static const int pair_min_k = [] { const char* e = getenv("GRAPPA_B200_GEMM_PAIR_MINK"); return e ? atoi(e) : 1024; }();   // tuning aids
+  static const int pair_min_m = [] { const char* e = getenv("GRAPPA_B200_GEMM_PAIR_MINM"); return e ? atoi(e) : 0; }();
+  bool pair = M > TC_BM && N >= 128 && forced_pair != 0 && ((K >= pair_min_k && (K >= 1024 || M >= pair_min_m)) || forced_pair == 1);
   int units = 0, tiles_m = 0, BN = 128;
   for (int attempt = 0; attempt < 2; ++attempt) {
     const int bm = pair ? 2 * TC_BM : TC_BM;

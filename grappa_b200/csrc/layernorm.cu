@@ -269,15 +269,18 @@ __global__ void __launch_bounds__(256) act_dropout_bwd_fused_kernel(const float*
   pdl_trigger();
   __shared__ float4 sh[256];
   const uint64_t seed = seed_with_offset(seed0, seed_off);
-  const int ncg = cols >> 2;                 // float4 column groups (<= 256)
+  // Rows wider than 1024 floats are cut into gridDim.y column slices of <= 256 float4 groups (GNN feed-forward: 2048).
+  const int ncg_row = cols >> 2;                                   // float4 groups per row
+  const int ncg = (ncg_row + gridDim.y - 1) / gridDim.y;           // ... per slice (<= 256)
+  const int cg0 = blockIdx.y * ncg;
   const int nrl = 256 / ncg;                 // row lanes
   const int cg = threadIdx.x % ncg, rl = threadIdx.x / ncg;
   const int r_begin = blockIdx.x * rows_per_cta;
   const int r_end = min(rows, r_begin + rows_per_cta);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (rl < nrl) {
+  if (rl < nrl && cg0 + cg < ncg_row) {
     for (int row = r_begin + rl; row < r_end; row += nrl) {
-      const size_t i4 = (size_t)row * ncg + cg;
+      const size_t i4 = (size_t)row * ncg_row + cg0 + cg;
       float4 v = __ldg(reinterpret_cast<const float4*>(dy) + i4);
       if (thresh) {
         const uint64_t base = (uint64_t)i4 * 4ull;
@@ -295,13 +298,13 @@ __global__ void __launch_bounds__(256) act_dropout_bwd_fused_kernel(const float*
   }
   sh[threadIdx.x] = acc;
   __syncthreads();
-  if (threadIdx.x < ncg) {
+  if (threadIdx.x < ncg && cg0 + threadIdx.x < ncg_row) {
     float4 a = sh[threadIdx.x];
     for (int l = 1; l < nrl; ++l) {
       const float4 o = sh[l * ncg + threadIdx.x];
       a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
     }
-    reinterpret_cast<float4*>(partial)[(size_t)blockIdx.x * ncg + threadIdx.x] = a;
+    reinterpret_cast<float4*>(partial)[(size_t)blockIdx.x * ncg_row + cg0 + threadIdx.x] = a;
   }
 }
 
@@ -433,7 +436,7 @@ extern "C" int grappa_b200_act_dropout_bwd_fused(const float* dy, const float* a
                                                  int32_t n_cta, int32_t rows, int32_t cols, float p, uint64_t seed,
                                                  const uint64_t* seed_offset, void* stream_) {
   GB_REQUIRE(p >= 0.f && p < 1.f, "act_dropout_bwd_fused: p must be in [0,1)");
-  GB_REQUIRE(rows > 0 && cols >= 4 && cols % 4 == 0 && cols <= 1024, "act_dropout_bwd_fused: cols must be a multiple of 4 and <= 1024 (got %d x %d)", rows, cols);
+  GB_REQUIRE(rows > 0 && cols >= 4 && cols % 4 == 0 && cols <= 8192, "act_dropout_bwd_fused: cols must be a multiple of 4 and <= 8192 (got %d x %d)", rows, cols);
   GB_REQUIRE(n_cta >= 1 && dy && dx && partial, "act_dropout_bwd_fused: bad arguments");
   uint32_t thresh = 0;
   if (p > 0.f) {
@@ -442,7 +445,8 @@ extern "C" int grappa_b200_act_dropout_bwd_fused(const float* dy, const float* a
     if (thresh == 0) thresh = 1;
   }
   const int rpc = (rows + n_cta - 1) / n_cta;
-  act_dropout_bwd_fused_kernel<<<n_cta, 256, 0, (cudaStream_t)stream_>>>(dy, act_out, dx, partial, rows, cols, rpc, thresh, 1.f / (1.f - p), seed, seed_offset);
+  const int slices = (cols / 4 + 255) / 256;
+  act_dropout_bwd_fused_kernel<<<dim3(n_cta, slices), 256, 0, (cudaStream_t)stream_>>>(dy, act_out, dx, partial, rows, cols, rpc, thresh, 1.f / (1.f - p), seed, seed_offset);
   GB_CHECK_LAUNCH();
   return GB_OK;
 }

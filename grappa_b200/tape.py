@@ -235,7 +235,7 @@ def linear(t: Tape, x: Var, W: torch.Tensor, b: Optional[torch.Tensor], *, act: 
         elif act != 0 or p > 0.0:
             saved = act_out if need_act_out else (y.v if act != 0 else None)
             dyc = dy_full.contiguous()
-            if b is not None and dyc.shape[1] == N and N % 4 == 0 and N <= 1024 and M > 0:
+            if b is not None and dyc.shape[1] == N and N % 4 == 0 and N <= 8192 and M > 0:
                 # one pass: dpre and the per-CTA partial sums of the bias gradient (folded later by tape.colsums)
                 dpre_full, bias_partial = ops.act_dropout_bwd_fused(dyc, saved, p, seed)
             else:

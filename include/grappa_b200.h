@@ -190,7 +190,7 @@ int grappa_b200_col_reduce(const float* dy, int32_t ld, const float* x, const fl
 /* Fused backward kernels with DEFERRED column sums.  They write dx and, per CTA, the column sums over the CTA's rows
  * into `partial` ([n_cta, 2, cols] for LayerNorm: set 0 = sum dy (beta), set 1 = sum dy * xhat (gamma);
  * [n_cta, cols] for act_dropout_bwd: sum dx = bias gradient).  grappa_b200_finalize_colsums then folds the partials
- * of up to GB_COLSUM_MAX reductions in ONE launch (fixed order: deterministic).  cols <= 512 / <= 1024. */
+ * of up to GB_COLSUM_MAX reductions in ONE launch (fixed order: deterministic).  cols <= 512 (LayerNorm) / <= 8192 (activation-dropout, column slices of 1024). */
 int grappa_b200_layernorm_bwd_fused(const float* dy, const float* x, const float* mean, const float* rstd,
                                     const float* gamma, float* dx, float* partial, int32_t n_cta, int32_t rows,
                                     int32_t cols, void* stream);
