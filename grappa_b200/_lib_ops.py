@@ -29,6 +29,8 @@ class GemmArgs(C.Structure):
         ("act_out", vp),
         ("ldact", i32),
         ("dropout_offset", vp),
+        ("colsum", vp),
+        ("ld_colsum", i32),
     ]
 
 
@@ -89,6 +91,8 @@ def declare(lib):
     lib.grappa_b200_neighbor_mean.restype = C.c_int
     lib.grappa_b200_pad_rows.argtypes = [vp, i32, i32, i32, vp, i32, vp]
     lib.grappa_b200_pad_rows.restype = C.c_int
+    lib.grappa_b200_gemm_can_fuse_colsum.argtypes = [P(GemmArgs)]
+    lib.grappa_b200_gemm_can_fuse_colsum.restype = C.c_int
     lib.grappa_b200_gemm_grouped.argtypes = [P(GemmArgs), i32, vp]
     lib.grappa_b200_gemm_grouped.restype = C.c_int
     lib.grappa_b200_layernorm_fwd.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, f32, vp]

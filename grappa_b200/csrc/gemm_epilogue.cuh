@@ -11,6 +11,8 @@ struct Epilogue {
   const float* residual;
   float* C;
   float* act_out;
+  float* colsum;     // [ceil(M/32), ldcs] column sums of the stored values per 32-row group, or NULL
+  int ldcs;
   int ldc, ldm, ldr, ldact, N;
   int act, accumulate;
   uint32_t drop_thresh;   // 0 = dropout off
@@ -115,8 +117,8 @@ struct Epilogue {
   // 64-bit address arithmetic -- the GEMM kernel was issue-bound in its EPILOGUE (22 us for a 14848 x 512 output with
   // K = 32); the plain variant is ~10x shorter.
   template <int MASK>
-  __device__ __forceinline__ void store4_masked(float4 acc, float* __restrict__ crow, float* __restrict__ act_row, uint64_t didx,
-                                                uint64_t sd, const float4& res, const float4& y) const {
+  __device__ __forceinline__ float4 store4_masked(float4 acc, float* __restrict__ crow, float* __restrict__ act_row, uint64_t didx,
+                                                  uint64_t sd, const float4& res, const float4& y) const {
     float v[4] = {acc.x, acc.y, acc.z, acc.w};
     if ((MASK & 16) && accumulate == 2) {
       const float4 o = *reinterpret_cast<const float4*>(crow);
@@ -142,12 +144,15 @@ struct Epilogue {
       const float4 o = *reinterpret_cast<const float4*>(crow);
       v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;
     }
-    *reinterpret_cast<float4*>(crow) = make_float4(v[0], v[1], v[2], v[3]);
+    const float4 out = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(crow) = out;
+    return out;
   }
-  // smallest compiled feature set that covers this problem's epilogue (0, 1, 12, 10 or 31)
+  // smallest compiled feature set that covers this problem's epilogue (0, 1, 12, 10, 31; +32 = column sums: 42 or 63)
   __device__ __forceinline__ int feature_mask() const {
     const int need = ((act != 0 || act_out) ? 1 : 0) | (mul_elu_out ? 2 : 0) | (drop_thresh ? 4 : 0) | (residual ? 8 : 0) |
                      (accumulate ? 16 : 0);
+    if (colsum) return (need & ~10) == 0 ? 42 : 63;
     if (need == 0) return 0;
     if ((need & ~1) == 0) return 1;
     if ((need & ~12) == 0) return 12;
@@ -170,6 +175,8 @@ inline Epilogue make_epilogue(const gb_gemm_args* a) {
   e.C = a->C;
   e.act_out = a->act_out;
   e.ldact = a->ldact;
+  e.colsum = a->colsum;
+  e.ldcs = a->ld_colsum;
   e.ldc = a->ldc;
   e.ldm = a->ldm;
   e.ldr = a->ldr;

@@ -410,10 +410,16 @@ int gemm_simt(const gb_gemm_args* a, cudaStream_t stream) {
 
 int gemm_tcgen05(const gb_gemm_args* a, cudaStream_t stream, bool* handled);
 int gemm_tcgen05_grouped(const gb_gemm_args* list, int n, cudaStream_t stream, bool* handled);
+bool gemm_tcgen05_can_fuse_colsum(const gb_gemm_args* a);
 
 }  // namespace gb
 
 extern "C" int grappa_b200_gemm(const gb_gemm_args* a, void* stream_);
+
+extern "C" int grappa_b200_gemm_can_fuse_colsum(const gb_gemm_args* a) {
+  if (!a || a->M <= 0 || a->N <= 0 || !(a->precision == 1 || a->precision == 2)) return 0;
+  return gb::gemm_tcgen05_can_fuse_colsum(a) ? 1 : 0;
+}
 
 extern "C" int grappa_b200_gemm_grouped(const gb_gemm_args* list, int32_t n, void* stream_) {
   GB_REQUIRE(list != nullptr || n == 0, "gemm_grouped: list is NULL");
@@ -455,5 +461,6 @@ extern "C" int grappa_b200_gemm(const gb_gemm_args* a, void* stream_) {
     GB_REQUIRE(a->precision == 2, "gemm: tcgen05 path cannot take this shape/alignment (M=%d N=%d K=%d lda=%d ldb=%d)",
                a->M, a->N, a->K, a->lda, a->ldb);
   }
+  GB_REQUIRE(a->colsum == nullptr, "gemm: fused column sums need the tensor-core path (ask grappa_b200_gemm_can_fuse_colsum)");
   return gb::gemm_simt(a, stream);
 }

@@ -163,16 +163,29 @@ __device__ __forceinline__ void epi_patch_rows(const Epilogue& ep, const float* 
   uint64_t didx = (uint64_t)(m0 + sub_r) * (uint64_t)ep.N + (uint64_t)col;
   const size_t cstep = (size_t)4 * ep.ldc, astep = (size_t)4 * ep.ldact;
   const uint64_t dstep = (uint64_t)4 * (uint64_t)ep.N;
+  float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     if (m0 + sub_r + 4 * i < M) {
       float4 acc = *reinterpret_cast<const float4*>(patch + (sub_r + 4 * i) * EPI_LD + sub_c);
       acc.x += b4.x; acc.y += b4.y; acc.z += b4.z; acc.w += b4.w;
-      ep.template store4_masked<MASK>(acc, crow, arow, didx, sd, res4[i], elu4[i]);
+      const float4 o = ep.template store4_masked<MASK>(acc, crow, arow, didx, sd, res4[i], elu4[i]);
+      if (MASK & 32) { csum.x += o.x; csum.y += o.y; csum.z += o.z; csum.w += o.w; }
     }
     crow += cstep;
     if ((MASK & 1) && arow) arow += astep;
     didx += dstep;
+  }
+  if (MASK & 32) {
+    // lanes l, l + 8, l + 16, l + 24 own the same four columns (rows sub_r = 0..3 mod 4): fold them in a fixed order
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+      csum.x += __shfl_xor_sync(0xffffffffu, csum.x, o);
+      csum.y += __shfl_xor_sync(0xffffffffu, csum.y, o);
+      csum.z += __shfl_xor_sync(0xffffffffu, csum.z, o);
+      csum.w += __shfl_xor_sync(0xffffffffu, csum.w, o);
+    }
+    if (sub_r == 0 && m0 < M) *reinterpret_cast<float4*>(ep.colsum + (size_t)(m0 >> 5) * ep.ldcs + col) = csum;
   }
 }
 
@@ -477,6 +490,8 @@ gemm_tf32_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Tc
             else if (fmask == 1) epi_patch_rows<1, Cfg::EPI_LD>(pq.ep, patch, sub_r, sub_c, m0, pq.M, col, res4, elu4);
             else if (fmask == 12) epi_patch_rows<12, Cfg::EPI_LD>(pq.ep, patch, sub_r, sub_c, m0, pq.M, col, res4, elu4);
             else if (fmask == 10) epi_patch_rows<10, Cfg::EPI_LD>(pq.ep, patch, sub_r, sub_c, m0, pq.M, col, res4, elu4);
+            else if (fmask == 42) epi_patch_rows<42, Cfg::EPI_LD>(pq.ep, patch, sub_r, sub_c, m0, pq.M, col, res4, elu4);
+            else if (fmask == 63) epi_patch_rows<63, Cfg::EPI_LD>(pq.ep, patch, sub_r, sub_c, m0, pq.M, col, res4, elu4);
             else epi_patch_rows<31, Cfg::EPI_LD>(pq.ep, patch, sub_r, sub_c, m0, pq.M, col, res4, elu4);
           } else {
 #pragma unroll 1
@@ -607,6 +622,17 @@ static int dispatch(int BN, bool pair, int ta, int tb, const TcMaps& maps, const
 
 int launch_splitk_reduce(const float* partial, int splits, int M, int N, const Epilogue& ep, cudaStream_t stream);
 
+// the fused column sums need the vector epilogue (16-byte aligned pointers / pitches) and whole 32-row patches
+static bool colsum_legal(const gb_gemm_args* a) {
+  if (!a->colsum) return true;
+  const Epilogue e = make_epilogue(a);
+  return ((uintptr_t)a->colsum & 15) == 0 && (a->ld_colsum & 3) == 0 && a->ld_colsum >= a->N && (a->N & 3) == 0 &&
+         ((uintptr_t)e.bias & 15) == 0 && ((uintptr_t)e.C & 15) == 0 && (e.ldc & 3) == 0 &&
+         ((uintptr_t)e.residual & 15) == 0 && (!e.residual || (e.ldr & 3) == 0) &&
+         ((uintptr_t)e.mul_elu_out & 15) == 0 && (!e.mul_elu_out || (e.ldm & 3) == 0) &&
+         ((uintptr_t)e.act_out & 15) == 0 && (!e.act_out || (e.ldact & 3) == 0);
+}
+
 static bool tma_legal(const gb_gemm_args* a) {
   // 16-byte aligned bases and row pitches (TMA), enough work to fill a tile
   if (((uintptr_t)a->A & 15) || ((uintptr_t)a->B & 15) || (a->lda & 3) || (a->ldb & 3)) return false;
@@ -621,7 +647,7 @@ static bool make_maps(const gb_gemm_args* a, int b_rows, CUtensorMap* ma, CUtens
 int gemm_tcgen05(const gb_gemm_args* a, cudaStream_t stream, bool* handled) {
   *handled = false;
   const int M = a->M, N = a->N, K = a->K;
-  if (!tma_legal(a)) return GB_OK;
+  if (!tma_legal(a) || !colsum_legal(a)) return GB_OK;
   // tile shape.  pair = a cluster of two CTAs computes 256 x BN (cta_group::2), each staging half of B.  Measured on
   // B200 (tools/gemm_one.py): 16384 x 4096 x 4096 runs at 526 / 626 TFLOP/s with single-CTA 128 x 128 / 128 x 256 tiles
   // and at 764 TFLOP/s with 256 x 256 pair tiles (the cuBLAS-measured TF32-equivalent peak), so the pair wins whenever
@@ -632,7 +658,7 @@ int gemm_tcgen05(const gb_gemm_args* a, cudaStream_t stream, bool* handled) {
   // by K slices instead, so the widest tile that divides N is always the cheapest in operand traffic.
   const int sms_ = sm_count();
   static const int forced_pair = [] { const char* e = getenv("GRAPPA_B200_GEMM_PAIR"); return e ? atoi(e) : -1; }();   // tuning aid
-  const bool can_split = a->workspace != nullptr && (K + TC_BK - 1) / TC_BK >= 16;
+  const bool can_split = a->workspace != nullptr && a->colsum == nullptr && (K + TC_BK - 1) / TC_BK >= 16;
   static const int pair_min_k = [] { const char* e = getenv("GRAPPA_B200_GEMM_PAIR_MINK"); return e ? atoi(e) : 1024; }();   // tuning aids
   static const int pair_min_m = [] { const char* e = getenv("GRAPPA_B200_GEMM_PAIR_MINM"); return e ? atoi(e) : 0; }();
   bool pair = M > TC_BM && N >= 128 && forced_pair != 0 && ((K >= pair_min_k && (K >= 1024 || M >= pair_min_m)) || forced_pair == 1);
@@ -665,7 +691,7 @@ int gemm_tcgen05(const gb_gemm_args* a, cudaStream_t stream, bool* handled) {
   const int gx = (N + BN - 1) / BN, gy = tiles_m;
   const int total_kb = (K + TC_BK - 1) / TC_BK;
   int splits = 1;
-  if (a->workspace && gx * gy * 2 <= units && total_kb >= 16) {
+  if (can_split && gx * gy * 2 <= units && total_kb >= 16) {
     static const int min_kb = [] { const char* e = getenv("GRAPPA_B200_GEMM_MINKB"); return e ? atoi(e) : 4; }();   // tuning aid
     splits = units / (gx * gy);
     if (splits > total_kb / min_kb) splits = total_kb / min_kb;
@@ -699,9 +725,13 @@ int gemm_tcgen05(const gb_gemm_args* a, cudaStream_t stream, bool* handled) {
 int launch_splitk_reduce_grouped(int n, const float* const* partial, const int* splits, const int* Ms, const int* Ns,
                                  const Epilogue* eps, cudaStream_t stream);
 
+bool gemm_tcgen05_can_fuse_colsum(const gb_gemm_args* a) { return tma_legal(a) && colsum_legal(a); }
+
 int gemm_tcgen05_grouped(const gb_gemm_args* list, int n, cudaStream_t stream, bool* handled) {
   *handled = false;
   if (n < 1 || n > TC_MAX_GROUP) return GB_OK;
+  for (int i = 0; i < n; ++i)
+    if (list[i].colsum) return GB_OK;   // fused column sums are a single-launch feature
   const int ta = list[0].trans_a, tb = list[0].trans_b;
   if (!(ta && tb)) return GB_OK;
   bool all256 = true, all128 = true, big_m = true, long_k = true;

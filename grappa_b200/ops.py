@@ -107,7 +107,7 @@ def drop_workspaces():
 
 def _gemm_args(a: torch.Tensor, b: torch.Tensor, *, trans_a=False, trans_b=False, bias=None, act=0, mul_elu_out=None,
                dropout_p=0.0, dropout_seed=0, residual=None, out=None, accumulate=False, m=None, n=None, k=None,
-               precision=None, act_out=None):
+               precision=None, act_out=None, colsum=None):
     """Fill a gb_gemm_args for C[M,N] = opA(a) opB(b)^T (+ fused epilogue); returns (args, out)."""
     _lib.require_cuda(a, b)
     assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
@@ -134,6 +134,8 @@ def _gemm_args(a: torch.Tensor, b: torch.Tensor, *, trans_a=False, trans_b=False
     g.act_out = _p(act_out)
     g.ldact = act_out.stride(0) if act_out is not None else 0
     g.precision = _precision if precision is None else precision
+    if colsum is not None:
+        g.colsum, g.ld_colsum = colsum.data_ptr(), colsum.stride(0)
     if (trans_a and M * N <= (1 << 22) and K >= 1024) or (M * N <= (1 << 20) and K >= 2048):
         # weight gradients (tiny output, very long K) and the 2048-deep feed-forward GEMMs of the GNN (13 row tiles):
         # split-K slices fill the SMs, a reduce kernel applies the epilogue
@@ -160,6 +162,21 @@ def gemm(a: torch.Tensor, b: torch.Tensor, **kw) -> torch.Tensor:
         return out
     _lib.check(lib.grappa_b200_gemm(C.byref(g), _s()), "gemm")
     return out
+
+
+def gemm_with_colsum(a: torch.Tensor, b: torch.Tensor, **kw):
+    """`gemm` whose epilogue also emits per-32-row column sums of the stored result: returns (out, partial[ceil(M/32), N])
+    or (out, None) when this call cannot run on the fused tensor-core path (the caller then reduces separately)."""
+    lib = _lib.lib()
+    g, out = _gemm_args(a, b, **kw)
+    partial = torch.empty(((g.M + 31) // 32, g.N), device=a.device, dtype=torch.float32)
+    g.colsum, g.ld_colsum = partial.data_ptr(), partial.stride(0)
+    if g.workspace or not lib.grappa_b200_gemm_can_fuse_colsum(C.byref(g)):
+        return gemm(a, b, **kw), None
+    if _gemm_record is not None:
+        _gemm_record.append(("single", g, 1, (a, b, out, kw, partial)))
+    _lib.check(lib.grappa_b200_gemm(C.byref(g), _s()), "gemm")
+    return out, partial
 
 
 def gemm_grouped(problems) -> None:

@@ -14,6 +14,7 @@ where possible (`residual=` existing gradient) instead of separate add kernels.
 from __future__ import annotations
 
 import contextlib
+import os
 from typing import Callable, Dict, List, Optional
 
 import torch
@@ -23,6 +24,7 @@ from . import ops
 # Weight / bias gradient kernels do not feed the backward chain, so they are issued on a per-stream helper
 # stream and overlap with the dgrad kernels (inside a captured CUDA graph this becomes a parallel branch).
 _CONCURRENT = True
+_FUSE_COLSUM = os.environ.get("GRAPPA_B200_FUSE_COLSUM", "1") != "0"   # bias-gradient column sums inside the dgrad epilogue
 _side_streams: Dict[tuple, "torch.cuda.Stream"] = {}
 
 
@@ -52,7 +54,7 @@ def helper_streams(n: int, tag: str):
 
 class Var:
     """A value on the tape with its (lazily created) gradient."""
-    __slots__ = ("v", "g", "needs", "elu_fusable", "g_is_pre")
+    __slots__ = ("v", "g", "needs", "elu_fusable", "g_is_pre", "g_colsum")
 
     def __init__(self, v: torch.Tensor, needs: bool = True):
         self.v = v
@@ -60,6 +62,7 @@ class Var:
         self.needs = needs
         self.elu_fusable = False   # v == ELU(pre) exactly and the single consumer is a linear layer
         self.g_is_pre = False      # g already holds d/d(pre-activation)
+        self.g_colsum = None       # per-32-row column sums of g emitted by the GEMM that produced it (bias-gradient partials)
 
 
 class Tape:
@@ -232,6 +235,8 @@ def linear(t: Tape, x: Var, W: torch.Tensor, b: Optional[torch.Tensor], *, act: 
         bias_partial = None
         if y.g_is_pre:
             dpre_full = dy_full
+            if b is not None and y.g_colsum is not None and dy_full.shape[1] == N:
+                bias_partial = y.g_colsum          # the dgrad GEMM that wrote dy also summed its columns
         elif act != 0 or p > 0.0:
             saved = act_out if need_act_out else (y.v if act != 0 else None)
             dyc = dy_full.contiguous()
@@ -272,8 +277,12 @@ def linear(t: Tape, x: Var, W: torch.Tensor, b: Optional[torch.Tensor], *, act: 
         if x.needs:
             fuse = x.elu_fusable and x.g is None
             if K == xv.shape[1]:
-                dx = ops.gemm(dpre, W, trans_b=True, m=M, n=K, k=N, residual=x.g,
-                              mul_elu_out=xv if fuse else None)
+                if fuse and _FUSE_COLSUM:
+                    # dx is the pre-activation gradient of the producing layer: let the epilogue also emit its column
+                    # sums (that layer's bias gradient) instead of re-reading dx in a separate reduction
+                    dx, x.g_colsum = ops.gemm_with_colsum(dpre, W, trans_b=True, m=M, n=K, k=N, residual=x.g, mul_elu_out=xv)
+                else:
+                    dx = ops.gemm(dpre, W, trans_b=True, m=M, n=K, k=N, residual=x.g, mul_elu_out=xv if fuse else None)
                 x.g = dx
                 x.g_is_pre = fuse
             else:   # consumer read only the first K columns of a wider buffer

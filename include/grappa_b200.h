@@ -154,6 +154,11 @@ typedef struct {
   int32_t ldact;
   const uint64_t* dropout_offset; /* optional DEVICE counter added to dropout_seed at run time: lets a captured CUDA
                                      graph draw a fresh mask on every replay (see grappa_b200_tick) */
+  float* colsum;              /* optional [ceil(M/32), ld_colsum]: row g receives the column sums of the STORED values of
+                                 rows 32g .. 32g+31 (bias-gradient partials of the layer that produced this GEMM's input,
+                                 folded later by grappa_b200_finalize_colsums).  Tensor-core path only and never combined
+                                 with split-K: ask grappa_b200_gemm_can_fuse_colsum first */
+  int32_t ld_colsum;
 } gb_gemm_args;
 
 int grappa_b200_gemm(const gb_gemm_args* a, void* stream);   /* accumulate: 0 = overwrite C, 1 = C += epilogue(acc), 2 = the old C is added to the
@@ -165,6 +170,8 @@ int grappa_b200_gemm(const gb_gemm_args* a, void* stream);   /* accumulate: 0 = 
  * order of split-K slices.  Used for the weight gradients of a layer (reference: torch autograd's per-Linear
  * weight.grad accumulation, e.g. models/network_utils.py:44-54 backward). */
 int grappa_b200_gemm_grouped(const gb_gemm_args* list, int32_t n, void* stream);
+/* 1 if grappa_b200_gemm would serve `a` with the tensor-core kernel whose epilogue can also emit `colsum`, else 0 */
+int grappa_b200_gemm_can_fuse_colsum(const gb_gemm_args* a);
 
 /* ---------------------------------------------------------------------------------------------
  * LayerNorm over the last dimension (eps, affine, biased variance = torch.nn.LayerNorm defaults;

@@ -486,3 +486,25 @@ def test_loss_ignores_padding_conformations_like_the_reference():
         # padding conformations receive exactly zero gradient
         nv = z["meta.n_confs"].tolist()
         assert all(float(grads[0][b, nv[b]:].abs().sum()) == 0.0 for b in range(len(nv)))
+
+
+@pytest.mark.parametrize("M,N,K", [(3264, 512, 512), (14848, 512, 512), (700, 256, 256), (1664, 512, 1100)])
+def test_gemm_fused_column_sums(M, N, K):
+    """dgrad GEMM whose epilogue also emits per-32-row column sums of the stored result (bias-gradient partials)."""
+    from grappa_b200 import ops
+    dev = "cuda"
+    dY = torch.randn(M, K, device=dev)
+    W = torch.randn(K, N, device=dev)
+    Y = F.elu(torch.randn(M, N, device=dev))
+    res = torch.randn(M, N, device=dev)
+    out, partial = ops.gemm_with_colsum(dY, W, trans_b=True, residual=res, mul_elu_out=Y, precision=ops.AUTO)
+    ref = ops.gemm(dY, W, trans_b=True, residual=res, mul_elu_out=Y, precision=ops.AUTO)
+    assert partial is not None and partial.shape == ((M + 31) // 32, N)
+    assert torch.equal(out, ref)
+    assert R(partial.sum(0), ref.double().sum(0)) < 1e-5
+    # row groups are exact sums of their 32 rows
+    g = min(5, partial.shape[0] - 1)
+    assert R(partial[g], ref[32 * g:32 * g + 32].double().sum(0)) < 1e-5
+    # fp32 requests cannot fuse: the helper falls back to a plain GEMM
+    out32, p32 = ops.gemm_with_colsum(dY, W, trans_b=True, precision=ops.FP32)
+    assert p32 is None and R(out32, dY.double() @ W.double()) < 1e-5
