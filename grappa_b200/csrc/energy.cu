@@ -248,8 +248,11 @@ __global__ void __launch_bounds__(32 * G, 4) energy_rounds_kernel(gb_energy_args
   // ---- bonds
   if ((a.level_mask & 1) && a.n_tuples[0] > 0) {
     const int r1 = __ldg(a.round_off[0] + b + 1);
-    for (int r = __ldg(a.round_off[0] + b); r < r1; ++r) {
-      const int t = __ldg(a.sched[0] + (size_t)r * G + grp);            // warp-uniform
+    const int r0 = __ldg(a.round_off[0] + b);
+    int t_next = r0 < r1 ? __ldg(a.sched[0] + (size_t)r0 * G + grp) : -1;   // the next round's tuple is fetched one round ahead
+    for (int r = r0; r < r1; ++r) {
+      const int t = t_next;                                                 // warp-uniform
+      if (r + 1 < r1) t_next = __ldg(a.sched[0] + (size_t)(r + 1) * G + grp);
       if (t >= 0 && active) {
         const int i0 = __ldg(a.idx[0] + 2 * t) - a0, i1 = __ldg(a.idx[0] + 2 * t + 1) - a0;
         const float k = __ldg(a.k[0] + t), eq = __ldg(a.eq[0] + t);
@@ -271,8 +274,11 @@ __global__ void __launch_bounds__(32 * G, 4) energy_rounds_kernel(gb_energy_args
   // ---- angles
   if ((a.level_mask & 2) && a.n_tuples[1] > 0) {
     const int r1 = __ldg(a.round_off[1] + b + 1);
-    for (int r = __ldg(a.round_off[1] + b); r < r1; ++r) {
-      const int t = __ldg(a.sched[1] + (size_t)r * G + grp);
+    const int r0 = __ldg(a.round_off[1] + b);
+    int t_next = r0 < r1 ? __ldg(a.sched[1] + (size_t)r0 * G + grp) : -1;
+    for (int r = r0; r < r1; ++r) {
+      const int t = t_next;
+      if (r + 1 < r1) t_next = __ldg(a.sched[1] + (size_t)(r + 1) * G + grp);
       if (t >= 0 && active) {
         const int i0 = __ldg(a.idx[1] + 3 * t) - a0, i1 = __ldg(a.idx[1] + 3 * t + 1) - a0,
                   i2 = __ldg(a.idx[1] + 3 * t + 2) - a0;
@@ -306,8 +312,11 @@ __global__ void __launch_bounds__(32 * G, 4) energy_rounds_kernel(gb_energy_args
     float* __restrict__ teo = a.tuple_energy[lv];
     const int r1 = __ldg(a.round_off[lv] + b + 1);
     float e_acc = 0.f;
-    for (int r = __ldg(a.round_off[lv] + b); r < r1; ++r) {
-      const int t = __ldg(sched + (size_t)r * G + grp);
+    const int r0 = __ldg(a.round_off[lv] + b);
+    int t_next = r0 < r1 ? __ldg(sched + (size_t)r0 * G + grp) : -1;
+    for (int r = r0; r < r1; ++r) {
+      const int t = t_next;
+      if (r + 1 < r1) t_next = __ldg(sched + (size_t)(r + 1) * G + grp);
       if (t >= 0 && active) {
         const int32_t* ip = idx + 4 * t;
         const int i0 = __ldg(ip) - a0, i1 = __ldg(ip + 1) - a0, i2 = __ldg(ip + 2) - a0, i3 = __ldg(ip + 3) - a0;
