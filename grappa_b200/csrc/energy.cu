@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(512) energy_tiled_kernel(gb_energy_args a, int
 // coordinates are staged once in shared memory as [atom][xyz][32] (bank-conflict-free columns).
 // ---------------------------------------------------------------------------------------------
 template <int G>
-__global__ void __launch_bounds__(32 * G, 4) energy_rounds_kernel(gb_energy_args a, int n_tiles, int wtile) {
+__global__ void __launch_bounds__(32 * G, 5) energy_rounds_kernel(gb_energy_args a, int n_tiles, int wtile) {
   pdl_trigger();
   extern __shared__ float smem[];
   constexpr int W = 32;
