@@ -349,7 +349,10 @@ static bool skinny_gemm(const gb_gemm_args* a, const Epilogue& ep, cudaStream_t 
   }
   if (a->trans_a && a->trans_b && M <= SK_MAX && a->workspace && K >= 256) {
     const int col_blocks = (N + 255) / 256;
+    // few, long chunks: the fold over chunks is a serial loop per output element (ncu: 296 chunks made the 2-CTA reduce
+    // 35 us), while 48 CTAs already stream a 7 MB operand in a few microseconds
     int chunks = (2 * sm_count()) / col_blocks;
+    if (chunks > 48) chunks = 48;
     if (chunks > (K + 63) / 64) chunks = (K + 63) / 64;
     const long long by_ws = a->workspace_bytes / ((long long)M * N * 4);
     if (chunks > by_ws) chunks = (int)by_ws;
