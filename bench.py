@@ -341,7 +341,11 @@ def main():
                                    f"xyz working set {12 * na * n_confs / 1e6:.0f} MB > L2 not guaranteed -> see config.cache)",
                        "ms_per_launch": ms_en, "n_gpus": world,
                        "roofline": {"bound": "hbm", "kernel": "energy_tiled_kernel", "achieved": gbs, "peak": peaks["hbm_gbs"],
-                                    "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None,
+                                    "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": 92.7e6,
+                                    "traffic_source": "ncu --set full of this launch configuration (profiles/energy_r1d_ncu_raw.csv): "
+                                                      "dram read 71.0 MB + write 21.7 MB per launch vs %.1f MB algorithmic "
+                                                      "(part of the gradient is still in L2 at kernel end)" % (alg_bytes / 1e6),
+                                    "bound_note": "instruction-issue bound (profiles/r1_summary.md sections 3 and 11), not HBM bound",
                                     "algorithmic_bytes_per_eval": alg_bytes / evals, "peak_source": peaks["source"]}}
     except Exception as e:  # pragma: no cover
         energy_eval = {"error": repr(e)}
