@@ -23,14 +23,19 @@ __global__ void __launch_bounds__(256) edge_attn_fwd_kernel(const float* __restr
                                                             float* __restrict__ alpha, int n_nodes, int H, int D) {
   pdl_trigger();
   const int lane = threadIdx.x & 31;
-  const int v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (v >= n_nodes) return;
+  // one warp per (atom, group of 32 float4 columns): the column groups are independent (a head never straddles one),
+  // and a warp per atom walking its 4 groups one after the other left the 1,664-atom GNN kernels latency-bound
   const int nchunks = (H * D) >> 2, gs = D >> 2;
+  const int ncg = (nchunks + 31) >> 5;
+  const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int v = wid / ncg;
+  if (v >= n_nodes) return;
   const float scale = rsqrtf((float)D);
   const int e0 = __ldg(indptr + v), e1 = __ldg(indptr + v + 1);
   const float4* ft4 = reinterpret_cast<const float4*>(ft);
   const bool leader = (lane & (gs - 1)) == 0;
-  for (int c0 = 0; c0 < nchunks; c0 += 32) {
+  {
+    const int c0 = (wid - v * ncg) << 5;
     const int c = c0 + lane;
     const bool valid = c < nchunks;
     const int h = valid ? (c << 2) / D : 0;
@@ -66,14 +71,17 @@ __global__ void __launch_bounds__(256) edge_attn_bwd1_kernel(const float* __rest
                                                              int n_nodes, int H, int D) {
   pdl_trigger();
   const int lane = threadIdx.x & 31;
-  const int v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (v >= n_nodes) return;
   const int nchunks = (H * D) >> 2, gs = D >> 2;
+  const int ncg = (nchunks + 31) >> 5;
+  const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int v = wid / ncg;
+  if (v >= n_nodes) return;
   const float scale = rsqrtf((float)D);
   const int e0 = __ldg(indptr + v), e1 = __ldg(indptr + v + 1);
   const float4* ft4 = reinterpret_cast<const float4*>(ft);
   const bool leader = (lane & (gs - 1)) == 0;
-  for (int c0 = 0; c0 < nchunks; c0 += 32) {
+  {
+    const int c0 = (wid - v * ncg) << 5;
     const int c = c0 + lane;
     const bool valid = c < nchunks;
     const int h = valid ? (c << 2) / D : 0;
@@ -103,13 +111,15 @@ __global__ void __launch_bounds__(256) edge_attn_bwd2_kernel(const float* __rest
                                                              int n_nodes, int H, int D) {
   pdl_trigger();
   const int lane = threadIdx.x & 31;
-  const int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (u >= n_nodes) return;
   const int nchunks = (H * D) >> 2;
+  const int ncg = (nchunks + 31) >> 5;
+  const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int u = wid / ncg;
+  if (u >= n_nodes) return;
   const int e0 = __ldg(indptr + u), e1 = __ldg(indptr + u + 1);
   const float4* ft4 = reinterpret_cast<const float4*>(ft);
   const float4* do4 = reinterpret_cast<const float4*>(dout);
-  for (int c = lane; c < nchunks; c += 32) {
+  for (int c = ((wid - u * ncg) << 5) + lane; c < nchunks; c += nchunks) {
     const int h = (c << 2) / D;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int e = e0; e < e1; ++e) {
@@ -186,7 +196,8 @@ extern "C" int grappa_b200_edge_attention_fwd(const float* ft, const int32_t* in
   if (rc) return rc;
   if (n_nodes == 0) return GB_OK;
   GB_REQUIRE(ft && indptr && esrc && out, "edge_attention_fwd: NULL pointer");
-  edge_attn_fwd_kernel<<<(n_nodes + 7) / 8, 256, 0, (cudaStream_t)stream_>>>(ft, indptr, esrc, out, alpha, n_nodes, heads, dim);
+  const int ncg = (heads * dim / 4 + 31) / 32;
+  edge_attn_fwd_kernel<<<(n_nodes * ncg + 7) / 8, 256, 0, (cudaStream_t)stream_>>>(ft, indptr, esrc, out, alpha, n_nodes, heads, dim);
   GB_CHECK_LAUNCH();
   return GB_OK;
 }
@@ -199,9 +210,10 @@ extern "C" int grappa_b200_edge_attention_bwd(const float* ft, const float* alph
   if (n_nodes == 0) return GB_OK;
   GB_REQUIRE(ft && alpha && dout && indptr && esrc && erev && ds && dft, "edge_attention_bwd: NULL pointer");
   cudaStream_t stream = (cudaStream_t)stream_;
-  edge_attn_bwd1_kernel<<<(n_nodes + 7) / 8, 256, 0, stream>>>(ft, alpha, dout, indptr, esrc, ds, n_nodes, heads, dim);
+  const int ncg = (heads * dim / 4 + 31) / 32;
+  edge_attn_bwd1_kernel<<<(n_nodes * ncg + 7) / 8, 256, 0, stream>>>(ft, alpha, dout, indptr, esrc, ds, n_nodes, heads, dim);
   GB_CHECK_LAUNCH();
-  edge_attn_bwd2_kernel<<<(n_nodes + 7) / 8, 256, 0, stream>>>(ft, alpha, dout, ds, indptr, esrc, erev, dft, n_nodes, heads, dim);
+  edge_attn_bwd2_kernel<<<(n_nodes * ncg + 7) / 8, 256, 0, stream>>>(ft, alpha, dout, ds, indptr, esrc, erev, dft, n_nodes, heads, dim);
   GB_CHECK_LAUNCH();
   return GB_OK;
 }
