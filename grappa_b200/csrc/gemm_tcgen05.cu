@@ -749,7 +749,13 @@ int gemm_tcgen05_grouped(const gb_gemm_args* list, int n, cudaStream_t stream, b
   const bool pair = big_m && long_k && forced_pair != 0;
   const int BN = all256 ? 256 : 128;
   const int bm = pair ? 2 * TC_BM : TC_BM;
-  const int units = pair ? sm_count() / 2 : sm_count();
+  // Grouped launches carry weight gradients, which run on a side stream NEXT TO the latency-critical backward chain: a
+  // persistent kernel on all 148 SMs makes every small kernel of that chain wait for a free SM (14 us gaps per GNN block in
+  // the CUPTI timeline).  Leaving a third of the machine to the chain is faster overall: 148 / 112 / 96 / 80 / 64 SMs ->
+  // 6.17 / 6.05 / 6.02-6.06 / 6.07 / 6.08 ms per step.  GRAPPA_B200_GEMM_GROUP_SMS overrides (tuning aid).
+  static const int group_sms = [] { const char* e = getenv("GRAPPA_B200_GEMM_GROUP_SMS"); return e ? atoi(e) : 96; }();
+  const int sms_avail = group_sms > 0 && group_sms < sm_count() ? group_sms : sm_count();
+  const int units = pair ? sms_avail / 2 : sms_avail;
   TcMaps maps;
   TcParams p;
   p.n_problems = n;
