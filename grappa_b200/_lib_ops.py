@@ -31,6 +31,7 @@ class GemmArgs(C.Structure):
         ("dropout_offset", vp),
         ("colsum", vp),
         ("ld_colsum", i32),
+        ("max_sms", i32),
     ]
 
 

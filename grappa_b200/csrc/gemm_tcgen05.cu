@@ -656,7 +656,9 @@ int gemm_tcgen05(const gb_gemm_args* a, cudaStream_t stream, bool* handled) {
   // Width without split-K: 256 when the grid still covers every SM, 64 (single CTA) when even 128-wide tiles cannot
   // fill half the machine.  With split-K available (weight gradients: small output, very long K) the SMs are filled
   // by K slices instead, so the widest tile that divides N is always the cheapest in operand traffic.
-  const int sms_ = sm_count();
+  static const int max_sms_env = [] { const char* e = getenv("GRAPPA_B200_GEMM_MAX_SMS"); return e ? atoi(e) : -1; }();   // tuning aid
+  const int max_sms = max_sms_env >= 0 ? max_sms_env : a->max_sms;
+  const int sms_ = max_sms > 0 && max_sms < sm_count() ? max_sms : sm_count();
   static const int forced_pair = [] { const char* e = getenv("GRAPPA_B200_GEMM_PAIR"); return e ? atoi(e) : -1; }();   // tuning aid
   const bool can_split = a->workspace != nullptr && a->colsum == nullptr && (K + TC_BK - 1) / TC_BK >= 16;
   static const int pair_min_k = [] { const char* e = getenv("GRAPPA_B200_GEMM_PAIR_MINK"); return e ? atoi(e) : 1024; }();   // tuning aids

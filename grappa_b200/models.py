@@ -81,6 +81,7 @@ class _StageFn(torch.autograd.Function):
                 tape.sinks[id(det)] = sink
         outs = runner(tape, ins, params)
         ctx.tape, ctx.ins, ctx.params, ctx.outs = tape, ins, params, outs
+        ctx.concurrent = bool(tensors) and tensors[0].is_cuda and T_.concurrency()
         ctx.set_materialize_grads(False)
         return tuple(o.v for o in outs)
 
@@ -89,7 +90,10 @@ class _StageFn(torch.autograd.Function):
         tape = ctx.tape
         for o, g in zip(ctx.outs, gouts):
             o.g = None if g is None else g.contiguous().float()
-        tape.backward()
+        # the backward of every stage runs next to its weight-gradient branch (and the writers next to each other):
+        # leave part of the machine to the other streams' kernels
+        with ops.gemm_sm_limit(ops.CONCURRENT_GEMM_SMS if ctx.concurrent else 0):
+            tape.backward()
         gin = [v.g if v.needs else None for v in ctx.ins]
         gp = [None if id(p) in tape.sinks else tape.pgrads.get(id(p)) for p in ctx.params]
         ctx.tape = ctx.outs = None
@@ -694,7 +698,7 @@ class WriteParameters(nn.Module):
         done = []
         for w, st in zip(writers, T_.helper_streams(len(writers), "writer")):
             st.wait_event(start)
-            with torch.cuda.stream(st):
+            with torch.cuda.stream(st), ops.gemm_sm_limit(ops.CONCURRENT_GEMM_SMS):
                 g = w(g)
                 ev = torch.cuda.Event()
                 ev.record(st)

@@ -47,6 +47,29 @@ def _rng_ptr() -> int:
 _gemm_profile = None   # list collecting (flops, start_event, stop_event, kernel) when profiling is on
 
 
+# SMs a tensor-core GEMM may occupy (0 = all).  Sections that run several streams side by side set it to CONCURRENT_GEMM_SMS:
+# a persistent GEMM on all 148 SMs makes every kernel of the other streams wait for a free SM (148 / 132 / 116 / 100 / 88
+# SMs -> 6.02 / 5.97 / 5.92 / 6.10 / 6.08 ms per training step); single-stream code (GNN forward, inference) uses all SMs.
+CONCURRENT_GEMM_SMS = 116
+_gemm_sm_limit = 0
+
+
+class gemm_sm_limit:
+    """Context manager: tensor-core GEMMs issued inside use at most `n` SMs (0 = all)."""
+
+    def __init__(self, n: int):
+        self.n = int(n)
+
+    def __enter__(self):
+        global _gemm_sm_limit
+        self.prev, _gemm_sm_limit = _gemm_sm_limit, self.n
+        return self
+
+    def __exit__(self, *exc):
+        global _gemm_sm_limit
+        _gemm_sm_limit = self.prev
+
+
 _gemm_record = None    # list collecting every GEMM call (argument structs + the tensors they point to) of a step
 
 
@@ -134,6 +157,7 @@ def _gemm_args(a: torch.Tensor, b: torch.Tensor, *, trans_a=False, trans_b=False
     g.act_out = _p(act_out)
     g.ldact = act_out.stride(0) if act_out is not None else 0
     g.precision = _precision if precision is None else precision
+    g.max_sms = _gemm_sm_limit
     if colsum is not None:
         g.colsum, g.ld_colsum = colsum.data_ptr(), colsum.stride(0)
     if (trans_a and M * N <= (1 << 22) and K >= 1024) or (M * N <= (1 << 20) and K >= 2048):

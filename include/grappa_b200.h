@@ -159,6 +159,9 @@ typedef struct {
                                  folded later by grappa_b200_finalize_colsums).  Tensor-core path only and never combined
                                  with split-K: ask grappa_b200_gemm_can_fuse_colsum first */
   int32_t ld_colsum;
+  int32_t max_sms;            /* 0 = all.  SMs the persistent tensor-core kernel may occupy: callers that run several
+                                 streams side by side (the four writers, the weight-gradient branch) leave part of the
+                                 machine to the other streams' kernels (measured optimum 116 of 148) */
 } gb_gemm_args;
 
 int grappa_b200_gemm(const gb_gemm_args* a, void* stream);   /* accumulate: 0 = overwrite C, 1 = C += epilogue(acc), 2 = the old C is added to the

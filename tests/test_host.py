@@ -47,6 +47,7 @@ def test_struct_layouts_match_the_header():
     from grappa_b200._lib_ops import GemmArgs, HeadOutArgs, LossArgs, Perms
     assert ctypes.sizeof(Perms) == 4 + 6 * 4 * 4
     assert ctypes.sizeof(GemmArgs) % 8 == 0 and ctypes.sizeof(EnergyArgs) % 8 == 0
+    assert GemmArgs._fields_[-1][0] == "max_sms" and GemmArgs._fields_[-3][0] == "colsum"
     assert ctypes.sizeof(EnergyBwdArgs) > ctypes.sizeof(EnergyArgs)
     assert ctypes.sizeof(HeadOutArgs) == 6 * 4 + 8 * 4 + 12 * 4 + 4
     assert ctypes.sizeof(LossArgs) == 9 * 8 + 4 * 4 + 4 * 4 + 9 * 8
