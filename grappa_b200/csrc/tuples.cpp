@@ -12,6 +12,8 @@
 #include <array>
 #include <set>
 #include <unordered_map>
+#include <climits>
+#include <cstdint>
 #include <vector>
 
 #include "../../include/grappa_b200.h"
@@ -203,8 +205,10 @@ extern "C" int64_t grappa_b200_conflict_free_rounds(const int32_t* idx, const in
     return GB_ERR_INVALID;
   }
   int64_t total = 0;
-  std::unordered_map<int32_t, std::vector<uint64_t>> busy;   // atom -> bitset over this molecule's rounds
-  std::vector<uint64_t> full, tmp;                           // rounds that already hold `groups` tuples
+  // busy[a * words + w]: rounds (bit set) in which atom a of the current molecule is already used.  A molecule's atoms form
+  // a contiguous index range, so a dense table replaces the hash map this started with (3.3 ms -> well under 1 ms per
+  // 32-molecule batch: the schedule is built on the data-loader path, once per batch).
+  std::vector<uint64_t> busy, full, tmp;                     // full: rounds that already hold `groups` tuples
   std::vector<int32_t> fill;                                 // tuples per round
   for (int32_t b = 0; b < n_mols; ++b) {
     const int32_t t0 = tup_off[b], t1 = tup_off[b + 1];
@@ -217,30 +221,32 @@ extern "C" int64_t grappa_b200_conflict_free_rounds(const int32_t* idx, const in
       return GB_ERR_INVALID;
     }
     if (round_off) round_off[b] = (int32_t)total;
-    busy.clear();
-    full.clear();
+    int32_t amin = INT32_MAX, amax = INT32_MIN;
+    for (int64_t i = (int64_t)t0 * L; i < (int64_t)t1 * L; ++i) {
+      amin = idx[i] < amin ? idx[i] : amin;
+      amax = idx[i] > amax ? idx[i] : amax;
+    }
+    const int64_t n_at = t1 > t0 ? (int64_t)amax - amin + 1 : 0;
+    // a round holds <= groups disjoint tuples, so (t1 - t0) rounds always suffice: size the bitsets for that
+    const size_t words = (size_t)((t1 - t0) + 63) / 64 + 1;
+    busy.assign((size_t)n_at * words, 0);
+    full.assign(words, 0);
+    tmp.resize(words);
     fill.clear();
     for (int32_t t = t0; t < t1; ++t) {
-      tmp = full;
+      for (size_t w = 0; w < words; ++w) tmp[w] = full[w];
       for (int j = 0; j < L; ++j) {
-        auto it = busy.find(idx[(int64_t)t * L + j]);
-        if (it == busy.end()) continue;
-        if (it->second.size() > tmp.size()) tmp.resize(it->second.size(), 0);
-        for (size_t w = 0; w < it->second.size(); ++w) tmp[w] |= it->second[w];
+        const uint64_t* row = &busy[(size_t)(idx[(int64_t)t * L + j] - amin) * words];
+        for (size_t w = 0; w < words; ++w) tmp[w] |= row[w];
       }
       int64_t r = -1;
-      for (size_t w = 0; w < tmp.size() && r < 0; ++w)
+      for (size_t w = 0; w < words && r < 0; ++w)
         if (~tmp[w]) r = (int64_t)w * 64 + __builtin_ctzll(~tmp[w]);
-      if (r < 0) r = (int64_t)tmp.size() * 64;
-      if (r > (int64_t)fill.size()) r = (int64_t)fill.size();   // first never-used round
+      if (r < 0 || r > (int64_t)fill.size()) r = (int64_t)fill.size();   // first never-used round
       if (r == (int64_t)fill.size()) fill.push_back(0);
       const size_t w = (size_t)r / 64;
       const uint64_t bit = 1ull << (r % 64);
-      for (int j = 0; j < L; ++j) {
-        auto& v = busy[idx[(int64_t)t * L + j]];
-        if (v.size() <= w) v.resize(w + 1, 0);
-        v[w] |= bit;
-      }
+      for (int j = 0; j < L; ++j) busy[(size_t)(idx[(int64_t)t * L + j] - amin) * words + w] |= bit;
       if (sched) {
         if (total + r >= capacity_rounds) {
           gb::set_error("conflict_free_rounds: schedule buffer too small");
@@ -248,10 +254,7 @@ extern "C" int64_t grappa_b200_conflict_free_rounds(const int32_t* idx, const in
         }
         sched[(total + r) * groups + fill[r]] = t;
       }
-      if (++fill[r] == groups) {
-        if (full.size() <= w) full.resize(w + 1, 0);
-        full[w] |= bit;
-      }
+      if (++fill[r] == groups) full[w] |= bit;
     }
     if (sched)
       for (size_t r = 0; r < fill.size(); ++r)

@@ -38,16 +38,16 @@ def conflict_free_rounds(idx: np.ndarray, tup_off: np.ndarray, n_mols: int, L: i
     tup_off = np.ascontiguousarray(tup_off, dtype=np.int32)
     ro = np.zeros(n_mols + 1, dtype=np.int32)
     ip = idx.ctypes.data_as(C.c_void_p) if idx.size else None
+    # a molecule never needs more rounds than it has tuples, so one pass into a buffer of n_tuples rounds is enough
+    # (this runs on the data-loader path once per level and batch)
+    cap = int(tup_off[n_mols]) if n_mols else 0
+    buf = np.empty((cap, groups), dtype=np.int32)
     n = lib.grappa_b200_conflict_free_rounds(ip, tup_off.ctypes.data_as(C.c_void_p), n_mols, L, groups,
-                                             ro.ctypes.data_as(C.c_void_p), None, 0)
+                                             ro.ctypes.data_as(C.c_void_p), buf.ctypes.data_as(C.c_void_p) if cap else None,
+                                             cap)
     if n < 0:
         _lib.check(int(n), "conflict_free_rounds")
-    sc = np.full((max(int(n), 0), groups), -1, dtype=np.int32)
-    if n > 0:
-        n2 = lib.grappa_b200_conflict_free_rounds(ip, tup_off.ctypes.data_as(C.c_void_p), n_mols, L, groups,
-                                                  ro.ctypes.data_as(C.c_void_p), sc.ctypes.data_as(C.c_void_p), int(n))
-        if n2 != n:
-            _lib.check(int(n2) if n2 < 0 else -1, "conflict_free_rounds")
+    sc = buf[:int(n)]
     return ro, sc
 
 

@@ -85,4 +85,15 @@ def test_packed_dataset_roundtrip_and_loader(tmp_path):
         assert g.batch_size == 2 and g.dsnames == [ds2.dsname(i) for i in idxs]
         assert g.num_nodes("n1") == sum(mols[i].num_nodes("n1") for i in idxs)
         assert g._pack_cache is not None
+    # the data do not depend on the number of worker threads (per-batch generator streams), and a worker's error surfaces
+    for w in (1, 3):
+        again = list(dataset.PrefetchLoader(ds2, batches, conf_strategy=3, seed=5, depth=3, pin=False, workers=w))
+        if w == 1:
+            first = again
+        else:
+            for ga, gb_ in zip(first, again):
+                assert torch.equal(ga.nodes["n1"].data["xyz"], gb_.nodes["n1"].data["xyz"])
+                assert torch.equal(ga.nodes["g"].data["energy_ref"], gb_.nodes["g"].data["energy_ref"])
+    with pytest.raises(IndexError):
+        list(dataset.PrefetchLoader(ds2, [[0, 1], [0, 10 ** 6]], pin=False))
     assert dataset.shard_indices(10, 1, 4) == [1, 5, 9]
