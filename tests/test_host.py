@@ -148,6 +148,49 @@ def test_pack_tables():
         PackedBatch(g, device="cpu")
 
 
+def test_conflict_free_rounds_schedule():
+    """The energy kernel's force scatter is atomics-free because no two tuples of one round share an atom: check that,
+    that every tuple is scheduled exactly once inside its molecule's rounds, and that the C++ scheduler is the first-fit
+    greedy it documents (same schedule as a plain Python restatement)."""
+    from grappa_b200 import synthetic
+    from grappa_b200.pack import PackedBatch, conflict_free_rounds
+    g = synthetic.espaloma_mix_batch(seed=3, batch_size=6, n_confs=1)
+    p = PackedBatch(g, device="cpu")
+    G = p.sched_groups
+    for l, lvl in enumerate(LEVELS):
+        idx, tup_off = p.host[f"idx{l}"], p.host[f"tup_off{l}"]
+        ro, sc = p.host[f"round_off{l}"], p.host[f"sched{l}"]
+        assert sc.shape == (ro[-1], G) and ro[0] == 0
+        used = sc[sc >= 0]
+        assert sorted(used.tolist()) == list(range(idx.shape[0]))
+        want = []
+        for b in range(p.n_mols):
+            rounds = sc[ro[b]:ro[b + 1]]
+            mine = rounds[rounds >= 0]
+            assert ((mine >= tup_off[b]) & (mine < tup_off[b + 1])).all()
+            for r in rounds:
+                atoms = idx[r[r >= 0]].reshape(-1)
+                assert len(set(atoms.tolist())) == atoms.size
+                assert (r[:int((r >= 0).sum())] >= 0).all()                    # filled slots come first
+            # first-fit: the lowest round with a free slot whose tuples share no atom with this one
+            mol_rounds = []
+            for t in range(tup_off[b], tup_off[b + 1]):
+                atoms = set(idx[t].tolist())
+                for rr in mol_rounds:
+                    if len(rr) < G and not any(atoms & set(idx[u].tolist()) for u in rr):
+                        rr.append(t)
+                        break
+                else:
+                    mol_rounds.append([t])
+            want += [rr + [-1] * (G - len(rr)) for rr in mol_rounds]
+        assert np.array_equal(sc, np.array(want, dtype=np.int32).reshape(-1, G))
+    # molecules without tuples, and an empty level
+    ro, sc = conflict_free_rounds(np.array([[0, 1], [1, 2], [5, 6]], np.int32), np.array([0, 2, 2, 3], np.int32), 3, 2, 4)
+    assert ro.tolist() == [0, 2, 2, 3] and sc.tolist() == [[0, -1, -1, -1], [1, -1, -1, -1], [2, -1, -1, -1]]
+    ro, sc = conflict_free_rounds(np.zeros((0, 4), np.int32), np.zeros(3, np.int32), 2, 4, 8)
+    assert ro.tolist() == [0, 0, 0] and sc.shape == (0, 8)
+
+
 def test_module_tree_state_dict_and_error_behaviour():
     from grappa_b200 import GrappaB200Error, models, synthetic
     from grappa_b200.energy import Energy
