@@ -62,7 +62,12 @@ class HeadOutArgs(C.Structure):
         ("eq_std_over_max", f32), ("eq_max", f32),
         ("tk_std", f32 * 6), ("tk_mean", f32 * 6),
         ("cutoff", f32),
+        ("stat", vp * 4),
     ]
+
+
+class HeadStatGrads(C.Structure):
+    _fields_ = [("d", vp * 4), ("accumulate", i32)]
 
 
 class LossArgs(C.Structure):
@@ -112,6 +117,7 @@ def declare(lib):
     lib.grappa_b200_featurize.argtypes = [P(FeaturizeArgs), vp, i32, i32, vp]
     lib.grappa_b200_head_output_fwd.argtypes = [P(HeadOutArgs), vp, vp, vp, vp]
     lib.grappa_b200_head_output_bwd.argtypes = [P(HeadOutArgs), vp, vp, vp, vp, vp]
+    lib.grappa_b200_head_output_stats_bwd.argtypes = [P(HeadOutArgs), vp, vp, vp, P(HeadStatGrads), vp]
     lib.grappa_b200_dropout.argtypes = [vp, vp, i64, f32, u64, vp, vp]
     lib.grappa_b200_act_dropout_bwd.argtypes = [vp, vp, vp, i64, f32, u64, vp, vp]
     lib.grappa_b200_axpby.argtypes = [vp, vp, i64, f32, f32, vp]
@@ -128,6 +134,6 @@ def declare(lib):
     lib.grappa_b200_param_loss.restype = C.c_int
     for name in ("gemm", "layernorm_fwd", "layernorm_bwd", "col_reduce", "edge_attention_fwd", "edge_attention_bwd",
                  "tuple_attention_fwd", "tuple_attention_bwd", "tuple_gather_fwd", "tuple_gather_bwd",
-                 "perm_concat_fwd", "perm_concat_bwd", "featurize", "head_output_fwd", "head_output_bwd", "dropout",
+                 "perm_concat_fwd", "perm_concat_bwd", "featurize", "head_output_fwd", "head_output_bwd", "head_output_stats_bwd", "dropout",
                  "act_dropout_bwd", "axpby", "sumsq", "sumsq_det", "adam_step", "adam_step_dev", "tick", "layernorm_bwd_fused", "act_dropout_bwd_fused", "finalize_colsums", "molwise_loss"):
         getattr(lib, "grappa_b200_" + name).restype = C.c_int

@@ -43,11 +43,44 @@ __device__ __forceinline__ float to_positive_grad(float x, float mos, float sd) 
   return sd * (z > 0.f ? 1.f : expf(z));
 }
 
+// The statistics either come from the argument struct (buffers: host copies baked into the launch) or, with
+// learnable_statistics, from the parameters themselves in device memory (a->stat[]: a captured step then sees every
+// optimizer update).  kind 0: {k m/s, k std, eq m/s, eq std}; kind 1: {k m/s, k std, eq std/max}; kind 2: {k_std[n], k_mean[n]}.
+struct HeadStats {
+  float k_mos, k_std, eq_mos, eq_std, eq_som;
+  float tk_std[6], tk_mean[6];
+};
+__device__ __forceinline__ HeadStats head_stats(const gb_head_out_args& a) {
+  HeadStats h;
+  h.k_mos = a.k_mean_over_std; h.k_std = a.k_std;
+  h.eq_mos = a.eq_mean_over_std; h.eq_std = a.eq_std; h.eq_som = a.eq_std_over_max;
+#pragma unroll
+  for (int n = 0; n < 6; ++n) { h.tk_std[n] = a.tk_std[n]; h.tk_mean[n] = a.tk_mean[n]; }
+  if (a.kind <= 1) {
+    if (a.stat[0]) h.k_mos = __ldg(a.stat[0]);
+    if (a.stat[1]) h.k_std = __ldg(a.stat[1]);
+    if (a.kind == 0) {
+      if (a.stat[2]) h.eq_mos = __ldg(a.stat[2]);
+      if (a.stat[3]) h.eq_std = __ldg(a.stat[3]);
+    } else if (a.stat[2]) {
+      h.eq_som = __ldg(a.stat[2]);
+    }
+  } else {
+#pragma unroll
+    for (int n = 0; n < 6; ++n) {
+      if (n < a.n_per && a.stat[0]) h.tk_std[n] = __ldg(a.stat[0] + n);
+      if (n < a.n_per && a.stat[1]) h.tk_mean[n] = __ldg(a.stat[1] + n);
+    }
+  }
+  return h;
+}
+
 __global__ void __launch_bounds__(256) head_output_fwd_kernel(gb_head_out_args a, const float* __restrict__ scores,
                                                               float* __restrict__ k, float* __restrict__ eq) {
   pdl_trigger();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= a.T) return;
+  const HeadStats h = head_stats(a);
   float c[12];
 #pragma unroll
   for (int j = 0; j < 12; ++j) {
@@ -56,16 +89,16 @@ __global__ void __launch_bounds__(256) head_output_fwd_kernel(gb_head_out_args a
       for (int p = 0; p < a.n_perm; ++p) c[j] += __ldg(scores + ((size_t)p * a.T + t) * a.n_out + j);
   }
   if (a.kind == 0) {
-    eq[t] = to_positive(c[0], a.eq_mean_over_std, a.eq_std, a.eq_min);
-    k[t] = to_positive(c[1], a.k_mean_over_std, a.k_std, a.k_min);
+    eq[t] = to_positive(c[0], h.eq_mos, h.eq_std, a.eq_min);
+    k[t] = to_positive(c[1], h.k_mos, h.k_std, a.k_min);
   } else if (a.kind == 1) {
-    eq[t] = a.eq_max * sigmoidf_(a.eq_std_over_max * c[0]);
-    k[t] = to_positive(c[1], a.k_mean_over_std, a.k_std, a.k_min);
+    eq[t] = a.eq_max * sigmoidf_(h.eq_som * c[0]);
+    k[t] = to_positive(c[1], h.k_mos, h.k_std, a.k_min);
   } else {
 #pragma unroll
     for (int n = 0; n < 6; ++n) {
       if (n < a.n_per) {
-        float v = a.gated ? c[n] * sigmoidf_(c[n + a.n_per]) * a.tk_std[n] : c[n] * a.tk_std[n] + a.tk_mean[n];
+        float v = a.gated ? c[n] * sigmoidf_(c[n + a.n_per]) * h.tk_std[n] : c[n] * h.tk_std[n] + h.tk_mean[n];
         if (a.cutoff > 0.f && !(fabsf(v) > a.cutoff)) v = 0.f;
         k[(size_t)t * a.n_per + n] = v;
       }
@@ -79,6 +112,7 @@ __global__ void __launch_bounds__(256) head_output_bwd_kernel(gb_head_out_args a
   pdl_trigger();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= a.T) return;
+  const HeadStats h = head_stats(a);
   float c[12], d[12];
 #pragma unroll
   for (int j = 0; j < 12; ++j) {
@@ -88,14 +122,14 @@ __global__ void __launch_bounds__(256) head_output_bwd_kernel(gb_head_out_args a
       for (int p = 0; p < a.n_perm; ++p) c[j] += __ldg(scores + ((size_t)p * a.T + t) * a.n_out + j);
   }
   if (a.kind == 0) {
-    if (deq) d[0] = __ldg(deq + t) * to_positive_grad(c[0], a.eq_mean_over_std, a.eq_std);
-    if (dk) d[1] = __ldg(dk + t) * to_positive_grad(c[1], a.k_mean_over_std, a.k_std);
+    if (deq) d[0] = __ldg(deq + t) * to_positive_grad(c[0], h.eq_mos, h.eq_std);
+    if (dk) d[1] = __ldg(dk + t) * to_positive_grad(c[1], h.k_mos, h.k_std);
   } else if (a.kind == 1) {
     if (deq) {
-      const float s = sigmoidf_(a.eq_std_over_max * c[0]);
-      d[0] = __ldg(deq + t) * a.eq_max * a.eq_std_over_max * s * (1.f - s);
+      const float s = sigmoidf_(h.eq_som * c[0]);
+      d[0] = __ldg(deq + t) * a.eq_max * h.eq_som * s * (1.f - s);
     }
-    if (dk) d[1] = __ldg(dk + t) * to_positive_grad(c[1], a.k_mean_over_std, a.k_std);
+    if (dk) d[1] = __ldg(dk + t) * to_positive_grad(c[1], h.k_mos, h.k_std);
   } else if (dk) {
 #pragma unroll
     for (int n = 0; n < 6; ++n) {
@@ -103,14 +137,14 @@ __global__ void __launch_bounds__(256) head_output_bwd_kernel(gb_head_out_args a
         const float g = __ldg(dk + (size_t)t * a.n_per + n);
         if (a.gated) {
           const float s = sigmoidf_(c[n + a.n_per]);
-          const float v = c[n] * s * a.tk_std[n];
+          const float v = c[n] * s * h.tk_std[n];
           const bool keep = !(a.cutoff > 0.f) || fabsf(v) > a.cutoff;
-          d[n] = keep ? g * s * a.tk_std[n] : 0.f;
-          d[n + a.n_per] = keep ? g * c[n] * s * (1.f - s) * a.tk_std[n] : 0.f;
+          d[n] = keep ? g * s * h.tk_std[n] : 0.f;
+          d[n + a.n_per] = keep ? g * c[n] * s * (1.f - s) * h.tk_std[n] : 0.f;
         } else {
-          const float v = c[n] * a.tk_std[n] + a.tk_mean[n];
+          const float v = c[n] * h.tk_std[n] + h.tk_mean[n];
           const bool keep = !(a.cutoff > 0.f) || fabsf(v) > a.cutoff;
-          d[n] = keep ? g * a.tk_std[n] : 0.f;
+          d[n] = keep ? g * h.tk_std[n] : 0.f;
         }
       }
     }
@@ -119,6 +153,82 @@ __global__ void __launch_bounds__(256) head_output_bwd_kernel(gb_head_out_args a
 #pragma unroll
     for (int j = 0; j < 12; ++j)
       if (j < a.n_out) dscores[((size_t)p * a.T + t) * a.n_out + j] = d[j];
+}
+
+// Gradients of the learnable statistics: one CTA walks all tuples and reduces up to 12 sums in a fixed order (no atomics:
+// the step stays bit-reproducible).  The slots follow a->stat[]: kinds 0/1 -> one value per pointer; kind 2 -> n_per values
+// for k_std (slots 0..5) and n_per for k_mean (slots 6..11; zero when gated, where the mean does not enter).
+__global__ void __launch_bounds__(1024) head_output_stats_bwd_kernel(gb_head_out_args a, const float* __restrict__ scores,
+                                                                     const float* __restrict__ dk,
+                                                                     const float* __restrict__ deq, gb_head_stat_grads o) {
+  pdl_trigger();
+  const HeadStats h = head_stats(a);
+  float acc[12];
+#pragma unroll
+  for (int j = 0; j < 12; ++j) acc[j] = 0.f;
+  for (int t = threadIdx.x; t < a.T; t += blockDim.x) {
+    float c[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+      c[j] = 0.f;
+      if (j < a.n_out)
+        for (int p = 0; p < a.n_perm; ++p) c[j] += __ldg(scores + ((size_t)p * a.T + t) * a.n_out + j);
+    }
+    if (a.kind <= 1) {
+      if (dk) {
+        const float g = __ldg(dk + t), z = h.k_mos + c[1] - 1.f;
+        acc[0] += g * h.k_std * (z > 0.f ? 1.f : expf(z));      // d/d(mean_over_std)
+        acc[1] += g * (elu1(z) + 1.f);                           // d/d(std)
+      }
+      if (deq) {
+        const float g = __ldg(deq + t);
+        if (a.kind == 0) {
+          const float z = h.eq_mos + c[0] - 1.f;
+          acc[2] += g * h.eq_std * (z > 0.f ? 1.f : expf(z));
+          acc[3] += g * (elu1(z) + 1.f);
+        } else {
+          const float s = sigmoidf_(h.eq_som * c[0]);
+          acc[2] += g * a.eq_max * s * (1.f - s) * c[0];         // d/d(std_over_max)
+        }
+      }
+    } else if (dk) {
+#pragma unroll
+      for (int n = 0; n < 6; ++n) {
+        if (n < a.n_per) {
+          const float g = __ldg(dk + (size_t)t * a.n_per + n);
+          if (a.gated) {
+            const float u = c[n] * sigmoidf_(c[n + a.n_per]);
+            const bool keep = !(a.cutoff > 0.f) || fabsf(u * h.tk_std[n]) > a.cutoff;
+            if (keep) acc[n] += g * u;
+          } else {
+            const bool keep = !(a.cutoff > 0.f) || fabsf(c[n] * h.tk_std[n] + h.tk_mean[n]) > a.cutoff;
+            if (keep) { acc[n] += g * c[n]; acc[6 + n] += g; }
+          }
+        }
+      }
+    }
+  }
+  __shared__ float red[32][12];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 12; ++j) {
+    float v = acc[j];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    if (lane == 0) red[w][j] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 12) {
+    float v = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) v += red[i][threadIdx.x];
+    const int j = threadIdx.x;
+    if (a.kind <= 1) {
+      if (j < 4 && o.d[j]) o.d[j][0] = (o.accumulate ? o.d[j][0] : 0.f) + v;
+    } else {
+      float* dst = o.d[j / 6];
+      if (dst && (j % 6) < a.n_per) dst[j % 6] = (o.accumulate ? dst[j % 6] : 0.f) + v;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -373,6 +483,22 @@ extern "C" int grappa_b200_head_output_fwd(const gb_head_out_args* a, const floa
   if (a->T == 0) return GB_OK;
   GB_REQUIRE(scores && k && (a->kind == 2 || eq), "head_output_fwd: NULL pointer");
   head_output_fwd_kernel<<<(a->T + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(*a, scores, k, eq);
+  GB_CHECK_LAUNCH();
+  return GB_OK;
+}
+
+extern "C" int grappa_b200_head_output_stats_bwd(const gb_head_out_args* a, const float* scores, const float* dk,
+                                                 const float* deq, const gb_head_stat_grads* out, void* stream_) {
+  int rc = check_head(a);
+  if (rc) return rc;
+  GB_REQUIRE(out != nullptr && (a->T <= 0 || scores != nullptr), "head_output_stats_bwd: NULL pointer");
+  if (a->T <= 0 && !out->accumulate) {   // no tuples: the gradients are zero
+    for (int j = 0; j < 4; ++j)
+      if (out->d[j]) GB_CHECK_CUDA(cudaMemsetAsync(out->d[j], 0, sizeof(float) * (a->kind == 2 ? a->n_per : 1), (cudaStream_t)stream_));
+    return GB_OK;
+  }
+  if (a->T <= 0) return GB_OK;
+  head_output_stats_bwd_kernel<<<1, 1024, 0, (cudaStream_t)stream_>>>(*a, scores, dk, deq, *out);
   GB_CHECK_LAUNCH();
   return GB_OK;
 }

@@ -123,27 +123,36 @@ class ResidualAttentionBlock(nn.Module):
                  dropout_behind_mha=0.1, dropout_behind_self_interaction=0.1, skip_connection=True):
         super().__init__()
         out_feats = in_feats if out_feats is None else out_feats
-        if not (layer_norm and self_interaction and skip_connection and out_feats == in_feats):
-            raise NotImplementedError("grappa_b200 implements the grappa-1.x block: layer_norm, self_interaction and "
+        if not (skip_connection and out_feats == in_feats):
+            raise NotImplementedError("grappa_b200 implements the block GrappaGNN builds (graph_attention.py:113-120): "
                                       "skip connection enabled, out_feats == in_feats")
         assert out_feats % num_heads == 0
         self.in_feats, self.out_feats, self.num_heads = in_feats, out_feats, num_heads
         self.feats_per_head = out_feats // num_heads
         self.graph_module = DotGatConv(in_feats, out_feats // num_heads, num_heads)
         self.p1, self.p2 = dropout_behind_mha, dropout_behind_self_interaction
-        self.layer_norm = nn.LayerNorm(in_feats)
+        self.do_layer_norm = layer_norm
+        if layer_norm:
+            self.layer_norm = nn.LayerNorm(in_feats)
         self.head_reducer = nn.Linear(num_heads * self.feats_per_head, out_feats)
-        self.interaction_norm = nn.LayerNorm(out_feats)
-        self.self_interaction = nn.Sequential(nn.Linear(out_feats, 4 * out_feats), nn.ELU(),
-                                              nn.Linear(4 * out_feats, out_feats), nn.ELU())
+        if self_interaction:
+            if layer_norm:
+                self.interaction_norm = nn.LayerNorm(out_feats)
+            self.self_interaction = nn.Sequential(nn.Linear(out_feats, 4 * out_feats), nn.ELU(),
+                                                  nn.Linear(4 * out_feats, out_feats), nn.ELU())
+        else:
+            self.self_interaction = None
 
     def tape_forward(self, t: Tape, pack, h: Var, P) -> Var:
-        """graph_attention.py:276-310: u=LN(h); y=W_r attn(u W_fc)+u; z=LN(y); out=ELU(W2 ELU(W1 z))+z."""
-        u = T_.layernorm(t, h, P(self.layer_norm.weight), P(self.layer_norm.bias))
+        """graph_attention.py:276-310: u=LN(h); y=W_r attn(u W_fc)+u; z=LN(y); out=ELU(W2 ELU(W1 z))+z  (the two
+        LayerNorms only with layer_norm=True, the second half only with self_interaction=True)."""
+        u = T_.layernorm(t, h, P(self.layer_norm.weight), P(self.layer_norm.bias)) if self.do_layer_norm else h
         ft = T_.linear(t, u, P(self.graph_module.fc.weight), None)
         m = T_.edge_attention(t, ft, pack, self.num_heads)
         y = T_.linear(t, m, P(self.head_reducer.weight), P(self.head_reducer.bias), dropout_p=self.p1, residual=u)
-        z = T_.layernorm(t, y, P(self.interaction_norm.weight), P(self.interaction_norm.bias))
+        if self.self_interaction is None:
+            return y
+        z = T_.layernorm(t, y, P(self.interaction_norm.weight), P(self.interaction_norm.bias)) if self.do_layer_norm else y
         a1 = T_.linear(t, z, P(self.self_interaction[0].weight), P(self.self_interaction[0].bias), act=ELU,
                        fuse_elu_into_consumer=True)
         return T_.linear(t, a1, P(self.self_interaction[2].weight), P(self.self_interaction[2].bias), act=ELU,
@@ -175,22 +184,30 @@ class ResidualConvBlock(nn.Module):
     def __init__(self, in_feats, out_feats=None, self_interaction=True, layer_norm=True, dropout=0.0, skip_connection=True):
         super().__init__()
         out_feats = in_feats if out_feats is None else out_feats
-        if not (layer_norm and self_interaction and skip_connection and out_feats == in_feats):
-            raise NotImplementedError("grappa_b200 implements the grappa-1.0 block: layer_norm, self_interaction and "
+        if not (skip_connection and out_feats == in_feats):
+            raise NotImplementedError("grappa_b200 implements the block GrappaGNN builds (graph_attention.py:106-109): "
                                       "skip connection enabled, out_feats == in_feats")
         self.in_feats, self.out_feats, self.p = in_feats, out_feats, dropout
         self.graph_module = SAGEConv(in_feats, out_feats, "mean")
-        self.layer_norm = nn.LayerNorm(in_feats)
-        self.self_interaction = nn.Sequential(nn.Linear(out_feats, out_feats), nn.ELU())
-        self.interaction_norm = nn.LayerNorm(out_feats)
+        self.do_layer_norm = layer_norm
+        if layer_norm:
+            self.layer_norm = nn.LayerNorm(in_feats)
+        if self_interaction:
+            self.self_interaction = nn.Sequential(nn.Linear(out_feats, out_feats), nn.ELU())
+            if layer_norm:
+                self.interaction_norm = nn.LayerNorm(out_feats)
+        else:
+            self.self_interaction = None
 
     def tape_forward(self, t: Tape, pack, h: Var, P) -> Var:
-        u = T_.layernorm(t, h, P(self.layer_norm.weight), P(self.layer_norm.bias))
+        u = T_.layernorm(t, h, P(self.layer_norm.weight), P(self.layer_norm.bias)) if self.do_layer_norm else h
         s_self = T_.linear(t, u, P(self.graph_module.fc_self.weight), None)
         hn = T_.neighbor_mean(t, u, pack)
         y = T_.linear(t, hn, P(self.graph_module.fc_neigh.weight), P(self.graph_module.fc_self.bias), act=ELU,
                       dropout_p=self.p, residual=u, pre_add=s_self)
-        z = T_.layernorm(t, y, P(self.interaction_norm.weight), P(self.interaction_norm.bias))
+        if self.self_interaction is None:
+            return y
+        z = T_.layernorm(t, y, P(self.interaction_norm.weight), P(self.interaction_norm.bias)) if self.do_layer_norm else y
         return T_.linear(t, z, P(self.self_interaction[0].weight), P(self.self_interaction[0].bias), act=ELU,
                          dropout_p=self.p, residual=z)
 
@@ -275,12 +292,15 @@ class ToPositive(nn.Module):
 
     def __init__(self, mean, std, min_=0., learnable_statistics=False):
         super().__init__()
-        if learnable_statistics:
-            raise NotImplementedError("learnable_statistics=True is not supported by grappa_b200")
         # the reference divides by the fp32-rounded std (final_layer.py:30-41): keep the same rounding
         std_t = torch.tensor(float(std)).float()
-        self.register_buffer("mean_over_std", torch.tensor(float(mean / std_t)))
-        self.register_buffer("std", torch.tensor(float(std)))
+        self.learnable = bool(learnable_statistics)
+        if self.learnable:      # final_layer.py:37-39: trained along with the weights, read from device memory by the kernels
+            self.mean_over_std = nn.Parameter(torch.tensor(float(mean / std_t)))
+            self.std = nn.Parameter(torch.tensor(float(std)))
+        else:
+            self.register_buffer("mean_over_std", torch.tensor(float(mean / std_t)))
+            self.register_buffer("std", torch.tensor(float(std)))
         self.register_buffer("min_", torch.tensor(float(min_)))
 
 
@@ -289,9 +309,11 @@ class ToRange(nn.Module):
 
     def __init__(self, max_, std, learnable_statistics=False):
         super().__init__()
-        if learnable_statistics:
-            raise NotImplementedError("learnable_statistics=True is not supported by grappa_b200")
-        self.register_buffer("std_over_max", torch.tensor(float(std / max_)).float())
+        self.learnable = bool(learnable_statistics)
+        if self.learnable:      # final_layer.py:84-85
+            self.std_over_max = nn.Parameter(torch.tensor(float(std / max_)).float())
+        else:
+            self.register_buffer("std_over_max", torch.tensor(float(std / max_)).float())
         self.register_buffer("max", torch.tensor(float(max_)).float())
 
 
@@ -313,19 +335,19 @@ class FeedForwardLayer(nn.Module):
         super().__init__()
         hidden_feats = in_feats if hidden_feats is None else hidden_feats
         out_feats = in_feats if out_feats is None else out_feats
-        if not layer_norm:
-            raise NotImplementedError("layer_norm=False is not supported by grappa_b200")
         self.in_feats, self.hidden_feats, self.out_feats = in_feats, hidden_feats, out_feats
         self.linear1 = nn.Linear(in_feats, hidden_feats)
         self.linear2 = nn.Linear(hidden_feats, out_feats)
         self.p, self.skip = dropout, skip
-        self.norm1 = nn.LayerNorm(in_feats)
+        self.layer_norm = layer_norm
+        if layer_norm:
+            self.norm1 = nn.LayerNorm(in_feats)
         assert (out_feats == in_feats) or not skip, \
             f"Skip connection is not possible with {in_feats} input features and {out_feats} output features."
 
     def tape_forward(self, t: Tape, x: Var, P) -> Var:
-        """network_utils.py:44-54: xn = LN(x); W2 ELU(W1 xn) (+ xn if skip)."""
-        xn = T_.layernorm(t, x, P(self.norm1.weight), P(self.norm1.bias))
+        """network_utils.py:44-54: xn = LN(x) (x itself with layer_norm=False); W2 ELU(W1 xn) (+ xn if skip)."""
+        xn = T_.layernorm(t, x, P(self.norm1.weight), P(self.norm1.bias)) if self.layer_norm else x
         f1 = T_.linear(t, xn, P(self.linear1.weight), P(self.linear1.bias), act=ELU, fuse_elu_into_consumer=True)
         return T_.linear(t, f1, P(self.linear2.weight), P(self.linear2.bias), dropout_p=self.p,
                          residual=xn if self.skip else None)
@@ -335,18 +357,18 @@ class DottedAttWithMLP(nn.Module):
     def __init__(self, n_feats, num_heads, hidden_feats=None, layer_norm=True, dropout=0.):
         super().__init__()
         hidden_feats = 4 * n_feats if hidden_feats is None else hidden_feats
-        if not layer_norm:
-            raise NotImplementedError("layer_norm=False is not supported by grappa_b200")
         assert n_feats % num_heads == 0, \
             f"Number of features ({n_feats}) must be divisible by the number of heads ({num_heads})."
         self.n_feats, self.num_heads, self.p = n_feats, num_heads, dropout
-        self.norm1 = nn.LayerNorm(n_feats)
+        self.layer_norm = layer_norm
+        if layer_norm:
+            self.norm1 = nn.LayerNorm(n_feats)
         self.attn = nn.MultiheadAttention(n_feats, num_heads, dropout=0)
         self.ff = FeedForwardLayer(n_feats, hidden_feats, out_feats=n_feats, dropout=dropout, skip=True, layer_norm=layer_norm)
 
     def tape_forward(self, t: Tape, x: Var, n_tuples: int, L: int, P) -> Var:
-        """network_utils.py:112-133: xn = LN(x); x = MHA(xn) + xn; x = FF(x)."""
-        xn = T_.layernorm(t, x, P(self.norm1.weight), P(self.norm1.bias))
+        """network_utils.py:112-133: xn = LN(x) (x itself with layer_norm=False); x = MHA(xn) + xn; x = FF(x)."""
+        xn = T_.layernorm(t, x, P(self.norm1.weight), P(self.norm1.bias)) if self.layer_norm else x
         qkv = T_.linear(t, xn, P(self.attn.in_proj_weight), P(self.attn.in_proj_bias))
         att = T_.tuple_attention(t, qkv, n_tuples, L, self.num_heads)
         x1 = T_.linear(t, att, P(self.attn.out_proj.weight), P(self.attn.out_proj.bias), dropout_p=self.p, residual=xn)
@@ -436,6 +458,10 @@ class _TupleWriter(nn.Module):
     def _head_args(self, T: int) -> HeadOutArgs:
         raise NotImplementedError
 
+    def _stat_params(self):
+        """learnable_statistics: the statistics parameters in the slot order of gb_head_out_args.stat, else None."""
+        return None
+
     def _host(self, name: str, buf: torch.Tensor):
         """Host copy of a small statistics buffer, refreshed when the buffer is modified."""
         cache = self.__dict__.setdefault("_host_cache", {})
@@ -454,6 +480,7 @@ class _TupleWriter(nn.Module):
         pe = gt.positional_encoding.flatten().contiguous() if (gt is not None and gt.positional_encoding is not None) else None
         sym = model.symmetriser
         args = self._head_args(T)
+        stat_params = self._stat_params()
 
         def run(t: Tape, ins, params):
             P = lambda p: params[index[id(p)]]
@@ -468,13 +495,34 @@ class _TupleWriter(nn.Module):
             s = T_.perm_concat(t, x, sym._perms_c, T, L, E)
             for ff in sym.mlp:
                 s = ff.tape_forward(t, s, P)
+            stats = None
+            if stat_params is not None:
+                # the kernels read the (trainable) statistics from the parameters' own device memory
+                stats = [None if p is None else P(p) for p in stat_params]
+                for i, sp in enumerate(stats):
+                    args.stat[i] = None if sp is None else sp.data_ptr()
             k, eq = ops.head_output_fwd(args, s.v)
             kv, eqv = Var(k), (Var(eq) if eq is not None else None)
 
             def bwd():
                 if kv.g is None and (eqv is None or eqv.g is None):
                     return
-                T_.add_grad(s, ops.head_output_bwd(args, s.v, kv.g, None if eqv is None else eqv.g))
+                deq = None if eqv is None else eqv.g
+                if stats is not None:
+                    targets, accs = [], []
+                    for sp in stats:
+                        if sp is None:
+                            targets.append(None)
+                            continue
+                        tgt, acc = t.grad_target(sp)
+                        if tgt is None:
+                            tgt, acc = torch.empty_like(sp), False
+                            t.pgrads[id(sp)] = tgt
+                        targets.append(tgt)
+                        accs.append(acc)
+                    assert len(set(accs)) == 1
+                    ops.head_output_stats_bwd(args, s.v, kv.g, deq, targets, accs[0])
+                T_.add_grad(s, ops.head_output_bwd(args, s.v, kv.g, deq))
             t.push(bwd)
             return [kv] if eqv is None else [kv, eqv]
         return run
@@ -514,11 +562,17 @@ class WriteBondParameters(_TupleWriter):
 
     def _head_args(self, T):
         a = HeadOutArgs(kind=0, T=T, n_perm=2, n_out=2 + int(self.gate), n_per=0, gated=0)
-        a.k_mean_over_std, a.k_std, a.k_min = (self._host("kmos", self.to_k.mean_over_std)[0],
-                                               self._host("kstd", self.to_k.std)[0], self._host("kmin", self.to_k.min_)[0])
-        a.eq_mean_over_std, a.eq_std, a.eq_min = (self._host("emos", self.to_eq.mean_over_std)[0],
-                                                  self._host("estd", self.to_eq.std)[0], self._host("emin", self.to_eq.min_)[0])
+        a.k_min, a.eq_min = self._host("kmin", self.to_k.min_)[0], self._host("emin", self.to_eq.min_)[0]
+        if not self.to_k.learnable:
+            a.k_mean_over_std, a.k_std = self._host("kmos", self.to_k.mean_over_std)[0], self._host("kstd", self.to_k.std)[0]
+            a.eq_mean_over_std, a.eq_std = (self._host("emos", self.to_eq.mean_over_std)[0],
+                                            self._host("estd", self.to_eq.std)[0])
         return a
+
+    def _stat_params(self):
+        if not self.to_k.learnable:
+            return None
+        return [self.to_k.mean_over_std, self.to_k.std, self.to_eq.mean_over_std, self.to_eq.std]
 
     def forward(self, g):
         h = g.nodes["n1"].data["h"]
@@ -559,10 +613,16 @@ class WriteAngleParameters(_TupleWriter):
 
     def _head_args(self, T):
         a = HeadOutArgs(kind=1, T=T, n_perm=2, n_out=2 + int(self.gate), n_per=0, gated=0)
-        a.k_mean_over_std, a.k_std, a.k_min = (self._host("kmos", self.to_k.mean_over_std)[0],
-                                               self._host("kstd", self.to_k.std)[0], self._host("kmin", self.to_k.min_)[0])
-        a.eq_std_over_max, a.eq_max = self._host("esom", self.to_eq.std_over_max)[0], self._host("emax", self.to_eq.max)[0]
+        a.k_min, a.eq_max = self._host("kmin", self.to_k.min_)[0], self._host("emax", self.to_eq.max)[0]
+        if not self.to_k.learnable:
+            a.k_mean_over_std, a.k_std = self._host("kmos", self.to_k.mean_over_std)[0], self._host("kstd", self.to_k.std)[0]
+            a.eq_std_over_max = self._host("esom", self.to_eq.std_over_max)[0]
         return a
+
+    def _stat_params(self):
+        if not self.to_k.learnable:
+            return None
+        return [self.to_k.mean_over_std, self.to_k.std, self.to_eq.std_over_max, None]
 
     def forward(self, g):
         if "n3" not in g.ntypes:
@@ -586,9 +646,8 @@ class WriteTorsionParameters(_TupleWriter):
                  param_statistics=None, positional_encoding=True, gated: bool = False, learnable_statistics: bool = False,
                  wrong_symmetry: bool = False, cutoff=1e-4):
         super().__init__()
-        if learnable_statistics:
-            raise NotImplementedError("learnable_statistics=True is not supported by grappa_b200")
         self.wrong_symmetry = wrong_symmetry
+        self.learnable = bool(learnable_statistics)
         EPS = 1e-1 if gated else 1e-2
         st = get_default_statistics() if param_statistics is None else param_statistics
         self.gated, self.improper, self.suffix = gated, improper, suffix
@@ -606,8 +665,12 @@ class WriteTorsionParameters(_TupleWriter):
             if len(k_mean) < n_periodicity or len(k_std) < n_periodicity:
                 raise ValueError(f"n_periodicity is {n_periodicity} but the param_statistics contains {len(k_mean)} "
                                  f"values for the improper torsion parameters.")
-        self.register_buffer("k_mean", k_mean[:n_periodicity].unsqueeze(0).clone())
-        self.register_buffer("k_std", k_std[:n_periodicity].unsqueeze(0).clone())
+        if self.learnable:      # interaction_parameters.py:465-467
+            self.k_mean = nn.Parameter(k_mean[:n_periodicity].unsqueeze(0).clone().float())
+            self.k_std = nn.Parameter(k_std[:n_periodicity].unsqueeze(0).clone().float())
+        else:
+            self.register_buffer("k_mean", k_mean[:n_periodicity].unsqueeze(0).clone())
+            self.register_buffer("k_std", k_std[:n_periodicity].unsqueeze(0).clone())
         proj_feats = between_feats - 1 if positional_encoding else between_feats
         self.rep_projector = RepProjector(4, rep_feats, proj_feats, improper=improper)
         symmetriser_feats = between_feats if symmetriser_feats is None else symmetriser_feats
@@ -627,11 +690,15 @@ class WriteTorsionParameters(_TupleWriter):
     def _head_args(self, T):
         n = self._n_per
         a = HeadOutArgs(kind=2, T=T, n_perm=self._n_perm, n_out=(2 * n if self.gated else n), n_per=n, gated=int(self.gated))
-        std, mean = self._host("kstd", self.k_std), self._host("kmean", self.k_mean)
-        for i in range(n):
-            a.tk_std[i], a.tk_mean[i] = std[i], mean[i]
+        if not self.learnable:
+            std, mean = self._host("kstd", self.k_std), self._host("kmean", self.k_mean)
+            for i in range(n):
+                a.tk_std[i], a.tk_mean[i] = std[i], mean[i]
         a.cutoff = float(self.cutoff.cutoff) if self.cutoff is not None else 0.0
         return a
+
+    def _stat_params(self):
+        return [self.k_std, self.k_mean, None, None] if self.learnable else None
 
     def forward(self, g):
         if self.level not in g.ntypes:

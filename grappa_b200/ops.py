@@ -12,7 +12,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib_ops import COLSUM_MAX, ColsumBatch, FeaturizeArgs, GemmArgs, HeadOutArgs, LossArgs, Perms
+from ._lib_ops import COLSUM_MAX, ColsumBatch, FeaturizeArgs, GemmArgs, HeadOutArgs, HeadStatGrads, LossArgs, Perms
 
 FP32, TF32, AUTO = 0, 1, 2
 _precision = FP32
@@ -412,6 +412,17 @@ def head_output_bwd(args: HeadOutArgs, scores, dk, deq):
     ds = torch.empty_like(scores)
     _lib.check(lib.grappa_b200_head_output_bwd(C.byref(args), _p(scores), _p(dk), _p(deq), _p(ds), _s()), "head_output_bwd")
     return ds
+
+
+def head_output_stats_bwd(args: HeadOutArgs, scores, dk, deq, targets, accumulate: bool):
+    """Gradients of the learnable statistics (gb_head_out_args.stat slot order) written into `targets` (None = skip)."""
+    lib = _lib.lib()
+    out = HeadStatGrads()
+    for i, tgt in enumerate(targets):
+        out.d[i] = None if tgt is None else tgt.data_ptr()
+    out.accumulate = int(bool(accumulate))
+    _lib.check(lib.grappa_b200_head_output_stats_bwd(C.byref(args), _p(scores), _p(dk), _p(deq), C.byref(out), _s()),
+               "head_output_stats_bwd")
 
 
 def dropout(x, p, seed, out=None):

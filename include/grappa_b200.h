@@ -303,11 +303,25 @@ typedef struct {
   float eq_std_over_max, eq_max;              /* ToRange for eq    (kind 1)     */
   float tk_std[6], tk_mean[6];                /* torsion statistics (kind 2)    */
   float cutoff;
+  /* learnable_statistics=True (reference final_layer.py:37-39,84-85; interaction_parameters.py:465-467): the statistics
+   * are parameters, read from DEVICE memory at run time so that a captured step sees every optimizer update.  A non-NULL
+   * entry overrides the scalar above.  kind 0: {k mean_over_std, k std, eq mean_over_std, eq std}; kind 1: {k
+   * mean_over_std, k std, eq std_over_max, NULL}; kind 2: {k_std[n_per], k_mean[n_per], NULL, NULL}. */
+  const float* stat[4];
 } gb_head_out_args;
+/* Where head_output_stats_bwd writes the gradients of the statistics, slot by slot like gb_head_out_args.stat
+ * (NULL = not wanted); accumulate != 0 adds to the existing values. */
+typedef struct {
+  float* d[4];
+  int32_t accumulate;
+} gb_head_stat_grads;
 int grappa_b200_head_output_fwd(const gb_head_out_args* a, const float* scores, float* k, float* eq, void* stream);
 /* dscores [n_perm*T, n_out] from dk, deq (either may be NULL = zero) */
 int grappa_b200_head_output_bwd(const gb_head_out_args* a, const float* scores, const float* dk, const float* deq,
                                 float* dscores, void* stream);
+/* d loss / d statistics from dk, deq (either may be NULL = zero): one CTA, fixed-order reduction over the tuples */
+int grappa_b200_head_output_stats_bwd(const gb_head_out_args* a, const float* scores, const float* dk, const float* deq,
+                                      const gb_head_stat_grads* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Small fused elementwise kernels.

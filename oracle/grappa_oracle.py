@@ -67,8 +67,11 @@ def linear(sd, key, x):
     return F.linear(x, sd[key + ".weight"].to(x.dtype), None if b is None else b.to(x.dtype))
 
 
-def layer_norm(sd, key, x):
-    # torch.nn.LayerNorm defaults: eps 1e-5, biased variance
+def layer_norm(sd, key, x, on: bool = True):
+    # torch.nn.LayerNorm defaults: eps 1e-5, biased variance; `on=False`: the model was built with
+    # layer_norm=False and the norm is skipped (graph_attention.py:279,298,398; network_utils.py:46,115)
+    if not on:
+        return x
     return F.layer_norm(x, (x.shape[-1],), sd[key + ".weight"].to(x.dtype), sd[key + ".bias"].to(x.dtype), 1e-5)
 
 
@@ -114,28 +117,35 @@ def gnn_forward(sd, g, cfg, prefix: str = "gnn.", dtype=torch.float32, taps: dic
     src, dst = src.long(), dst.long()
     heads = cfg["gnn_attention_heads"]
     n_conv = cfg.get("gnn_convolutions", 0)
+    ln, self_int = cfg.get("layer_norm", True), cfg.get("self_interaction", True)
     for i in range(n_conv):
         # ResidualConvBlock.forward (graph_attention.py:378-415) around dgl.nn.SAGEConv(in, out, 'mean') as restated in
         # oracle/dgl_shim (fc_self with bias + bias-free fc_neigh on the mean over in-neighbours)
         p = f"{prefix}conv_blocks.{i}."
-        u = layer_norm(sd, p + "layer_norm", h)
+        u = layer_norm(sd, p + "layer_norm", h, ln)
         agg = torch.zeros_like(u).index_add(0, dst, u[src])
         deg = torch.zeros(len(u), dtype=u.dtype).index_add(0, dst, torch.ones(len(dst), dtype=u.dtype)).clamp(min=1)
         conv = linear(sd, p + "graph_module.fc_self", u) + F.linear(agg / deg[:, None], sd[p + "graph_module.fc_neigh.weight"].to(dtype))
         y = F.elu(conv) + u
-        z = layer_norm(sd, p + "interaction_norm", y)
-        h = F.elu(linear(sd, p + "self_interaction.0", z)) + z
+        if self_int:
+            z = layer_norm(sd, p + "interaction_norm", y, ln)
+            h = F.elu(linear(sd, p + "self_interaction.0", z)) + z
+        else:
+            h = y
         if taps is not None:
             taps[f"conv{i}"] = h
     for i in range(cfg["gnn_attentional_layers"]):
         p = f"{prefix}att_blocks.{i}."          # same parameters as blocks.{n_conv + i} (graph_attention.py:129)
-        u = layer_norm(sd, p + "layer_norm", h)
+        u = layer_norm(sd, p + "layer_norm", h, ln)
         ft = F.linear(u, sd[p + "graph_module.fc.weight"].to(dtype)).view(len(u), heads, -1)
         m = dot_gat(ft, src, dst).flatten(1)
         y = linear(sd, p + "head_reducer", m) + u          # skip adds the LayerNorm-ed u
-        z = layer_norm(sd, p + "interaction_norm", y)
-        w = F.elu(linear(sd, p + "self_interaction.2", F.elu(linear(sd, p + "self_interaction.0", z))))
-        h = w + z                                          # skip adds z
+        if self_int:
+            z = layer_norm(sd, p + "interaction_norm", y, ln)
+            w = F.elu(linear(sd, p + "self_interaction.2", F.elu(linear(sd, p + "self_interaction.0", z))))
+            h = w + z                                      # skip adds z
+        else:
+            h = y
         if taps is not None:
             taps[f"block{i}"] = h
     return linear(sd, prefix + "post_dense.0", h)
@@ -175,11 +185,12 @@ def writer_scores(sd, h, idxs, level, cfg, prefix="parameter_writer.", taps: dic
         pe = torch.tensor(pos_enc, dtype=x.dtype)[:, None, None].expand(L, T, 1)
         x = torch.cat([x, pe], dim=-1)
     n_heads = cfg[f"{short}_n_heads"]
+    ln = cfg.get("layer_norm", True)
     for i in range(cfg[f"{short}_transformer_depth"]):
         q = f"{p}{mname}.grappa_transformer.transformer.{i}."
-        x = layer_norm(sd, q + "norm1", x)
+        x = layer_norm(sd, q + "norm1", x, ln)
         x = _mha(sd, q + "attn.", x, n_heads) + x                          # residual is the post-LN x
-        xn = layer_norm(sd, q + "ff.norm1", x)
+        xn = layer_norm(sd, q + "ff.norm1", x, ln)
         x = linear(sd, q + "ff.linear2", F.elu(linear(sd, q + "ff.linear1", xn))) + xn
         if taps is not None:
             taps[f"{level}_layer{i}"] = x
@@ -189,7 +200,7 @@ def writer_scores(sd, h, idxs, level, cfg, prefix="parameter_writer.", taps: dic
         s = torch.cat([x[j] for j in perm], dim=-1)                        # (T, L*E)
         for i in range(depth):
             q = f"{p}{mname}.symmetriser.mlp.{i}."
-            sn = layer_norm(sd, q + "norm1", s)
+            sn = layer_norm(sd, q + "norm1", s, ln)
             y = linear(sd, q + "linear2", F.elu(linear(sd, q + "linear1", sn)))
             s = y + sn if (0 < i < depth - 1) else y                       # skip only on middle layers
         out = out + s

@@ -49,7 +49,10 @@ def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(GemmArgs) % 8 == 0 and ctypes.sizeof(EnergyArgs) % 8 == 0
     assert GemmArgs._fields_[-1][0] == "max_sms" and GemmArgs._fields_[-3][0] == "colsum"
     assert ctypes.sizeof(EnergyBwdArgs) > ctypes.sizeof(EnergyArgs)
-    assert ctypes.sizeof(HeadOutArgs) == 6 * 4 + 8 * 4 + 12 * 4 + 4
+    # 27 4-byte scalars (108 bytes), 4 bytes of padding, then the four statistics pointers
+    assert HeadOutArgs.stat.offset == 112 and ctypes.sizeof(HeadOutArgs) == 112 + 4 * 8
+    from grappa_b200._lib_ops import HeadStatGrads
+    assert ctypes.sizeof(HeadStatGrads) == 4 * 8 + 8
     assert ctypes.sizeof(LossArgs) == 9 * 8 + 4 * 4 + 4 * 4 + 9 * 8
     from grappa_b200._lib_ops import ParamLossArgs
     assert ctypes.sizeof(ParamLossArgs) == 2 * 4 + 3 * 5 * 8 + 3 * 5 * 4 + 4 + 2 * 8 + 5 * 8 + 8   # 4 bytes of padding after fac[5]
@@ -205,8 +208,13 @@ def test_module_tree_state_dict_and_error_behaviour():
     m.load_state_dict({k: v for k, v in {("model.0." + k)[8:]: v for k, v in sd.items()}.items()})
     gnn10 = models.GrappaGNN(n_conv=2, n_att=1, out_feats=32, node_feats=64, n_heads=4)     # grappa-1.0 layout
     assert "conv_blocks.1.graph_module.fc_neigh.weight" in gnn10.state_dict() and len(gnn10.blocks) == 3
-    with pytest.raises(NotImplementedError):
-        models.ToPositive(1.0, 1.0, learnable_statistics=True)
+    # learnable_statistics turns the statistics into parameters under the same state_dict names; layer_norm=False /
+    # self_interaction=False drop the corresponding sub-modules (reference final_layer.py:37-39, graph_attention.py:257-274)
+    tp = models.ToPositive(1.0, 0.5, learnable_statistics=True)
+    assert sorted(k for k, _ in tp.named_parameters()) == ["mean_over_std", "std"] and float(tp.mean_over_std) == 2.0
+    assert sorted(models.ToPositive(1.0, 0.5).state_dict()) == sorted(tp.state_dict())
+    blk = models.ResidualAttentionBlock(64, num_heads=4, layer_norm=False, self_interaction=False)
+    assert sorted(blk.state_dict()) == ["graph_module.fc.weight", "head_reducer.bias", "head_reducer.weight"]
     g = synthetic.dipeptide(seed=0, n_confs=2)
     with pytest.raises(ValueError):
         Energy(terms="n2")

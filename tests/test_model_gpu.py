@@ -260,3 +260,64 @@ def test_conv_block_model_matches_oracle_forward_and_gradients():
             assert rel_err(named[k].grad.cpu().numpy(), gr.numpy()) < 1e-4, k
             checked += 1
     assert checked >= 16
+
+
+@pytest.mark.parametrize("switches", [
+    dict(layer_norm=False, learnable_statistics=True, gated_torsion=False),
+    dict(self_interaction=False, learnable_statistics=True, gated_torsion=True, gnn_convolutions=1),
+])
+def test_constructor_switches_match_oracle_forward_and_gradients(switches):
+    """the whole GrappaModel argument list is part of the surface -- layer_norm=False (blocks, transformer
+    layers and symmetriser without LayerNorm), self_interaction=False (blocks end after the attention / convolution
+    half), learnable_statistics=True (the output maps' statistics are parameters: read from device memory by the
+    head-output kernels, gradients from the one-CTA reduction kernel), ungated torsions (mean shift).  Forward, loss and
+    parameter gradients against the CPU oracle, which tests/test_oracle.py pins against the live reference for exactly
+    these switches."""
+    import grappa_oracle as orc
+    from grappa_b200 import ops, synthetic
+    from grappa_b200.energy import Energy
+    from grappa_b200.loss import MolwiseLoss
+    ops.set_matmul_precision("fp32")
+    cfg = orc.small_model_config()
+    cfg.update(switches)
+    model = _model(cfg, seed=13).eval()
+    g = synthetic.espaloma_mix_batch(seed=9, batch_size=4, n_confs=5)
+    stat_names = ("mean_over_std", "std", "std_over_max", "k_mean", "k_std")
+    param_names = {k for k, _ in model.named_parameters()}
+
+    def wanted(k):
+        return k in param_names and (k.rsplit(".", 1)[-1] in stat_names or ".0." in k or "pre_dense" in k)
+    sd = {k: v.detach().cpu().double().requires_grad_(wanted(k)) for k, v in model.state_dict().items()}
+    h, params, en = orc.path_forward(sd, g, cfg, dtype=torch.float64, create_graph=True)
+    ref_loss = orc.molwise_loss(en, params, g)
+    leaves = {k: v for k, v in sd.items() if v.requires_grad}
+    ref_grads = dict(zip(leaves, torch.autograd.grad(ref_loss, list(leaves.values()), allow_unused=True)))
+    gd = torch.nn.Sequential(model, Energy(write_tuple_terms=False))(g.to("cuda"))
+    assert rel_err(gd.nodes["n1"].data["h"].detach().cpu().numpy(), h.detach().numpy()) < 1e-5
+    assert rel_err(gd.nodes["g"].data["energy"].detach().cpu().numpy(), en["energy"].detach().numpy()) < 1e-5
+    for l in LEVELS:
+        assert rel_err(gd.nodes[l].data["k"].detach().cpu().numpy(), params[l]["k"].detach().numpy()) < 1e-5, l
+        if l in ("n2", "n3"):
+            assert rel_err(gd.nodes[l].data["eq"].detach().cpu().numpy(), params[l]["eq"].detach().numpy()) < 1e-5, l
+    loss = MolwiseLoss(gradient_weight=0.8, energy_weight=1.0, param_weight=0.0, proper_regularisation=1e-3,
+                       improper_regularisation=1e-3)(gd)
+    assert abs(loss.item() - float(ref_loss)) < 1e-5 * abs(float(ref_loss))
+    model.zero_grad()
+    loss.backward()
+    named = dict(model.named_parameters())
+    n_stats = 0
+    for k, gr in ref_grads.items():
+        got = named[k].grad
+        if gr is None:          # gated torsions: k_mean does not enter; the kernel writes zeros
+            assert k.endswith("k_mean") and (got is None or float(got.abs().max()) == 0.0), k
+            continue
+        assert rel_err(got.cpu().numpy(), gr.numpy()) < 1e-4, k
+        n_stats += k.rsplit(".", 1)[-1] in stat_names
+    assert n_stats >= 9 and len(ref_grads) >= 30
+    # a second evaluation after changing a statistic in place sees the new value (nothing host-cached)
+    with torch.no_grad():
+        model.parameter_writer.bond_writer.to_eq.std.mul_(2.0)
+        g2 = model(g.to("cuda"))
+        sd2 = {k: v.detach().cpu().double() for k, v in model.state_dict().items()}
+        _, params2, _ = orc.path_forward(sd2, g, cfg, dtype=torch.float64, gradients=False)
+    assert rel_err(g2.nodes["n2"].data["eq"].cpu().numpy(), params2["n2"]["eq"].numpy()) < 1e-5

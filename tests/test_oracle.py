@@ -151,3 +151,54 @@ def test_oracle_conv_blocks_vs_live_reference():
     assert rel_err(en["energy"].detach().numpy(), dg.nodes["g"].data["energy"].detach().numpy()) < 1e-5
     for l in LEVELS:
         assert rel_err(params[l]["k"].detach().numpy(), dg.nodes[l].data["k"].detach().numpy()) < 2e-5
+
+
+def test_oracle_ablation_switches_vs_live_reference():
+    """Constructor switches of GrappaModel that grappa-1.x leaves at their defaults (the whole argument list
+    is part of the surface): layer_norm=False, self_interaction=False, learnable_statistics=True, ungated torsions.  The
+    oracle restatement vs the unmodified reference on the dgl shim -- forward, state_dict key set (the statistics become
+    parameters) and the gradients of the learnable statistics."""
+    from ref_import import import_reference, no_dihedral_noise, reference_available, to_reference_graph
+    if not reference_available():
+        pytest.skip("/root/reference not mounted (GPU box)")
+    from grappa_b200 import models, synthetic
+    ns = import_reference()
+    for switches in (dict(layer_norm=False, learnable_statistics=True, gated_torsion=False),
+                     dict(self_interaction=False, learnable_statistics=True, gated_torsion=True, gnn_convolutions=1)):
+        cfg = orc.small_model_config()
+        cfg.update(switches)
+        torch.manual_seed(0)
+        ref = ns.deploy.model_from_config(dict(cfg), param_statistics=ns.graph_utils.get_default_statistics()).eval()
+        sd = {k: v.clone() for k, v in ref.state_dict().items()}
+        ours = models.model_from_config(dict(cfg))
+        assert sorted(ours.state_dict().keys()) == sorted(sd.keys())
+        assert all(tuple(ours.state_dict()[k].shape) == tuple(v.shape) for k, v in sd.items())
+        assert sorted(k for k, _ in ours.named_parameters()) == sorted(k for k, _ in ref.named_parameters())
+        g = synthetic.espaloma_mix_batch(seed=8, batch_size=3, n_confs=4)
+        dg = to_reference_graph(ns, g)
+        with no_dihedral_noise():
+            dg = torch.nn.Sequential(ref, ns.energy.Energy())(dg)
+        stat_keys = [k for k, _ in ref.named_parameters()
+                     if k.rsplit(".", 1)[-1] in ("mean_over_std", "std", "std_over_max", "k_mean", "k_std")]
+        assert len(stat_keys) == 4 + 3 + 2 + 2
+        sd_o = {k: (v.clone().requires_grad_(True) if k in stat_keys else v) for k, v in sd.items()}
+        h, params, en = orc.path_forward(sd_o, g, cfg, create_graph=True)
+        assert rel_err(h.detach().numpy(), dg.nodes["n1"].data["h"].detach().numpy()) < 2e-5
+        assert rel_err(en["energy"].detach().numpy(), dg.nodes["g"].data["energy"].detach().numpy()) < 1e-5
+        for l in LEVELS:
+            assert rel_err(params[l]["k"].detach().numpy(), dg.nodes[l].data["k"].detach().numpy()) < 2e-5
+        # a scalar that touches energies, forces and every parameter type
+        def scalar(energy, gradient, p):
+            return (energy ** 2).mean() + 1e-2 * (gradient ** 2).mean() + sum((p[l]["k"] ** 2).mean() for l in LEVELS) \
+                + p["n2"]["eq"].sum() + p["n3"]["eq"].sum()
+        ref_params = {l: {k: dg.nodes[l].data[k] for k in (("k", "eq") if l in ("n2", "n3") else ("k",))} for l in LEVELS}
+        named = dict(ref.named_parameters())
+        g_ref = torch.autograd.grad(scalar(dg.nodes["g"].data["energy"], dg.nodes["n1"].data["gradient"], ref_params),
+                                    [named[k] for k in stat_keys], allow_unused=True)
+        g_orc = torch.autograd.grad(scalar(en["energy"], en["gradient"], params), [sd_o[k] for k in stat_keys],
+                                    allow_unused=True)
+        for k, a, b in zip(stat_keys, g_orc, g_ref):
+            if b is None:                       # gated torsions: k_mean does not enter (interaction_parameters.py:546-550)
+                assert a is None and k.endswith("k_mean") and cfg["gated_torsion"]
+                continue
+            assert rel_err(a.numpy(), b.numpy()) < 1e-4, k
