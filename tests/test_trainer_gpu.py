@@ -10,7 +10,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _setup(dropout: float, seed: int = 5):
+def _setup(dropout: float, seed: int = 5, **switches):
     import grappa_oracle as orc
     from grappa_b200 import models, ops, synthetic
     from grappa_b200.energy import Energy
@@ -19,6 +19,7 @@ def _setup(dropout: float, seed: int = 5):
     cfg = dict(orc.small_model_config())
     for k in ("gnn_dropout_attention", "gnn_dropout_initial", "gnn_dropout_final", "parameter_dropout"):
         cfg[k] = dropout
+    cfg.update(switches)
     model = models.model_from_config(cfg)
     model.load_state_dict(synthetic.deterministic_state_dict(model.state_dict(), seed=seed))
     loss = MolwiseLoss(gradient_weight=0.8, energy_weight=1.0, param_weight=0.0, proper_regularisation=1e-3,
@@ -56,6 +57,28 @@ def test_graph_replay_equals_eager_steps():
     print("graph vs eager: max |dp| =", d.max())
     assert d.max() == 0.0, d.max()
     assert l0[-1] != l0[0]
+
+
+def test_learnable_statistics_train_inside_the_captured_step():
+    """learnable_statistics=True: the statistics live in the flat parameter buffer, the head-output kernels read them
+    from there, so graph replays must see each Adam update -- same losses and bit-identical parameters as eager steps,
+    and the statistics really move."""
+    from grappa_b200.training import Trainer
+    batches = _batches(4)
+    results = []
+    for use_graph in (False, True):
+        model, energy, loss = _setup(0.0, learnable_statistics=True, layer_norm=False)
+        tr = Trainer(model, energy, loss, lr=1e-3, clip=10.0, device="cuda", use_cuda_graph=use_graph)
+        std0 = float(model.parameter_writer.bond_writer.to_eq.std)
+        losses = [float(tr.step(g).item()) for g in batches]
+        stats = [float(model.parameter_writer.bond_writer.to_eq.std), float(model.parameter_writer.angle_writer.to_eq.std_over_max),
+                 model.parameter_writer.proper_writer.k_std.detach().cpu().numpy().copy()]
+        assert abs(stats[0] - std0) > 1e-4, "the statistic did not train"
+        results.append((losses, tr.fp.flat.detach().cpu().numpy().copy(), stats))
+    (l0, p0, s0), (l1, p1, s1) = results
+    assert l1 == l0, (l0, l1)
+    assert np.abs(p1 - p0).max() == 0.0
+    assert s0[0] == s1[0] and s0[1] == s1[1] and np.array_equal(s0[2], s1[2])
 
 
 def test_graph_replay_draws_fresh_dropout_masks_and_honours_lr():
