@@ -30,7 +30,7 @@ from typing import Dict, Iterable, Iterator, List, Optional, Sequence, Union
 import numpy as np
 import torch
 
-from .graph import LEVELS, NTYPES, MolGraph
+from .graph import NTYPES, MolGraph
 
 _CONF_FIELDS_G = ("energy",)        # substring match, as the reference does ('energy' in feat)
 _CONF_FIELDS_N1 = ("gradient",)

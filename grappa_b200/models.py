@@ -18,8 +18,7 @@ Reference classes mirrored (file:line in /root/reference/src/grappa/models/):
 from __future__ import annotations
 
 import copy
-import math
-from typing import Dict, List, Optional, Union
+from typing import Dict, List, Union
 
 import torch
 from torch import nn

@@ -12,7 +12,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib_ops import COLSUM_MAX, ColsumBatch, FeaturizeArgs, GemmArgs, HeadOutArgs, HeadStatGrads, LossArgs, Perms
+from ._lib_ops import COLSUM_MAX, ColsumBatch, FeaturizeArgs, GemmArgs, HeadOutArgs, HeadStatGrads, Perms
 
 FP32, TF32, AUTO = 0, 1, 2
 _precision = FP32

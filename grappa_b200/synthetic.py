@@ -20,7 +20,7 @@ gradient_ref ~ N(0, 10^2).
 """
 from __future__ import annotations
 
-from typing import Dict, List, Sequence, Tuple
+from typing import Dict, List, Tuple
 
 import numpy as np
 import torch

@@ -19,7 +19,7 @@ Each rank draws its own batch (weak scaling); the global loss is the mean of the
 from __future__ import annotations
 
 import os
-from typing import Callable, List, Optional, Tuple
+from typing import List, Optional, Tuple
 
 import torch
 import torch.distributed as dist

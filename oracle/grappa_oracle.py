@@ -18,7 +18,7 @@ Dropout is omitted (eval mode); the random noise the reference adds inside `dihe
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Sequence
+from typing import Dict, Sequence
 
 import torch
 import torch.nn.functional as F
