@@ -73,6 +73,8 @@ def _declare(lib):
     lib.grappa_b200_conflict_free_rounds.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                                      C.c_void_p, C.c_int64]
     lib.grappa_b200_conflict_free_rounds.restype = C.c_int64
+    lib.grappa_b200_ring_encoding.argtypes = [C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.grappa_b200_ring_encoding.restype = C.c_int
     lib.grappa_b200_energy_fwd.argtypes = [C.POINTER(EnergyArgs), C.c_int, C.c_void_p]
     lib.grappa_b200_energy_bwd.argtypes = [C.POINTER(EnergyBwdArgs), C.c_void_p]
     lib.grappa_b200_energy_bwd_workspace.argtypes = [C.POINTER(EnergyArgs)]

@@ -197,6 +197,119 @@ extern "C" int grappa_b200_torsions_classify(const int64_t* bonds, int64_t n_bon
 // ---------------------------------------------------------------------------------------------
 // Conflict-free rounds for the energy kernel (see include/grappa_b200.h)
 // ---------------------------------------------------------------------------------------------
+// Ring-membership features without rdkit: for every bond (a, b) the shortest cycle through it is found by a breadth-first
+// search from a to b that may not use the bond itself (depth <= 7, i.e. rings of <= 8 atoms); every atom on that cycle is
+// flagged "in a ring" (column 0) and "in a ring of that size" (column size - 2).  For the ring systems force fields see
+// (isolated and fused 3..8-rings) this marks the same atoms as rdkit's IsInRing / IsInRingSize(3..8), which the
+// reference reads (utils/rdkit_utils.py:7-24).  Neighbours are visited in bond-list order, so the result does not
+// depend on anything but the bond list.
+extern "C" int grappa_b200_ring_encoding(int64_t n_atoms, const int64_t* bonds, int64_t n_bonds, float* enc) {
+  if (n_atoms < 0 || n_bonds < 0 || (n_bonds > 0 && !bonds) || (n_atoms > 0 && !enc)) {
+    gb::set_error("ring_encoding: bad arguments (n_atoms=%lld n_bonds=%lld)", (long long)n_atoms, (long long)n_bonds);
+    return GB_ERR_INVALID;
+  }
+  for (int64_t i = 0; i < n_atoms * 7; ++i) enc[i] = 0.f;
+  // CSR adjacency in bond-list order
+  std::vector<int64_t> ptr((size_t)n_atoms + 1, 0);
+  for (int64_t e = 0; e < 2 * n_bonds; ++e) {
+    if (bonds[e] < 0 || bonds[e] >= n_atoms) {
+      gb::set_error("ring_encoding: bond %lld references atom %lld outside [0, %lld)", (long long)(e / 2),
+                    (long long)bonds[e], (long long)n_atoms);
+      return GB_ERR_INVALID;
+    }
+    ++ptr[(size_t)bonds[e] + 1];
+  }
+  for (int64_t i = 0; i < n_atoms; ++i) ptr[(size_t)i + 1] += ptr[(size_t)i];
+  std::vector<int64_t> nbr((size_t)(2 * n_bonds)), fillp(ptr.begin(), ptr.end() - 1);
+  for (int64_t e = 0; e < n_bonds; ++e) {
+    const int64_t a = bonds[2 * e], b = bonds[2 * e + 1];
+    nbr[(size_t)fillp[(size_t)a]++] = b;
+    nbr[(size_t)fillp[(size_t)b]++] = a;
+  }
+  std::vector<int32_t> dist((size_t)n_atoms, -1);
+  std::vector<int64_t> parent((size_t)n_atoms, -1), queue;
+  for (int64_t e = 0; e < n_bonds; ++e) {
+    const int64_t a = bonds[2 * e], b = bonds[2 * e + 1];
+    queue.clear();
+    queue.push_back(a);
+    dist[(size_t)a] = 0;
+    parent[(size_t)a] = -1;
+    bool found = false;
+    for (size_t h = 0; h < queue.size() && !found; ++h) {
+      const int64_t u = queue[h];
+      if (dist[(size_t)u] >= 7) break;
+      for (int64_t j = ptr[(size_t)u]; j < ptr[(size_t)u + 1]; ++j) {
+        const int64_t v = nbr[(size_t)j];
+        if (u == a && v == b) continue;            // the bond itself (every parallel copy of it)
+        if (dist[(size_t)v] >= 0) continue;
+        dist[(size_t)v] = dist[(size_t)u] + 1;
+        parent[(size_t)v] = u;
+        queue.push_back(v);
+        if (v == b) {
+          found = true;
+          break;
+        }
+      }
+    }
+    if (found) {
+      const int size = dist[(size_t)b] + 1;
+      if (size >= 3 && size <= 8)
+        for (int64_t v = b; v != -1; v = parent[(size_t)v]) {
+          enc[v * 7] = 1.f;
+          enc[v * 7 + size - 2] = 1.f;
+        }
+    }
+    for (int64_t v : queue) dist[(size_t)v] = -1;  // reset only what this search touched
+  }
+  // Column 0 also has to be set for atoms whose smallest ring is larger than 8 (macrocycles: rdkit's IsInRing is true
+  // there): an atom lies on a cycle iff one of its bonds is not a bridge.  Bridges by one iterative depth-first search
+  // (low-link values; the tree edge is skipped by edge id so that a doubled bond counts as a 2-cycle, not as a bridge).
+  std::vector<int64_t> eid((size_t)(2 * n_bonds));
+  {
+    std::vector<int64_t> fp(ptr.begin(), ptr.end() - 1);
+    for (int64_t e = 0; e < n_bonds; ++e) {
+      eid[(size_t)fp[(size_t)bonds[2 * e]]++] = e;
+      eid[(size_t)fp[(size_t)bonds[2 * e + 1]]++] = e;
+    }
+  }
+  std::vector<int64_t> tin((size_t)n_atoms, -1), low((size_t)n_atoms, 0), it((size_t)n_atoms, 0), via((size_t)n_atoms, -1);
+  std::vector<char> bridge((size_t)n_bonds, 0);
+  std::vector<int64_t> stack;
+  int64_t timer = 0;
+  for (int64_t root = 0; root < n_atoms; ++root) {
+    if (tin[(size_t)root] >= 0) continue;
+    tin[(size_t)root] = low[(size_t)root] = timer++;
+    it[(size_t)root] = ptr[(size_t)root];
+    stack.assign(1, root);
+    while (!stack.empty()) {
+      const int64_t u = stack.back();
+      if (it[(size_t)u] < ptr[(size_t)u + 1]) {
+        const int64_t j = it[(size_t)u]++;
+        const int64_t v = nbr[(size_t)j];
+        if (eid[(size_t)j] == via[(size_t)u]) continue;           // the edge we came in by
+        if (tin[(size_t)v] >= 0) {
+          low[(size_t)u] = std::min(low[(size_t)u], tin[(size_t)v]);
+        } else {
+          tin[(size_t)v] = low[(size_t)v] = timer++;
+          via[(size_t)v] = eid[(size_t)j];
+          it[(size_t)v] = ptr[(size_t)v];
+          stack.push_back(v);
+        }
+      } else {
+        stack.pop_back();
+        if (!stack.empty()) {
+          const int64_t p = stack.back();
+          low[(size_t)p] = std::min(low[(size_t)p], low[(size_t)u]);
+          if (low[(size_t)u] > tin[(size_t)p]) bridge[(size_t)via[(size_t)u]] = 1;
+        }
+      }
+    }
+  }
+  for (int64_t e = 0; e < n_bonds; ++e)
+    if (!bridge[(size_t)e] && bonds[2 * e] != bonds[2 * e + 1]) enc[bonds[2 * e] * 7] = enc[bonds[2 * e + 1] * 7] = 1.f;
+  return GB_OK;
+}
+
 extern "C" int64_t grappa_b200_conflict_free_rounds(const int32_t* idx, const int32_t* tup_off, int32_t n_mols, int32_t L,
                                                     int32_t groups, int32_t* round_off, int32_t* sched,
                                                     int64_t capacity_rounds) {

@@ -49,6 +49,16 @@ def get_torsions(torsion_ids, bonds, central_atom_position: int = IMPROPER_CENTR
     return pro[:npr.value].copy(), imp[:nim.value].copy()
 
 
+def ring_encoding(n_atoms: int, bonds) -> np.ndarray:
+    """(n_atoms, 7) float32: [in a ring, in a ring of 3, 4, ..., 8 atoms] per atom -- the feature the reference reads
+    from rdkit (utils/rdkit_utils.py:7-24), computed from the bond list alone (csrc/tuples.cpp)."""
+    b = _as_bonds(bonds)
+    enc = np.empty((int(n_atoms), 7), dtype=np.float32)
+    _lib.check(_lib.lib().grappa_b200_ring_encoding(int(n_atoms), b.ctypes.data if len(b) else None, len(b),
+                                                    enc.ctypes.data if n_atoms else None), "ring_encoding")
+    return enc
+
+
 def build_tuples(n_atoms: int, bonds, improper_candidates: Sequence = ()) -> Dict[str, np.ndarray]:
     """All four tuple levels of one molecule from its bond list (+ candidate improper centres)."""
     d = get_idx_tuples(bonds)

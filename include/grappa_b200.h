@@ -52,6 +52,14 @@ int grappa_b200_torsions_classify(const int64_t* bonds, int64_t n_bonds, const i
                                   int64_t* impropers_out, int64_t* n_impropers_out);
 
 /* ---------------------------------------------------------------------------------------------
+ * Ring-membership atom features without rdkit (host code).  Replaces rdkit_utils.get_ring_encoding (reference
+ * utils/rdkit_utils.py:7-24: IsInRing, IsInRingSize(3..8)) for topologies given as a bond list: enc [n_atoms, 7],
+ * column 0 = in a ring, column s-2 = on a shortest cycle of s atoms through one of its bonds (3 <= s <= 8).
+ * bonds: [n_bonds, 2] atom indices in [0, n_atoms), each bond once.
+ * ------------------------------------------------------------------------------------------- */
+int grappa_b200_ring_encoding(int64_t n_atoms, const int64_t* bonds, int64_t n_bonds, float* enc);
+
+/* ---------------------------------------------------------------------------------------------
  * MM energy + analytic forces over conformations (kernel K13) and its backward (K14).
  * Replaces internal_coordinates (reference src/grappa/models/internal_coordinates.py:15-125),
  * harmonic_energy / torsion_energy / pool_energy (models/energy.py:8-71) and the

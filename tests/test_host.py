@@ -194,6 +194,38 @@ def test_conflict_free_rounds_schedule():
     assert ro.tolist() == [0, 0, 0] and sc.shape == (0, 8)
 
 
+def test_ring_encoding_known_answers_and_python_restatement():
+    """Ring-membership features without rdkit (reference utils/rdkit_utils.py:7-24: IsInRing, IsInRingSize(3..8)): the
+    host C++ routine against known answers and against the search written out in Python (synthetic.ring_encoding_py)."""
+    from grappa_b200 import GrappaB200Error, synthetic, tuples
+
+    def ring(n, o=0):
+        return [(o + i, o + (i + 1) % n) for i in range(n)]
+    for n in range(3, 13):
+        e = tuples.ring_encoding(n, ring(n))
+        want = [1.0] + [float(n == s) for s in range(3, 9)]          # a 9+-ring is a ring of no listed size
+        assert (e == np.array(want, dtype=np.float32)).all(), n
+    # fused 6-6 system (atoms 0-9), a substituent (10) that carries a cyclopropane (11-13): bridges are not ring bonds
+    bonds = ring(6) + [(0, 6), (6, 7), (7, 8), (8, 9), (9, 5)] + [(3, 10), (10, 11)] + ring(3, 11)
+    e = tuples.ring_encoding(14, bonds)
+    assert e[:10].tolist() == [[1, 0, 0, 0, 1, 0, 0]] * 10 and e[10].tolist() == [0] * 7
+    assert e[11:].tolist() == [[1, 1, 0, 0, 0, 0, 0]] * 3
+    # norbornane: two five-rings (the six-membered envelope is not a smallest ring of any bond)
+    nb = [(0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (5, 0), (0, 6), (6, 3)]
+    assert tuples.ring_encoding(7, nb).tolist() == [[1, 0, 0, 1, 0, 0, 0]] * 7
+    rng = np.random.default_rng(0)
+    for kind, kw in (("peptide", dict(n_res=2)), ("small", dict(n_atoms=30)), ("rna", dict(n_atoms=93))):
+        for _ in range(8):
+            m = synthetic.make_molecule(rng, kind, n_confs=1, **kw)
+            src, dst = [t.numpy() for t in m.edges()]
+            b = np.stack([src, dst], 1)[src < dst]
+            n = m.num_nodes("n1")
+            assert np.array_equal(tuples.ring_encoding(n, b), synthetic.ring_encoding_py(n, b))
+    assert tuples.ring_encoding(4, np.zeros((0, 2), np.int64)).tolist() == [[0] * 7] * 4
+    with pytest.raises(GrappaB200Error):
+        tuples.ring_encoding(3, [(0, 5)])
+
+
 def test_module_tree_state_dict_and_error_behaviour():
     from grappa_b200 import GrappaB200Error, models, synthetic
     from grappa_b200.energy import Energy
