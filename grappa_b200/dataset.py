@@ -316,6 +316,28 @@ def shard_indices(n: int, rank: int, world: int) -> List[int]:
     return list(range(rank, n, world))
 
 
+def shard_conformations(g: MolGraph, rank: int, world: int) -> MolGraph:
+    """This rank's slice of the conformation axis of a (batched) graph -- the sharding of the energy / force sweep when
+    there are few molecules and many conformations: conformations [C*rank/world, C*(rank+1)/world)
+    of xyz (N, C, 3), of every `*gradient*` field and of every (B, C) `*energy*` field, repacked contiguously once
+    (xyz is atom-major, so a conformation slice of the original is a strided view).  Topology, indices and parameters
+    are shared with `g`; concatenating the shards' results along the conformation axis gives the unsharded result, so
+    the path needs no collective."""
+    C = _n_confs_of(g)
+    if not 0 <= rank < world:
+        raise ValueError(f"rank {rank} outside [0, {world})")
+    lo, hi = C * rank // world, C * (rank + 1) // world
+    out = MolGraph({nt: g.num_nodes(nt) for nt in g.ntypes}, g._src, g._dst,
+                   {nt: g.batch_num_nodes(nt) for nt in g.ntypes})
+    for nt in g.ntypes:
+        for k, v in g.nodes[nt].data.items():
+            if PackedDataset._is_conf_field(nt, k) or (nt == "g" and k == "is_dummy"):
+                v = v[:, lo:hi].contiguous()
+            out.nodes[nt].data[k] = v
+    out._pack_cache = g._pack_cache            # same topology: the index tables are shared
+    return out
+
+
 def batch_sampler(indices: Sequence[int], batch_size: int, rng: Optional[np.random.Generator] = None,
                   drop_last: bool = True) -> Iterator[List[int]]:
     """Shuffled fixed-size batches of `indices` (one epoch)."""

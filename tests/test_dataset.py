@@ -97,3 +97,39 @@ def test_packed_dataset_roundtrip_and_loader(tmp_path):
     with pytest.raises(IndexError):
         list(dataset.PrefetchLoader(ds2, [[0, 1], [0, 10 ** 6]], pin=False))
     assert dataset.shard_indices(10, 1, 4) == [1, 5, 9]
+
+
+def test_conformation_shards_tile_the_conformation_axis():
+    """SURVEY.md 8e, energy / force sweep with few molecules and many conformations: the ranks' conformation slices are
+    contiguous, disjoint, cover every conformation once (uneven counts included), share topology and parameters, and the
+    oracle's energies / forces of the shards concatenate to the unsharded result -- no collective on the data path."""
+    from grappa_b200 import dataset, synthetic
+    g = synthetic.peptide_batch(seed=3, batch_size=2, n_res=1, n_confs=7)
+    gen = torch.Generator().manual_seed(0)
+    for l in LEVELS:
+        T = g.num_nodes(l)
+        if l in ("n2", "n3"):
+            g.nodes[l].data["k"] = 100 + 300 * torch.rand(T, generator=gen)
+            g.nodes[l].data["eq"] = 1.2 + 0.6 * torch.rand(T, generator=gen)
+        else:
+            g.nodes[l].data["k"] = torch.randn(T, 3, generator=gen)
+    world = 3
+    shards = [dataset.shard_conformations(g, r, world) for r in range(world)]
+    assert [s.nodes["n1"].data["xyz"].shape[1] for s in shards] == [2, 2, 3]
+    for k in ("xyz", "gradient_ref"):
+        assert torch.equal(torch.cat([s.nodes["n1"].data[k] for s in shards], dim=1), g.nodes["n1"].data[k])
+        assert all(s.nodes["n1"].data[k].is_contiguous() for s in shards)
+    assert torch.equal(torch.cat([s.nodes["g"].data["energy_ref"] for s in shards], dim=1), g.nodes["g"].data["energy_ref"])
+    assert all(s.nodes["n4"].data["idxs"] is g.nodes["n4"].data["idxs"] for s in shards)
+
+    def evaluate(graph):
+        idxs = {l: graph.nodes[l].data["idxs"] for l in LEVELS}
+        params = {l: {k: graph.nodes[l].data[k] for k in (("k", "eq") if l in ("n2", "n3") else ("k",))} for l in LEVELS}
+        counts = {l: graph.batch_num_nodes(l) for l in LEVELS}
+        return orc.energy_forward(graph.nodes["n1"].data["xyz"], idxs, params, counts)
+    whole, parts = evaluate(g), [evaluate(s) for s in shards]
+    # fp32 torch reductions vectorise differently for different shapes: equal up to rounding
+    assert rel_err(torch.cat([p["energy"] for p in parts], dim=1).detach().numpy(), whole["energy"].detach().numpy()) < 1e-6
+    assert rel_err(torch.cat([p["gradient"] for p in parts], dim=1).numpy(), whole["gradient"].numpy()) < 1e-6
+    with pytest.raises(ValueError):
+        dataset.shard_conformations(g, 3, 3)
