@@ -399,17 +399,27 @@ def deterministic_state_dict(reference_sd: Dict[str, torch.Tensor], seed: int = 
     Floating tensors that are trainable-shaped get U(-1/sqrt(fan_in), 1/sqrt(fan_in)) (torch's
     nn.Linear default scale); LayerNorm weights 1 + 0.1 U(-1,1), LayerNorm / Linear biases
     0.1 U(-1,1) scaled.  Buffers (statistics, permutations, positional encodings, n_periodicity)
-    are passed through unchanged.  Aliased keys (gnn.blocks.* == gnn.att_blocks.*) hash to the same
-    values because the alias prefix is normalised first.
+    are passed through unchanged.  Aliased keys (gnn.blocks.i == gnn.conv_blocks.i for the first n_conv blocks, then
+    gnn.att_blocks.(i - n_conv); reference graph_attention.py:129) hash to the same values because the alias is
+    normalised first.
     """
     import hashlib
+    import re
     out = {}
+    n_conv = len({k.split(".")[2] for k in reference_sd if k.startswith("gnn.conv_blocks.")})
+
+    def canonical(key):
+        m = re.match(r"gnn\.blocks\.(\d+)\.(.*)", key)
+        if not m:
+            return key
+        i = int(m.group(1))
+        return f"gnn.conv_blocks.{i}.{m.group(2)}" if i < n_conv else f"gnn.att_blocks.{i - n_conv}.{m.group(2)}"
     buffer_tags = ("positional_encoding", "permutation", "n_periodicity", "k_mean", "k_std", "to_k.", "to_eq.")
     for key, ref in reference_sd.items():
         if any(t in key for t in buffer_tags) or not torch.is_floating_point(ref):
             out[key] = ref.clone()
             continue
-        canon = key.replace("gnn.blocks.", "gnn.att_blocks.")
+        canon = canonical(key)
         h = int.from_bytes(hashlib.sha256(f"{seed}:{canon}".encode()).digest()[:8], "little") % (2 ** 63)
         gen = torch.Generator().manual_seed(h)
         u = torch.rand(ref.shape, generator=gen, dtype=torch.float32) * 2.0 - 1.0

@@ -174,15 +174,74 @@ def ragged_conformations_case(ns):
     print("ragged_confs: loss =", out["out.loss"], "confs =", confs)
 
 
+SWITCH_CASES = {
+    "noln_learnable_ungated": dict(layer_norm=False, learnable_statistics=True, gated_torsion=False),
+    "noselfint_learnable_conv": dict(self_interaction=False, learnable_statistics=True, gated_torsion=True, gnn_convolutions=1),
+}
+
+
+def switches_case(ns):
+    """GrappaModel constructor switches that grappa-1.x leaves at their defaults: outputs, loss and the gradients of the
+    (learnable) statistics + a few weights from the unmodified reference -> switches_small_model.npz."""
+    rng = np.random.default_rng(17)
+    mols = [synthetic.make_molecule(rng, "peptide", n_confs=5, n_res=1), synthetic.make_molecule(rng, "small", n_confs=5, n_atoms=24),
+            synthetic.make_molecule(rng, "rna", n_confs=5, n_atoms=91)]
+    mols = [m for m in mols if m.num_nodes("n4_improper") > 0]
+    g = gbgraph.batch(mols)
+    out_all = dict(graph_inputs(g))
+    stat_names = ("mean_over_std", "std", "std_over_max", "k_mean", "k_std")
+    for name, switches in SWITCH_CASES.items():
+        cfg = orc.small_model_config()
+        cfg.update(switches)
+        torch.manual_seed(99)
+        model = ns.deploy.model_from_config(dict(cfg), param_statistics=ns.graph_utils.get_default_statistics())
+        sd = synthetic.deterministic_state_dict(model.state_dict(), seed=31)
+        model.load_state_dict(sd)
+        model.eval()
+        dg = to_reference_graph(ns, g)
+        with no_dihedral_noise():
+            dg = torch.nn.Sequential(model, ns.energy.Energy())(dg)
+        loss = ns.loss.MolwiseLoss(gradient_weight=0.8, energy_weight=1.0, param_weight=0.0, proper_regularisation=1e-3,
+                                   improper_regularisation=1e-3)(dg)
+        model.zero_grad()
+        loss.backward()
+        pre = f"{name}."
+        out_all[pre + "out.h"] = dg.nodes["n1"].data["h"].detach().numpy()
+        for lvl in LEVELS:
+            out_all[pre + f"out.{lvl}.k"] = dg.nodes[lvl].data["k"].detach().numpy()
+            if lvl in ("n2", "n3"):
+                out_all[pre + f"out.{lvl}.eq"] = dg.nodes[lvl].data["eq"].detach().numpy()
+        out_all[pre + "out.g.energy"] = dg.nodes["g"].data["energy"].detach().numpy()
+        out_all[pre + "out.n1.gradient"] = dg.nodes["n1"].data["gradient"].detach().numpy()
+        out_all[pre + "out.loss"] = np.array(loss.item(), dtype=np.float64)
+        named = dict(model.named_parameters())
+        out_all[pre + "meta.parameter_names"] = np.array(sorted(named))
+        out_all[pre + "meta.state_dict_keys"] = np.array(sorted(model.state_dict().keys()))
+        for k, p in named.items():
+            if k.rsplit(".", 1)[-1] in stat_names or k in ("gnn.pre_dense.0.weight", "gnn.att_blocks.0.head_reducer.weight",
+                                                           "parameter_writer.angle_writer.angle_model.symmetriser.mlp.0.linear1.weight"):
+                out_all[pre + f"grad.{k}"] = (np.zeros(p.shape, np.float32) if p.grad is None else p.grad.detach().numpy())
+                out_all[pre + f"gradnone.{k}"] = np.array(p.grad is None)
+        # the restatement must agree before the fixture is written
+        h, params, en = orc.path_forward(sd, g, cfg)
+        err = np.abs(h.detach().numpy() - out_all[pre + "out.h"]).max() / np.abs(out_all[pre + "out.h"]).max()
+        assert err < 2e-5, (name, err)
+        print(name, "loss =", loss.item(), "oracle-vs-reference h error", err)
+    np.savez_compressed(os.path.join(OUT, "switches_small_model.npz"), **out_all)
+
+
 def main():
     ns = import_reference()
     torch.set_num_threads(8)
+    if "--only-switches" in sys.argv:
+        return switches_case(ns)
     if "--only-param-loss" in sys.argv:
         return param_loss_case(ns)
     if "--only-ragged" in sys.argv:
         return ragged_conformations_case(ns)
     param_loss_case(ns)
     ragged_conformations_case(ns)
+    switches_case(ns)
 
     # ---- case 1: BASELINE config 1 -- grappa-1.2 architecture, capped dipeptide, 50 conformations
     g = synthetic.dipeptide(seed=11, n_confs=50)

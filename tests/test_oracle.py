@@ -202,3 +202,39 @@ def test_oracle_ablation_switches_vs_live_reference():
                 assert a is None and k.endswith("k_mean") and cfg["gated_torsion"]
                 continue
             assert rel_err(a.numpy(), b.numpy()) < 1e-4, k
+
+
+@pytest.mark.parametrize("case,switches", [
+    ("noln_learnable_ungated", dict(layer_norm=False, learnable_statistics=True, gated_torsion=False)),
+    ("noselfint_learnable_conv", dict(self_interaction=False, learnable_statistics=True, gated_torsion=True, gnn_convolutions=1)),
+])
+def test_oracle_matches_reference_fixture_constructor_switches(case, switches):
+    """tests/golden/switches_small_model.npz (make_golden.py --only-switches, unmodified reference): outputs, loss and the
+    gradients of the learnable statistics for the constructor switches -- available on the GPU box too, where the live
+    reference is not."""
+    z = load_golden("switches_small_model.npz")
+    cfg = orc.small_model_config()
+    cfg.update(switches)
+    sd, ours = _sd(cfg, seed=31)
+    assert sorted(sd.keys()) == list(z[f"{case}.meta.state_dict_keys"])
+    assert sorted(k for k, _ in ours.named_parameters()) == list(z[f"{case}.meta.parameter_names"])
+    pre = case + ".grad."
+    leaves = {k: v.requires_grad_(True) for k, v in sd.items() if (pre + k) in z.files}
+    assert len(leaves) >= 12
+    g = graph_from_fixture(z)
+    h, params, en = orc.path_forward(sd, g, cfg, create_graph=True)
+    assert rel_err(h.detach().numpy(), z[f"{case}.out.h"]) < 2e-5
+    for l in LEVELS:
+        assert rel_err(params[l]["k"].detach().numpy(), z[f"{case}.out.{l}.k"]) < 2e-5
+        if l in ("n2", "n3"):
+            assert rel_err(params[l]["eq"].detach().numpy(), z[f"{case}.out.{l}.eq"]) < 2e-5
+    assert rel_err(en["energy"].detach().numpy(), z[f"{case}.out.g.energy"]) < 2e-5
+    assert rel_err(en["gradient"].detach().numpy(), z[f"{case}.out.n1.gradient"]) < 2e-5
+    loss = orc.molwise_loss(en, params, g)
+    assert abs(float(loss) - float(z[f"{case}.out.loss"])) < 1e-5 * abs(float(z[f"{case}.out.loss"]))
+    grads = torch.autograd.grad(loss, list(leaves.values()), allow_unused=True)
+    for (k, _), gr in zip(leaves.items(), grads):
+        if bool(z[f"{case}.gradnone.{k}"]):
+            assert gr is None, k               # gated torsions: k_mean does not enter
+        else:
+            assert rel_err(gr.numpy(), z[pre + k]) < 1e-4, k
