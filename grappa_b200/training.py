@@ -139,6 +139,45 @@ class Trainer:
     def step_count(self) -> int:
         return self._host_steps
 
+    # ---- optimizer restart / checkpoint ---------------------------------------------------------
+    def reset_optimizer(self, lr: Optional[float] = None):
+        """A fresh Adam on the current parameters: moments and the bias-correction step count back to zero -- what the
+        reference does when it replaces the optimizer at `param_loss_epochs` / after a restart
+        (training/lightning_model.py:142-150).  In place, so captured steps stay valid; the dropout RNG offset keeps
+        advancing."""
+        self.fp.m.zero_()
+        self.fp.v.zero_()
+        self.counters[0:1].zero_()
+        if lr is not None:
+            self.lr = lr
+
+    def state_dict(self) -> dict:
+        """Everything a resumed run needs (reference: the Lightning checkpoint -- model + optimizer state + `lr`,
+        training/lightning_model.py:300-304): parameters by name, Adam moments by name, step / RNG counters, lr."""
+        names = {id(p): k for k, p in self.model.named_parameters()}
+        sd = {"model": {k: v.detach().cpu().clone() for k, v in self.model.state_dict().items()},
+              "exp_avg": {}, "exp_avg_sq": {}, "counters": self.counters.detach().cpu().clone(), "lr": self._lr,
+              "host_steps": self._host_steps}
+        for p, o in zip(self.fp.params, self.fp.offsets):
+            n = p.numel()
+            sd["exp_avg"][names[id(p)]] = self.fp.m[o:o + n].view_as(p).detach().cpu().clone()
+            sd["exp_avg_sq"][names[id(p)]] = self.fp.v[o:o + n].view_as(p).detach().cpu().clone()
+        return sd
+
+    def load_state_dict(self, sd: dict):
+        """Inverse of `state_dict`, written INTO the flat buffers (parameters stay views of them, captured steps stay
+        valid).  Keyed by parameter name, so a checkpoint survives a different flattening order."""
+        with torch.no_grad():
+            self.model.load_state_dict(sd["model"])        # copy_ into the existing views
+            names = {id(p): k for k, p in self.model.named_parameters()}
+            for p, o in zip(self.fp.params, self.fp.offsets):
+                n, k = p.numel(), names[id(p)]
+                self.fp.m[o:o + n].view_as(p).copy_(sd["exp_avg"][k])
+                self.fp.v[o:o + n].view_as(p).copy_(sd["exp_avg_sq"][k])
+            self.counters.copy_(sd["counters"])
+        self.lr = float(sd["lr"])
+        self._host_steps = int(sd.get("host_steps", int(sd["counters"][0])))
+
     # ---- gradient exchange ---------------------------------------------------------------------
     def _launch_allreduce(self, start: int, end: int):
         if end <= start:

@@ -276,3 +276,37 @@ def test_flat_params_are_views_and_buckets_tile_the_buffer():
     assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
     fp.flat.zero_()
     assert all(float(q.abs().sum()) == 0 for q in m.parameters())
+
+
+def test_trainer_checkpoint_roundtrip_and_optimizer_restart():
+    """Host bookkeeping of training.Trainer on CPU (no kernels): the flat buffers stay the parameters' storage through
+    load_state_dict, Adam moments / counters / lr round-trip by parameter name, reset_optimizer clears exactly the
+    optimizer state (reference training/lightning_model.py:142-150, 300-304)."""
+    import grappa_oracle as orc
+    from grappa_b200 import models
+    from grappa_b200.training import Trainer
+    torch.manual_seed(0)
+    tr = Trainer(models.model_from_config(orc.small_model_config()), None, None, lr=3e-4, device="cpu", distributed=False)
+    tr.fp.m.normal_()
+    tr.fp.v.uniform_()
+    tr.counters[0], tr.counters[1] = 17, 4242
+    tr._host_steps = 17
+    ck = tr.state_dict()
+    assert set(ck["exp_avg"]) == {k for k, _ in tr.model.named_parameters()}
+    flat0, m0, v0 = tr.fp.flat.clone(), tr.fp.m.clone(), tr.fp.v.clone()
+    torch.manual_seed(1)
+    tr2 = Trainer(models.model_from_config(orc.small_model_config()), None, None, lr=1.0, device="cpu", distributed=False)
+    assert not torch.equal(tr2.fp.flat, flat0)
+    ptr = tr2.fp.flat.data_ptr()
+    tr2.load_state_dict(ck)
+    real = torch.zeros_like(flat0, dtype=torch.bool)                    # the slices are padded to 16-byte multiples
+    for q, o in zip(tr.fp.params, tr.fp.offsets):
+        real[o:o + q.numel()] = True
+    assert torch.equal(tr2.fp.flat, flat0) and torch.equal(tr2.fp.m[real], m0[real]) and torch.equal(tr2.fp.v[real], v0[real])
+    assert tr2.counters.tolist() == [17, 4242] and tr2.lr == 3e-4 and float(tr2.lr_dev) == pytest.approx(3e-4)
+    assert tr2.step_count == 17 and tr2.fp.flat.data_ptr() == ptr
+    p = next(tr2.model.parameters())
+    assert p.data_ptr() == ptr + 4 * tr2.fp.offsets[0]                 # still a view of the flat buffer
+    tr2.reset_optimizer(lr=1e-5)
+    assert float(tr2.fp.m.abs().max()) == 0 and float(tr2.fp.v.abs().max()) == 0
+    assert tr2.counters.tolist() == [0, 4242] and tr2.lr == 1e-5 and torch.equal(tr2.fp.flat, flat0)
