@@ -238,3 +238,54 @@ def test_oracle_matches_reference_fixture_constructor_switches(case, switches):
             assert gr is None, k               # gated torsions: k_mean does not enter
         else:
             assert rel_err(gr.numpy(), z[pre + k]) < 1e-4, k
+
+
+def test_graph_convolutions_vs_dense_adjacency_restatement_fp64():
+    """DGL is absent from /root/reference and unpinned: the two DGL layers on the path are restated twice,
+    independently -- edge-list form (oracle.dot_gat, oracle/dgl_shim's DotGatConv / SAGEConv, which the unmodified
+    reference runs on here) and a dense N x N adjacency form written from the published definitions: DotGatConv =
+    softmax over the in-neighbours of <ft_u, ft_v> / sqrt(d) per head, aggregation of ft_u; SAGEConv('mean') =
+    fc_self(h) + fc_neigh(mean of in-neighbour features).  fp64, random graphs with the bonded-graph structure (both
+    directions of every bond, no self loops, no isolated atoms)."""
+    import os
+    import sys
+    shim = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "dgl_shim")
+    from grappa_b200 import synthetic
+    rng = np.random.default_rng(2)
+    g = synthetic.make_molecule(rng, "rna", n_confs=1, n_atoms=60)
+    src, dst = [t.long() for t in g.edges()]
+    n, heads, d = g.num_nodes("n1"), 4, 8
+    torch.manual_seed(0)
+    A = torch.zeros(n, n, dtype=torch.bool)
+    A[dst, src] = True                                         # A[v, u]: edge u -> v
+    assert not A.diagonal().any() and A.any(1).all()
+    ft = torch.randn(n, heads, d, dtype=torch.float64)
+    scores = torch.einsum("vhd,uhd->hvu", ft, ft) / d ** 0.5
+    scores = scores.masked_fill(~A[None], -float("inf"))
+    dense = torch.einsum("hvu,uhd->vhd", torch.softmax(scores, dim=-1), ft)
+    assert rel_err(orc.dot_gat(ft, src, dst).numpy(), dense.numpy()) < 1e-13
+    sys.path.insert(0, shim)
+    try:
+        saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "dgl" or k.startswith("dgl.")}
+        from dgl.nn.pytorch.conv import DotGatConv, SAGEConv
+
+        class G:                                               # the only graph method the layers use
+            @staticmethod
+            def edges():
+                return src, dst
+        h = torch.randn(n, 24, dtype=torch.float64)
+        conv = DotGatConv(24, d, heads).double()
+        ftc = conv.fc(h).view(n, heads, d)
+        sc = (torch.einsum("vhd,uhd->hvu", ftc, ftc) / d ** 0.5).masked_fill(~A[None], -float("inf"))
+        want = torch.einsum("hvu,uhd->vhd", torch.softmax(sc, dim=-1), ftc)
+        assert rel_err(conv(G, h).detach().numpy(), want.detach().numpy()) < 1e-13
+        assert [k for k, _ in conv.named_parameters()] == ["fc.weight"]          # DGL's parameter name
+        sage = SAGEConv(24, 16, "mean").double()
+        mean = (A.double() @ h) / A.sum(1, keepdim=True)
+        want = sage.fc_self(h) + sage.fc_neigh(mean)
+        assert rel_err(sage(G, h).detach().numpy(), want.detach().numpy()) < 1e-13
+    finally:
+        sys.path.remove(shim)
+        for k in [k for k in sys.modules if k == "dgl" or k.startswith("dgl.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
