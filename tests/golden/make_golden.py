@@ -230,9 +230,50 @@ def switches_case(ns):
     np.savez_compressed(os.path.join(OUT, "switches_small_model.npz"), **out_all)
 
 
+def train_batch_case(ns):
+    """BASELINE configs[1] at full size -- 32 x ACE-(ALA)4-NME, 50 conformations, grappa-1.2 architecture -- through the
+    unmodified reference: energies, parameters, loss and per-parameter gradient norms -> train_batch_grappa12.npz.  The
+    inputs are NOT stored (1 MB of coordinates): synthetic.peptide_batch(seed=100, ...) regenerates them; a checksum
+    guards the regeneration."""
+    g = synthetic.peptide_batch(seed=100, batch_size=32, n_res=4, n_confs=50)
+    cfg = orc.grappa_1_2_model_config()
+    torch.manual_seed(5)
+    model = ns.deploy.model_from_config(dict(cfg), param_statistics=ns.graph_utils.get_default_statistics())
+    sd = synthetic.deterministic_state_dict(model.state_dict(), seed=11)
+    model.load_state_dict(sd)
+    model.eval()
+    dg = to_reference_graph(ns, g)
+    with no_dihedral_noise():
+        dg = torch.nn.Sequential(model, ns.energy.Energy())(dg)
+    loss = ns.loss.MolwiseLoss(gradient_weight=0.8, energy_weight=1.0, param_weight=0.0, proper_regularisation=1e-3,
+                               improper_regularisation=1e-3)(dg)
+    model.zero_grad()
+    loss.backward()
+    named = dict(model.named_parameters())
+    keys = sorted(named)
+    out = {"meta.seed": np.array(100), "meta.weights_seed": np.array(11),
+           "meta.xyz_checksum": np.array(float(g.nodes["n1"].data["xyz"].double().sum())),
+           "meta.xyz_abs_checksum": np.array(float(g.nodes["n1"].data["xyz"].double().abs().sum())),
+           "out.g.energy": dg.nodes["g"].data["energy"].detach().numpy(),
+           "out.gradient_norm_per_atom": dg.nodes["n1"].data["gradient"].detach().norm(dim=(1, 2)).numpy(),
+           "out.loss": np.array(loss.item(), dtype=np.float64),
+           "meta.grad_norms_keys": np.array(keys),
+           "meta.grad_norms": np.array([float(named[k].grad.norm()) if named[k].grad is not None else 0.0 for k in keys])}
+    for lvl in LEVELS:
+        out[f"out.{lvl}.k"] = dg.nodes[lvl].data["k"].detach().numpy()
+        if lvl in ("n2", "n3"):
+            out[f"out.{lvl}.eq"] = dg.nodes[lvl].data["eq"].detach().numpy()
+    for k in ("gnn.att_blocks.6.head_reducer.bias", "parameter_writer.proper_writer.torsion_model.symmetriser.mlp.2.linear2.weight"):
+        out[f"grad.{k}"] = named[k].grad.detach().numpy()
+    np.savez_compressed(os.path.join(OUT, "train_batch_grappa12.npz"), **out)
+    print("train_batch_grappa12: loss =", loss.item())
+
+
 def main():
     ns = import_reference()
     torch.set_num_threads(8)
+    if "--only-train-batch" in sys.argv:
+        return train_batch_case(ns)
     if "--only-switches" in sys.argv:
         return switches_case(ns)
     if "--only-param-loss" in sys.argv:
@@ -242,6 +283,7 @@ def main():
     param_loss_case(ns)
     ragged_conformations_case(ns)
     switches_case(ns)
+    train_batch_case(ns)
 
     # ---- case 1: BASELINE config 1 -- grappa-1.2 architecture, capped dipeptide, 50 conformations
     g = synthetic.dipeptide(seed=11, n_confs=50)

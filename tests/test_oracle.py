@@ -289,3 +289,36 @@ def test_graph_convolutions_vs_dense_adjacency_restatement_fp64():
         for k in [k for k in sys.modules if k == "dgl" or k.startswith("dgl.")]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+def test_oracle_matches_reference_fixture_full_size_training_batch():
+    """BASELINE configs[1] at full size (32 x ACE-(ALA)4-NME, 50 conformations, grappa-1.2): energies, parameters, loss
+    and per-parameter gradient norms of the unmodified reference (tests/golden/train_batch_grappa12.npz; the inputs are
+    regenerated from the seed and guarded by a checksum)."""
+    from grappa_b200 import synthetic
+    z = load_golden("train_batch_grappa12.npz")
+    g = synthetic.peptide_batch(seed=int(z["meta.seed"]), batch_size=32, n_res=4, n_confs=50)
+    xyz = g.nodes["n1"].data["xyz"].double()
+    assert abs(float(xyz.sum()) - float(z["meta.xyz_checksum"])) < 1e-6 * float(z["meta.xyz_abs_checksum"])
+    assert abs(float(xyz.abs().sum()) - float(z["meta.xyz_abs_checksum"])) < 1e-9 * float(z["meta.xyz_abs_checksum"])
+    cfg = orc.grappa_1_2_model_config()
+    sd, _ = _sd(cfg, seed=int(z["meta.weights_seed"]))
+    keys = list(z["meta.grad_norms_keys"])
+    leaves = {k: sd[k].requires_grad_(True) for k in keys}
+    h, params, en = orc.path_forward(sd, g, cfg, create_graph=True)
+    assert rel_err(en["energy"].detach().numpy(), z["out.g.energy"]) < 2e-5
+    assert rel_err(en["gradient"].detach().norm(dim=(1, 2)).numpy(), z["out.gradient_norm_per_atom"]) < 2e-5
+    for l in LEVELS:
+        assert rel_err(params[l]["k"].detach().numpy(), z[f"out.{l}.k"]) < 2e-5, l
+        if l in ("n2", "n3"):
+            assert rel_err(params[l]["eq"].detach().numpy(), z[f"out.{l}.eq"]) < 2e-5, l
+    loss = orc.molwise_loss(en, params, g)
+    assert abs(float(loss) - float(z["out.loss"])) < 1e-5 * abs(float(z["out.loss"]))
+    grads = dict(zip(leaves, torch.autograd.grad(loss, list(leaves.values()), allow_unused=True)))
+    norms = np.array([0.0 if grads[k] is None else float(grads[k].norm()) for k in keys])
+    ref = z["meta.grad_norms"]
+    rel = np.abs(norms - ref) / np.maximum(ref, 1e-6 * ref.max())
+    assert rel.max() < 1e-3, (keys[int(rel.argmax())], rel.max())
+    for k in z.files:
+        if k.startswith("grad."):
+            assert rel_err(grads[k[5:]].numpy(), z[k]) < 1e-4, k
