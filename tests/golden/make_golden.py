@@ -269,9 +269,58 @@ def train_batch_case(ns):
     print("train_batch_grappa12: loss =", loss.item())
 
 
+def protein_and_mix_cases(ns):
+    """BASELINE configs[2] (ACE-(ALA)149-NME, 1,502 atoms, grappa-1.2 parametrisation) and configs[4] (Espaloma-shaped
+    mix of 32 molecules, 32 conformations, narrow model, energies + forces) through the unmodified reference, with the
+    seeds tests/test_baseline_configs_gpu.py uses -> protein_grappa12.npz, espaloma_mix_small_model.npz.  Inputs are
+    regenerated from the seeds (checksummed).  No loss for the mix: the reference's MolwiseLoss is NaN for molecules
+    without impropers (training/loss.py:130-132)."""
+    g = synthetic.protein(seed=0)
+    cfg = orc.grappa_1_2_model_config()
+    torch.manual_seed(5)
+    model = ns.deploy.model_from_config(dict(cfg), param_statistics=ns.graph_utils.get_default_statistics())
+    model.load_state_dict(synthetic.deterministic_state_dict(model.state_dict(), seed=12))
+    model.eval()
+    with torch.no_grad():
+        dg = model(to_reference_graph(ns, g))
+    q = g.nodes["n1"].data["partial_charge"].double()
+    out = {"meta.seed": np.array(0), "meta.weights_seed": np.array(12), "meta.charge_checksum": np.array(float(q.abs().sum())),
+           "out.h_norm_per_atom": dg.nodes["n1"].data["h"].norm(dim=1).numpy(),
+           "out.h_first_atoms": dg.nodes["n1"].data["h"][:8].numpy()}
+    for lvl in LEVELS:
+        out[f"out.{lvl}.k"] = dg.nodes[lvl].data["k"].numpy()
+        if lvl in ("n2", "n3"):
+            out[f"out.{lvl}.eq"] = dg.nodes[lvl].data["eq"].numpy()
+    np.savez_compressed(os.path.join(OUT, "protein_grappa12.npz"), **out)
+    print("protein_grappa12: atoms", g.num_nodes("n1"), "k[0] =", out["out.n2.k"][0])
+
+    g = synthetic.espaloma_mix_batch(seed=4, batch_size=32, n_confs=32)
+    cfg = orc.small_model_config()
+    torch.manual_seed(5)
+    model = ns.deploy.model_from_config(dict(cfg), param_statistics=ns.graph_utils.get_default_statistics())
+    model.load_state_dict(synthetic.deterministic_state_dict(model.state_dict(), seed=13))
+    model.eval()
+    dg = to_reference_graph(ns, g)
+    with no_dihedral_noise():
+        dg = torch.nn.Sequential(model, ns.energy.Energy())(dg)
+    xyz = g.nodes["n1"].data["xyz"].double()
+    out = {"meta.seed": np.array(4), "meta.weights_seed": np.array(13), "meta.xyz_abs_checksum": np.array(float(xyz.abs().sum())),
+           "meta.atom_counts": g.batch_num_nodes("n1").numpy(),
+           "out.g.energy": dg.nodes["g"].data["energy"].detach().numpy(),
+           "out.n1.gradient": dg.nodes["n1"].data["gradient"].detach().numpy()}
+    for lvl in LEVELS:
+        out[f"out.{lvl}.k"] = dg.nodes[lvl].data["k"].detach().numpy()
+        if lvl in ("n2", "n3"):
+            out[f"out.{lvl}.eq"] = dg.nodes[lvl].data["eq"].detach().numpy()
+    np.savez_compressed(os.path.join(OUT, "espaloma_mix_small_model.npz"), **out)
+    print("espaloma_mix_small_model: atoms", g.num_nodes("n1"), "E[0,0] =", out["out.g.energy"][0, 0])
+
+
 def main():
     ns = import_reference()
     torch.set_num_threads(8)
+    if "--only-protein-mix" in sys.argv:
+        return protein_and_mix_cases(ns)
     if "--only-train-batch" in sys.argv:
         return train_batch_case(ns)
     if "--only-switches" in sys.argv:
@@ -284,6 +333,7 @@ def main():
     ragged_conformations_case(ns)
     switches_case(ns)
     train_batch_case(ns)
+    protein_and_mix_cases(ns)
 
     # ---- case 1: BASELINE config 1 -- grappa-1.2 architecture, capped dipeptide, 50 conformations
     g = synthetic.dipeptide(seed=11, n_confs=50)

@@ -322,3 +322,39 @@ def test_oracle_matches_reference_fixture_full_size_training_batch():
     for k in z.files:
         if k.startswith("grad."):
             assert rel_err(grads[k[5:]].numpy(), z[k]) < 1e-4, k
+
+
+def test_oracle_matches_reference_fixtures_protein_and_espaloma_mix():
+    """BASELINE configs[2] (1,502-atom protein, grappa-1.2 parametrisation) and configs[4] (Espaloma-shaped mix, narrow
+    model, energies + forces) at full size: oracle vs outputs of the unmodified reference, same seeds as
+    tests/test_baseline_configs_gpu.py (which compares the CUDA path with the oracle on the same inputs)."""
+    from grappa_b200 import synthetic
+    z = load_golden("protein_grappa12.npz")
+    g = synthetic.protein(seed=int(z["meta.seed"]))
+    assert abs(float(g.nodes["n1"].data["partial_charge"].double().abs().sum()) - float(z["meta.charge_checksum"])) < 1e-9
+    cfg = orc.grappa_1_2_model_config()
+    sd, _ = _sd(cfg, seed=int(z["meta.weights_seed"]))
+    with torch.no_grad():
+        h, params = orc.model_forward(sd, g, cfg)
+    assert rel_err(h.norm(dim=1).numpy(), z["out.h_norm_per_atom"]) < 2e-5
+    assert rel_err(h[:8].numpy(), z["out.h_first_atoms"]) < 2e-5
+    for l in LEVELS:
+        assert params[l]["k"].shape == z[f"out.{l}.k"].shape
+        assert rel_err(params[l]["k"].numpy(), z[f"out.{l}.k"]) < 2e-5, l
+        if l in ("n2", "n3"):
+            assert rel_err(params[l]["eq"].numpy(), z[f"out.{l}.eq"]) < 2e-5, l
+
+    z = load_golden("espaloma_mix_small_model.npz")
+    g = synthetic.espaloma_mix_batch(seed=int(z["meta.seed"]), batch_size=32, n_confs=32)
+    assert g.batch_num_nodes("n1").tolist() == z["meta.atom_counts"].tolist()
+    xyz = g.nodes["n1"].data["xyz"].double()
+    assert abs(float(xyz.abs().sum()) - float(z["meta.xyz_abs_checksum"])) < 1e-9 * float(z["meta.xyz_abs_checksum"])
+    cfg = orc.small_model_config()
+    sd, _ = _sd(cfg, seed=int(z["meta.weights_seed"]))
+    h, params, en = orc.path_forward(sd, g, cfg)
+    assert rel_err(en["energy"].detach().numpy(), z["out.g.energy"]) < 2e-5
+    assert rel_err(en["gradient"].detach().numpy(), z["out.n1.gradient"]) < 2e-5
+    for l in LEVELS:
+        assert rel_err(params[l]["k"].detach().numpy(), z[f"out.{l}.k"]) < 2e-5, l
+        if l in ("n2", "n3"):
+            assert rel_err(params[l]["eq"].detach().numpy(), z[f"out.{l}.eq"]) < 2e-5, l
