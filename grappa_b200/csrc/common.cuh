@@ -41,6 +41,17 @@ void set_error(const char* fmt, ...);
 void count_launch();  // bumps the process-wide kernel launch counter (grappa_b200_launch_count)
 int sm_count();  // cached multiprocessor count of the current device (148 on B200)
 
+// true the first time it is called for `mask` on the CURRENT device: function attributes (max dynamic shared memory) are
+// per device, so one-off kernel set-up is tracked per device ordinal, not per process
+inline bool first_use_on_device(unsigned long long& mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (mask & bit) return false;
+  mask |= bit;
+  return true;
+}
+
 #ifdef __CUDACC__
 // Programmatic dependent launch (PDL).  Every kernel calls pdl_trigger() first thing: once all CTAs of a grid have done
 // so (or exited), a following kernel that was launched with the programmatic-stream-serialization attribute may start

@@ -298,10 +298,16 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                    float grad_scale) {
   pdl_trigger();
   float coef = grad_scale;
-  if (gnorm_sq && clip > 0.f) {
-    // the norm was accumulated on UNSCALED gradients: total norm of the scaled gradient = scale * sqrt(sumsq)
-    const float total = grad_scale * sqrtf(__ldg(gnorm_sq));
-    coef *= fminf(1.f, clip / (total + 1e-6f));
+  if (gnorm_sq) {
+    const float ss = __ldg(gnorm_sq);
+    // a non-finite gradient norm (one NaN / inf anywhere in the flat gradient) would turn EVERY parameter and both
+    // moment buffers into NaN in this one step: the step is skipped instead, parameters and moments stay as they are
+    if (!(ss >= 0.f && ss <= 3.0e38f)) return;
+    if (clip > 0.f) {
+      // the norm was accumulated on UNSCALED gradients: total norm of the scaled gradient = scale * sqrt(sumsq)
+      const float total = grad_scale * sqrtf(ss);
+      coef *= fminf(1.f, clip / (total + 1e-6f));
+    }
   }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float gi = g[i] * coef;
@@ -647,9 +653,13 @@ __global__ void __launch_bounds__(256) adam_dev_kernel(float* __restrict__ p, co
   const float bc1 = 1.f - powf(b1, step);
   const float bc2_sqrt = sqrtf(1.f - powf(b2, step));
   float coef = grad_scale;
-  if (gnorm_sq && clip > 0.f) {
-    const float total = grad_scale * sqrtf(__ldg(gnorm_sq));
-    coef *= fminf(1.f, clip / (total + 1e-6f));
+  if (gnorm_sq) {
+    const float ss = __ldg(gnorm_sq);
+    if (!(ss >= 0.f && ss <= 3.0e38f)) return;   // non-finite gradient: skip the step (see adam_kernel)
+    if (clip > 0.f) {
+      const float total = grad_scale * sqrtf(ss);
+      coef *= fminf(1.f, clip / (total + 1e-6f));
+    }
   }
   const long long n4 = n >> 2;   // flat buffers are 16-byte aligned (cudaMalloc / torch allocator)
   float4* p4 = reinterpret_cast<float4*>(p);

@@ -751,11 +751,9 @@ extern "C" int grappa_b200_energy_fwd(const gb_energy_args* a, int variant, void
     GB_REQUIRE(mode != 4 || (have && fits), "energy: round-scheduled variant needs sched/round_off with sched_groups == 8 "
                "and a molecule tile that fits in shared memory (max_atoms=%d)", max_atoms);
     if (mode == 4 || (mode == 0 && have && fits)) {
-      static bool configured = false;
-      if (!configured) {
+      static unsigned long long configured = 0;   // per device: a process-wide flag left a second GPU unconfigured
+      if (first_use_on_device(configured))
         GB_CHECK_CUDA(cudaFuncSetAttribute(energy_rounds_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
-      }
       const int nt = (C + 31) / 32;
       const int wtile = (C + nt - 1) / nt;          // balanced tiles of <= 32 conformations
       energy_rounds_kernel<8><<<B * nt, 256, smem_r, stream>>>(*a, nt, wtile);
@@ -770,11 +768,9 @@ extern "C" int grappa_b200_energy_fwd(const gb_energy_args* a, int variant, void
     const bool conf_ok = max_atoms > 0 && smem_c <= 100 * 1024;
     GB_REQUIRE(mode != 3 || conf_ok, "energy: conformation-per-thread variant requested but max_atoms=%d does not fit", max_atoms);
     if (mode == 3) {
-      static bool configured = false;
-      if (!configured) {
+      static unsigned long long configured = 0;
+      if (first_use_on_device(configured))
         GB_CHECK_CUDA(cudaFuncSetAttribute(energy_conf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        configured = true;
-      }
       const int nt = (C + Wc - 1) / Wc;
       energy_conf_kernel<<<B * nt, Wc, smem_c, stream>>>(*a, nt);
       GB_CHECK_LAUNCH();

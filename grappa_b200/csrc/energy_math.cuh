@@ -62,10 +62,16 @@ struct BondGeom {
   float r;      // bond length
   V3 d0;        // dr/dx0 (= -dr/dx1)
 };
+// Degenerate geometry follows the reference's autograd conventions instead of producing inf * 0 = NaN:
+//   * coincident bond atoms: r = 0, zero derivative (torch.norm's subgradient at 0 is 0);
+//   * exactly collinear angle (nitriles, alkynes, CO2-type molecules stored on an axis): theta = atan2(0, c) in {0, pi},
+//     zero derivative (internal_coordinates.py:155-170: atan2's partials vanish at s = 0 and norm's backward is 0);
+//   * torsion with three collinear atoms: the reference hides the singularity behind randn * 1e-5 noise
+//     (internal_coordinates.py:194-196); the noise-free definition here is phi = atan2(0, 0) = 0 with zero derivative.
 GB_HD BondGeom bond_geom(V3 x0, V3 x1) {
   V3 d = x0 - x1;
   float r2 = dot(d, d);
-  float ir = inv_sqrt(r2);
+  float ir = r2 > 0.f ? inv_sqrt(r2) : 0.f;
   BondGeom g;
   g.r = r2 * ir;
   g.d0 = ir * d;
@@ -81,10 +87,11 @@ GB_HD AngleGeom angle_geom(V3 x0, V3 x1, V3 x2) {
   V3 a = x0 - x1, b = x2 - x1;
   V3 n = cross(a, b);
   float s2 = dot(n, n);
-  float is = inv_sqrt(s2);
+  float is = s2 > 0.f ? inv_sqrt(s2) : 0.f;   // collinear: s = 0, d0 = d2 = 0
   float s = s2 * is;              // |a||b| sin(theta)
   float c = dot(a, b);            // |a||b| cos(theta)
-  float ia2 = recip(dot(a, a)), ib2 = recip(dot(b, b));
+  float a2 = dot(a, a), b2 = dot(b, b);
+  float ia2 = a2 > 0.f ? recip(a2) : 0.f, ib2 = b2 > 0.f ? recip(b2) : 0.f;
   AngleGeom g;
   g.theta = atan2f(s, c);
   // dtheta/da = (c/|a|^2 a - b) / s ,  dtheta/db = (c/|b|^2 b - a) / s
@@ -102,12 +109,14 @@ GB_HD TorsionGeom torsion_geom(V3 x0, V3 x1, V3 x2, V3 x3) {
   V3 F = x0 - x1, G = x1 - x2, H = x3 - x2;
   V3 A = cross(F, G), B = cross(H, G);
   float A2 = dot(A, A), B2 = dot(B, B), G2 = dot(G, G);
-  float iG = inv_sqrt(G2);
+  float iG = G2 > 0.f ? inv_sqrt(G2) : 0.f;
   float gl = G2 * iG;                      // |G|
-  float iA2 = recip(A2), iB2 = recip(B2);
-  float iAB = inv_sqrt(A2 * B2);
+  float AB2 = A2 * B2;
+  const bool ok = AB2 > 0.f;               // false: three collinear atoms -> phi = 0, zero derivative
+  float iA2 = ok ? recip(A2) : 0.f, iB2 = ok ? recip(B2) : 0.f;
+  float iAB = ok ? inv_sqrt(AB2) : 0.f;
   TorsionGeom t;
-  t.cphi = dot(A, B) * iAB;
+  t.cphi = ok ? dot(A, B) * iAB : 1.f;
   // (A x B).G = ((F x G) x (H x G)).G = -[F,G,H] |G|^2 = -(A.H) |G|^2   (vector quadruple product)
   t.sphi = -dot(A, H) * gl * iAB;
   float fg = dot(F, G) * iG, hg = dot(H, G) * iG;

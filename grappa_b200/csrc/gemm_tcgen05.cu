@@ -557,11 +557,9 @@ static bool make_map(CUtensorMap* map, const float* base, int rows, int cols, in
 template <int BN, int TA, int TB, int CTAS, bool GROUPED>
 static int launch(const TcMaps& maps, const TcParams& p, int grid, cudaStream_t stream) {
   constexpr int smem = TcCfg<BN, CTAS>::SMEM;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;   // per device ordinal
+  if (first_use_on_device(configured))
     GB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN, TA, TB, CTAS, GROUPED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid, 1, 1);
   cfg.blockDim = dim3(TC_THREADS, 1, 1);

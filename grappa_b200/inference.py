@@ -100,7 +100,8 @@ def molecule_graph(atoms: Sequence[int], bonds: Sequence[Sequence[int]], atomic_
     deg = np.zeros(n, dtype=np.int64)
     np.add.at(deg, b.reshape(-1), 1)
     degree = np.zeros((n, 6), dtype=np.float32)
-    degree[np.arange(n), np.clip(deg, 1, 6) - 1] = 1.0
+    ok = (deg >= 1) & (deg <= 6)     # reference utils/rdkit_utils.py:55-67: degree outside 1..6 -> all-zero row
+    degree[np.arange(n)[ok], deg[ok] - 1] = 1.0
     if charge_model not in CHARGE_MODELS:
         raise ValueError(f"charge_model must be one of {CHARGE_MODELS}")
     cm = np.zeros((n, len(CHARGE_MODELS)), dtype=np.float32)

@@ -176,6 +176,20 @@ class SAGEConv(nn.Module):
         return super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
 
 
+def to_dgl_state_dict(state_dict: Dict[str, torch.Tensor], separate_sage_bias: bool = True) -> Dict[str, torch.Tensor]:
+    """Checkpoint export for the reference running on DGL >= 0.8, whose SAGEConv keeps its bias as a separate
+    `graph_module.bias` parameter (older DGL: `graph_module.fc_self.bias`, the layout `state_dict()` emits here; loading
+    accepts both).  Only convolution models (gnn_convolutions > 0, grappa-1.0) are affected -- grappa-1.1 / 1.2 have none."""
+    if not separate_sage_bias:
+        return dict(state_dict)
+    out = {}
+    for k, v in state_dict.items():
+        if k.endswith("graph_module.fc_self.bias"):
+            k = k[:-len("fc_self.bias")] + "bias"
+        out[k] = v
+    return out
+
+
 class ResidualConvBlock(nn.Module):
     """grappa-1.0 convolution block (reference models/graph_attention.py:314-415): u = LN(h);
     y = dropout(ELU(SAGEConv(u))) + u; z = LN(y); out = dropout(ELU(W z + b)) + z."""

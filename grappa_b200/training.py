@@ -82,7 +82,11 @@ class Trainer:
     eagerly (it also performs the one-off kernel attribute set-up), the second one is captured.
     """
 
-    INPUT_KEYS = ("xyz", "energy_ref", "gradient_ref", "partial_charge")
+    # per-batch inputs of the captured step: coordinates, labels, features and the loss's per-batch fields -- the
+    # padded-conformation bookkeeping (`n_valid` / `is_dummy`, reference utils/dgl_utils.py:63-118) and the per-molecule
+    # classical-parameter weights (`param_weight`, training/loss.py:72-76).  A field missing here would be deleted from
+    # the static graph and the replayed step would optimise a different loss than the eager one.
+    INPUT_KEYS = ("xyz", "energy_ref", "gradient_ref", "partial_charge", "n_valid", "is_dummy", "param_weight")
 
     def __init__(self, model: models.GrappaModel, energy, loss_fn, lr: float = 1.5e-5, clip: float = 10.0,
                  betas=(0.9, 0.999), eps: float = 1e-8, device="cuda", distributed: Optional[bool] = None,
@@ -121,6 +125,8 @@ class Trainer:
         self._block_spans = [self.fp.span(b) for b in g.att_blocks] if not g.no_convs else []
         self.comm_stream = torch.cuda.Stream(device=self.device) if self.distributed and self.device.type == "cuda" else None
         self._pending: List = []
+        self._ready = set()        # writer buckets whose gradients are final but whose all-reduce has not been issued yet
+        self._next_bucket = 0
         if self.distributed:
             models.set_backward_hook(self._on_stage_backward)
 
@@ -198,10 +204,13 @@ class Trainer:
     def _on_stage_backward(self, tag):
         """Called from the backward pass when all gradients of a stage / GNN block are final."""
         kind, obj = tag
+        if kind != "writer" and self.distributed:
+            self._drain_writer_buckets(final=True)    # the GNN's backward starts after every writer's: nothing is left pending
         if kind == "writer":
             for name, mod in self.buckets:
                 if mod is obj:
-                    self._launch_allreduce(*self._bucket_spans[name])
+                    self._ready.add(name)
+            self._drain_writer_buckets()
         elif kind == "gnn_block":
             self._launch_allreduce(*self._block_spans[obj])
         elif kind == "gnn_rest":
@@ -214,6 +223,23 @@ class Trainer:
             else:
                 self._launch_allreduce(s, e)
 
+    def _bucket_order(self) -> List[str]:
+        """Writer buckets in the order autograd finishes them: the reverse of the order `WriteParameters.forward` ran the
+        writers in (concurrent streams: proper, angle, bond, improper; one stream: bond, angle, proper, improper)."""
+        from . import tape as T_
+        if self.device.type == "cuda" and T_.concurrency():
+            return ["improper", "bond", "angle", "proper"]
+        return ["improper", "proper", "angle", "bond"]
+
+    def _drain_writer_buckets(self, final: bool = False):
+        """Issue the writer-bucket all-reduces in ONE canonical order on every rank.  NCCL matches collectives by issue
+        order, so a rank whose batch has no tuples at some level (that writer never runs, its bucket is zero) must
+        issue that bucket at the same position as the ranks that do run it -- not before its forward pass."""
+        order = self._bucket_order()
+        while self._next_bucket < len(order) and (final or order[self._next_bucket] in self._ready):
+            self._launch_allreduce(*self._bucket_spans[order[self._next_bucket]])
+            self._next_bucket += 1
+
     def _wait_comm(self):
         for ev in self._pending:
             torch.cuda.current_stream().wait_event(ev)
@@ -223,16 +249,18 @@ class Trainer:
     def forward_backward(self, g) -> torch.Tensor:
         from .pack import get_pack
         pack = get_pack(g)
+        self._ready, self._next_bucket = set(), 0
         for (name, _), lvl in zip(self.buckets, (3, 2, 1, 0)):
             if pack.n_tuples[lvl] == 0:      # writer unused by this batch: its gradient is zero, not stale
                 s, e = self._bucket_spans[name]
                 self.fp.grad[s:e].zero_()
-                if self.distributed:
-                    self._launch_allreduce(s, e)
+                self._ready.add(name)        # exchanged at its usual position in the bucket order (all ranks alike)
         g = self.model(g)
         g = self.energy(g)
         loss = self.loss_fn(g)
         loss.backward()
+        if self.distributed:
+            self._drain_writer_buckets(final=True)
         # the outputs left on the graph (h, k, eq, energy, gradient ...) must not keep the autograd graph -- and with
         # it per-parameter autograd nodes bound to this step's streams -- alive beyond the step
         for nt in g.ntypes:

@@ -35,7 +35,14 @@ def _worker(rank, world, port, out):
     tr.fp.grad.fill_(float(rank + 1))
     # fire the hooks in the order the backward pass does
     w_ = model.parameter_writer
-    for mod in (w_.improper_writer, w_.proper_writer, w_.angle_writer, w_.bond_writer):
+    # rank 1's batch has no propers: that writer never runs there, its (zero) bucket is only marked ready -- and the
+    # hooks of the other writers fire in a different order than on rank 0.  The collectives must still pair up.
+    if rank == 1:
+        tr._ready.add("proper")
+        fire = (w_.bond_writer, w_.improper_writer, w_.angle_writer)
+    else:
+        fire = (w_.improper_writer, w_.proper_writer, w_.angle_writer, w_.bond_writer)
+    for mod in fire:
         tr._on_stage_backward(("writer", mod))
     for i in reversed(range(len(model.gnn.att_blocks))):
         tr._on_stage_backward(("gnn_block", i))

@@ -191,3 +191,56 @@ def test_energy_full_size_properties():
     out4 = e2(g.to("cuda"))
     assert rel_err(out4.nodes["g"].data["energy"].cpu().numpy(), E.cpu().numpy()) < 1e-5
     assert rel_err(out4.nodes["n1"].data["gradient"].cpu().numpy(), F.cpu().numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("variant", [0, 1, 3, 4])
+def test_energy_collinear_geometry_is_finite_and_matches_the_oracle(variant):
+    """A linear molecule stored on an axis (CO2 / nitrile / alkyne type): |a x b| = 0 exactly.  The reference returns
+    theta = atan2(0, c) = pi with a zero angle derivative (torch.norm's subgradient at 0); an rsqrt(0) = inf would turn
+    energy, forces and -- through the loss -- every parameter into NaN.  Torsions over three collinear atoms are defined
+    as phi = 0 with zero derivative (the reference masks that singularity with random noise)."""
+    import grappa_oracle as orc
+    from grappa_b200.energy import Energy
+    from grappa_b200.graph import MolGraph
+    C = 4
+    # four atoms on the x axis, C conformations differing by a shift / scale along the axis (still exactly collinear)
+    base = torch.tensor([[0.0, 0, 0], [1.25, 0, 0], [2.5, 0, 0], [3.5, 0, 0]])
+    xyz = torch.stack([base * (1.0 + 0.125 * c) + torch.tensor([0.5 * c, 0, 0]) for c in range(C)], dim=1)   # (4, C, 3)
+    src = torch.tensor([0, 1, 1, 2, 2, 3]); dst = torch.tensor([1, 0, 2, 1, 3, 2])
+    g = MolGraph({"g": 1, "n1": 4, "n2": 3, "n3": 2, "n4": 1, "n4_improper": 0}, src, dst)
+    g.nodes["n1"].data["xyz"] = xyz
+    g.nodes["n2"].data["idxs"] = torch.tensor([[0, 1], [1, 2], [2, 3]])
+    g.nodes["n3"].data["idxs"] = torch.tensor([[0, 1, 2], [1, 2, 3]])
+    g.nodes["n4"].data["idxs"] = torch.tensor([[0, 1, 2, 3]])
+    g.nodes["n4_improper"].data["idxs"] = torch.zeros((0, 4), dtype=torch.int64)
+    g.nodes["n2"].data["k"] = torch.tensor([300.0, 310.0, 290.0]); g.nodes["n2"].data["eq"] = torch.tensor([1.1, 1.2, 1.0])
+    g.nodes["n3"].data["k"] = torch.tensor([80.0, 70.0]); g.nodes["n3"].data["eq"] = torch.tensor([2.9, 3.0])
+    g.nodes["n4"].data["k"] = torch.tensor([[0.5, -0.25, 0.125]])
+    g.nodes["n4_improper"].data["k"] = torch.zeros(0, 3)
+    # oracle on bonds + angles (its noise-free dihedral has a NaN gradient at the singularity, as the reference would)
+    idxs = {l: g.nodes[l].data["idxs"] for l in ("n2", "n3")}
+    counts = {l: g.batch_num_nodes(l).tolist() for l in ("n2", "n3")}
+    prm = {l: {n: g.nodes[l].data[n].double() for n in ("k", "eq")} for l in ("n2", "n3")}
+    ref = orc.energy_forward(xyz.double(), idxs, prm, counts)
+    gd = g.to("cuda")
+    for l in LEVELS:
+        for n in ("k", "eq"):
+            if n in gd.nodes[l].data:
+                gd.nodes[l].data[n].requires_grad_(True)
+    en = Energy()
+    en.kernel_variant = variant
+    out = en(gd)
+    E = out.nodes["g"].data["energy"]
+    F = out.nodes["n1"].data["gradient"]
+    assert torch.isfinite(E).all() and torch.isfinite(F).all()
+    e_tors = float(g.nodes["n4"].data["k"].sum())                  # phi = 0: sum_n k_n cos(0)
+    assert rel_err((E.detach().cpu() - e_tors).numpy(), ref["energy"].detach().numpy()) < TOL_E
+    assert rel_err(F.detach().cpu().numpy(), ref["gradient"].numpy()) < TOL_E
+    assert torch.allclose(out.nodes["n3"].data["x"].cpu(), torch.full((2, C), float(np.pi)), atol=1e-6)
+    # the double backward (K14) stays finite as well
+    (E.sum() + (F * torch.randn_like(F)).sum()).backward()
+    for l in LEVELS:
+        for n in ("k", "eq"):
+            t = gd.nodes[l].data.get(n)
+            if t is not None and t.grad is not None:
+                assert torch.isfinite(t.grad).all(), (l, n)

@@ -139,3 +139,56 @@ def test_training_from_packed_dataset_through_the_prefetch_loader():
             assert g.nodes["g"].data["is_dummy"].shape == (4, g.nodes["n1"].data["xyz"].shape[1])
             losses.append(tr.step(g).item())
     assert len(losses) == 3 * (len(ds) // 4) and all(np.isfinite(losses))
+
+
+def test_captured_step_keeps_padding_and_param_weights():
+    """The per-batch loss inputs `n_valid` / `is_dummy` (padded conformations) and `param_weight` (per-dataset weights of the
+    classical-parameter term) are inputs of the captured step like xyz: a replay must optimise exactly the loss the eager
+    step optimises -- same losses, bit-identical parameters.  (Round 1 dropped them from the static graph: replays counted
+    the padded conformations and fell back to the uniform weight.)"""
+    from grappa_b200 import dataset, synthetic
+    from grappa_b200.loss import MolwiseLoss
+    from grappa_b200.training import Trainer
+    rng = np.random.default_rng(3)
+    mols = []
+    for i in range(12):
+        m = synthetic.make_molecule(rng, "peptide", n_confs=(2, 3, 4, 6)[i % 4], n_res=1)     # one topology, ragged confs
+        for lvl, names in (("n2", ("k", "eq")), ("n3", ("k", "eq")), ("n4", ("k",))):
+            T = m.num_nodes(lvl)
+            for n in names:
+                shape = (T, 3) if lvl == "n4" else (T,)
+                m.nodes[lvl].data[n + "_ref"] = torch.from_numpy(rng.normal(1.0, 0.3, size=shape).astype(np.float32))
+        mols.append(m)
+    ds = dataset.PackedDataset.from_graphs(mols, dsnames=["a", "b", "c"] * 4)
+    batches = [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9, 10, 11], [3, 7, 11, 0], [1, 5, 9, 2]]
+
+    def run(use_graph):
+        model, energy, _ = _setup(0.0)
+        loss = MolwiseLoss(gradient_weight=0.8, energy_weight=1.0, param_weight=1e-3, proper_regularisation=1e-3,
+                           improper_regularisation=1e-3)
+        tr = Trainer(model, energy, loss, lr=1e-3, clip=10.0, device="cuda", use_cuda_graph=use_graph)
+        losses = []
+        for g in dataset.PrefetchLoader(ds, batches, conf_strategy=5, seed=1, depth=2, param_weight=1e-3,
+                                        param_weights_by_dataset={"a": 0.0, "b": 5e-2}):
+            assert float(g.nodes["g"].data["is_dummy"].sum()) > 0, "the test needs padded conformations"
+            losses.append(float(tr.step(g).item()))
+        return losses, tr.fp.flat.detach().cpu().numpy().copy(), tr
+
+    l0, p0, _ = run(False)
+    l1, p1, tr = run(True)
+    assert len(tr._captured) == 1, "same-shaped batches must share one captured graph"
+    keys = {k for _, k in next(iter(tr._captured.values())).keys}
+    assert {"n_valid", "is_dummy", "param_weight"} <= keys, keys
+    assert l1 == l0, (l0, l1)
+    assert np.abs(p1 - p0).max() == 0.0
+    # and the fields matter: ignoring them changes the loss of the same batch
+    model, energy, _ = _setup(0.0)
+    loss = MolwiseLoss(gradient_weight=0.8, energy_weight=1.0, param_weight=1e-3, proper_regularisation=1e-3,
+                       improper_regularisation=1e-3)
+    g = next(iter(dataset.PrefetchLoader(ds, batches[:1], conf_strategy=5, seed=1, param_weight=1e-3,
+                                         param_weights_by_dataset={"a": 0.0, "b": 5e-2}))).to("cuda")
+    full = float(loss(energy(model.cuda()(g))).item())
+    for k in ("n_valid", "is_dummy", "param_weight"):
+        del g.nodes["g"].data[k]
+    stripped = float(loss(energy(model(g))).item())
+    assert abs(full - stripped) > 1e-6 * abs(full)
