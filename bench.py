@@ -151,7 +151,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--precision", default=None, help="GEMM arithmetic: bf16x3 (default, grappa_b200.ops.BENCH_PRECISION) | tf32 | fp32 "
+                    "| a per-family policy such as 'fwd=bf16x3,dgrad=bf16x3,wgrad=tf32'")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true", help="launch every kernel from the host instead of replaying a captured step")
     args = ap.parse_args()
@@ -174,6 +175,8 @@ def main():
     peaks = load_peaks()
     W = max(args.warmup, 3)
     K = args.steps
+    if args.precision is None:
+        args.precision = ops.BENCH_PRECISION
     ops.set_matmul_precision(args.precision)
 
     # ---- model / data ---------------------------------------------------------------------------
@@ -290,8 +293,12 @@ def main():
     gb_tape.set_concurrency(True)
     trainer.reset_graphs()
     achieved_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-    tensor_path = args.precision == "tf32"
-    roofline = {"bound": "tensor", "kernel": "gemm_tf32_kernel (tcgen05 + TMA)" if tensor_path else "sgemm_kernel (fp32 FFMA)",
+    prec = ops.get_matmul_precision()
+    tensor_path = prec != "fp32"
+    dtype = {"fp32": "f32", "tf32": "tf32 (tcgen05 kind::tf32, fp32 accumulate)",
+             "bf16x3": "bf16x3 (tcgen05 kind::f16 on in-kernel bf16 hi/lo splits of the fp32 operands: hi*hi + lo*hi + hi*lo, "
+                       "fp32 accumulate in TMEM)"}.get(prec, prec)
+    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 + TMA)" if tensor_path else "sgemm_kernel (fp32 FFMA)",
                 "achieved": achieved_tf, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                 "frac": achieved_tf / peaks["tflops_sustained"], "traffic": 65.4e6 if tensor_path else None,
                 "traffic_source": "ncu --set full of the step's largest token GEMM, M=14848 N=K=512 with the fused epilogue "
@@ -386,7 +393,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "molecules/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32 (tcgen05, fp32 accumulate)" if tensor_path else "f32", "data": "synthetic",
+            "dtype": dtype, "data": "synthetic",
             "config": {"workload": WORKLOAD, "architecture": "grappa-1.2 (40.8 M parameters, random init)",
                        "molecules_per_gpu": B, "atoms_per_gpu": n_atoms, "conformations": 50, "dropout": "on (train mode)",
                        "optimizer": "Adam + global-norm clip 10", "parallelism": f"dp{world}",

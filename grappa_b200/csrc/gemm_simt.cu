@@ -420,7 +420,7 @@ bool gemm_tcgen05_can_fuse_colsum(const gb_gemm_args* a);
 extern "C" int grappa_b200_gemm(const gb_gemm_args* a, void* stream_);
 
 extern "C" int grappa_b200_gemm_can_fuse_colsum(const gb_gemm_args* a) {
-  if (!a || a->M <= 0 || a->N <= 0 || !(a->precision == 1 || a->precision == 2)) return 0;
+  if (!a || a->M <= 0 || a->N <= 0 || !(a->precision >= 1 && a->precision <= 3)) return 0;
   return gb::gemm_tcgen05_can_fuse_colsum(a) ? 1 : 0;
 }
 
@@ -432,7 +432,8 @@ extern "C" int grappa_b200_gemm_grouped(const gb_gemm_args* list, int32_t n, voi
   while (i < n) {
     // longest run (<= 4) of non-empty tensor-core problems that one persistent launch can serve
     int j = i;
-    while (j < n && j - i < 4 && list[j].M > 0 && list[j].N > 0 && (list[j].precision == 1 || list[j].precision == 2)) ++j;
+    while (j < n && j - i < 4 && list[j].M > 0 && list[j].N > 0 && list[j].precision >= 1 && list[j].precision <= 3 &&
+           (list[j].precision == 3) == (list[i].precision == 3)) ++j;
     if (j - i >= 2) {
       bool handled = false;
       int rc = gb::gemm_tcgen05_grouped(list + i, j - i, stream, &handled);
@@ -456,12 +457,13 @@ extern "C" int grappa_b200_gemm(const gb_gemm_args* a, void* stream_) {
              a->lda, a->ldb, a->ldc, a->trans_a, a->trans_b);
   GB_REQUIRE(a->dropout_p >= 0.f && a->dropout_p < 1.f, "gemm: dropout_p must be in [0,1)");
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (a->precision == 1 || a->precision == 2) {
+  GB_REQUIRE(a->precision >= 0 && a->precision <= 3, "gemm: precision must be 0 (fp32), 1 (tf32), 2 (auto tf32) or 3 (bf16x3)");
+  if (a->precision >= 1) {
     bool handled = false;
     int rc = gb::gemm_tcgen05(a, stream, &handled);
     if (rc != GB_OK) return rc;
     if (handled) return GB_OK;
-    GB_REQUIRE(a->precision == 2, "gemm: tcgen05 path cannot take this shape/alignment (M=%d N=%d K=%d lda=%d ldb=%d)",
+    GB_REQUIRE(a->precision != 1, "gemm: tcgen05 path cannot take this shape/alignment (M=%d N=%d K=%d lda=%d ldb=%d)",
                a->M, a->N, a->K, a->lda, a->ldb);
   }
   GB_REQUIRE(a->colsum == nullptr, "gemm: fused column sums need the tensor-core path (ask grappa_b200_gemm_can_fuse_colsum)");

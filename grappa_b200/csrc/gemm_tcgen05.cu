@@ -19,6 +19,18 @@
 //                           operands only exist in the 32-byte-atom flavour of the 128-byte swizzle
 //                           (TMA SWIZZLE_128B_ATOM_32B, UMMA layout SWIZZLE_128B_BASE32B, atoms of 4 k-rows)
 // Rows / K tails are handled by TMA out-of-bounds zero fill and predicated stores.
+//
+// X3 = true ("bf16x3", gb_gemm_args.precision = 3): fp32-class accuracy on the tensor cores.  TF32 keeps 10 mantissa
+// bits per operand; through the ~45 dependent GEMMs of the model that is 2e-3 .. 3.5e-3 on the gated torsion amplitudes,
+// outside the 1e-3 contract.  Here four converter warps split every staged fp32 operand element into bf16 hi + bf16 lo
+// (hi = rn(a), lo = rn(a - hi): 16 mantissa bits together) and the MMA warp issues hi*hi + lo*hi + hi*lo with
+// kind::f16 -- three bf16 MMAs run at 1.5x the time of one TF32 MMA and the split operands take exactly the bytes of the
+// fp32 ones, so HBM / L2 traffic is unchanged and nothing but this kernel knows about the format:
+//     TMA (fp32 tile, as above) -> raw ring -> converter warps -> conv ring -> tcgen05.mma kind::f16 x3 -> TMEM
+// conv tile = rows x 128 B, row = [32 bf16 hi | 32 bf16 lo] of one 32-float k-block, ALWAYS K-major SWIZZLE_128B: the
+// same shared-memory descriptor form the TF32 path uses for K-major fp32 (hi part at +0 / +32, lo part at +64 / +96
+// bytes inside the swizzle atom).  MN-major fp32 operands (dgrad / wgrad) are transposed by the converter on the fly
+// (un-swizzled TMA boxes, conflict-free 4-byte column reads), so the MMA only ever sees K-major bf16.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -140,6 +152,86 @@ __device__ __forceinline__ void tc_mma_tf32_pair(uint32_t d_tmem, uint64_t a_des
       : "memory");
 }
 
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// generic-proxy shared-memory writes (the converter's st.shared) -> visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// {bf16(hi_elem) << 16 | bf16(lo_elem)}, round to nearest even
+__device__ __forceinline__ uint32_t cvt_bf16x2(float hi_elem, float lo_elem) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
+// (a0, a1) -> packed bf16 pair of the leading parts and packed bf16 pair of the remainders (a0 in the low half)
+__device__ __forceinline__ void split_pair(float a0, float a1, uint32_t& hi, uint32_t& lo) {
+  hi = cvt_bf16x2(a1, a0);
+  const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+  lo = cvt_bf16x2(a1 - h1, a0 - h0);
+}
+__device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo) {
+  split_pair(v[0], v[1], hi.x, lo.x);
+  split_pair(v[2], v[3], hi.y, lo.y);
+  split_pair(v[4], v[5], hi.z, lo.z);
+  split_pair(v[6], v[7], hi.w, lo.w);
+}
+
+constexpr int TC_CONV_WARPS = 4;   // converter warps of the bf16x3 kernel (warps 10..13)
+
+// One operand tile of one k-block: fp32 (as TMA staged it) -> [32 bf16 hi | 32 bf16 lo] rows, K-major SWIZZLE_128B
+// (16-byte chunk j of row r lives at chunk j ^ (r & 7) of the row's 128 bytes).  `cw` = converter warp 0..3.
+//   K-major source : the fp32 tile has the same swizzle; lane -> (row 8 i + lane % 8, floats 8 c .. 8 c + 7, c = lane / 8):
+//                    two 16-byte reads, two 16-byte writes, every quarter-warp touches 8 distinct chunk positions.
+//   MN-major source: un-swizzled boxes [32 k][32 mn]; lane = mn column, eight 4-byte reads down the k-group cw (a warp
+//                    reads one 128-byte row per instruction), two 16-byte writes into row mn (8 consecutive rows per
+//                    quarter-warp -> 8 distinct chunk positions).
+template <int ROWS, bool MN_MAJOR>
+__device__ __forceinline__ void convert_tile(const uint8_t* __restrict__ raw, uint8_t* __restrict__ conv, int cw, int lane) {
+  if (!MN_MAJOR) {
+    const int x = lane & 7, c = lane >> 3;
+#pragma unroll 2
+    for (int i = cw; i < ROWS / 8; i += TC_CONV_WARPS) {
+      const uint32_t rowoff = (uint32_t)(8 * i + x) * 128u;
+      const float4 v0 = *reinterpret_cast<const float4*>(raw + rowoff + (((2 * c) ^ x) << 4));
+      const float4 v1 = *reinterpret_cast<const float4*>(raw + rowoff + (((2 * c + 1) ^ x) << 4));
+      const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      uint4 hi, lo;
+      split8(v, hi, lo);
+      *reinterpret_cast<uint4*>(conv + rowoff + ((c ^ x) << 4)) = hi;
+      *reinterpret_cast<uint4*>(conv + rowoff + (((4 + c) ^ x) << 4)) = lo;
+    }
+  } else {
+    const int q = cw;   // k-group: k = 8 q .. 8 q + 7 of this k-block
+#pragma unroll 2
+    for (int j = 0; j < ROWS / 32; ++j) {
+      const float* src = reinterpret_cast<const float*>(raw + j * (TC_BK * 128) + q * (8 * 128)) + lane;
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = src[i * 32];
+      uint4 hi, lo;
+      split8(v, hi, lo);
+      const int r = 32 * j + lane;
+      uint8_t* row = conv + (uint32_t)r * 128u;
+      *reinterpret_cast<uint4*>(row + ((q ^ (r & 7)) << 4)) = hi;
+      *reinterpret_cast<uint4*>(row + (((4 + q) ^ (r & 7)) << 4)) = lo;
+    }
+  }
+}
+
 // 64-bit shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 128-byte swizzle, version 1
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
                                                    uint32_t layout_type) {
@@ -220,27 +312,33 @@ __device__ __forceinline__ int find_problem(const TcParams& p, int item) {
 // CTAS = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) computes a 256 x BN tile; each CTA stages its own 128 rows
 // of A but only HALF of the B tile, so a pair moves 32 KB per k-block and CTA where two independent 128 x 256 CTAs move
 // 48 KB for the same FLOPs -- the kernel is bound by exactly that L2 -> SM operand traffic (profiles/r1_summary.md).
-template <int BN, int CTAS = 1>
+template <int BN, int CTAS = 1, bool X3 = false>
 struct TcCfg {
   static constexpr int A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
   static constexpr int B_ROWS = BN / CTAS;            // rows of the B tile this CTA stages
   static constexpr int B_BYTES = B_ROWS * TC_BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = CTAS == 2 ? (BN == 256 ? 5 : 7) : (BN == 256 ? 3 : (BN == 128 ? 5 : 7));   // 144-168 KB of operand ring
+  // TF32: 144-168 KB of operand ring.  bf16x3: a raw fp32 ring (TMA -> converter) plus a ring of converted tiles
+  // (converter -> MMA); a converted k-block takes exactly the bytes of the raw one.
+  static constexpr int STAGES = X3 ? (STAGE_BYTES <= 24 * 1024 ? 4 : 3)
+                                   : (CTAS == 2 ? (BN == 256 ? 5 : 7) : (BN == 256 ? 3 : (BN == 128 ? 5 : 7)));
+  static constexpr int CONV_STAGES = X3 ? (STAGE_BYTES <= 24 * 1024 ? 3 : 2) : 0;
+  static constexpr int THREADS = X3 ? TC_THREADS + 32 * TC_CONV_WARPS : TC_THREADS;
   static constexpr int EPI_LD = 36;                     // floats per staged row (float4-aligned, conflict-free)
   static constexpr int EPI_BYTES = 8 * 32 * EPI_LD * 4; // one 32x32 transpose patch per epilogue warp
-  static_assert(STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256 <= 232448, "shared memory budget");
-  static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int RING_BYTES = (STAGES + CONV_STAGES) * STAGE_BYTES;
+  static_assert(RING_BYTES + EPI_BYTES + 1024 + 512 <= 232448, "shared memory budget");
+  static constexpr int SMEM = RING_BYTES + EPI_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 };
 
 // Persistent kernel: grid = min(#work items, #SMs); work item = (split-K slice, m tile, n tile), n fastest.
 // Two TMEM accumulator stages: the epilogue of item i overlaps the mainloop of item i+1.
 // GROUPED = false: exactly one problem, indexed statically (its fields stay immediate constant-bank operands).
-template <int BN, int TA, int TB, int CTAS, bool GROUPED>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tf32_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
+template <int BN, int TA, int TB, int CTAS, bool GROUPED, bool X3>
+__global__ void __launch_bounds__(X3 ? TC_THREADS + 32 * TC_CONV_WARPS : TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  using Cfg = TcCfg<BN, CTAS>;
+  using Cfg = TcCfg<BN, CTAS, X3>;
   constexpr bool PAIR = CTAS == 2;
   constexpr int B_ROWS = Cfg::B_ROWS;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;      // 0 = leader (issues the MMAs)
@@ -249,13 +347,17 @@ gemm_tf32_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Tc
   constexpr int A_BYTES = Cfg::A_BYTES;
   constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int CONV = Cfg::CONV_STAGES;
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  float* epi = (float*)(smem + STAGES * STAGE_BYTES);
-  uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES + Cfg::EPI_BYTES);
+  uint8_t* conv_base = smem + STAGES * STAGE_BYTES;   // [CONV] converted tiles (bf16x3 only)
+  float* epi = (float*)(smem + Cfg::RING_BYTES);
+  uint64_t* full_bar = (uint64_t*)(smem + Cfg::RING_BYTES + Cfg::EPI_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* acc_full = empty_bar + STAGES;    // [2] MMA -> epilogue
   uint64_t* acc_empty = acc_full + 2;         // [2] epilogue -> MMA
-  uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
+  uint64_t* cfull = acc_empty + 2;            // [CONV] converter -> MMA (pair: both CTAs' converters, on the leader)
+  uint64_t* cempty = cfull + (X3 ? CONV : 0); // [CONV] MMA -> converter
+  uint32_t* tmem_slot = (uint32_t*)(cempty + (X3 ? CONV : 0));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items = p.n_items;
@@ -268,11 +370,17 @@ gemm_tf32_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Tc
     }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], X3 ? TC_CONV_WARPS : 1);   // bf16x3: the raw stage is released by this CTA's converter warps
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], 8 * CTAS);   // one arrival per epilogue warp (of both CTAs of a pair, on the leader)
+    }
+    if (X3) {
+      for (int c = 0; c < CONV; ++c) {
+        mbar_init(&cfull[c], TC_CONV_WARPS * CTAS);
+        mbar_init(&cempty[c], 1);
+      }
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -317,7 +425,7 @@ gemm_tf32_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Tc
           uint8_t* sa = smem + s * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           const int k = (kb0 + i) * TC_BK;
-          if (PAIR) {
+          if (PAIR && !X3) {
             // both CTAs' bytes are counted on the LEADER's full barrier (the leader's MMA reads both shared memories)
             if (rank == 0) mbar_expect_tx(&full_bar[s], CTAS * STAGE_BYTES);
             const uint32_t fb = mapa_rank(smem_u32(&full_bar[s]), 0);
@@ -334,6 +442,8 @@ gemm_tf32_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Tc
               for (int j = 0; j < B_ROWS / 32; ++j) tma_load_2d_pair(&map_b, fb, sb + j * (TC_BK * 128), n0 + j * 32, k);
             }
           } else {
+            // single CTA, or a bf16x3 pair: every CTA's bytes land behind its OWN full barrier (its converter warps
+            // consume them; the leader's MMA is signalled through cfull)
             mbar_expect_tx(&full_bar[s], STAGE_BYTES);
             if (TA == 0) {
               tma_load_2d(&map_a, &full_bar[s], sa, k, m0);                     // box {32 k, 128 rows}
@@ -346,7 +456,7 @@ gemm_tf32_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Tc
               tma_load_2d(&map_b, &full_bar[s], sb, k, n0);
             } else {
 #pragma unroll
-              for (int j = 0; j < BN / 32; ++j)
+              for (int j = 0; j < B_ROWS / 32; ++j)
                 tma_load_2d(&map_b, &full_bar[s], sb + j * (TC_BK * 128), n0 + j * 32, k);
             }
           }
@@ -370,6 +480,43 @@ gemm_tf32_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Tc
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * BN;
       for (int i = 0; i < num_kb; ++i, ++it) {
+        if (X3) {
+          // ---- bf16x3: operands come from the converter warps' ring; hi*hi + lo*hi + hi*lo per 16-wide k step
+          constexpr uint32_t idesc16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                       ((uint32_t)((TC_BM * CTAS) >> 4) << 24);   // D = F32, A = B = BF16, both K-major
+          const int c = it % (X3 ? CONV : 1);
+          const uint32_t cph = (it / (X3 ? CONV : 1)) & 1;
+          mbar_wait(&cfull[c], cph);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t sa = smem_u32(conv_base + c * STAGE_BYTES);
+            const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+            for (int kk = 0; kk < TC_BK / 16; ++kk) {   // UMMA_K = 16 for bf16; hi part at +0, lo part at +64 bytes of the row
+              const uint64_t a_hi = make_smem_desc(sa + kk * 32, 16, 1024, 2), a_lo = make_smem_desc(sa + 64 + kk * 32, 16, 1024, 2);
+              const uint64_t b_hi = make_smem_desc(sb + kk * 32, 16, 1024, 2), b_lo = make_smem_desc(sb + 64 + kk * 32, 16, 1024, 2);
+              const uint32_t acc0 = (i > 0 || kk > 0) ? 1u : 0u;
+              if (PAIR) {
+                tc_mma_bf16_pair(d_tmem, a_hi, b_hi, idesc16, acc0);
+                tc_mma_bf16_pair(d_tmem, a_lo, b_hi, idesc16, 1u);
+                tc_mma_bf16_pair(d_tmem, a_hi, b_lo, idesc16, 1u);
+              } else {
+                tc_mma_bf16(d_tmem, a_hi, b_hi, idesc16, acc0);
+                tc_mma_bf16(d_tmem, a_lo, b_hi, idesc16, 1u);
+                tc_mma_bf16(d_tmem, a_hi, b_lo, idesc16, 1u);
+              }
+            }
+            if (PAIR) {
+              tc_commit_pair(&cempty[c], 3);                          // frees this converted stage in BOTH CTAs
+              if (i == num_kb - 1) tc_commit_pair(&acc_full[as], 3);
+            } else {
+              tc_commit(&cempty[c]);
+              if (i == num_kb - 1) tc_commit(&acc_full[as]);
+            }
+          }
+          __syncwarp();
+          continue;
+        }
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
@@ -396,6 +543,38 @@ gemm_tf32_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Tc
           }
         }
         __syncwarp();
+      }
+    }
+  } else if (X3 && warp >= TC_THREADS / 32) {
+    // ===================== converter warps (bf16x3): raw fp32 stage -> [bf16 hi | bf16 lo] stage =====================
+    const int cw = warp - TC_THREADS / 32;
+    const uint32_t cfull_leader = PAIR ? mapa_rank(smem_u32(&cfull[0]), 0) : 0u;
+    uint32_t it = 0;
+    for (int item = first_item; item < n_items; item += item_stride) {
+      const TcProblem& q = p.pr[GROUPED ? find_problem(p, item) : 0];
+      const int z = (item - q.item_begin) / (q.tiles_n * q.tiles_m);
+      const int total_kb = (q.K + TC_BK - 1) / TC_BK;
+      const int kb0 = z * q.k_blocks_per_split;
+      const int num_kb = min(total_kb, kb0 + q.k_blocks_per_split) - kb0;
+      for (int i = 0; i < num_kb; ++i, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        const int c = it % (X3 ? CONV : 1);
+        const uint32_t cph = (it / (X3 ? CONV : 1)) & 1;
+        mbar_wait(&full_bar[s], ph);          // TMA bytes of the raw stage have landed
+        mbar_wait(&cempty[c], cph ^ 1);       // the MMAs that read this converted stage have retired
+        tc_fence_after();
+        const uint8_t* raw = smem + s * STAGE_BYTES;
+        uint8_t* cv = conv_base + c * STAGE_BYTES;
+        convert_tile<TC_BM, TA != 0>(raw, cv, cw, lane);
+        convert_tile<B_ROWS, TB != 0>(raw + A_BYTES, cv + A_BYTES, cw, lane);
+        asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy writes -> visible to the tensor core's operand reads
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR && rank != 0) mbar_arrive_cluster(cfull_leader + (uint32_t)c * 8u);
+          else mbar_arrive(&cfull[c]);
+          mbar_arrive(&empty_bar[s]);          // the raw stage may be refilled
+        }
       }
     }
   } else {
@@ -539,30 +718,33 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 2-D fp32 tensor [rows, cols] with row pitch ld; box = {32 floats, box_rows}; 128-byte swizzle
-static bool make_map(CUtensorMap* map, const float* base, int rows, int cols, int ld, int box_rows, bool mn_major) {
+// 2-D fp32 tensor [rows, cols] with row pitch ld; box = {32 floats, box_rows}.  TF32 path: TFLOAT32 elements, 128-byte
+// swizzle (32-byte atoms for MN-major operands).  bf16x3 path (`exact`): FLOAT32 elements (every bit reaches the
+// converter warps), 128-byte swizzle for K-major operands, NO swizzle for MN-major ones (the converter transposes them
+// with plain 4-byte column reads).
+static bool make_map(CUtensorMap* map, const float* base, int rows, int cols, int ld, int box_rows, bool mn_major, bool exact) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
   cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, (void*)base, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUtensorMapSwizzle sw = mn_major ? (exact ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) : CU_TENSOR_MAP_SWIZZLE_128B;
+  CUresult r = enc(map, exact ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, (void*)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
-template <int BN, int TA, int TB, int CTAS, bool GROUPED>
+template <int BN, int TA, int TB, int CTAS, bool GROUPED, bool X3>
 static int launch(const TcMaps& maps, const TcParams& p, int grid, cudaStream_t stream) {
-  constexpr int smem = TcCfg<BN, CTAS>::SMEM;
+  using Cfg = TcCfg<BN, CTAS, X3>;
+  constexpr int smem = Cfg::SMEM;
   static unsigned long long configured = 0;   // per device ordinal
   if (first_use_on_device(configured))
-    GB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN, TA, TB, CTAS, GROUPED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    GB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, TA, TB, CTAS, GROUPED, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid, 1, 1);
-  cfg.blockDim = dim3(TC_THREADS, 1, 1);
+  cfg.blockDim = dim3(Cfg::THREADS, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
@@ -582,20 +764,27 @@ static int launch(const TcMaps& maps, const TcParams& p, int grid, cudaStream_t 
   }
   cfg.attrs = attr;
   cfg.numAttrs = n_attr;
-  GB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BN, TA, TB, CTAS, GROUPED>, maps, p));
+  GB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, TA, TB, CTAS, GROUPED, X3>, maps, p));
   GB_CHECK_LAUNCH();
   return GB_OK;
 }
 
-static int dispatch(int BN, bool pair, int ta, int tb, const TcMaps& maps, const TcParams& p, int grid, cudaStream_t stream) {
+// tile configurations: TF32 -- 128 x {64,128,256} single CTA, 256 x {128,256} pairs; bf16x3 -- the raw + converted rings
+// leave no room for a single-CTA 256-wide tile (48 KB per stage), so 128 x {64,128} single CTA, 256 x {128,256} pairs
+template <bool X3>
+static int dispatch_x(int BN, bool pair, int ta, int tb, const TcMaps& maps, const TcParams& p, int grid, cudaStream_t stream) {
   int rc = GB_OK;
   if (p.n_problems > 1) {   // grouped launches exist for weight gradients only (both operands MN-major)
-    if (!(ta && tb) || BN == 64) { set_error("gemm: grouped launch needs trans_a = trans_b = 1 and 128/256-wide tiles"); return GB_ERR_INVALID; }
-    if (pair) rc = BN == 256 ? launch<256, 1, 1, 2, true>(maps, p, grid, stream) : launch<128, 1, 1, 2, true>(maps, p, grid, stream);
-    else rc = BN == 256 ? launch<256, 1, 1, 1, true>(maps, p, grid, stream) : launch<128, 1, 1, 1, true>(maps, p, grid, stream);
+    if (!(ta && tb) || BN == 64 || (X3 && BN == 256 && !pair)) {
+      set_error("gemm: grouped launch needs trans_a = trans_b = 1 and 128/256-wide tiles");
+      return GB_ERR_INVALID;
+    }
+    if (pair) rc = BN == 256 ? launch<256, 1, 1, 2, true, X3>(maps, p, grid, stream) : launch<128, 1, 1, 2, true, X3>(maps, p, grid, stream);
+    else if (BN == 256) { if constexpr (!X3) rc = launch<256, 1, 1, 1, true, false>(maps, p, grid, stream); }
+    else rc = launch<128, 1, 1, 1, true, X3>(maps, p, grid, stream);
     return rc;
   }
-#define GB_TC(BN_, TA_, TB_, C_) rc = launch<BN_, TA_, TB_, C_, false>(maps, p, grid, stream)
+#define GB_TC(BN_, TA_, TB_, C_) rc = launch<BN_, TA_, TB_, C_, false, X3>(maps, p, grid, stream)
 #define GB_TC4(BN_, C_)                     \
   do {                                      \
     if (!ta && !tb) GB_TC(BN_, 0, 0, C_);   \
@@ -607,7 +796,8 @@ static int dispatch(int BN, bool pair, int ta, int tb, const TcMaps& maps, const
     if (BN == 256) GB_TC4(256, 2);
     else GB_TC4(128, 2);
   } else if (BN == 256) {
-    GB_TC4(256, 1);
+    if constexpr (!X3) GB_TC4(256, 1);
+    else { set_error("gemm: bf16x3 has no single-CTA 128 x 256 tile"); return GB_ERR_INVALID; }
   } else if (BN == 128) {
     GB_TC4(128, 1);
   } else {
@@ -616,6 +806,10 @@ static int dispatch(int BN, bool pair, int ta, int tb, const TcMaps& maps, const
 #undef GB_TC4
 #undef GB_TC
   return rc;
+}
+
+static int dispatch(bool x3, int BN, bool pair, int ta, int tb, const TcMaps& maps, const TcParams& p, int grid, cudaStream_t stream) {
+  return x3 ? dispatch_x<true>(BN, pair, ta, tb, maps, p, grid, stream) : dispatch_x<false>(BN, pair, ta, tb, maps, p, grid, stream);
 }
 
 int launch_splitk_reduce(const float* partial, int splits, int M, int N, const Epilogue& ep, cudaStream_t stream);
@@ -637,15 +831,16 @@ static bool tma_legal(const gb_gemm_args* a) {
   return a->K >= 8 && a->N >= 16 && a->M >= 1;
 }
 
-static bool make_maps(const gb_gemm_args* a, int b_rows, CUtensorMap* ma, CUtensorMap* mb) {
-  bool ok = a->trans_a ? make_map(ma, a->A, a->K, a->M, a->lda, TC_BK, true) : make_map(ma, a->A, a->M, a->K, a->lda, TC_BM, false);
-  return ok && (a->trans_b ? make_map(mb, a->B, a->K, a->N, a->ldb, TC_BK, true) : make_map(mb, a->B, a->N, a->K, a->ldb, b_rows, false));
+static bool make_maps(const gb_gemm_args* a, int b_rows, bool x3, CUtensorMap* ma, CUtensorMap* mb) {
+  bool ok = a->trans_a ? make_map(ma, a->A, a->K, a->M, a->lda, TC_BK, true, x3) : make_map(ma, a->A, a->M, a->K, a->lda, TC_BM, false, x3);
+  return ok && (a->trans_b ? make_map(mb, a->B, a->K, a->N, a->ldb, TC_BK, true, x3) : make_map(mb, a->B, a->N, a->K, a->ldb, b_rows, false, x3));
 }
 
 int gemm_tcgen05(const gb_gemm_args* a, cudaStream_t stream, bool* handled) {
   *handled = false;
   const int M = a->M, N = a->N, K = a->K;
   if (!tma_legal(a) || !colsum_legal(a)) return GB_OK;
+  const bool x3 = a->precision == 3;
   // tile shape.  pair = a cluster of two CTAs computes 256 x BN (cta_group::2), each staging half of B.  Measured on
   // B200 (tools/gemm_one.py): 16384 x 4096 x 4096 runs at 526 / 626 TFLOP/s with single-CTA 128 x 128 / 128 x 256 tiles
   // and at 764 TFLOP/s with 256 x 256 pair tiles (the cuBLAS-measured TF32-equivalent peak), so the pair wins whenever
@@ -671,8 +866,9 @@ int gemm_tcgen05(const gb_gemm_args* a, cudaStream_t stream, bool* handled) {
     if (can_split && ((N + 127) / 128) * tiles_m * 2 <= units) BN = (N % 256 == 0) ? 256 : (N >= 128 ? 128 : 64);
     else if (N <= 64 || ((N + 127) / 128) * tiles_m < units / 2) BN = 64;
     else if (N % 256 == 0 && (N / 256) * tiles_m >= units) BN = 256;
+    if (x3 && !pair && BN == 256) BN = 128;   // no single-CTA 128 x 256 tile in the bf16x3 kernel (shared-memory budget)
     static const int forced = [] { const char* e = getenv("GRAPPA_B200_GEMM_BN"); return e ? atoi(e) : 0; }();   // tuning aid
-    if ((forced == 64 || forced == 128 || forced == 256) && (forced != 256 || N % 256 == 0)) BN = forced;
+    if ((forced == 64 || forced == 128 || forced == 256) && (forced != 256 || (N % 256 == 0 && (pair || !x3)))) BN = forced;
     if (pair && BN == 64) {
       if (forced_pair == 1) { BN = 128; break; }
       pair = false;   // too little work for 256-row tiles: single CTAs with 128 x 64 tiles
@@ -681,7 +877,7 @@ int gemm_tcgen05(const gb_gemm_args* a, cudaStream_t stream, bool* handled) {
     break;
   }
   TcMaps maps;
-  if (!make_maps(a, pair ? BN / 2 : BN, &maps.a[0], &maps.b[0])) return GB_OK;   // no driver entry point: FFMA path
+  if (!make_maps(a, pair ? BN / 2 : BN, x3, &maps.a[0], &maps.b[0])) return GB_OK;   // no driver entry point: FFMA path
 
   TcParams p;
   p.n_problems = 1;
@@ -709,7 +905,7 @@ int gemm_tcgen05(const gb_gemm_args* a, cudaStream_t stream, bool* handled) {
   const int n_items = gx * gy * splits;
   p.n_items = n_items;
   const int grid = pair ? 2 * (n_items < units ? n_items : units) : (n_items < units ? n_items : units);
-  int rc = dispatch(BN, pair, a->trans_a, a->trans_b, maps, p, grid, stream);
+  int rc = dispatch(x3, BN, pair, a->trans_a, a->trans_b, maps, p, grid, stream);
   if (rc) return rc;
   if (splits > 1) {
     rc = launch_splitk_reduce(q.partial, splits, M, N, q.ep, stream);
@@ -734,10 +930,11 @@ int gemm_tcgen05_grouped(const gb_gemm_args* list, int n, cudaStream_t stream, b
     if (list[i].colsum) return GB_OK;   // fused column sums are a single-launch feature
   const int ta = list[0].trans_a, tb = list[0].trans_b;
   if (!(ta && tb)) return GB_OK;
+  const bool x3 = list[0].precision == 3;
   bool all256 = true, all128 = true, big_m = true, long_k = true;
   for (int i = 0; i < n; ++i) {
     const gb_gemm_args* a = &list[i];
-    if (!tma_legal(a) || a->trans_a != ta || a->trans_b != tb) return GB_OK;
+    if (!tma_legal(a) || a->trans_a != ta || a->trans_b != tb || (a->precision == 3) != x3) return GB_OK;
     if (a->workspace != list[0].workspace || a->workspace_bytes != list[0].workspace_bytes) return GB_OK;
     all256 = all256 && (a->N % 256 == 0);
     all128 = all128 && (a->N >= 128);
@@ -747,7 +944,7 @@ int gemm_tcgen05_grouped(const gb_gemm_args* list, int n, cudaStream_t stream, b
   if (!all128) return GB_OK;
   static const int forced_pair = [] { const char* e = getenv("GRAPPA_B200_GEMM_PAIR"); return e ? atoi(e) : -1; }();
   const bool pair = big_m && long_k && forced_pair != 0;
-  const int BN = all256 ? 256 : 128;
+  const int BN = (all256 && (pair || !x3)) ? 256 : 128;
   const int bm = pair ? 2 * TC_BM : TC_BM;
   // Grouped launches carry weight gradients, which run on a side stream NEXT TO the latency-critical backward chain: a
   // persistent kernel on all 148 SMs makes every small kernel of that chain wait for a free SM (14 us gaps per GNN block in
@@ -762,7 +959,7 @@ int gemm_tcgen05_grouped(const gb_gemm_args* list, int n, cudaStream_t stream, b
   int total_tiles = 0;
   for (int i = 0; i < n; ++i) {
     const gb_gemm_args* a = &list[i];
-    if (!make_maps(a, pair ? BN / 2 : BN, &maps.a[i], &maps.b[i])) return GB_OK;
+    if (!make_maps(a, pair ? BN / 2 : BN, x3, &maps.a[i], &maps.b[i])) return GB_OK;
     TcProblem& q = p.pr[i];
     q.M = a->M; q.N = a->N; q.K = a->K;
     q.ep = make_epilogue(a);
@@ -812,7 +1009,7 @@ int gemm_tcgen05_grouped(const gb_gemm_args* list, int n, cudaStream_t stream, b
   }
   p.n_items = items;
   const int grid = pair ? 2 * (items < units ? items : units) : (items < units ? items : units);
-  int rc = dispatch(BN, pair, ta, tb, maps, p, grid, stream);
+  int rc = dispatch(x3, BN, pair, ta, tb, maps, p, grid, stream);
   if (rc) return rc;
   if (any_split) {
     rc = launch_splitk_reduce_grouped(n, partials, splits_v, Ms, Ns, eps, stream);

@@ -78,7 +78,9 @@ class _StageFn(torch.autograd.Function):
             sink = getattr(raw, "_gb_sink", None)
             if sink is not None:
                 tape.sinks[id(det)] = sink
-        outs = runner(tape, ins, params)
+        ctx.tag = getattr(runner, "tag", None)
+        with ops.stage_tag(ctx.tag):
+            outs = runner(tape, ins, params)
         ctx.tape, ctx.ins, ctx.params, ctx.outs = tape, ins, params, outs
         ctx.concurrent = bool(tensors) and tensors[0].is_cuda and T_.concurrency()
         ctx.set_materialize_grads(False)
@@ -91,7 +93,7 @@ class _StageFn(torch.autograd.Function):
             o.g = None if g is None else g.contiguous().float()
         # the backward of every stage runs next to its weight-gradient branch (and the writers next to each other):
         # leave part of the machine to the other streams' kernels
-        with ops.gemm_sm_limit(ops.CONCURRENT_GEMM_SMS if ctx.concurrent else 0):
+        with ops.stage_tag(ctx.tag), ops.gemm_sm_limit(ops.CONCURRENT_GEMM_SMS if ctx.concurrent else 0):
             tape.backward()
         gin = [v.g if v.needs else None for v in ctx.ins]
         gp = [None if id(p) in tape.sinks else tape.pgrads.get(id(p)) for p in ctx.params]
@@ -278,6 +280,7 @@ class GrappaGNN(nn.Module):
                     h = blk.tape_forward(t, pack, h, P)
             h = T_.linear(t, h, P(self.post_dense[0].weight), P(self.post_dense[0].bias), dropout_p=self.p_final)
             return [h]
+        run.tag = "gnn"
         return run
 
     def forward(self, g, in_feature=None):
@@ -538,6 +541,7 @@ class _TupleWriter(nn.Module):
                 T_.add_grad(s, ops.head_output_bwd(args, s.v, kv.g, deq))
             t.push(bwd)
             return [kv] if eqv is None else [kv, eqv]
+        run.tag = "writer"
         return run
 
     def _write(self, g, h):

@@ -14,20 +14,81 @@ import torch
 from . import _lib
 from ._lib_ops import COLSUM_MAX, ColsumBatch, FeaturizeArgs, GemmArgs, HeadOutArgs, HeadStatGrads, Perms
 
-FP32, TF32, AUTO = 0, 1, 2
-_precision = FP32
+FP32, TF32, AUTO, BF16X3 = 0, 1, 2, 3
+_PREC_CODES = {"fp32": FP32, "tf32": AUTO, "bf16x3": BF16X3}
+_PREC_NAMES = {FP32: "fp32", AUTO: "tf32", TF32: "tf32", BF16X3: "bf16x3"}
+FAMILIES = ("fwd", "dgrad", "wgrad")
+BENCH_PRECISION = "bf16x3"      # what bench.py measures and the full-size parity tests check (bench.py --precision overrides)
+# GEMM precision per family (forward Linear / input gradient / weight gradient), optionally overridden per stage
+# ("gnn.fwd", "writer.dgrad", ...): the error budget of profiles/r2_error_budget.md is measured by switching one entry.
+_policy = {f: FP32 for f in FAMILIES}
+_stage_tag = None
 
 
-def set_matmul_precision(mode: str):
-    """'fp32' (FFMA, 1e-5 parity) | 'tf32' (tcgen05 tensor cores where legal, 1e-3 parity)."""
-    global _precision
-    if mode not in ("fp32", "tf32"):
-        raise ValueError("matmul precision must be 'fp32' or 'tf32'")
-    _precision = FP32 if mode == "fp32" else AUTO
+def set_matmul_precision(mode):
+    """GEMM arithmetic of the Linear layers.
+
+    'fp32'    FFMA on the CUDA cores (1e-5 parity path)
+    'tf32'    tcgen05 kind::tf32 on the raw fp32 operands (10-bit mantissa; misses the 1e-3 contract on gated torsion k)
+    'bf16x3'  tcgen05 kind::f16: every fp32 operand is split in-kernel into bf16 hi + bf16 lo and the product is
+              hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM (16-bit mantissa: fp32-class parity on tensor cores)
+    or a policy string / dict per family and stage: 'fwd=bf16x3,dgrad=tf32,wgrad=tf32', 'tf32,gnn.fwd=fp32', ...
+    """
+    global _policy
+    pol = {}
+    if isinstance(mode, dict):
+        items = list(mode.items())
+    else:
+        items = []
+        for part in str(mode).split(","):
+            part = part.strip()
+            if not part:
+                continue
+            if "=" in part:
+                k, v = part.split("=")
+                items.append((k.strip(), v.strip()))
+            else:
+                items.extend((f, part) for f in FAMILIES)
+    for k, v in items:
+        if v not in _PREC_CODES:
+            raise ValueError("matmul precision must be 'fp32', 'tf32' or 'bf16x3'")
+        if k.split(".")[-1] not in FAMILIES:
+            raise ValueError(f"unknown GEMM family {k!r} (families: {FAMILIES}, optionally prefixed by 'gnn.' / 'writer.')")
+        pol[k] = _PREC_CODES[v]
+    for f in FAMILIES:
+        pol.setdefault(f, FP32)
+    _policy = pol
 
 
 def get_matmul_precision() -> str:
-    return "fp32" if _precision == FP32 else "tf32"
+    vals = {_PREC_NAMES[_policy[f]] for f in FAMILIES}
+    if len(vals) == 1 and len(_policy) == len(FAMILIES):
+        return vals.pop()
+    return ",".join(f"{k}={_PREC_NAMES[v]}" for k, v in sorted(_policy.items()))
+
+
+class stage_tag:
+    """Context manager naming the stage ('gnn' / 'writer') whose GEMMs are being issued (per-stage precision overrides)."""
+
+    def __init__(self, tag):
+        self.tag = tag
+
+    def __enter__(self):
+        global _stage_tag
+        self.prev, _stage_tag = _stage_tag, self.tag
+        return self
+
+    def __exit__(self, *exc):
+        global _stage_tag
+        _stage_tag = self.prev
+
+
+def matmul_precision(family: str = "fwd") -> int:
+    if _stage_tag is not None:
+        v = _policy.get(f"{_stage_tag}.{family}")
+        if v is not None:
+            return v
+    return _policy[family]
 
 
 _rng_offset = None     # device uint64 counter mixed into every dropout seed (None = static seeds)
@@ -130,7 +191,7 @@ def drop_workspaces():
 
 def _gemm_args(a: torch.Tensor, b: torch.Tensor, *, trans_a=False, trans_b=False, bias=None, act=0, mul_elu_out=None,
                dropout_p=0.0, dropout_seed=0, residual=None, out=None, accumulate=False, m=None, n=None, k=None,
-               precision=None, act_out=None, colsum=None):
+               precision=None, act_out=None, colsum=None, family="fwd"):
     """Fill a gb_gemm_args for C[M,N] = opA(a) opB(b)^T (+ fused epilogue); returns (args, out)."""
     _lib.require_cuda(a, b)
     assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
@@ -156,7 +217,7 @@ def _gemm_args(a: torch.Tensor, b: torch.Tensor, *, trans_a=False, trans_b=False
     g.accumulate = int(accumulate)          # 0 overwrite, 1 C += result, 2 old C added before bias / activation
     g.act_out = _p(act_out)
     g.ldact = act_out.stride(0) if act_out is not None else 0
-    g.precision = _precision if precision is None else precision
+    g.precision = matmul_precision(family) if precision is None else precision
     g.max_sms = _gemm_sm_limit
     if colsum is not None:
         g.colsum, g.ld_colsum = colsum.data_ptr(), colsum.stride(0)
@@ -246,10 +307,6 @@ def pad_rows(w: torch.Tensor, ld: int) -> torch.Tensor:
     out = torch.empty((w.shape[0], ld), device=w.device, dtype=torch.float32)
     _lib.check(lib.grappa_b200_pad_rows(w.data_ptr(), w.shape[0], w.shape[1], w.stride(0), out.data_ptr(), ld, _s()), "pad_rows")
     return out
-
-
-def matmul_precision() -> int:
-    return _precision
 
 
 def layernorm_fwd(x, gamma, beta, eps=1e-5):

@@ -256,13 +256,13 @@ def linear(t: Tape, x: Var, W: torch.Tensor, b: Optional[torch.Tensor], *, act: 
             if id(W) in t.pgrads:       # second use of a weight inside one stage: keep the simple ordered path
                 t.flush_wgrads()
                 with t.side_branch(dpre_full, xv):
-                    t.add_pgrad(W, ops.gemm(dpre, xv, trans_a=True, trans_b=True, m=N, n=K, k=M))
+                    t.add_pgrad(W, ops.gemm(dpre, xv, trans_a=True, trans_b=True, m=N, n=K, k=M, family="wgrad"))
             else:
                 gw = torch.empty((N, K), device=xv.device, dtype=torch.float32)
                 t.pgrads[id(W)] = gw
-                t.defer_wgrad(dpre, xv, gw, False, m=N, n=K, k=M)
+                t.defer_wgrad(dpre, xv, gw, False, m=N, n=K, k=M, family="wgrad")
         else:
-            t.defer_wgrad(dpre, xv, tgt, acc, m=N, n=K, k=M)
+            t.defer_wgrad(dpre, xv, tgt, acc, m=N, n=K, k=M, family="wgrad")
         with t.side_branch(dpre_full, xv) if (b is not None and bias_partial is None) else contextlib.nullcontext():
             if b is not None and bias_partial is None:
                 tgt, acc = t.grad_target(b)
@@ -280,14 +280,16 @@ def linear(t: Tape, x: Var, W: torch.Tensor, b: Optional[torch.Tensor], *, act: 
                 if fuse and _FUSE_COLSUM:
                     # dx is the pre-activation gradient of the producing layer: let the epilogue also emit its column
                     # sums (that layer's bias gradient) instead of re-reading dx in a separate reduction
-                    dx, x.g_colsum = ops.gemm_with_colsum(dpre, W, trans_b=True, m=M, n=K, k=N, residual=x.g, mul_elu_out=xv)
+                    dx, x.g_colsum = ops.gemm_with_colsum(dpre, W, trans_b=True, m=M, n=K, k=N, residual=x.g, mul_elu_out=xv,
+                                                          family="dgrad")
                 else:
-                    dx = ops.gemm(dpre, W, trans_b=True, m=M, n=K, k=N, residual=x.g, mul_elu_out=xv if fuse else None)
+                    dx = ops.gemm(dpre, W, trans_b=True, m=M, n=K, k=N, residual=x.g, mul_elu_out=xv if fuse else None,
+                                  family="dgrad")
                 x.g = dx
                 x.g_is_pre = fuse
             else:   # consumer read only the first K columns of a wider buffer
                 dx = torch.zeros_like(xv)
-                ops.gemm(dpre, W, trans_b=True, m=M, n=K, k=N, out=dx[:, :K])
+                ops.gemm(dpre, W, trans_b=True, m=M, n=K, k=N, out=dx[:, :K], family="dgrad")
                 add_grad(x, dx)
 
     t.push(bwd)

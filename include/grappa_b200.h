@@ -137,7 +137,10 @@ int grappa_b200_energy_bwd(const gb_energy_bwd_args* a, void* stream);
  * trans_a = 0: A is [M,K] row-major (lda >= K);  1: A is stored [K,M] row-major (lda >= M)
  * trans_b = 0: B is [N,K] row-major (nn.Linear weight layout, C = A B^T);  1: B is stored [K,N]
  * precision: 0 = fp32 FFMA (CUDA cores), 1 = TF32 tcgen05 tensor cores (TMA-staged, TMEM accumulator;
- *            needs 16-byte aligned rows, otherwise GB_ERR_INVALID), 2 = auto (tcgen05 when legal)
+ *            needs 16-byte aligned rows, otherwise GB_ERR_INVALID), 2 = auto (TF32 tcgen05 when legal, else FFMA),
+ *            3 = bf16x3 tcgen05 when legal, else FFMA: every fp32 operand element is split inside the kernel into
+ *            bf16 hi + bf16 lo and the product is hi*hi + lo*hi + hi*lo with fp32 accumulation (16 mantissa bits per
+ *            operand -- fp32-class results at tensor-core speed; operands stay plain fp32 arrays in HBM)
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
   const float* A;

@@ -53,6 +53,69 @@ def test_config1_training_batch_forward_matches_oracle():
             ops.set_matmul_precision("fp32")
 
 
+# Tolerances of the full-size checks per GEMM arithmetic (north_star: 1e-5 outputs / 1e-4 gradients in fp32; 1e-3 outputs
+# where reduced-precision tensor-core GEMMs are used).  'bench' = the arithmetic bench.py runs and prints in `dtype`.
+FULL_SIZE_TOL = {
+    # precision: (outputs k / eq / energy / forces, loss, gradient norms, sampled gradient entries)
+    "fp32": (2e-5, 1e-5, 1e-3, 1e-4),
+    "bench": (1e-3, 1e-3, 2e-3, 1e-3),
+}
+
+
+@pytest.mark.parametrize("which", ["fp32", "bench"])
+def test_config1_training_batch_loss_and_backward_match_reference_fixture(which):
+    """BASELINE configs[1] at FULL size and width (32 x ACE-(ALA)4-NME, 50 conformations, grappa-1.2, 40.8 M parameters):
+    forward, MolwiseLoss and the whole backward on the GPU against the UNMODIFIED reference's outputs
+    (tests/golden/train_batch_grappa12.npz: energies, parameters, loss, the norms of all 305 gradient tensors, 16 sampled
+    entries of each, two full gradient tensors) -- in fp32 and at the precision bench.py measures."""
+    import grappa_oracle as orc
+    from grappa_b200 import ops, synthetic
+    from grappa_b200.energy import Energy
+    from grappa_b200.loss import MolwiseLoss
+    from util import load_golden, sampled_gradient_errors
+    z = load_golden("train_batch_grappa12.npz")
+    prec = "fp32" if which == "fp32" else ops.BENCH_PRECISION
+    tol_out, tol_loss, tol_norm, tol_grad = FULL_SIZE_TOL[which]
+    g = synthetic.peptide_batch(seed=int(z["meta.seed"]), batch_size=32, n_res=4, n_confs=50)
+    xyz = g.nodes["n1"].data["xyz"].double()
+    assert abs(float(xyz.abs().sum()) - float(z["meta.xyz_abs_checksum"])) < 1e-9 * float(z["meta.xyz_abs_checksum"])
+    model = _model(orc.grappa_1_2_model_config(), seed=int(z["meta.weights_seed"])).eval().cuda()
+    ops.set_matmul_precision(prec)
+    try:
+        gd = torch.nn.Sequential(model, Energy(write_tuple_terms=False))(g.to("cuda"))
+        loss = MolwiseLoss(gradient_weight=0.8, energy_weight=1.0, param_weight=0.0, proper_regularisation=1e-3,
+                           improper_regularisation=1e-3)(gd)
+        model.zero_grad()
+        loss.backward()
+        torch.cuda.synchronize()
+    finally:
+        ops.set_matmul_precision("fp32")
+    errs = {"energy": rel_err(gd.nodes["g"].data["energy"].detach().cpu().numpy(), z["out.g.energy"]),
+            "gradient_norm_per_atom": rel_err(gd.nodes["n1"].data["gradient"].detach().norm(dim=(1, 2)).cpu().numpy(),
+                                              z["out.gradient_norm_per_atom"])}
+    for l in LEVELS:
+        errs[f"{l}.k"] = rel_err(gd.nodes[l].data["k"].detach().cpu().numpy(), z[f"out.{l}.k"])
+        if l in ("n2", "n3"):
+            errs[f"{l}.eq"] = rel_err(gd.nodes[l].data["eq"].detach().cpu().numpy(), z[f"out.{l}.eq"])
+    loss_err = abs(loss.item() - float(z["out.loss"])) / abs(float(z["out.loss"]))
+    named = dict(model.named_parameters())
+    keys = list(z["meta.grad_norms_keys"])
+    norms = np.array([0.0 if named[k].grad is None else float(named[k].grad.norm()) for k in keys])
+    ref = z["meta.grad_norms"]
+    norm_rel = np.abs(norms - ref) / np.maximum(ref, 1e-6 * ref.max())
+    sampled = sampled_gradient_errors(z, {k: (None if named[k].grad is None else named[k].grad.cpu().numpy()) for k in keys})
+    worst_k = max(sampled, key=sampled.get)
+    full = {k[5:]: rel_err(named[k[5:]].grad.cpu().numpy(), z[k]) for k in z.files if k.startswith("grad.")}
+    print(f"[{prec}] outputs {errs}; loss {loss_err:.2e}; gradient norms worst {norm_rel.max():.2e} "
+          f"({keys[int(norm_rel.argmax())]}); sampled gradients worst {sampled[worst_k]:.2e} ({worst_k}); full tensors {full}")
+    bad = {k: v for k, v in errs.items() if v > tol_out}
+    assert not bad, (prec, bad)
+    assert loss_err < tol_loss, (prec, loss_err)
+    assert norm_rel.max() < tol_norm, (prec, keys[int(norm_rel.argmax())], norm_rel.max())
+    assert sampled[worst_k] < tol_grad, (prec, worst_k, sampled[worst_k])
+    assert max(full.values()) < tol_grad, (prec, full)
+
+
 def test_config2_protein_1502_atoms_parametrisation_matches_oracle():
     import grappa_oracle as orc
     from grappa_b200 import ops, synthetic

@@ -508,3 +508,103 @@ def test_gemm_fused_column_sums(M, N, K):
     # fp32 requests cannot fuse: the helper falls back to a plain GEMM
     out32, p32 = ops.gemm_with_colsum(dY, W, trans_b=True, precision=ops.FP32)
     assert p32 is None and R(out32, dY.double() @ W.double()) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------
+# bf16x3 tensor-core GEMM: fp32 operands split in-kernel into bf16 hi + lo, hi*hi + lo*hi + hi*lo, fp32 accumulation
+# ---------------------------------------------------------------------------------------------------
+X3_TOL = 2e-5      # 16 operand mantissa bits + the dropped lo*lo term; TF32 sits at ~5e-4 on the same inputs
+
+
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", TC_SHAPES)
+def test_gemm_bf16x3_exact_on_small_integers(ta, tb, M, N, K):
+    """Small integers are exact in bf16 (lo part = 0) and fp32 accumulation is exact: bit-equality with the fp64 product
+    pins the converter's layout (swizzle, transposition of MN-major operands) and the MMA descriptors."""
+    from grappa_b200 import ops
+    dev = "cuda"
+    ld_a = ((M if ta else K) + 3) // 4 * 4
+    ld_b = ((N if tb else K) + 3) // 4 * 4
+    A = torch.randint(-3, 4, ((K if ta else M), ld_a), device=dev).float()[:, :(M if ta else K)]
+    B = torch.randint(-3, 4, ((K if tb else N), ld_b), device=dev).float()[:, :(N if tb else K)]
+    ref = ((A.double().T if ta else A.double()) @ (B.double() if tb else B.double().T)).float()
+    out = ops.gemm(A, B, trans_a=ta, trans_b=tb, precision=ops.BF16X3)
+    assert torch.equal(out, ref), f"max abs diff {(out - ref).abs().max().item()}"
+
+
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
+def test_gemm_bf16x3_hi_lo_terms_exact(ta, tb):
+    """a = ah + al with ah in {-2..2} and al in {-3..3} * 2^-10: hi = ah, lo = al exactly; with B integer-valued the
+    product needs exactly hi*hi + lo*hi (and with the roles swapped hi*lo): every cross term is checked bit for bit."""
+    from grappa_b200 import ops
+    dev = "cuda"
+    M, N, K = 300, 192, 160
+    def two_part(shape):
+        ah = torch.randint(-2, 3, shape, device=dev).float()
+        ah = torch.where(ah == 0, torch.ones_like(ah), ah)                      # hi part never zero, so lo stays the lo part
+        return ah + torch.randint(-3, 4, shape, device=dev).float() * 2.0 ** -10
+    ints = lambda shape: torch.randint(-3, 4, shape, device=dev).float()
+    for split_a in (True, False):
+        A = (two_part if split_a else ints)((K, M) if ta else (M, K))
+        B = (ints if split_a else two_part)((K, N) if tb else (N, K))
+        ref = ((A.double().T if ta else A.double()) @ (B.double() if tb else B.double().T)).float()
+        out = ops.gemm(A, B, trans_a=ta, trans_b=tb, precision=ops.BF16X3)
+        assert torch.equal(out, ref), (split_a, (out - ref).abs().max().item())
+
+
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(1111, 511, 512), (1664, 512, 2048), (700, 256, 1024), (300, 1536, 1100), (14848, 512, 512), (64, 16, 8)])
+def test_gemm_bf16x3_accuracy_epilogue_and_pairs(ta, tb, M, N, K):
+    """Random operands against fp64 at fp32-class tolerance (single-CTA tiles, CTA pairs for K >= 1024, ragged edges,
+    fused bias / ELU / residual epilogue), deterministic."""
+    from grappa_b200 import ops
+    dev = "cuda"
+    pa, pb = ((M if ta else K) + 3) // 4 * 4, ((N if tb else K) + 3) // 4 * 4
+    A = torch.randn((K if ta else M), pa, device=dev)[:, :(M if ta else K)]
+    B = (torch.randn((K if tb else N), pb, device=dev) / math.sqrt(K))[:, :(N if tb else K)]
+    bias = torch.randn(N, device=dev)
+    res = torch.randn(M, N, device=dev)
+    pre = (A.double().T if ta else A.double()) @ (B.double() if tb else B.double().T)
+    out = ops.gemm(A, B, trans_a=ta, trans_b=tb, bias=bias, act=1, residual=res, precision=ops.BF16X3)
+    assert R(out, F.elu(pre + bias.double()) + res.double()) < X3_TOL
+    plain = ops.gemm(A, B, trans_a=ta, trans_b=tb, precision=ops.BF16X3)
+    err = R(plain, pre)
+    tf = R(ops.gemm(A, B, trans_a=ta, trans_b=tb, precision=ops.AUTO), pre)
+    print(f"bf16x3 {err:.2e} vs tf32 {tf:.2e}")
+    assert err < X3_TOL
+    assert torch.equal(plain, ops.gemm(A, B, trans_a=ta, trans_b=tb, precision=ops.BF16X3))
+
+
+def test_gemm_bf16x3_splitk_grouped_and_column_sums():
+    from grappa_b200 import ops
+    dev = "cuda"
+    # split-K weight gradient (ops.gemm hands in the workspace), exact on integers
+    dY = torch.randint(-2, 3, (14848, 512), device=dev).float()
+    X = torch.randint(-2, 3, (14848, 512), device=dev).float()
+    assert torch.equal(ops.gemm(dY, X, trans_a=True, trans_b=True, precision=ops.BF16X3), (dY.double().T @ X.double()).float())
+    # grouped launch of four weight gradients
+    shapes = [(512, 512, 14848), (1536, 512, 14848), (512, 512, 3264), (256, 2048, 1920), (512, 256, 1664)]
+    probs, refs = [], []
+    for i, (M, N, K) in enumerate(shapes):
+        dY = torch.randn(K, M, device=dev)
+        X = torch.randn(K, N, device=dev)
+        out = torch.randn(M, N, device=dev)
+        acc = i % 2 == 1
+        refs.append(dY.double().T @ X.double() + (out.double() if acc else 0))
+        probs.append((dY, X, dict(trans_a=True, trans_b=True, out=out, accumulate=acc, precision=ops.BF16X3)))
+    ops.gemm_grouped(probs)
+    for (_, _, kw), exact in zip(probs, refs):
+        assert R(kw["out"], exact) < X3_TOL
+    # fused column sums in the dgrad epilogue
+    M, N, K = 3264, 512, 512
+    dY = torch.randn(M, K, device=dev)
+    W = torch.randn(K, N, device=dev)
+    Y = F.elu(torch.randn(M, N, device=dev))
+    res = torch.randn(M, N, device=dev)
+    out, partial = ops.gemm_with_colsum(dY, W, trans_b=True, residual=res, mul_elu_out=Y, precision=ops.BF16X3)
+    exact = (dY.double() @ W.double()) * torch.where(Y > 0, torch.ones_like(Y), Y + 1).double() + res.double()
+    assert partial is not None and R(out, exact) < X3_TOL and R(partial.sum(0), out.double().sum(0)) < 1e-5
+    # not TMA-legal -> FFMA fallback, still correct
+    A = torch.randn(64, 85, device=dev)
+    B = torch.randn(32, 85, device=dev)
+    assert R(ops.gemm(A, B, precision=ops.BF16X3), A.double() @ B.double().T) < 1e-5

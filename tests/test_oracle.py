@@ -6,7 +6,7 @@ import pytest
 import torch
 
 import grappa_oracle as orc
-from util import LEVELS, graph_from_fixture, load_golden, rel_err
+from util import sampled_gradient_errors, LEVELS, graph_from_fixture, load_golden, rel_err
 
 
 def _sd(cfg, seed):
@@ -322,6 +322,9 @@ def test_oracle_matches_reference_fixture_full_size_training_batch():
     for k in z.files:
         if k.startswith("grad."):
             assert rel_err(grads[k[5:]].numpy(), z[k]) < 1e-4, k
+    # 16 sampled entries of every gradient tensor, relative to the tensor's max |grad|
+    worst = sampled_gradient_errors(z, {k: (None if grads[k] is None else grads[k].numpy()) for k in keys})
+    assert max(worst.values()) < 1e-4, max(worst.items(), key=lambda kv: kv[1])
 
 
 def test_oracle_matches_reference_fixtures_protein_and_espaloma_mix():

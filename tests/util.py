@@ -36,3 +36,17 @@ def rel_err(a, b):
     if b.size == 0:
         return 0.0
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+def sampled_gradient_errors(z, grads):
+    """{parameter name: max |g - g_ref| / max |g_ref|} over the 16 sampled entries per tensor that
+    tests/golden/train_batch_grappa12.npz stores for all 305 parameter tensors (`grads`: name -> array or None)."""
+    keys = list(z["meta.grad_norms_keys"])
+    sidx, sval, gmax = z["meta.grad_sample_idx"], z["meta.grad_sample_val"], z["meta.grad_maxabs"]
+    floor = 1e-6 * float(gmax.max())
+    out = {}
+    for i, k in enumerate(keys):
+        g = grads.get(k)
+        got = np.zeros(16) if g is None else np.asarray(g, dtype=np.float64).reshape(-1)[sidx[i]]
+        out[k] = float(np.max(np.abs(got - sval[i].astype(np.float64))) / max(gmax[i], floor))
+    return out

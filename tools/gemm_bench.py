@@ -84,7 +84,9 @@ def main():
         if args.check:
             A = a.t() if ta else a
             Bm = b if tb else b.t()
-            ref = torch.nn.functional.elu(A.double() @ Bm.double() + bias.double())
+            ref = A.double() @ Bm.double()
+            if not ta:
+                ref = torch.nn.functional.elu(ref + bias.double())
             err = f" max rel err {((out.double() - ref).abs().max() / ref.abs().max()).item():.2e}"
         print(f"{tag:28s} M={M:6d} N={N:5d} K={K:6d} ta={ta} tb={tb}  {ms * 1e3:8.1f} us  {fl / ms / 1e9:8.1f} TFLOP/s{err}", flush=True)
     print(f"TOTAL {tot_ms * 1e3:.1f} us, {tot_fl / tot_ms / 1e9:.1f} TFLOP/s")

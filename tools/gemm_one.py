@@ -5,7 +5,7 @@ import torch
 from grappa_b200 import ops
 M, N, K = (int(x) for x in sys.argv[1:4])
 ta, tb = (int(sys.argv[4]), int(sys.argv[5])) if len(sys.argv) > 5 else (0, 0)
-ops.set_matmul_precision("tf32")
+ops.set_matmul_precision(os.environ.get("GRAPPA_B200_PREC", "tf32"))
 dev = torch.device("cuda")
 a = torch.randn((K, M) if ta else (M, K), device=dev)
 b = torch.randn((K, N) if tb else (N, K), device=dev)
@@ -23,5 +23,5 @@ for _ in range(reps):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
-print(f"M={M} N={N} K={K} ta={ta} tb={tb} BN={os.environ.get('GRAPPA_B200_GEMM_BN','auto')} PAIR={os.environ.get('GRAPPA_B200_GEMM_PAIR','auto')}: "
+print(f"{os.environ.get('GRAPPA_B200_PREC', 'tf32'):7s} M={M} N={N} K={K} ta={ta} tb={tb} BN={os.environ.get('GRAPPA_B200_GEMM_BN','auto')} PAIR={os.environ.get('GRAPPA_B200_GEMM_PAIR','auto')}: "
       f"{ms * 1e3:8.1f} us  {2.0 * M * N * K / ms / 1e9:7.1f} TFLOP/s  max rel err {err:.2e}", flush=True)

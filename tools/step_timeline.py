@@ -14,7 +14,7 @@ eager = "--eager" in sys.argv
 if "--serial" in sys.argv:      # one stream: every kernel alone on the GPU -> clean per-kernel durations
     from grappa_b200 import tape as _tape
     _tape.set_concurrency(False)
-ops.set_matmul_precision("tf32")
+ops.set_matmul_precision(os.environ.get("GRAPPA_B200_PREC", ops.BENCH_PRECISION))
 from grappa_b200.training import init_distributed
 rank, local, world = init_distributed()
 torch.cuda.set_device(local)
@@ -38,7 +38,7 @@ if rank != 0:
     import torch.distributed as dist
     dist.barrier()
     os._exit(0)
-out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "step_trace.json")
+out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", os.environ.get("GRAPPA_B200_TRACE", "step_trace.json"))
 prof.export_chrome_trace(out)
 ev = json.load(open(out))["traceEvents"]
 ks = [e for e in ev if e.get("cat") == "kernel"]
