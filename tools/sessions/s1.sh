@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 O=gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/s1_smi.txt 2>&1
 # (1) everything that does not touch the new kernel
-timeout 900 python -m pytest tests -m gpu -q -x -k "not bf16x3 and not bench-" --deselect "tests/test_baseline_configs_gpu.py::test_config1_training_batch_loss_and_backward_match_reference_fixture[bench]" > $O/s1_pytest_base.log 2>&1
+timeout 900 python -m pytest tests -m gpu -q -x -k "not bf16x3" --deselect "tests/test_baseline_configs_gpu.py::test_config1_training_batch_loss_and_backward_match_reference_fixture[bench]" > $O/s1_pytest_base.log 2>&1
 echo "base rc=$?" >> $O/s1_pytest_base.log
 # (2) the new kernel's unit tests (own process: a trap would poison the CUDA context)
 timeout 900 python -m pytest tests/test_ops_gpu.py -m gpu -q -k "bf16x3" > $O/s1_pytest_x3.log 2>&1
@@ -27,4 +27,5 @@ done
 GRAPPA_B200_PREC=bf16x3 GRAPPA_B200_TRACE=s1_trace_x3.json timeout 300 python tools/step_timeline.py > $O/s1_timeline_x3.txt 2>&1
 GRAPPA_B200_PREC=bf16x3 GRAPPA_B200_TRACE=s1_trace_x3_serial.json timeout 300 python tools/step_timeline.py --serial > $O/s1_timeline_x3_serial.txt 2>&1
 rm -f $O/s1_trace_x3.json $O/s1_trace_x3_serial.json
-tail -3 $O/s1_pytest_base.log $O/s1_pytest_x3.log $O/s1_pytest_full.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/s1_smoke.log 2>&1
+tail -3 $O/s1_smoke.log $O/s1_pytest_base.log $O/s1_pytest_x3.log $O/s1_pytest_full.log
