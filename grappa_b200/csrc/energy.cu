@@ -698,6 +698,8 @@ __global__ void __launch_bounds__(256) energy_bwd_kernel(gb_energy_bwd_args ba) 
   }
 }
 
+int launch_energy_pairs(const gb_energy_args* a, cudaStream_t stream, bool* handled);   // energy_pairs.cu
+
 static int validate(const gb_energy_args* a) {
   GB_REQUIRE(a != nullptr, "energy: args is NULL");
   GB_REQUIRE(a->xyz != nullptr, "energy: xyz is NULL (xyz coordinates must be stored in g.nodes['n1'].data['xyz'])");
@@ -740,6 +742,16 @@ extern "C" int grappa_b200_energy_fwd(const gb_energy_args* a, int variant, void
   const size_t smem = smem_floats * sizeof(float);
   const bool tile_ok = max_atoms > 0 && smem <= 200 * 1024;
   GB_REQUIRE(mode != 2 || tile_ok, "energy: tiled variant requested but max_atoms=%d does not fit", max_atoms);
+  // packed-pair kernel (two conformations per lane, f32x2 arithmetic): the default whenever the pack carries the
+  // conflict-free schedule and the molecule's tiles fit in shared memory
+  if (mode == 0 || mode == 5) {
+    bool handled = false;
+    rc = launch_energy_pairs(a, stream, &handled);
+    if (rc) return rc;
+    if (handled) return GB_OK;
+    GB_REQUIRE(mode != 5, "energy: packed-pair variant needs sched/round_off with sched_groups == 8, 16-byte aligned index "
+               "tables and a molecule tile that fits in shared memory (max_atoms=%d)", max_atoms);
+  }
   // round-scheduled kernel: needs the host schedule and the molecule tile (xyz + forces, 32 conformations) in smem
   {
     bool have = a->sched_groups == 8;

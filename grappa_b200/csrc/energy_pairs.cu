@@ -1,0 +1,307 @@
+// K13, packed-pair kernel: MM bonded energy + analytic forces with TWO conformations per lane (f32x2 arithmetic).
+//
+// Replaces reference src/grappa/models/internal_coordinates.py:15-125, models/energy.py:8-71 and the autograd call at
+// models/energy.py:139, like energy.cu's kernels; math in energy_math2.cuh.
+//
+// Why: the round-scheduled kernel of round 1 (energy_rounds_kernel) ran at 5.7 % of the HBM roofline with the issue
+// slots 67 % busy -- ~2570 warp instructions per (molecule, conformation) evaluation, 78 % lane utilisation, one block
+// barrier per 8 tuples.  Here
+//   * a lane owns a PAIR of conformations held in one 64-bit register; subtract / cross / dot / FMA run as FADD2 / FMUL2 /
+//     FFMA2 (one issue slot for both), shared-memory traffic is 64-bit per lane, indices / parameters / address
+//     arithmetic are paid once per pair;
+//   * a warp carries two tuple slots (half-warps of 16 lanes = 32 conformations per tile): every 64-bit shared-memory
+//     access of a warp is two conflict-free 128-byte wavefronts, one per half;
+//   * each half-warp adds into its OWN copy of the force tile (copy 0 / copy 1, summed at write-back), so one block
+//     barrier covers TWO rounds of the host's conflict-free schedule: half the barriers, and a backbone atom that sits in
+//     25 torsions no longer forces 25 serial rounds;
+//   * theta = atan2(|a x b|, a.b) is a packed polynomial instead of two ~40-instruction atan2f calls.
+// CTA = (molecule, tile of <= 32 conformations), 8 warps = 16 tuple slots per barrier; shared memory = xyz tile + 2 force
+// tiles = 3 * 384 B per atom (60 KB for a 52-atom peptide: 3 CTAs / SM).  Forces and energies are bit-reproducible (fixed
+// schedule, fixed summation order).
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "energy_math2.cuh"
+
+namespace gb {
+
+constexpr int EP_W = 32;       // conformations per tile = 16 lanes x 2
+constexpr int EP_WARPS = 8;    // = sched_groups of the host schedule (tuples per conflict-free round)
+
+// shared-memory access through 32-bit shared-window addresses (one IMAD per atom row, immediate offsets per component)
+__device__ __forceinline__ F2 lds2(uint32_t addr) {
+  F2 r;
+  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(r.v) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ void sts2(uint32_t addr, F2 v) { asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v.v) : "memory"); }
+constexpr uint32_t EP_ROW = EP_W * 4;          // bytes between the x / y / z rows of an atom
+constexpr uint32_t EP_ATOM = 3 * EP_ROW;       // bytes per atom
+__device__ __forceinline__ W3 ld_pos(uint32_t row) { return {lds2(row), lds2(row + EP_ROW), lds2(row + 2 * EP_ROW)}; }
+// g += s * v   /   g -= s * v   on one atom's force row
+__device__ __forceinline__ void gadd(uint32_t row, F2 s, W3 v) {
+  const F2 gx = lds2(row), gy = lds2(row + EP_ROW), gz = lds2(row + 2 * EP_ROW);
+  sts2(row, fma2(s, v.x, gx));
+  sts2(row + EP_ROW, fma2(s, v.y, gy));
+  sts2(row + 2 * EP_ROW, fma2(s, v.z, gz));
+}
+__device__ __forceinline__ void gsub(uint32_t row, F2 s, W3 v) {
+  const F2 gx = lds2(row), gy = lds2(row + EP_ROW), gz = lds2(row + 2 * EP_ROW);
+  sts2(row, gx - s * v.x);
+  sts2(row + EP_ROW, gy - s * v.y);
+  sts2(row + 2 * EP_ROW, gz - s * v.z);
+}
+// the pair (c, c + 1) of a (T, C) output row; c + 1 may lie beyond the tile
+__device__ __forceinline__ void st_pair(float* p, F2 v, bool second) {
+  p[0] = lo(v);
+  if (second) p[1] = hi(v);
+}
+
+struct EpCtx {
+  uint32_t xl, gd;      // shared address of (atom 0 of the batch, lane's pair) in the position tile; offset to this half's force tile
+  int b, C, c, warp, h;
+  bool active, second, want_grad;
+};
+
+// One torsion level (LV = 2 propers, 3 impropers) with a compile-time periodicity (NPER = 3: grappa-1.1 / 1.2; 6: generic,
+// unused amplitudes are zero): level pointers are immediate constant-bank operands, the series is fully unrolled.
+template <bool FULL, int LV, int NPER>
+__device__ __forceinline__ F2 torsion_level(const gb_energy_args& a, const EpCtx& x) {
+  const int nper = a.n_per[LV - 2];
+  const int32_t* __restrict__ sched = a.sched[LV];
+  const int4* __restrict__ idx4 = reinterpret_cast<const int4*>(a.idx[LV]);
+  const float* __restrict__ kp = a.k[LV];
+  const int r0 = __ldg(a.round_off[LV] + x.b), r1 = __ldg(a.round_off[LV] + x.b + 1);
+  F2 e_acc = f2(0.f);
+  const int32_t* sp = sched + (size_t)(r0 + x.h) * EP_WARPS + x.warp;
+  int t_next = r0 + x.h < r1 ? __ldg(sp) : -1;
+  for (int r = r0 + x.h; r < r1 + x.h; r += 2) {      // both halves run the same number of iterations (block barrier inside)
+    const int t = t_next;                             // uniform per half-warp
+    sp += 2 * EP_WARPS;
+    t_next = r + 2 < r1 ? __ldg(sp) : -1;
+    if (t >= 0 && x.active) {
+      const int4 id = __ldg(idx4 + t);
+      const uint32_t a0r = x.xl + (uint32_t)id.x * EP_ATOM, a1r = x.xl + (uint32_t)id.y * EP_ATOM,
+                     a2r = x.xl + (uint32_t)id.z * EP_ATOM, a3r = x.xl + (uint32_t)id.w * EP_ATOM;
+      const TorsionGeom2 g = torsion_geom2(ld_pos(a0r), ld_pos(a1r), ld_pos(a2r), ld_pos(a3r));
+      float kk[NPER];
+      if (NPER == 3) {
+        kk[0] = __ldg(kp + 3 * t); kk[1] = __ldg(kp + 3 * t + 1); kk[2] = __ldg(kp + 3 * t + 2);
+      } else {
+#pragma unroll
+        for (int n = 0; n < NPER; ++n) kk[n] = n < nper ? __ldg(kp + (size_t)t * nper + n) : 0.f;
+      }
+      F2 e, dedphi;
+      torsion_series2<NPER>(kk, g.cphi, g.sphi, e, dedphi);
+      if (a.offset_torsion) {
+        float off = 0.f;
+#pragma unroll
+        for (int n = 0; n < NPER; ++n) off += fabsf(kk[n]);
+        e = e + f2(off);
+      }
+      e_acc = e_acc + e;
+      if (FULL) {
+        if (a.x[LV]) st_pair(a.x[LV] + (size_t)t * x.C + x.c, atan2_2(g.sphi, g.cphi), x.second);
+        if (a.tuple_energy[LV]) st_pair(a.tuple_energy[LV] + (size_t)t * x.C + x.c, e, x.second);
+      }
+      if (x.want_grad) {
+        gadd(a0r + x.gd, dedphi, g.p0);                                     // dphi/dx0 = p0
+        gsub(a3r + x.gd, dedphi, g.p3);                                     // dphi/dx3 = -p3
+        const W3 m1 = {g.p0.x + g.u.x, g.p0.y + g.u.y, g.p0.z + g.u.z};
+        const W3 m2 = {g.p3.x + g.u.x, g.p3.y + g.u.y, g.p3.z + g.u.z};
+        gsub(a1r + x.gd, dedphi, m1);                                       // dphi/dx1 = -(p0 + u)
+        gadd(a2r + x.gd, dedphi, m2);                                       // dphi/dx2 = p3 + u
+      }
+    }
+    __syncthreads();
+  }
+  return e_acc;
+}
+
+template <bool FULL, int MINB>
+__global__ void __launch_bounds__(32 * EP_WARPS, MINB) energy_pairs_kernel(const __grid_constant__ gb_energy_args a, int n_tiles, int wtile) {
+  pdl_trigger();
+  extern __shared__ __align__(16) float smem[];
+  const int b = blockIdx.x / n_tiles;
+  const int tile = blockIdx.x - b * n_tiles;
+  const int a0 = __ldg(a.atom_off + b);
+  const int n_at = __ldg(a.atom_off + b + 1) - a0;
+  const int C = a.n_confs;
+  const int c0 = tile * wtile;
+  const int wc = min(wtile, C - c0);            // valid conformations of this tile (<= 32)
+  const int tile_floats = n_at * 3 * EP_W;
+  float* xs = smem;                             // [n_at][3][32] positions
+  float* gs = smem + tile_floats;               // [2][n_at][3][32] force accumulators, one copy per half-warp
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int h = lane >> 4, pl = lane & 15;      // half-warp = tuple slot within the warp, lane's pair of conformations
+
+  // One warp per atom row: the tile slice of an atom is 3 * wc contiguous floats.  Columns beyond wc replicate the last
+  // valid conformation, so padded lanes compute ordinary finite numbers (never stored).
+  for (int at = warp; at < n_at; at += EP_WARPS) {
+    const float* src = a.xyz + ((size_t)(a0 + at) * C + c0) * 3;
+    float* xrow = xs + at * 3 * EP_W;
+    float* g0 = gs + at * 3 * EP_W;
+#pragma unroll
+    for (int j = lane; j < 3 * EP_W; j += 32) {
+      const int cc = j / 3, comp = j - cc * 3;
+      xrow[comp * EP_W + cc] = __ldg(src + min(cc, wc - 1) * 3 + comp);
+      g0[comp * EP_W + cc] = 0.f;
+      g0[tile_floats + comp * EP_W + cc] = 0.f;
+    }
+  }
+  __syncthreads();
+
+  EpCtx x;
+  x.b = b; x.C = C; x.warp = warp; x.h = h;
+  x.active = 2 * pl < wc;
+  x.second = 2 * pl + 1 < wc;
+  x.c = c0 + 2 * pl;
+  x.want_grad = a.grad != nullptr;
+  // shared address of (global atom index 0, lane's pair): + atom index * EP_ATOM = that atom's row (wraps modulo 2^32)
+  x.xl = (uint32_t)__cvta_generic_to_shared(xs) + (uint32_t)(2 * pl) * 4u - (uint32_t)a0 * EP_ATOM;
+  x.gd = (uint32_t)(tile_floats * 4) * (uint32_t)(1 + h);      // position row -> the same row of force copy h
+  F2 e_lvl[4] = {f2(0.f), f2(0.f), f2(0.f), f2(0.f)};
+
+  // ---- bonds
+  if ((a.level_mask & 1) && a.n_tuples[0] > 0) {
+    const int r0 = __ldg(a.round_off[0] + b), r1 = __ldg(a.round_off[0] + b + 1);
+    const int32_t* sp = a.sched[0] + (size_t)(r0 + h) * EP_WARPS + warp;
+    int t_next = r0 + h < r1 ? __ldg(sp) : -1;
+    for (int r = r0 + h; r < r1 + h; r += 2) {
+      const int t = t_next;
+      sp += 2 * EP_WARPS;
+      t_next = r + 2 < r1 ? __ldg(sp) : -1;
+      if (t >= 0 && x.active) {
+        const int2 id = __ldg(reinterpret_cast<const int2*>(a.idx[0]) + t);
+        const float k = __ldg(a.k[0] + t), eq = __ldg(a.eq[0] + t);
+        const uint32_t a0r = x.xl + (uint32_t)id.x * EP_ATOM, a1r = x.xl + (uint32_t)id.y * EP_ATOM;
+        const BondGeom2 g = bond_geom2(ld_pos(a0r), ld_pos(a1r));
+        const F2 d = g.r - f2(eq);
+        const F2 kd = f2(k) * d;
+        const F2 e = f2(0.5f) * kd * d;
+        e_lvl[0] = e_lvl[0] + e;
+        if (FULL) {
+          if (a.x[0]) st_pair(a.x[0] + (size_t)t * C + x.c, g.r, x.second);
+          if (a.tuple_energy[0]) st_pair(a.tuple_energy[0] + (size_t)t * C + x.c, e, x.second);
+        }
+        if (x.want_grad) {
+          gadd(a0r + x.gd, kd, g.d0);
+          gsub(a1r + x.gd, kd, g.d0);
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // ---- angles
+  if ((a.level_mask & 2) && a.n_tuples[1] > 0) {
+    const int r0 = __ldg(a.round_off[1] + b), r1 = __ldg(a.round_off[1] + b + 1);
+    const int32_t* sp = a.sched[1] + (size_t)(r0 + h) * EP_WARPS + warp;
+    int t_next = r0 + h < r1 ? __ldg(sp) : -1;
+    for (int r = r0 + h; r < r1 + h; r += 2) {
+      const int t = t_next;
+      sp += 2 * EP_WARPS;
+      t_next = r + 2 < r1 ? __ldg(sp) : -1;
+      if (t >= 0 && x.active) {
+        const int32_t* ip = a.idx[1] + 3 * t;
+        const int i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2);
+        const float k = __ldg(a.k[1] + t), eq = __ldg(a.eq[1] + t);
+        const uint32_t a0r = x.xl + (uint32_t)i0 * EP_ATOM, a1r = x.xl + (uint32_t)i1 * EP_ATOM, a2r = x.xl + (uint32_t)i2 * EP_ATOM;
+        const AngleGeom2 g = angle_geom2(ld_pos(a0r), ld_pos(a1r), ld_pos(a2r));
+        const F2 d = g.theta - f2(eq);
+        const F2 kd = f2(k) * d;
+        const F2 e = f2(0.5f) * kd * d;
+        e_lvl[1] = e_lvl[1] + e;
+        if (FULL) {
+          if (a.x[1]) st_pair(a.x[1] + (size_t)t * C + x.c, g.theta, x.second);
+          if (a.tuple_energy[1]) st_pair(a.tuple_energy[1] + (size_t)t * C + x.c, e, x.second);
+        }
+        if (x.want_grad) {
+          gadd(a0r + x.gd, kd, g.d0);
+          gadd(a2r + x.gd, kd, g.d2);
+          const W3 dm = {g.d0.x + g.d2.x, g.d0.y + g.d2.y, g.d0.z + g.d2.z};
+          gsub(a1r + x.gd, kd, dm);
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // ---- torsions
+  if (((a.level_mask >> 2) & 1) && a.n_tuples[2] > 0)
+    e_lvl[2] = a.n_per[0] == 3 ? torsion_level<FULL, 2, 3>(a, x) : torsion_level<FULL, 2, GB_MAX_PERIODICITY>(a, x);
+  if (((a.level_mask >> 3) & 1) && a.n_tuples[3] > 0)
+    e_lvl[3] = a.n_per[1] == 3 ? torsion_level<FULL, 3, 3>(a, x) : torsion_level<FULL, 3, GB_MAX_PERIODICITY>(a, x);
+
+  // forces back to global, coalesced: the two copies are summed in a fixed order (the last round ended with a barrier)
+  if (x.want_grad) {
+    for (int at = warp; at < n_at; at += EP_WARPS) {
+      float* dst = a.grad + ((size_t)(a0 + at) * C + c0) * 3;
+      const float* g0 = gs + at * 3 * EP_W;
+#pragma unroll
+      for (int j = lane; j < 3 * EP_W; j += 32) {
+        const int cc = j / 3, comp = j - cc * 3;
+        if (cc < wc) dst[j] = g0[comp * EP_W + cc] + g0[tile_floats + comp * EP_W + cc];
+      }
+    }
+  }
+  __syncthreads();
+  // per-level energies: 16 tuple slots per conformation, folded in slot order
+  float* red = smem;   // [4][16][32] floats (the host sizes shared memory for it)
+  const int slot = warp * 2 + h;
+#pragma unroll
+  for (int lv = 0; lv < 4; ++lv)
+    *reinterpret_cast<unsigned long long*>(red + (lv * 16 + slot) * EP_W + 2 * pl) = x.active ? e_lvl[lv].v : 0ull;
+  __syncthreads();
+  if (tid < wc) {
+    float tot = 0.f;
+#pragma unroll
+    for (int lv = 0; lv < 4; ++lv) {
+      float s2 = 0.f;
+#pragma unroll
+      for (int g2 = 0; g2 < 16; ++g2) s2 += red[(lv * 16 + g2) * EP_W + tid];
+      if (a.term_energy[lv]) a.term_energy[lv][(size_t)b * C + c0 + tid] = s2;
+      tot += s2;
+    }
+    if (a.energy) a.energy[(size_t)b * C + c0 + tid] = tot;
+  }
+}
+
+// handled = false: the pack carries no schedule or the molecule tile does not fit -> the caller falls back
+int launch_energy_pairs(const gb_energy_args* a, cudaStream_t stream, bool* handled) {
+  *handled = false;
+  const int C = a->n_confs, B = a->n_mols;
+  bool have = a->sched_groups == EP_WARPS;
+  for (int l = 0; l < 4 && have; ++l)
+    if (a->n_tuples[l] > 0 && ((a->level_mask >> l) & 1)) have = a->sched[l] && a->round_off[l];
+  for (int l = 2; l < 4 && have; ++l)   // 16-byte index loads
+    if (a->n_tuples[l] > 0 && ((a->level_mask >> l) & 1)) have = ((uintptr_t)a->idx[l] & 15) == 0;
+  if (have && a->n_tuples[0] > 0 && (a->level_mask & 1)) have = ((uintptr_t)a->idx[0] & 7) == 0;
+  size_t smem = (size_t)a->max_atoms_per_mol * 3 * EP_W * 3 * sizeof(float);
+  if (smem < (size_t)4 * 16 * EP_W * sizeof(float)) smem = (size_t)4 * 16 * EP_W * sizeof(float);
+  if (!have || a->max_atoms_per_mol <= 0 || smem > 200 * 1024) return GB_OK;
+  bool full = false;
+  for (int l = 0; l < 4; ++l) full = full || a->x[l] || a->tuple_energy[l];
+  const int nt = (C + EP_W - 1) / EP_W;
+  int wtile = (C + nt - 1) / nt;             // balanced tiles, an even number of conformations each (pairs)
+  wtile = (wtile + 1) & ~1;
+  static const int minb = [] { const char* e = getenv("GRAPPA_B200_ENERGY_MINB"); return e ? atoi(e) : 3; }();   // tuning aid
+  static unsigned long long configured = 0;
+  if (first_use_on_device(configured)) {
+    GB_CHECK_CUDA(cudaFuncSetAttribute(energy_pairs_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    GB_CHECK_CUDA(cudaFuncSetAttribute(energy_pairs_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    GB_CHECK_CUDA(cudaFuncSetAttribute(energy_pairs_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    GB_CHECK_CUDA(cudaFuncSetAttribute(energy_pairs_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  }
+  const dim3 grid((unsigned)(B * nt));
+  if (full) {
+    if (minb == 2) energy_pairs_kernel<true, 2><<<grid, 32 * EP_WARPS, smem, stream>>>(*a, nt, wtile);
+    else energy_pairs_kernel<true, 3><<<grid, 32 * EP_WARPS, smem, stream>>>(*a, nt, wtile);
+  } else {
+    if (minb == 2) energy_pairs_kernel<false, 2><<<grid, 32 * EP_WARPS, smem, stream>>>(*a, nt, wtile);
+    else energy_pairs_kernel<false, 3><<<grid, 32 * EP_WARPS, smem, stream>>>(*a, nt, wtile);
+  }
+  GB_CHECK_LAUNCH();
+  *handled = true;
+  return GB_OK;
+}
+
+}  // namespace gb

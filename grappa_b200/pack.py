@@ -122,13 +122,16 @@ class PackedBatch:
         self.host = host
         self._names = list(host.keys())
         self._sizes = [host[k].size for k in self._names]
-        total = int(sum(self._sizes))
+        # every table starts on a 16-byte boundary of the staging buffer (the energy kernel fetches a torsion's four atom
+        # indices with one 16-byte load)
+        self._offsets, total = [], 0
+        for s in self._sizes:
+            self._offsets.append(total)
+            total += (int(s) + 3) // 4 * 4
         # one (pinned) staging buffer so that the whole pack moves with a single H2D copy
-        stage = torch.empty(total, dtype=torch.int32)
-        off = 0
-        for k, s in zip(self._names, self._sizes):
+        stage = torch.zeros(total, dtype=torch.int32)
+        for k, s, off in zip(self._names, self._sizes, self._offsets):
             stage[off:off + s] = torch.from_numpy(host[k].reshape(-1))
-            off += s
         if torch.cuda.is_available():
             try:
                 stage = stage.pin_memory()
@@ -143,11 +146,9 @@ class PackedBatch:
         self.device = torch.device(device)
         flat = self._stage.to(self.device, non_blocking=True)
         self._flat = flat
-        off = 0
         self._dev = {}
-        for k, s in zip(self._names, self._sizes):
+        for k, s, off in zip(self._names, self._sizes, self._offsets):
             self._dev[k] = flat[off:off + s].view(self.host[k].shape)
-            off += s
 
     def to(self, device) -> "PackedBatch":
         """Copy of the pack on another device (one H2D transfer of the staging buffer)."""

@@ -106,8 +106,10 @@ int64_t grappa_b200_conflict_free_rounds(const int32_t* idx, const int32_t* tup_
 /* Zeroes and fills every non-NULL output.  variant: 0 = auto, 1 = global-atomics kernel (any molecule size),
  * 2 = shared-memory tiled kernel (CTA per molecule x conformation tile, tuple groups, shared atomics),
  * 3 = conformation-per-thread kernel (no atomics; latency-bound, kept for cross-checks),
- * 4 = round-scheduled tiled kernel (needs sched/round_off: no atomics, bit-reproducible; what `auto` picks when a
- *     schedule is given and the molecule tile fits in shared memory). */
+ * 4 = round-scheduled tiled kernel (needs sched/round_off: no atomics, bit-reproducible),
+ * 5 = packed-pair kernel (two conformations per lane on the f32x2 pipe, two schedule rounds per barrier with one force
+ *     tile per half-warp; needs sched/round_off with 8 groups and 16-byte aligned index tables; bit-reproducible) --
+ *     what `auto` picks when a schedule is given and the molecule's tiles fit in shared memory (<= 177 atoms). */
 int grappa_b200_energy_fwd(const gb_energy_args* a, int variant, void* stream);
 
 typedef struct {

@@ -28,7 +28,7 @@ def _graph_with_params(z, dev, requires_grad=False):
     return g, leaves
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5])
 def test_energy_forward_matches_reference_fixture(variant):
     from grappa_b200.energy import Energy
     z = load_golden("energy_mixed_batch.npz")
@@ -193,7 +193,7 @@ def test_energy_full_size_properties():
     assert rel_err(out4.nodes["n1"].data["gradient"].cpu().numpy(), F.cpu().numpy()) < 1e-5
 
 
-@pytest.mark.parametrize("variant", [0, 1, 3, 4])
+@pytest.mark.parametrize("variant", [0, 1, 3, 4, 5])
 def test_energy_collinear_geometry_is_finite_and_matches_the_oracle(variant):
     """A linear molecule stored on an axis (CO2 / nitrile / alkyne type): |a x b| = 0 exactly.  The reference returns
     theta = atan2(0, c) = pi with a zero angle derivative (torch.norm's subgradient at 0); an rsqrt(0) = inf would turn
@@ -221,7 +221,7 @@ def test_energy_collinear_geometry_is_finite_and_matches_the_oracle(variant):
     idxs = {l: g.nodes[l].data["idxs"] for l in ("n2", "n3")}
     counts = {l: g.batch_num_nodes(l).tolist() for l in ("n2", "n3")}
     prm = {l: {n: g.nodes[l].data[n].double() for n in ("k", "eq")} for l in ("n2", "n3")}
-    ref = orc.energy_forward(xyz.double(), idxs, prm, counts)
+    ref = orc.energy_forward(xyz.double(), idxs, prm, counts, terms=("n2", "n3"))
     gd = g.to("cuda")
     for l in LEVELS:
         for n in ("k", "eq"):

@@ -6,7 +6,8 @@ from grappa_b200 import graph as gbg, synthetic
 from grappa_b200.energy import Energy
 
 dev = torch.device("cuda")
-HBM = 6551.7
+HBM = 6562.6
+FULL = "--full" in sys.argv      # also time the full-contract mode (per-tuple x / energy written)
 
 
 def build(n_mols, n_confs):
@@ -29,25 +30,29 @@ for n_mols, n_confs in ((1000, 100), (104, 1000), (32, 50)):
     tup = [ge.num_nodes(l) for l in ("n2", "n3", "n4", "n4_improper")]
     alg = n_confs * (24 * na + 4 * n_mols) + 4 * (2 * tup[0] + 3 * tup[1] + 4 * tup[2] + 4 * tup[3]) + 4 * (2 * tup[0] + 2 * tup[1] + 3 * tup[2] + 3 * tup[3])
     ref = None
-    for variant in (2, 4, 3, 1):
-        en = Energy(write_tuple_terms=False)
-        en.kernel_variant = variant
-        with torch.no_grad():
-            for _ in range(3):
-                g = en(ge)
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            reps = 20
-            e0.record()
-            for _ in range(reps):
-                g = en(ge)
-            e1.record()
-            torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / reps
-        E, F = g.nodes["g"].data["energy"].clone(), g.nodes["n1"].data["gradient"].clone()
-        if ref is None:
-            ref = (E, F)
-        dE = ((E - ref[0]).abs().max() / ref[0].abs().max()).item()
-        dF = ((F - ref[1]).abs().max() / ref[1].abs().max()).item()
-        print(f"mols={n_mols} confs={n_confs} variant={variant}: {ms * 1e3:8.1f} us  {n_mols * n_confs / ms / 1e6:8.1f} M evals/s  "
-              f"{alg / ms / 1e6:7.1f} GB/s = {alg / ms / 1e6 / HBM * 100:5.1f}% HBM   dE={dE:.1e} dF={dF:.1e}", flush=True)
+    alg_full = alg + n_confs * (8 * sum(tup) + 16 * n_mols)
+    for full in ((False, True) if FULL else (False,)):
+        for variant in ((5, 4) if full else (5, 4, 2, 3, 1)):
+            en = Energy(write_tuple_terms=full)
+            en.kernel_variant = variant
+            with torch.no_grad():
+                for _ in range(3):
+                    g = en(ge)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                reps = 20
+                e0.record()
+                for _ in range(reps):
+                    g = en(ge)
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            E, F = g.nodes["g"].data["energy"].clone(), g.nodes["n1"].data["gradient"].clone()
+            if ref is None:
+                ref = (E, F)
+            dE = ((E - ref[0]).abs().max() / ref[0].abs().max()).item()
+            dF = ((F - ref[1]).abs().max() / ref[1].abs().max()).item()
+            by = alg_full if full else alg
+            print(f"mols={n_mols} confs={n_confs} {'full' if full else 'lean'} variant={variant}: {ms * 1e3:8.1f} us  "
+                  f"{n_mols * n_confs / ms / 1e6:8.1f} M evals/s  {by / ms / 1e6:7.1f} GB/s = {by / ms / 1e6 / HBM * 100:5.1f}% HBM "
+                  f"({by / (n_mols * n_confs):.0f} B/eval)   dE={dE:.1e} dF={dF:.1e}", flush=True)

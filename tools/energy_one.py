@@ -1,4 +1,4 @@
-"""One K13 launch configuration for ncu: python tools/energy_one.py [n_mols n_confs variant]"""
+"""One K13 launch configuration for ncu: python tools/energy_one.py [n_mols n_confs variant [full]]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -18,7 +18,7 @@ for l in ("n2", "n3", "n4", "n4_improper"):
         ge.nodes[l].data["eq"] = (1.2 + 0.6 * torch.rand(T, generator=gen)).to(dev)
     else:
         ge.nodes[l].data["k"] = torch.randn(T, 3, generator=gen).to(dev)
-en = Energy(write_tuple_terms=False)
+en = Energy(write_tuple_terms=(len(sys.argv) > 4 and sys.argv[4] == "full"))
 en.kernel_variant = variant
 with torch.no_grad():
     for _ in range(3):
