@@ -156,6 +156,21 @@ def graph_from_molecule(n_atoms: int, bonds, angles, propers, impropers, feats: 
     return g
 
 
+def as_molgraph(g) -> MolGraph:
+    """Any graph object with the duck-typed surface of the module docstring (e.g. a `dgl.DGLHeteroGraph` built by the
+    reference's Molecule.to_dgl, data/Molecule.py:429-520) -> MolGraph sharing its tensors.  A MolGraph is returned as is."""
+    if isinstance(g, MolGraph):
+        return g
+    src, dst = g.edges(etype="n1_edge")
+    ntypes = [nt for nt in NTYPES if nt in g.ntypes]
+    out = MolGraph({nt: int(g.num_nodes(nt)) for nt in ntypes}, src, dst,
+                   {nt: torch.as_tensor(g.batch_num_nodes(nt)).detach().cpu().to(torch.int64) for nt in ntypes})
+    for nt in ntypes:
+        for k, v in g.nodes[nt].data.items():
+            out.nodes[nt].data[k] = v
+    return out
+
+
 def batch(graphs: Sequence[MolGraph]) -> MolGraph:
     """Concatenate molecules; tuple indices and edges are shifted by the atom offset.
 

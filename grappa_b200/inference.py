@@ -215,6 +215,7 @@ class Grappa:
         """Parametrise many systems: molecules are packed greedily into batches of <= `max_atoms_per_batch` atoms (a
         1,500-atom protein is ~0.4 ms of tensor math; launch count, not FLOPs, is what batching saves), each batch is
         one model call, results come back in input order."""
+        molecules = [_graph.as_molgraph(m) for m in molecules]      # DGL-shaped graphs (Molecule.to_dgl) are accepted as they are
         if not allow_disconnected:
             for i, m in enumerate(molecules):
                 if connected_components(m) > 1:

@@ -26,6 +26,7 @@ from typing import Dict, List, Tuple
 import torch
 
 from . import nn  # noqa: F401  (dgl.nn.pytorch.conv.DotGatConv)
+from . import heterograph as _heterograph_module  # noqa: F401  (sub-module first; the function `heterograph` below re-binds the name)
 
 
 class _NodeView:

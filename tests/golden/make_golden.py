@@ -331,9 +331,88 @@ def protein_and_mix_cases(ns):
     print("espaloma_mix_small_model: atoms", g.num_nodes("n1"), "E[0,0] =", out["out.g.energy"][0, 0])
 
 
+def tiny_model_config():
+    """A very small architecture whose reference-saved state_dict (~0.4 MB) can be committed."""
+    cfg = orc.grappa_1_2_model_config()
+    cfg.update(graph_node_features=32, gnn_width=64, gnn_attentional_layers=2, gnn_attention_heads=4)
+    for w in ("bond", "angle", "proper", "improper"):
+        cfg.update({f"{w}_transformer_depth": 1, f"{w}_n_heads": 4, f"{w}_transformer_width": 64,
+                    f"{w}_symmetriser_depth": 2, f"{w}_symmetriser_width": 32})
+    return cfg
+
+
+def import_reference_parameters():
+    """The reference's output dataclass `grappa.data.Parameters` (data/Parameters.py:19-140).  It imports matplotlib at
+    module top (absent here; only its plotting helpers use it) -> stubbed; everything else imports unmodified."""
+    import importlib
+    import types
+    if "matplotlib" not in sys.modules:
+        class _Stub(types.ModuleType):
+            __path__ = []
+
+            def __getattr__(self, name):
+                return _Stub(name)
+        for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.colors", "matplotlib.cm"):
+            sys.modules[name] = _Stub(name)
+    pkg = sys.modules["grappa"]
+    pkg.units = importlib.import_module("grappa.units")
+    return importlib.import_module("grappa.data.Parameters").Parameters
+
+
+def dropin_case(ns):
+    """Drop-in fixtures (task 8): (i) a state_dict SAVED BY THE REFERENCE model with the reference's own
+    initialisation (torch.save -> reference_tiny_state_dict.pt), (ii) the reference's outputs, loss and
+    Parameters.from_dgl (grappa.py:36-57 flow: eval, no_grad, to cpu) for it on a small batch -> dropin_tiny.npz."""
+    cfg = tiny_model_config()
+    torch.manual_seed(21)
+    model = ns.deploy.model_from_config(dict(cfg), param_statistics=ns.graph_utils.get_default_statistics())
+    with torch.no_grad():       # LayerNorm / bias parameters away from their 1 / 0 defaults, like a trained checkpoint
+        gen = torch.Generator().manual_seed(22)
+        for k, p in model.named_parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn(p.shape, generator=gen))
+    model.eval()
+    torch.save({k: v.clone() for k, v in model.state_dict().items()}, os.path.join(OUT, "reference_tiny_state_dict.pt"))
+    rng = np.random.default_rng(23)
+    mols = [synthetic.make_molecule(rng, "peptide", n_confs=5, n_res=1), synthetic.make_molecule(rng, "small", n_confs=5, n_atoms=14),
+            synthetic.make_molecule(rng, "peptide", n_confs=5, n_res=2)]
+    mols = [m for m in mols if m.num_nodes("n4_improper") > 0]
+    for i, m in enumerate(mols):     # atom ids as a topology would carry them: not consecutive, not starting at zero
+        m.nodes["n1"].data["ids"] = torch.arange(m.num_nodes("n1")) * 3 + 7 + 100 * i
+    g = gbgraph.batch(mols)
+    dg = to_reference_graph(ns, g)
+    with no_dihedral_noise():
+        dg = torch.nn.Sequential(model, ns.energy.Energy())(dg)
+    loss = ns.loss.MolwiseLoss(gradient_weight=0.8, energy_weight=1.0, param_weight=0.0, proper_regularisation=1e-3,
+                               improper_regularisation=1e-3)(dg)
+    out = {"out.h": dg.nodes["n1"].data["h"].detach().numpy(), "out.g.energy": dg.nodes["g"].data["energy"].detach().numpy(),
+           "out.n1.gradient": dg.nodes["n1"].data["gradient"].detach().numpy(), "out.loss": np.array(loss.item(), dtype=np.float64),
+           "meta.config_keys": np.array(sorted(cfg.keys())),
+           "meta.config_vals": np.array([repr(cfg[k]) for k in sorted(cfg.keys())])}
+    for lvl in LEVELS:
+        out[f"out.{lvl}.k"] = dg.nodes[lvl].data["k"].detach().numpy()
+        if lvl in ("n2", "n3"):
+            out[f"out.{lvl}.eq"] = dg.nodes[lvl].data["eq"].detach().numpy()
+    # Grappa.predict flow on the first molecule alone (grappa.py:36-57): model in eval mode, no_grad, to cpu, from_dgl
+    Parameters = import_reference_parameters()
+    d1 = to_reference_graph(ns, mols[0])
+    with torch.no_grad():
+        d1 = model(d1)
+    d1 = d1.to("cpu")
+    prm = Parameters.from_dgl(d1)
+    for f in ("atoms", "bonds", "bond_k", "bond_eq", "angles", "angle_k", "angle_eq", "propers", "proper_ks", "proper_phases",
+              "impropers", "improper_ks", "improper_phases"):
+        out[f"params.{f}"] = np.asarray(getattr(prm, f))
+    np.savez_compressed(os.path.join(OUT, "dropin_tiny.npz"), **graph_inputs(g), **out)
+    print("dropin_tiny: loss =", loss.item(), "state_dict entries", len(model.state_dict()),
+          "bytes", os.path.getsize(os.path.join(OUT, "reference_tiny_state_dict.pt")))
+
+
 def main():
     ns = import_reference()
     torch.set_num_threads(8)
+    if "--only-dropin" in sys.argv:
+        return dropin_case(ns)
     if "--only-protein-mix" in sys.argv:
         return protein_and_mix_cases(ns)
     if "--only-train-batch" in sys.argv:
@@ -344,6 +423,7 @@ def main():
         return param_loss_case(ns)
     if "--only-ragged" in sys.argv:
         return ragged_conformations_case(ns)
+    dropin_case(ns)
     param_loss_case(ns)
     ragged_conformations_case(ns)
     switches_case(ns)

@@ -88,3 +88,27 @@ def test_graph_replay_inference_equals_eager():
     assert len(graphed._captured) == 1
     assert not np.array_equal(graphed.predict(variants[0], check_eq_values=False).bond_k,
                               graphed.predict(variants[3], check_eq_values=False).bond_k)
+
+
+def test_parameters_from_graph_matches_the_reference_class():
+    """`Parameters.from_graph` against the REFERENCE's own `Parameters.from_dgl` (data/Parameters.py:63-140), run in the
+    build container on the reference model's outputs for a molecule with non-trivial atom ids
+    (tests/golden/dropin_tiny.npz, generated by tests/golden/make_golden.py::dropin_case)."""
+    from grappa_b200 import graph as gbg, inference
+    from util import LEVELS, graph_from_fixture, load_golden
+    z = load_golden("dropin_tiny.npz")
+    g = graph_from_fixture(z)
+    for l in LEVELS:                       # the reference's parameter outputs, written where the model writes them
+        g.nodes[l].data["k"] = torch.from_numpy(z[f"out.{l}.k"])
+        if l in ("n2", "n3"):
+            g.nodes[l].data["eq"] = torch.from_numpy(z[f"out.{l}.eq"])
+    m0 = gbg.unbatch(g)[0]
+    p = inference.Parameters.from_graph(m0)
+    for f in ("atoms", "bonds", "angles", "propers", "impropers"):
+        assert np.array_equal(getattr(p, f), z[f"params.{f}"]), f
+    for f in ("bond_k", "bond_eq", "angle_k", "angle_eq", "proper_ks", "improper_ks"):
+        # the fixture's Parameters come from a single-molecule model call, k / eq above from the batched one: fp32 rounding
+        np.testing.assert_allclose(getattr(p, f), z[f"params.{f}"], rtol=2e-5, atol=2e-6, err_msg=f)
+    for f, ks in (("proper_phases", "proper_ks"), ("improper_phases", "improper_ks")):
+        settled = z[f"params.{ks}"] > 1e-5                     # an amplitude at the cutoff may round to either side of zero
+        assert np.array_equal(getattr(p, f)[settled], z[f"params.{f}"][settled]), f
