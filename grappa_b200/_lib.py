@@ -42,6 +42,8 @@ class EnergyArgs(C.Structure):
         ("sched", c_i32p * 4),
         ("round_off", c_i32p * 4),
         ("sched_groups", C.c_int32),
+        ("max_tuples_per_mol", C.c_int32 * 4),
+        ("max_rounds_per_mol", C.c_int32 * 4),
     ]
 
 
@@ -96,7 +98,7 @@ def lib():
         except OSError as e:  # pragma: no cover
             raise GrappaB200Error(f"cannot load {LIB_PATH}: {e}") from e
         _declare(l)
-        if l.grappa_b200_abi_version() != 2:
+        if l.grappa_b200_abi_version() != 3:
             raise GrappaB200Error("libgrappa_b200.so ABI version mismatch; rebuild")
         _lib = l
     return _lib

@@ -22,6 +22,7 @@
 
 #include "common.cuh"
 #include "energy_math2.cuh"
+#include "mbar.cuh"
 
 namespace gb {
 
@@ -57,41 +58,129 @@ __device__ __forceinline__ void st_pair(float* p, F2 v, bool second) {
   if (second) p[1] = hi(v);
 }
 
+// One molecule's tuple records of one level, staged in shared memory by the whole CTA before the rounds start: the
+// round loop then depends on ~30-cycle shared loads instead of a chain of three dependent global loads (schedule ->
+// indices -> positions; 22 % of all stall samples in the first version of this kernel).
+struct EpLevel {
+  uint32_t sched;   // [n_rounds][8] tuple ids RELATIVE to the molecule's first tuple (or -1)
+  uint32_t idx;     // [n][L] atom indices RELATIVE to the molecule's first atom (16-byte aligned rows for L = 4)
+  uint32_t k;       // [n][width]
+  uint32_t eq;      // [n] (bonds / angles)
+  int n_rounds, t0;
+};
+
 struct EpCtx {
-  uint32_t xl, gd;      // shared address of (atom 0 of the batch, lane's pair) in the position tile; offset to this half's force tile
-  int b, C, c, warp, h;
+  uint32_t xl, gd;      // shared address of (atom 0 of the molecule, lane's pair) in the position tile; offset to this half's force tile
+  uint32_t bar;         // shared address of the round mbarrier
+  uint32_t it;          // rounds this warp has completed (mbarrier phase)
+  int b, C, c, warp, h, lane;
   bool active, second, want_grad;
 };
 
+// words of shared memory the records of a level need (each array padded to 16 bytes)
+__host__ __device__ inline int ep_level_words(int n_rounds, int n, int L, int width, bool has_eq) {
+  auto pad = [](int w) { return (w + 3) & ~3; };
+  return pad(n_rounds * EP_WARPS) + pad(n * L) + pad(n * width) + (has_eq ? pad(n) : 0);
+}
+
+template <int L>
+__device__ __forceinline__ EpLevel stage_level(const gb_energy_args& a, int lv, int b, int a0, int width, bool has_eq, float*& cursor) {
+  EpLevel e;
+  const int t0 = __ldg(a.tup_off[lv] + b), n = __ldg(a.tup_off[lv] + b + 1) - t0;
+  const int r0 = __ldg(a.round_off[lv] + b), nr = __ldg(a.round_off[lv] + b + 1) - r0;
+  e.n_rounds = nr;
+  e.t0 = t0;
+  auto pad = [](int w) { return (w + 3) & ~3; };
+  int32_t* s_sched = reinterpret_cast<int32_t*>(cursor);
+  int32_t* s_idx = s_sched + pad(nr * EP_WARPS);
+  float* s_k = reinterpret_cast<float*>(s_idx + pad(n * L));
+  float* s_eq = s_k + pad(n * width);
+  cursor = s_eq + (has_eq ? pad(n) : 0);
+  const int tid = threadIdx.x;
+  for (int i = tid; i < nr * EP_WARPS; i += 32 * EP_WARPS) {
+    const int t = __ldg(a.sched[lv] + (size_t)r0 * EP_WARPS + i);
+    s_sched[i] = t < 0 ? -1 : t - t0;
+  }
+  for (int i = tid; i < n * L; i += 32 * EP_WARPS) s_idx[i] = __ldg(a.idx[lv] + (size_t)t0 * L + i) - a0;
+  for (int i = tid; i < n * width; i += 32 * EP_WARPS) s_k[i] = __ldg(a.k[lv] + (size_t)t0 * width + i);
+  if (has_eq)
+    for (int i = tid; i < n; i += 32 * EP_WARPS) s_eq[i] = __ldg(a.eq[lv] + t0 + i);
+  e.sched = smem_u32(s_sched);
+  e.idx = smem_u32(s_idx);
+  e.k = smem_u32(s_k);
+  e.eq = smem_u32(s_eq);
+  return e;
+}
+
+__device__ __forceinline__ int lds_i(uint32_t addr) {
+  int r;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(r) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ float lds_f(uint32_t addr) {
+  float r;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ int4 lds_i4(uint32_t addr) {
+  int4 r;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+
+// Round synchronisation.  Tuples of consecutive rounds may touch the same atoms, so the force updates (read-modify-write
+// of shared rows) of round r + 1 must follow those of round r -- but only the UPDATES: geometry and energies of round
+// r + 1 read nothing that round r writes.  Instead of a block barrier per round (32 % of all stall samples), every warp
+// ARRIVES on an mbarrier after its updates and WAITS for the previous round's phase only right before its next updates:
+// the wait overlaps the ~200 instructions of geometry in between.
+__device__ __forceinline__ void round_wait(EpCtx& x) {
+  if (x.it > 0) {
+    uint32_t done = 0, spins = 0;
+    const uint32_t parity = (x.it - 1) & 1;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.b32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(x.bar), "r"(parity)
+          : "memory");
+      if (!done && ++spins > SPIN_LIMIT) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void round_arrive(EpCtx& x) {
+  __syncwarp();
+  if (x.lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(x.bar) : "memory");
+  ++x.it;
+}
+
 // One torsion level (LV = 2 propers, 3 impropers) with a compile-time periodicity (NPER = 3: grappa-1.1 / 1.2; 6: generic,
-// unused amplitudes are zero): level pointers are immediate constant-bank operands, the series is fully unrolled.
+// unused amplitudes are zero).
 template <bool FULL, int LV, int NPER>
-__device__ __forceinline__ F2 torsion_level(const gb_energy_args& a, const EpCtx& x) {
+__device__ __forceinline__ F2 torsion_level(const gb_energy_args& a, EpCtx& x, const EpLevel& lv) {
   const int nper = a.n_per[LV - 2];
-  const int32_t* __restrict__ sched = a.sched[LV];
-  const int4* __restrict__ idx4 = reinterpret_cast<const int4*>(a.idx[LV]);
-  const float* __restrict__ kp = a.k[LV];
-  const int r0 = __ldg(a.round_off[LV] + x.b), r1 = __ldg(a.round_off[LV] + x.b + 1);
   F2 e_acc = f2(0.f);
-  const int32_t* sp = sched + (size_t)(r0 + x.h) * EP_WARPS + x.warp;
-  int t_next = r0 + x.h < r1 ? __ldg(sp) : -1;
-  for (int r = r0 + x.h; r < r1 + x.h; r += 2) {      // both halves run the same number of iterations (block barrier inside)
-    const int t = t_next;                             // uniform per half-warp
-    sp += 2 * EP_WARPS;
-    t_next = r + 2 < r1 ? __ldg(sp) : -1;
-    if (t >= 0 && x.active) {
-      const int4 id = __ldg(idx4 + t);
-      const uint32_t a0r = x.xl + (uint32_t)id.x * EP_ATOM, a1r = x.xl + (uint32_t)id.y * EP_ATOM,
-                     a2r = x.xl + (uint32_t)id.z * EP_ATOM, a3r = x.xl + (uint32_t)id.w * EP_ATOM;
-      const TorsionGeom2 g = torsion_geom2(ld_pos(a0r), ld_pos(a1r), ld_pos(a2r), ld_pos(a3r));
+  uint32_t sp = lv.sched + (uint32_t)(x.h * EP_WARPS + x.warp) * 4u;
+  for (int r = x.h; r < lv.n_rounds + x.h; r += 2, sp += 2 * EP_WARPS * 4) {   // both halves run the same number of iterations
+    const int t = r < lv.n_rounds ? lds_i(sp) : -1;                             // uniform per half-warp
+    const bool on = t >= 0 && x.active;
+    uint32_t a0r = 0, a1r = 0, a2r = 0, a3r = 0;
+    F2 dedphi = f2(0.f);
+    TorsionGeom2 g;
+    if (on) {
+      const int4 id = lds_i4(lv.idx + (uint32_t)t * 16u);
+      a0r = x.xl + (uint32_t)id.x * EP_ATOM; a1r = x.xl + (uint32_t)id.y * EP_ATOM;
+      a2r = x.xl + (uint32_t)id.z * EP_ATOM; a3r = x.xl + (uint32_t)id.w * EP_ATOM;
+      g = torsion_geom2(ld_pos(a0r), ld_pos(a1r), ld_pos(a2r), ld_pos(a3r));
       float kk[NPER];
       if (NPER == 3) {
-        kk[0] = __ldg(kp + 3 * t); kk[1] = __ldg(kp + 3 * t + 1); kk[2] = __ldg(kp + 3 * t + 2);
+        kk[0] = lds_f(lv.k + (uint32_t)t * 12u); kk[1] = lds_f(lv.k + (uint32_t)t * 12u + 4u); kk[2] = lds_f(lv.k + (uint32_t)t * 12u + 8u);
       } else {
 #pragma unroll
-        for (int n = 0; n < NPER; ++n) kk[n] = n < nper ? __ldg(kp + (size_t)t * nper + n) : 0.f;
+        for (int n = 0; n < NPER; ++n) kk[n] = n < nper ? lds_f(lv.k + (uint32_t)(t * nper + n) * 4u) : 0.f;
       }
-      F2 e, dedphi;
+      F2 e;
       torsion_series2<NPER>(kk, g.cphi, g.sphi, e, dedphi);
       if (a.offset_torsion) {
         float off = 0.f;
@@ -101,19 +190,21 @@ __device__ __forceinline__ F2 torsion_level(const gb_energy_args& a, const EpCtx
       }
       e_acc = e_acc + e;
       if (FULL) {
-        if (a.x[LV]) st_pair(a.x[LV] + (size_t)t * x.C + x.c, atan2_2(g.sphi, g.cphi), x.second);
-        if (a.tuple_energy[LV]) st_pair(a.tuple_energy[LV] + (size_t)t * x.C + x.c, e, x.second);
-      }
-      if (x.want_grad) {
-        gadd(a0r + x.gd, dedphi, g.p0);                                     // dphi/dx0 = p0
-        gsub(a3r + x.gd, dedphi, g.p3);                                     // dphi/dx3 = -p3
-        const W3 m1 = {g.p0.x + g.u.x, g.p0.y + g.u.y, g.p0.z + g.u.z};
-        const W3 m2 = {g.p3.x + g.u.x, g.p3.y + g.u.y, g.p3.z + g.u.z};
-        gsub(a1r + x.gd, dedphi, m1);                                       // dphi/dx1 = -(p0 + u)
-        gadd(a2r + x.gd, dedphi, m2);                                       // dphi/dx2 = p3 + u
+        const size_t o = (size_t)(t + lv.t0) * x.C + x.c;
+        if (a.x[LV]) st_pair(a.x[LV] + o, atan2_2(g.sphi, g.cphi), x.second);
+        if (a.tuple_energy[LV]) st_pair(a.tuple_energy[LV] + o, e, x.second);
       }
     }
-    __syncthreads();
+    round_wait(x);
+    if (on && x.want_grad) {
+      gadd(a0r + x.gd, dedphi, g.p0);                                     // dphi/dx0 = p0
+      gsub(a3r + x.gd, dedphi, g.p3);                                     // dphi/dx3 = -p3
+      const W3 m1 = {g.p0.x + g.u.x, g.p0.y + g.u.y, g.p0.z + g.u.z};
+      const W3 m2 = {g.p3.x + g.u.x, g.p3.y + g.u.y, g.p3.z + g.u.z};
+      gsub(a1r + x.gd, dedphi, m1);                                       // dphi/dx1 = -(p0 + u)
+      gadd(a2r + x.gd, dedphi, m2);                                       // dphi/dx2 = p3 + u
+    }
+    round_arrive(x);
   }
   return e_acc;
 }
@@ -134,6 +225,8 @@ __global__ void __launch_bounds__(32 * EP_WARPS, MINB) energy_pairs_kernel(const
   float* gs = smem + tile_floats;               // [2][n_at][3][32] force accumulators, one copy per half-warp
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int h = lane >> 4, pl = lane & 15;      // half-warp = tuple slot within the warp, lane's pair of conformations
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 3 * tile_floats);   // round barrier (16-byte slot), then the tuple records
+  float* cursor = smem + 3 * tile_floats + 4;
 
   // One warp per atom row: the tile slice of an atom is 3 * wc contiguous floats.  Columns beyond wc replicate the last
   // valid conformation, so padded lanes compute ordinary finite numbers (never stored).
@@ -149,89 +242,101 @@ __global__ void __launch_bounds__(32 * EP_WARPS, MINB) energy_pairs_kernel(const
       g0[tile_floats + comp * EP_W + cc] = 0.f;
     }
   }
+  const bool on0 = (a.level_mask & 1) && a.n_tuples[0] > 0, on1 = (a.level_mask & 2) && a.n_tuples[1] > 0;
+  const bool on2 = ((a.level_mask >> 2) & 1) && a.n_tuples[2] > 0, on3 = ((a.level_mask >> 3) & 1) && a.n_tuples[3] > 0;
+  EpLevel l0 = {}, l1 = {}, l2 = {}, l3 = {};
+  if (on0) l0 = stage_level<2>(a, 0, b, a0, 1, true, cursor);
+  if (on1) l1 = stage_level<3>(a, 1, b, a0, 1, true, cursor);
+  if (on2) l2 = stage_level<4>(a, 2, b, a0, a.n_per[0], false, cursor);
+  if (on3) l3 = stage_level<4>(a, 3, b, a0, a.n_per[1], false, cursor);
+  if (tid == 0) mbar_init(bar, EP_WARPS);
   __syncthreads();
 
   EpCtx x;
-  x.b = b; x.C = C; x.warp = warp; x.h = h;
+  x.b = b; x.C = C; x.warp = warp; x.h = h; x.lane = lane;
   x.active = 2 * pl < wc;
   x.second = 2 * pl + 1 < wc;
   x.c = c0 + 2 * pl;
   x.want_grad = a.grad != nullptr;
-  // shared address of (global atom index 0, lane's pair): + atom index * EP_ATOM = that atom's row (wraps modulo 2^32)
-  x.xl = (uint32_t)__cvta_generic_to_shared(xs) + (uint32_t)(2 * pl) * 4u - (uint32_t)a0 * EP_ATOM;
+  x.xl = smem_u32(xs) + (uint32_t)(2 * pl) * 4u;               // + local atom index * EP_ATOM = that atom's row, lane's pair
   x.gd = (uint32_t)(tile_floats * 4) * (uint32_t)(1 + h);      // position row -> the same row of force copy h
+  x.bar = smem_u32(bar);
+  x.it = 0;
   F2 e_lvl[4] = {f2(0.f), f2(0.f), f2(0.f), f2(0.f)};
 
   // ---- bonds
-  if ((a.level_mask & 1) && a.n_tuples[0] > 0) {
-    const int r0 = __ldg(a.round_off[0] + b), r1 = __ldg(a.round_off[0] + b + 1);
-    const int32_t* sp = a.sched[0] + (size_t)(r0 + h) * EP_WARPS + warp;
-    int t_next = r0 + h < r1 ? __ldg(sp) : -1;
-    for (int r = r0 + h; r < r1 + h; r += 2) {
-      const int t = t_next;
-      sp += 2 * EP_WARPS;
-      t_next = r + 2 < r1 ? __ldg(sp) : -1;
-      if (t >= 0 && x.active) {
-        const int2 id = __ldg(reinterpret_cast<const int2*>(a.idx[0]) + t);
-        const float k = __ldg(a.k[0] + t), eq = __ldg(a.eq[0] + t);
-        const uint32_t a0r = x.xl + (uint32_t)id.x * EP_ATOM, a1r = x.xl + (uint32_t)id.y * EP_ATOM;
-        const BondGeom2 g = bond_geom2(ld_pos(a0r), ld_pos(a1r));
+  if (on0) {
+    uint32_t sp = l0.sched + (uint32_t)(h * EP_WARPS + warp) * 4u;
+    for (int r = h; r < l0.n_rounds + h; r += 2, sp += 2 * EP_WARPS * 4) {
+      const int t = r < l0.n_rounds ? lds_i(sp) : -1;
+      const bool on = t >= 0 && x.active;
+      uint32_t a0r = 0, a1r = 0;
+      F2 kd = f2(0.f);
+      BondGeom2 g;
+      if (on) {
+        const int i0 = lds_i(l0.idx + (uint32_t)t * 8u), i1 = lds_i(l0.idx + (uint32_t)t * 8u + 4u);
+        const float k = lds_f(l0.k + (uint32_t)t * 4u), eq = lds_f(l0.eq + (uint32_t)t * 4u);
+        a0r = x.xl + (uint32_t)i0 * EP_ATOM; a1r = x.xl + (uint32_t)i1 * EP_ATOM;
+        g = bond_geom2(ld_pos(a0r), ld_pos(a1r));
         const F2 d = g.r - f2(eq);
-        const F2 kd = f2(k) * d;
+        kd = f2(k) * d;
         const F2 e = f2(0.5f) * kd * d;
         e_lvl[0] = e_lvl[0] + e;
         if (FULL) {
-          if (a.x[0]) st_pair(a.x[0] + (size_t)t * C + x.c, g.r, x.second);
-          if (a.tuple_energy[0]) st_pair(a.tuple_energy[0] + (size_t)t * C + x.c, e, x.second);
-        }
-        if (x.want_grad) {
-          gadd(a0r + x.gd, kd, g.d0);
-          gsub(a1r + x.gd, kd, g.d0);
+          const size_t o = (size_t)(t + l0.t0) * C + x.c;
+          if (a.x[0]) st_pair(a.x[0] + o, g.r, x.second);
+          if (a.tuple_energy[0]) st_pair(a.tuple_energy[0] + o, e, x.second);
         }
       }
-      __syncthreads();
+      round_wait(x);
+      if (on && x.want_grad) {
+        gadd(a0r + x.gd, kd, g.d0);
+        gsub(a1r + x.gd, kd, g.d0);
+      }
+      round_arrive(x);
     }
   }
   // ---- angles
-  if ((a.level_mask & 2) && a.n_tuples[1] > 0) {
-    const int r0 = __ldg(a.round_off[1] + b), r1 = __ldg(a.round_off[1] + b + 1);
-    const int32_t* sp = a.sched[1] + (size_t)(r0 + h) * EP_WARPS + warp;
-    int t_next = r0 + h < r1 ? __ldg(sp) : -1;
-    for (int r = r0 + h; r < r1 + h; r += 2) {
-      const int t = t_next;
-      sp += 2 * EP_WARPS;
-      t_next = r + 2 < r1 ? __ldg(sp) : -1;
-      if (t >= 0 && x.active) {
-        const int32_t* ip = a.idx[1] + 3 * t;
-        const int i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2);
-        const float k = __ldg(a.k[1] + t), eq = __ldg(a.eq[1] + t);
-        const uint32_t a0r = x.xl + (uint32_t)i0 * EP_ATOM, a1r = x.xl + (uint32_t)i1 * EP_ATOM, a2r = x.xl + (uint32_t)i2 * EP_ATOM;
-        const AngleGeom2 g = angle_geom2(ld_pos(a0r), ld_pos(a1r), ld_pos(a2r));
+  if (on1) {
+    uint32_t sp = l1.sched + (uint32_t)(h * EP_WARPS + warp) * 4u;
+    for (int r = h; r < l1.n_rounds + h; r += 2, sp += 2 * EP_WARPS * 4) {
+      const int t = r < l1.n_rounds ? lds_i(sp) : -1;
+      const bool on = t >= 0 && x.active;
+      uint32_t a0r = 0, a1r = 0, a2r = 0;
+      F2 kd = f2(0.f);
+      AngleGeom2 g;
+      if (on) {
+        const uint32_t ia = l1.idx + (uint32_t)t * 12u;
+        const int i0 = lds_i(ia), i1 = lds_i(ia + 4u), i2 = lds_i(ia + 8u);
+        const float k = lds_f(l1.k + (uint32_t)t * 4u), eq = lds_f(l1.eq + (uint32_t)t * 4u);
+        a0r = x.xl + (uint32_t)i0 * EP_ATOM; a1r = x.xl + (uint32_t)i1 * EP_ATOM; a2r = x.xl + (uint32_t)i2 * EP_ATOM;
+        g = angle_geom2(ld_pos(a0r), ld_pos(a1r), ld_pos(a2r));
         const F2 d = g.theta - f2(eq);
-        const F2 kd = f2(k) * d;
+        kd = f2(k) * d;
         const F2 e = f2(0.5f) * kd * d;
         e_lvl[1] = e_lvl[1] + e;
         if (FULL) {
-          if (a.x[1]) st_pair(a.x[1] + (size_t)t * C + x.c, g.theta, x.second);
-          if (a.tuple_energy[1]) st_pair(a.tuple_energy[1] + (size_t)t * C + x.c, e, x.second);
-        }
-        if (x.want_grad) {
-          gadd(a0r + x.gd, kd, g.d0);
-          gadd(a2r + x.gd, kd, g.d2);
-          const W3 dm = {g.d0.x + g.d2.x, g.d0.y + g.d2.y, g.d0.z + g.d2.z};
-          gsub(a1r + x.gd, kd, dm);
+          const size_t o = (size_t)(t + l1.t0) * C + x.c;
+          if (a.x[1]) st_pair(a.x[1] + o, g.theta, x.second);
+          if (a.tuple_energy[1]) st_pair(a.tuple_energy[1] + o, e, x.second);
         }
       }
-      __syncthreads();
+      round_wait(x);
+      if (on && x.want_grad) {
+        gadd(a0r + x.gd, kd, g.d0);
+        gadd(a2r + x.gd, kd, g.d2);
+        const W3 dm = {g.d0.x + g.d2.x, g.d0.y + g.d2.y, g.d0.z + g.d2.z};
+        gsub(a1r + x.gd, kd, dm);
+      }
+      round_arrive(x);
     }
   }
   // ---- torsions
-  if (((a.level_mask >> 2) & 1) && a.n_tuples[2] > 0)
-    e_lvl[2] = a.n_per[0] == 3 ? torsion_level<FULL, 2, 3>(a, x) : torsion_level<FULL, 2, GB_MAX_PERIODICITY>(a, x);
-  if (((a.level_mask >> 3) & 1) && a.n_tuples[3] > 0)
-    e_lvl[3] = a.n_per[1] == 3 ? torsion_level<FULL, 3, 3>(a, x) : torsion_level<FULL, 3, GB_MAX_PERIODICITY>(a, x);
+  if (on2) e_lvl[2] = a.n_per[0] == 3 ? torsion_level<FULL, 2, 3>(a, x, l2) : torsion_level<FULL, 2, GB_MAX_PERIODICITY>(a, x, l2);
+  if (on3) e_lvl[3] = a.n_per[1] == 3 ? torsion_level<FULL, 3, 3>(a, x, l3) : torsion_level<FULL, 3, GB_MAX_PERIODICITY>(a, x, l3);
+  __syncthreads();
 
-  // forces back to global, coalesced: the two copies are summed in a fixed order (the last round ended with a barrier)
+  // forces back to global, coalesced: the two copies are summed in a fixed order
   if (x.want_grad) {
     for (int at = warp; at < n_at; at += EP_WARPS) {
       float* dst = a.grad + ((size_t)(a0 + at) * C + c0) * 3;
@@ -265,17 +370,20 @@ __global__ void __launch_bounds__(32 * EP_WARPS, MINB) energy_pairs_kernel(const
   }
 }
 
-// handled = false: the pack carries no schedule or the molecule tile does not fit -> the caller falls back
+// handled = false: the pack carries no schedule / per-molecule maxima, or the molecule's tiles + records do not fit
 int launch_energy_pairs(const gb_energy_args* a, cudaStream_t stream, bool* handled) {
   *handled = false;
   const int C = a->n_confs, B = a->n_mols;
   bool have = a->sched_groups == EP_WARPS;
-  for (int l = 0; l < 4 && have; ++l)
-    if (a->n_tuples[l] > 0 && ((a->level_mask >> l) & 1)) have = a->sched[l] && a->round_off[l];
-  for (int l = 2; l < 4 && have; ++l)   // 16-byte index loads
-    if (a->n_tuples[l] > 0 && ((a->level_mask >> l) & 1)) have = ((uintptr_t)a->idx[l] & 15) == 0;
-  if (have && a->n_tuples[0] > 0 && (a->level_mask & 1)) have = ((uintptr_t)a->idx[0] & 7) == 0;
-  size_t smem = (size_t)a->max_atoms_per_mol * 3 * EP_W * 3 * sizeof(float);
+  int rec_words = 4;   // the round barrier
+  const int Ls[4] = {2, 3, 4, 4};
+  for (int l = 0; l < 4 && have; ++l) {
+    if (!(a->n_tuples[l] > 0 && ((a->level_mask >> l) & 1))) continue;
+    have = a->sched[l] && a->round_off[l] && a->max_tuples_per_mol[l] > 0 && a->max_rounds_per_mol[l] > 0;
+    const int width = l < 2 ? 1 : a->n_per[l - 2];
+    rec_words += ep_level_words(a->max_rounds_per_mol[l], a->max_tuples_per_mol[l], Ls[l], width, l < 2);
+  }
+  size_t smem = (size_t)a->max_atoms_per_mol * 3 * EP_W * 3 * sizeof(float) + (size_t)rec_words * 4;
   if (smem < (size_t)4 * 16 * EP_W * sizeof(float)) smem = (size_t)4 * 16 * EP_W * sizeof(float);
   if (!have || a->max_atoms_per_mol <= 0 || smem > 200 * 1024) return GB_OK;
   bool full = false;

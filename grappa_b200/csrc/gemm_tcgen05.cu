@@ -36,40 +36,13 @@
 
 #include "common.cuh"
 #include "gemm_epilogue.cuh"
+#include "mbar.cuh"
 
 namespace gb {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;          // floats per stage along K = one 128-byte swizzle atom
 constexpr int TC_THREADS = 320;        // TMA warp + MMA warp + 8 epilogue warps
-constexpr uint32_t SPIN_LIMIT = 1u << 28;
-
-// ---- PTX wrappers ---------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done = 0, spins = 0;
-  while (!done) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (!done && ++spins > SPIN_LIMIT) __trap();   // never hang the device: surface a launch failure instead
-  }
-}
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -171,17 +144,17 @@ __device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t a_des
 // generic-proxy shared-memory writes (the converter's st.shared) -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// {bf16(hi_elem) << 16 | bf16(lo_elem)}, round to nearest even
-__device__ __forceinline__ uint32_t cvt_bf16x2(float hi_elem, float lo_elem) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
-  return r;
-}
-// (a0, a1) -> packed bf16 pair of the leading parts and packed bf16 pair of the remainders (a0 in the low half)
+// (a0, a1) -> packed bf16 pair of the leading parts and packed bf16 pair of the remainders (a0 in the low half).
+// Rounding to bf16 is done on the BIT PATTERN with integer adds (+ 0x8000, keep the upper half: round half away from
+// zero), not with cvt.rn.bf16x2.f32: F2FP issues on the XU pipe (one warp instruction per ~7 cycles per SM -- ncu showed
+// that pipe 84 % busy and the converter warps 3x slower than the MMAs they feed); IADD / LOP / PRMT / FADD run on the
+// ALU and FMA pipes at full rate.  hi = rn8(a); lo = rn8(a - hi): a - hi is exact, |lo| <= 2^-9 |a|, so hi + lo carries
+// 16 significant bits and the dropped lo * lo term is below 2^-17 relative with no sign preference.
 __device__ __forceinline__ void split_pair(float a0, float a1, uint32_t& hi, uint32_t& lo) {
-  hi = cvt_bf16x2(a1, a0);
-  const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
-  lo = cvt_bf16x2(a1 - h1, a0 - h0);
+  const uint32_t t0 = __float_as_uint(a0) + 0x8000u, t1 = __float_as_uint(a1) + 0x8000u;
+  hi = __byte_perm(t0, t1, 0x7632);                         // {t1[31:16], t0[31:16]}
+  const float l0 = a0 - __uint_as_float(t0 & 0xffff0000u), l1 = a1 - __uint_as_float(t1 & 0xffff0000u);
+  lo = __byte_perm(__float_as_uint(l0) + 0x8000u, __float_as_uint(l1) + 0x8000u, 0x7632);
 }
 __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo) {
   split_pair(v[0], v[1], hi.x, lo.x);

@@ -52,6 +52,8 @@ def _fill_common(a: _lib.EnergyArgs, pack, xyz, ks, eqs, n_per, level_mask, offs
         for l in range(4):
             a.sched[l] = pack.ptr(f"sched{l}")
             a.round_off[l] = pack.ptr(f"round_off{l}")
+            a.max_tuples_per_mol[l] = pack.max_tuples_per_mol[l]
+            a.max_rounds_per_mol[l] = pack.max_rounds_per_mol[l]
 
 
 class _EnergyFn(torch.autograd.Function):

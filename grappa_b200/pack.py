@@ -95,9 +95,13 @@ class PackedBatch:
             host[f"inv_ent{l}"] = order
         # conflict-free rounds for the energy kernel (host C++, include/grappa_b200.h)
         self.sched_groups = ENERGY_SCHED_GROUPS
+        self.max_tuples_per_mol, self.max_rounds_per_mol = [], []
         for l, L in enumerate(TUPLE_LEN):
             ro, sc = conflict_free_rounds(host[f"idx{l}"], host[f"tup_off{l}"], self.n_mols, L, self.sched_groups)
             host[f"round_off{l}"], host[f"sched{l}"] = ro, sc
+            # largest molecule per level: sizes the energy kernel's shared-memory copy of one molecule's records
+            self.max_tuples_per_mol.append(int(np.diff(host[f"tup_off{l}"]).max()) if self.n_mols else 0)
+            self.max_rounds_per_mol.append(int(np.diff(ro).max()) if self.n_mols else 0)
         # bonded graph CSR by destination
         src, dst = g.edges(etype="n1_edge")
         src = src.detach().cpu().numpy().astype(np.int64)
@@ -161,7 +165,7 @@ class PackedBatch:
         """Everything the host bakes into kernel arguments / grids: two packs with equal signatures can share a
         captured CUDA graph (training.Trainer)."""
         return (self.n_atoms, self.n_mols, self.n_edges, tuple(self.n_tuples), self.max_atoms_per_mol, self.max_degree,
-                tuple(self._sizes))
+                tuple(self._sizes), tuple(self.max_tuples_per_mol), tuple(self.max_rounds_per_mol))
 
     def copy_from(self, other: "PackedBatch"):
         """Overwrite the device tables in place with another pack of the same signature (one async H2D copy)."""

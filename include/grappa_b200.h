@@ -25,7 +25,7 @@ extern "C" {
 #define GB_ERR_INVALID (-1) /* bad argument / unsupported shape */
 #define GB_ERR_CUDA (-2)    /* CUDA runtime / launch failure     */
 
-#define GB_ABI_VERSION 2
+#define GB_ABI_VERSION 3
 
 const char* grappa_b200_last_error(void);
 int grappa_b200_abi_version(void);
@@ -92,6 +92,10 @@ typedef struct {
   const int32_t* sched[4];     /* [n_rounds_l, sched_groups] tuple index or -1                         */
   const int32_t* round_off[4]; /* [n_mols+1] first round of each molecule at level l                   */
   int32_t sched_groups;        /* tuples per round (0 = no schedule)                                   */
+  /* per-molecule maxima of the batch (host-computed; 0 = unknown): size the shared-memory copy of one molecule's
+   * tuple records in the packed-pair kernel (variant 5) */
+  int32_t max_tuples_per_mol[4];
+  int32_t max_rounds_per_mol[4];
 } gb_energy_args;
 
 /* Conflict-free processing order for K13 (host code).  Within one molecule and level, tuples are packed first-fit

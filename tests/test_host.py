@@ -21,7 +21,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert len(names) >= 30
     for n in names:
         assert hasattr(lib, n), f"libgrappa_b200.so does not export {n}"
-    assert lib.grappa_b200_abi_version() == 2
+    assert lib.grappa_b200_abi_version() == 3
     assert isinstance(_lib.launch_count(), int)
 
 
