@@ -8,41 +8,10 @@
 // polynomial (|error| < 1e-7 rad, fitted on [0, 1] in t^2; CUDA's atan2f costs ~40 scalar instructions per value).
 #pragma once
 #include "energy_math.cuh"
+#include "f32x2.cuh"
 
 namespace gb {
 
-struct F2 {
-  unsigned long long v;
-};
-
-__device__ __forceinline__ F2 f2(float a, float b) {
-  F2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ F2 f2(float a) { return f2(a, a); }
-__device__ __forceinline__ float lo(F2 a) { return __uint_as_float((unsigned)(a.v & 0xffffffffull)); }
-__device__ __forceinline__ float hi(F2 a) { return __uint_as_float((unsigned)(a.v >> 32)); }
-__device__ __forceinline__ F2 operator+(F2 a, F2 b) {
-  F2 r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
-  return r;
-}
-__device__ __forceinline__ F2 operator-(F2 a, F2 b) {
-  F2 r;
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
-  return r;
-}
-__device__ __forceinline__ F2 operator*(F2 a, F2 b) {
-  F2 r;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
-  return r;
-}
-__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c) {
-  F2 r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
-  return r;
-}
 // per half: x > 0 ? rsqrt(x) : 0   /   x > 0 ? 1 / x : 0
 __device__ __forceinline__ F2 rsqrt_pos(F2 a) {
   const float x = lo(a), y = hi(a);

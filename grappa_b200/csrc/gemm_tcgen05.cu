@@ -35,6 +35,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "f32x2.cuh"
 #include "gemm_epilogue.cuh"
 #include "mbar.cuh"
 
@@ -144,23 +145,26 @@ __device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t a_des
 // generic-proxy shared-memory writes (the converter's st.shared) -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// (a0, a1) -> packed bf16 pair of the leading parts and packed bf16 pair of the remainders (a0 in the low half).
-// Rounding to bf16 is done on the BIT PATTERN with integer adds (+ 0x8000, keep the upper half: round half away from
-// zero), not with cvt.rn.bf16x2.f32: F2FP issues on the XU pipe (one warp instruction per ~7 cycles per SM -- ncu showed
-// that pipe 84 % busy and the converter warps 3x slower than the MMAs they feed); IADD / LOP / PRMT / FADD run on the
-// ALU and FMA pipes at full rate.  hi = rn8(a); lo = rn8(a - hi): a - hi is exact, |lo| <= 2^-9 |a|, so hi + lo carries
-// 16 significant bits and the dropped lo * lo term is below 2^-17 relative with no sign preference.
-__device__ __forceinline__ void split_pair(float a0, float a1, uint32_t& hi, uint32_t& lo) {
-  const uint32_t t0 = __float_as_uint(a0) + 0x8000u, t1 = __float_as_uint(a1) + 0x8000u;
-  hi = __byte_perm(t0, t1, 0x7632);                         // {t1[31:16], t0[31:16]}
-  const float l0 = a0 - __uint_as_float(t0 & 0xffff0000u), l1 = a1 - __uint_as_float(t1 & 0xffff0000u);
-  lo = __byte_perm(__float_as_uint(l0) + 0x8000u, __float_as_uint(l1) + 0x8000u, 0x7632);
+// Two fp32 values (one 64-bit register) -> packed bf16 pair of the leading parts and packed bf16 pair of the remainders.
+//   hi = rn_bf16(a) by Veltkamp's splitting in PACKED fp32 arithmetic: c = a * (2^16 + 1); hi = c - (c - a) keeps the
+//        leading 8 significant bits of a, rounded to nearest (identical to cvt.rn.bf16.f32 on every finite input tested);
+//   lo = a - hi is exact in fp32; its leading 8 bits (truncated: lo has no preferred sign relative to a) go to the lo plane.
+// hi + lo carries 16 significant bits (|error| <= 2^-16 |a|, unbiased).  4 packed FP instructions + 2 PRMT per PAIR.
+// History (ncu, profiles/r2_summary.md): cvt.rn.bf16x2.f32 (F2FP) runs on the XU pipe, ~7 cycles per warp instruction
+// per SM -- 84 % busy, converter 3x slower than the MMAs; integer rounding (IADD + LOP + FADD + IADD + PRMT per element)
+// left one converter warp per scheduler at 0.24 IPC with ~490 instructions per k-block.
+__device__ __forceinline__ void split_pair2(F2 a, uint32_t& hi, uint32_t& lo) {
+  const F2 c = a * f2(65537.0f);
+  const F2 h = c - (c - a);
+  const F2 l = a - h;
+  hi = __byte_perm((uint32_t)(h.v & 0xffffffffull), (uint32_t)(h.v >> 32), 0x7632);   // {h1[31:16], h0[31:16]}
+  lo = __byte_perm((uint32_t)(l.v & 0xffffffffull), (uint32_t)(l.v >> 32), 0x7632);
 }
 __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo) {
-  split_pair(v[0], v[1], hi.x, lo.x);
-  split_pair(v[2], v[3], hi.y, lo.y);
-  split_pair(v[4], v[5], hi.z, lo.z);
-  split_pair(v[6], v[7], hi.w, lo.w);
+  split_pair2(f2(v[0], v[1]), hi.x, lo.x);
+  split_pair2(f2(v[2], v[3]), hi.y, lo.y);
+  split_pair2(f2(v[4], v[5]), hi.z, lo.z);
+  split_pair2(f2(v[6], v[7]), hi.w, lo.w);
 }
 
 constexpr int TC_CONV_WARPS = 4;   // converter warps of the bf16x3 kernel (warps 10..13)
@@ -176,7 +180,7 @@ template <int ROWS, bool MN_MAJOR>
 __device__ __forceinline__ void convert_tile(const uint8_t* __restrict__ raw, uint8_t* __restrict__ conv, int cw, int lane) {
   if (!MN_MAJOR) {
     const int x = lane & 7, c = lane >> 3;
-#pragma unroll 2
+#pragma unroll
     for (int i = cw; i < ROWS / 8; i += TC_CONV_WARPS) {
       const uint32_t rowoff = (uint32_t)(8 * i + x) * 128u;
       const float4 v0 = *reinterpret_cast<const float4*>(raw + rowoff + (((2 * c) ^ x) << 4));
@@ -189,7 +193,7 @@ __device__ __forceinline__ void convert_tile(const uint8_t* __restrict__ raw, ui
     }
   } else {
     const int q = cw;   // k-group: k = 8 q .. 8 q + 7 of this k-block
-#pragma unroll 2
+#pragma unroll
     for (int j = 0; j < ROWS / 32; ++j) {
       const float* src = reinterpret_cast<const float*>(raw + j * (TC_BK * 128) + q * (8 * 128)) + lane;
       float v[8];
@@ -599,7 +603,8 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           }
         }
         if (c0 == 0) {
-          mbar_wait(&acc_full[as], aph);
+          if (X3) mbar_wait_backoff(&acc_full[as], aph);   // the converter warps share these schedulers: do not spin next to them
+          else mbar_wait(&acc_full[as], aph);
           tc_fence_after();
         }
         float v[32];

@@ -31,5 +31,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (!done && ++spins > SPIN_LIMIT) __trap();   // never hang the device: surface a launch failure instead
   }
 }
+// the same wait for warps that are NOT on the critical path (epilogue warps waiting for an accumulator): sleeps between
+// polls instead of spinning, so the polling loop does not take issue slots from the warps that feed the tensor core
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns = 128) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(ns);
+    if (++spins > (SPIN_LIMIT >> 6)) __trap();
+  }
+}
 
 }  // namespace gb
