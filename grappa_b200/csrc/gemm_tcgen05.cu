@@ -153,18 +153,22 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 // History (ncu, profiles/r2_summary.md): cvt.rn.bf16x2.f32 (F2FP) runs on the XU pipe, ~7 cycles per warp instruction
 // per SM -- 84 % busy, converter 3x slower than the MMAs; integer rounding (IADD + LOP + FADD + IADD + PRMT per element)
 // left one converter warp per scheduler at 0.24 IPC with ~490 instructions per k-block.
-__device__ __forceinline__ void split_pair2(F2 a, uint32_t& hi, uint32_t& lo) {
-  const F2 c = a * f2(65537.0f);
+// `z` is a packed zero the compiler cannot see through: c must be ROUNDED before c - a is formed, but ptxas contracts a
+// packed multiply into the dependent add / sub even with explicit .rn (c - a became fma(a, 65537, -a) = 65536 a exactly,
+// the lo plane lost its meaning and results fell back to bf16 accuracy).  With c = fma(a, K, z) there is no bare multiply
+// left to contract.
+__device__ __forceinline__ void split_pair2(F2 a, F2 z, uint32_t& hi, uint32_t& lo) {
+  const F2 c = fma2(a, f2(65537.0f), z);
   const F2 h = c - (c - a);
   const F2 l = a - h;
   hi = __byte_perm((uint32_t)(h.v & 0xffffffffull), (uint32_t)(h.v >> 32), 0x7632);   // {h1[31:16], h0[31:16]}
   lo = __byte_perm((uint32_t)(l.v & 0xffffffffull), (uint32_t)(l.v >> 32), 0x7632);
 }
-__device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo) {
-  split_pair2(f2(v[0], v[1]), hi.x, lo.x);
-  split_pair2(f2(v[2], v[3]), hi.y, lo.y);
-  split_pair2(f2(v[4], v[5]), hi.z, lo.z);
-  split_pair2(f2(v[6], v[7]), hi.w, lo.w);
+__device__ __forceinline__ void split8(const float (&v)[8], F2 z, uint4& hi, uint4& lo) {
+  split_pair2(f2(v[0], v[1]), z, hi.x, lo.x);
+  split_pair2(f2(v[2], v[3]), z, hi.y, lo.y);
+  split_pair2(f2(v[4], v[5]), z, hi.z, lo.z);
+  split_pair2(f2(v[6], v[7]), z, hi.w, lo.w);
 }
 
 constexpr int TC_CONV_WARPS = 4;   // converter warps of the bf16x3 kernel (warps 10..13)
@@ -177,7 +181,7 @@ constexpr int TC_CONV_WARPS = 4;   // converter warps of the bf16x3 kernel (warp
 //                    reads one 128-byte row per instruction), two 16-byte writes into row mn (8 consecutive rows per
 //                    quarter-warp -> 8 distinct chunk positions).
 template <int ROWS, bool MN_MAJOR>
-__device__ __forceinline__ void convert_tile(const uint8_t* __restrict__ raw, uint8_t* __restrict__ conv, int cw, int lane) {
+__device__ __forceinline__ void convert_tile(const uint8_t* __restrict__ raw, uint8_t* __restrict__ conv, int cw, int lane, F2 z) {
   if (!MN_MAJOR) {
     const int x = lane & 7, c = lane >> 3;
 #pragma unroll
@@ -187,7 +191,7 @@ __device__ __forceinline__ void convert_tile(const uint8_t* __restrict__ raw, ui
       const float4 v1 = *reinterpret_cast<const float4*>(raw + rowoff + (((2 * c + 1) ^ x) << 4));
       const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
       uint4 hi, lo;
-      split8(v, hi, lo);
+      split8(v, z, hi, lo);
       *reinterpret_cast<uint4*>(conv + rowoff + ((c ^ x) << 4)) = hi;
       *reinterpret_cast<uint4*>(conv + rowoff + (((4 + c) ^ x) << 4)) = lo;
     }
@@ -200,7 +204,7 @@ __device__ __forceinline__ void convert_tile(const uint8_t* __restrict__ raw, ui
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = src[i * 32];
       uint4 hi, lo;
-      split8(v, hi, lo);
+      split8(v, z, hi, lo);
       const int r = 32 * j + lane;
       uint8_t* row = conv + (uint32_t)r * 128u;
       *reinterpret_cast<uint4*>(row + ((q ^ (r & 7)) << 4)) = hi;
@@ -529,6 +533,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     // ===================== converter warps (bf16x3): raw fp32 stage -> [bf16 hi | bf16 lo] stage =====================
     const int cw = warp - TC_THREADS / 32;
     const uint32_t cfull_leader = PAIR ? mapa_rank(smem_u32(&cfull[0]), 0) : 0u;
+    const F2 zero2 = f2(__int_as_float(p.n_items >> 30));   // 0.0f the compiler cannot fold (see split_pair2)
     uint32_t it = 0;
     for (int item = first_item; item < n_items; item += item_stride) {
       const TcProblem& q = p.pr[GROUPED ? find_problem(p, item) : 0];
@@ -546,8 +551,8 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         tc_fence_after();
         const uint8_t* raw = smem + s * STAGE_BYTES;
         uint8_t* cv = conv_base + c * STAGE_BYTES;
-        convert_tile<TC_BM, TA != 0>(raw, cv, cw, lane);
-        convert_tile<B_ROWS, TB != 0>(raw + A_BYTES, cv + A_BYTES, cw, lane);
+        convert_tile<TC_BM, TA != 0>(raw, cv, cw, lane, zero2);
+        convert_tile<B_ROWS, TB != 0>(raw + A_BYTES, cv + A_BYTES, cw, lane, zero2);
         // generic-proxy writes -> visible to the tensor core's operand reads.  The .shared::cta form is one FENCE.VIEW.ASYNC.S;
         // the unqualified fence also issues MEMBAR.ALL.GPU (ncu: 9 % of all stall samples, the converter warps 3x slower)
         fence_proxy_async_smem();

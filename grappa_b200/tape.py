@@ -38,15 +38,17 @@ def concurrency() -> bool:
     return _CONCURRENT
 
 
-def helper_streams(n: int, tag: str):
-    """`n` cached helper streams tied to the current stream (one set per (device, current stream, tag))."""
+def helper_streams(n: int, tag: str, priorities=None):
+    """`n` cached helper streams tied to the current stream (one set per (device, current stream, tag)).  `priorities`:
+    optional CUDA stream priority per stream (0 = default, negative = scheduled first)."""
     cur = torch.cuda.current_stream()
     out = []
     for i in range(n):
-        key = (cur.device, cur.cuda_stream, tag, i)
+        prio = 0 if priorities is None else int(priorities[i])
+        key = (cur.device, cur.cuda_stream, tag, i, prio)
         st = _side_streams.get(key)
         if st is None:
-            st = torch.cuda.Stream(device=cur.device)
+            st = torch.cuda.Stream(device=cur.device, priority=prio)
             _side_streams[key] = st
         out.append(st)
     return out
@@ -103,7 +105,8 @@ class Tape:
             yield
             return
         if self._side is None:
-            self._side = helper_streams(1, "wgrad")[0]
+            cur = torch.cuda.current_stream()
+            self._side = helper_streams(1, "wgrad", [getattr(cur, "priority", 0)])[0]   # the branch inherits its stage's priority
         ev = torch.cuda.Event()
         ev.record()
         self._side.wait_event(ev)
