@@ -844,7 +844,12 @@ int gemm_tcgen05(const gb_gemm_args* a, cudaStream_t stream, bool* handled) {
   const bool can_split = a->workspace != nullptr && a->colsum == nullptr && (K + TC_BK - 1) / TC_BK >= 16;
   static const int pair_min_k = [] { const char* e = getenv("GRAPPA_B200_GEMM_PAIR_MINK"); return e ? atoi(e) : 1024; }();   // tuning aids
   static const int pair_min_m = [] { const char* e = getenv("GRAPPA_B200_GEMM_PAIR_MINM"); return e ? atoi(e) : 0; }();
-  bool pair = M > TC_BM && N >= 128 && forced_pair != 0 && ((K >= pair_min_k && (K >= 1024 || M >= pair_min_m)) || forced_pair == 1);
+  // bf16x3: the converter doubles the shared-memory traffic per k-block (TMA 32 KB + converter 64 KB + three MMAs' operand
+  // reads 48 KB against 64 KB for TF32) and the kernel is bound by exactly that (ncu: LSU + tensor wavefronts 71 % of the
+  // shared-memory pipe); a CTA pair computes twice the FLOPs per staged byte, so pairs are used from K = 128 on.
+  static const int pair_min_k_x3 = [] { const char* e = getenv("GRAPPA_B200_GEMM_PAIR_MINK_X3"); return e ? atoi(e) : 128; }();
+  const int min_k = x3 ? pair_min_k_x3 : pair_min_k;
+  bool pair = M > TC_BM && N >= 128 && forced_pair != 0 && ((K >= min_k && (K >= 1024 || x3 || M >= pair_min_m)) || forced_pair == 1);
   int units = 0, tiles_m = 0, BN = 128;
   for (int attempt = 0; attempt < 2; ++attempt) {
     const int bm = pair ? 2 * TC_BM : TC_BM;
@@ -853,7 +858,8 @@ int gemm_tcgen05(const gb_gemm_args* a, cudaStream_t stream, bool* handled) {
     BN = 128;
     if (can_split && ((N + 127) / 128) * tiles_m * 2 <= units) BN = (N % 256 == 0) ? 256 : (N >= 128 ? 128 : 64);
     else if (N <= 64 || ((N + 127) / 128) * tiles_m < units / 2) BN = 64;
-    else if (N % 256 == 0 && (N / 256) * tiles_m >= units) BN = 256;
+    else if (N % 256 == 0 && (N / 256) * tiles_m >= (x3 && pair ? units / 2 : units)) BN = 256;   // bf16x3 pairs: one wave of
+    // 256-wide tiles on half the machine beats two waves of 128-wide ones (half the shared-memory traffic per FLOP)
     if (x3 && !pair && BN == 256) BN = 128;   // no single-CTA 128 x 256 tile in the bf16x3 kernel (shared-memory budget)
     static const int forced = [] { const char* e = getenv("GRAPPA_B200_GEMM_BN"); return e ? atoi(e) : 0; }();   // tuning aid
     if ((forced == 64 || forced == 128 || forced == 256) && (forced != 256 || (N % 256 == 0 && (pair || !x3)))) BN = forced;
