@@ -26,8 +26,8 @@
 // (hi = rn(a), lo = rn(a - hi): 16 mantissa bits together) and the MMA warp issues hi*hi + lo*hi + hi*lo with
 // kind::f16 -- three bf16 MMAs run at 1.5x the time of one TF32 MMA and the split operands take exactly the bytes of the
 // fp32 ones, so HBM / L2 traffic is unchanged and nothing but this kernel knows about the format:
-//     TMA (fp32 tile, as above) -> raw ring -> converter warps -> conv ring -> tcgen05.mma kind::f16 x3 -> TMEM
-// conv tile = rows x 128 B, row = [32 bf16 hi | 32 bf16 lo] of one 32-float k-block, ALWAYS K-major SWIZZLE_128B: the
+//     TMA (fp32 tile, as above) -> ring stage -> converter warps rewrite the stage in place -> tcgen05.mma kind::f16 x3 -> TMEM
+// converted tile = rows x 128 B, row = [32 bf16 hi | 32 bf16 lo] of one 32-float k-block, ALWAYS K-major SWIZZLE_128B: the
 // same shared-memory descriptor form the TF32 path uses for K-major fp32 (hi part at +0 / +32, lo part at +64 / +96
 // bytes inside the swizzle atom).  MN-major fp32 operands (dgrad / wgrad) are transposed by the converter on the fly
 // (un-swizzled TMA boxes, conflict-free 4-byte column reads), so the MMA only ever sees K-major bf16.
@@ -173,42 +173,58 @@ __device__ __forceinline__ void split8(const float (&v)[8], F2 z, uint4& hi, uin
 
 constexpr int TC_CONV_WARPS = 4;   // converter warps of the bf16x3 kernel (warps 10..13)
 
-// One operand tile of one k-block: fp32 (as TMA staged it) -> [32 bf16 hi | 32 bf16 lo] rows, K-major SWIZZLE_128B
-// (16-byte chunk j of row r lives at chunk j ^ (r & 7) of the row's 128 bytes).  `cw` = converter warp 0..3.
+// One operand tile of one k-block, converted IN PLACE: fp32 (as TMA staged it) -> [32 bf16 hi | 32 bf16 lo] rows, K-major
+// SWIZZLE_128B (16-byte chunk j of row r lives at chunk j ^ (r & 7) of the row's 128 bytes).  The converted tile takes
+// exactly the bytes of the fp32 tile, so the operand ring keeps the depth of the TF32 kernel (a separate ring of
+// converted tiles left room for only 3 raw stages -- too little data in flight to cover the TMA latency).  Every warp
+// reads ALL the fp32 data of the rows / boxes it owns, __syncwarp()s, then overwrites them.  `cw` = converter warp 0..3.
 //   K-major source : the fp32 tile has the same swizzle; lane -> (row 8 i + lane % 8, floats 8 c .. 8 c + 7, c = lane / 8):
-//                    two 16-byte reads, two 16-byte writes, every quarter-warp touches 8 distinct chunk positions.
-//   MN-major source: un-swizzled boxes [32 k][32 mn]; lane = mn column, eight 4-byte reads down the k-group cw (a warp
-//                    reads one 128-byte row per instruction), two 16-byte writes into row mn (8 consecutive rows per
-//                    quarter-warp -> 8 distinct chunk positions).
+//                    two 16-byte reads, two 16-byte writes into the same row, every quarter-warp touches 8 distinct
+//                    chunk positions; the four lanes of a row sit in one warp.
+//   MN-major source: un-swizzled boxes [32 k][32 mn] = the 4 KB the 32 converted rows of those mn occupy; a warp owns a
+//                    whole box: lane = mn column, 32 four-byte reads down k (one 128-byte row per instruction), eight
+//                    16-byte writes into row mn (8 consecutive rows per quarter-warp -> 8 distinct chunk positions).
 template <int ROWS, bool MN_MAJOR>
-__device__ __forceinline__ void convert_tile(const uint8_t* __restrict__ raw, uint8_t* __restrict__ conv, int cw, int lane, F2 z) {
+__device__ __forceinline__ void convert_tile(uint8_t* __restrict__ tile, int cw, int lane, F2 z) {
   if (!MN_MAJOR) {
     const int x = lane & 7, c = lane >> 3;
+    constexpr int IT = ROWS / 8 / TC_CONV_WARPS;       // 4 (128 rows) or 2 (64 rows)
+    float4 v0[IT], v1[IT];
 #pragma unroll
-    for (int i = cw; i < ROWS / 8; i += TC_CONV_WARPS) {
-      const uint32_t rowoff = (uint32_t)(8 * i + x) * 128u;
-      const float4 v0 = *reinterpret_cast<const float4*>(raw + rowoff + (((2 * c) ^ x) << 4));
-      const float4 v1 = *reinterpret_cast<const float4*>(raw + rowoff + (((2 * c + 1) ^ x) << 4));
-      const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    for (int i = 0; i < IT; ++i) {
+      const uint32_t rowoff = (uint32_t)(8 * (cw + i * TC_CONV_WARPS) + x) * 128u;
+      v0[i] = *reinterpret_cast<const float4*>(tile + rowoff + (((2 * c) ^ x) << 4));
+      v1[i] = *reinterpret_cast<const float4*>(tile + rowoff + (((2 * c + 1) ^ x) << 4));
+    }
+    __syncwarp();    // every lane of the rows has its fp32 values before any lane overwrites the rows
+#pragma unroll
+    for (int i = 0; i < IT; ++i) {
+      const uint32_t rowoff = (uint32_t)(8 * (cw + i * TC_CONV_WARPS) + x) * 128u;
+      const float v[8] = {v0[i].x, v0[i].y, v0[i].z, v0[i].w, v1[i].x, v1[i].y, v1[i].z, v1[i].w};
       uint4 hi, lo;
       split8(v, z, hi, lo);
-      *reinterpret_cast<uint4*>(conv + rowoff + ((c ^ x) << 4)) = hi;
-      *reinterpret_cast<uint4*>(conv + rowoff + (((4 + c) ^ x) << 4)) = lo;
+      *reinterpret_cast<uint4*>(tile + rowoff + ((c ^ x) << 4)) = hi;
+      *reinterpret_cast<uint4*>(tile + rowoff + (((4 + c) ^ x) << 4)) = lo;
     }
   } else {
-    const int q = cw;   // k-group: k = 8 q .. 8 q + 7 of this k-block
+#pragma unroll 1
+    for (int j = cw; j < ROWS / 32; j += TC_CONV_WARPS) {
+      uint8_t* box = tile + j * (TC_BK * 128);
+      const float* src = reinterpret_cast<const float*>(box) + lane;
+      float v[32];
 #pragma unroll
-    for (int j = 0; j < ROWS / 32; ++j) {
-      const float* src = reinterpret_cast<const float*>(raw + j * (TC_BK * 128) + q * (8 * 128)) + lane;
-      float v[8];
+      for (int k = 0; k < 32; ++k) v[k] = src[k * 32];
+      __syncwarp();
+      uint8_t* row = box + (uint32_t)lane * 128u;      // converted row of mn = 32 j + lane
+      const int x = lane & 7;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = src[i * 32];
-      uint4 hi, lo;
-      split8(v, z, hi, lo);
-      const int r = 32 * j + lane;
-      uint8_t* row = conv + (uint32_t)r * 128u;
-      *reinterpret_cast<uint4*>(row + ((q ^ (r & 7)) << 4)) = hi;
-      *reinterpret_cast<uint4*>(row + (((4 + q) ^ (r & 7)) << 4)) = lo;
+      for (int q = 0; q < 4; ++q) {
+        const float w[8] = {v[8 * q], v[8 * q + 1], v[8 * q + 2], v[8 * q + 3], v[8 * q + 4], v[8 * q + 5], v[8 * q + 6], v[8 * q + 7]};
+        uint4 hi, lo;
+        split8(w, z, hi, lo);
+        *reinterpret_cast<uint4*>(row + ((q ^ x) << 4)) = hi;
+        *reinterpret_cast<uint4*>(row + (((4 + q) ^ x) << 4)) = lo;
+      }
     }
   }
 }
@@ -299,15 +315,13 @@ struct TcCfg {
   static constexpr int B_ROWS = BN / CTAS;            // rows of the B tile this CTA stages
   static constexpr int B_BYTES = B_ROWS * TC_BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  // TF32: 144-168 KB of operand ring.  bf16x3: a raw fp32 ring (TMA -> converter) plus a ring of converted tiles
-  // (converter -> MMA); a converted k-block takes exactly the bytes of the raw one.
-  static constexpr int STAGES = X3 ? (STAGE_BYTES <= 24 * 1024 ? 4 : 3)
-                                   : (CTAS == 2 ? (BN == 256 ? 5 : 7) : (BN == 256 ? 3 : (BN == 128 ? 5 : 7)));
-  static constexpr int CONV_STAGES = X3 ? (STAGE_BYTES <= 24 * 1024 ? 3 : 2) : 0;
+  // 144-168 KB of operand ring.  bf16x3 converts every stage in place (same bytes), so both arithmetics share the ring depth.
+  static constexpr int STAGES = CTAS == 2 ? (BN == 256 ? 5 : 7) : (BN == 256 ? 3 : (BN == 128 ? 5 : 7));
+  static constexpr int CONV_STAGES = X3 ? STAGES : 0;   // one "converted" barrier per stage
   static constexpr int THREADS = X3 ? TC_THREADS + 32 * TC_CONV_WARPS : TC_THREADS;
   static constexpr int EPI_LD = 36;                     // floats per staged row (float4-aligned, conflict-free)
   static constexpr int EPI_BYTES = 8 * 32 * EPI_LD * 4; // one 32x32 transpose patch per epilogue warp
-  static constexpr int RING_BYTES = (STAGES + CONV_STAGES) * STAGE_BYTES;
+  static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
   static_assert(RING_BYTES + EPI_BYTES + 1024 + 512 <= 232448, "shared memory budget");
   static constexpr int SMEM = RING_BYTES + EPI_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 };
@@ -333,15 +347,13 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   // space: the compiler then emits GENERIC ld / st for every shared-memory access derived from it -- the converter warps
   // of the bf16x3 path ran 4x slower that way)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* conv_base = smem + STAGES * STAGE_BYTES;   // [CONV] converted tiles (bf16x3 only)
   float* epi = (float*)(smem + Cfg::RING_BYTES);
   uint64_t* full_bar = (uint64_t*)(smem + Cfg::RING_BYTES + Cfg::EPI_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* acc_full = empty_bar + STAGES;    // [2] MMA -> epilogue
   uint64_t* acc_empty = acc_full + 2;         // [2] epilogue -> MMA
-  uint64_t* cfull = acc_empty + 2;            // [CONV] converter -> MMA (pair: both CTAs' converters, on the leader)
-  uint64_t* cempty = cfull + (X3 ? CONV : 0); // [CONV] MMA -> converter
-  uint32_t* tmem_slot = (uint32_t*)(cempty + (X3 ? CONV : 0));
+  uint64_t* cfull = acc_empty + 2;            // [STAGES] converter -> MMA (bf16x3; pair: both CTAs' converters, on the leader)
+  uint32_t* tmem_slot = (uint32_t*)(cfull + CONV);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items = p.n_items;
@@ -354,17 +366,14 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], X3 ? TC_CONV_WARPS : 1);   // bf16x3: the raw stage is released by this CTA's converter warps
+      mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], 8 * CTAS);   // one arrival per epilogue warp (of both CTAs of a pair, on the leader)
     }
     if (X3) {
-      for (int c = 0; c < CONV; ++c) {
-        mbar_init(&cfull[c], TC_CONV_WARPS * CTAS);
-        mbar_init(&cempty[c], 1);
-      }
+      for (int c = 0; c < CONV; ++c) mbar_init(&cfull[c], TC_CONV_WARPS * CTAS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -468,12 +477,12 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           // ---- bf16x3: operands come from the converter warps' ring; hi*hi + lo*hi + hi*lo per 16-wide k step
           constexpr uint32_t idesc16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
                                        ((uint32_t)((TC_BM * CTAS) >> 4) << 24);   // D = F32, A = B = BF16, both K-major
-          const int c = it % (X3 ? CONV : 1);
-          const uint32_t cph = (it / (X3 ? CONV : 1)) & 1;
-          mbar_wait(&cfull[c], cph);
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&cfull[s], ph);
           tc_fence_after();
           if (elect_one()) {
-            const uint32_t sa = smem_u32(conv_base + c * STAGE_BYTES);
+            const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
             const uint32_t sb = sa + A_BYTES;
 #pragma unroll
             for (int kk = 0; kk < TC_BK / 16; ++kk) {   // UMMA_K = 16 for bf16; hi part at +0, lo part at +64 bytes of the row
@@ -491,10 +500,10 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
               }
             }
             if (PAIR) {
-              tc_commit_pair(&cempty[c], 3);                          // frees this converted stage in BOTH CTAs
+              tc_commit_pair(&empty_bar[s], 3);                       // frees this stage in BOTH CTAs
               if (i == num_kb - 1) tc_commit_pair(&acc_full[as], 3);
             } else {
-              tc_commit(&cempty[c]);
+              tc_commit(&empty_bar[s]);
               if (i == num_kb - 1) tc_commit(&acc_full[as]);
             }
           }
@@ -530,7 +539,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       }
     }
   } else if (X3 && warp >= TC_THREADS / 32) {
-    // ===================== converter warps (bf16x3): raw fp32 stage -> [bf16 hi | bf16 lo] stage =====================
+    // ===================== converter warps (bf16x3): fp32 stage -> [bf16 hi | bf16 lo] stage, in place =====================
     const int cw = warp - TC_THREADS / 32;
     const uint32_t cfull_leader = PAIR ? mapa_rank(smem_u32(&cfull[0]), 0) : 0u;
     const F2 zero2 = f2(__int_as_float(p.n_items >> 30));   // 0.0f the compiler cannot fold (see split_pair2)
@@ -544,23 +553,17 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       for (int i = 0; i < num_kb; ++i, ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
-        const int c = it % (X3 ? CONV : 1);
-        const uint32_t cph = (it / (X3 ? CONV : 1)) & 1;
-        mbar_wait(&full_bar[s], ph);          // TMA bytes of the raw stage have landed
-        mbar_wait(&cempty[c], cph ^ 1);       // the MMAs that read this converted stage have retired
-        tc_fence_after();
-        const uint8_t* raw = smem + s * STAGE_BYTES;
-        uint8_t* cv = conv_base + c * STAGE_BYTES;
-        convert_tile<TC_BM, TA != 0>(raw, cv, cw, lane, zero2);
-        convert_tile<B_ROWS, TB != 0>(raw + A_BYTES, cv + A_BYTES, cw, lane, zero2);
+        mbar_wait(&full_bar[s], ph);          // TMA bytes of this stage have landed
+        uint8_t* st = smem + s * STAGE_BYTES;
+        convert_tile<TC_BM, TA != 0>(st, cw, lane, zero2);
+        convert_tile<B_ROWS, TB != 0>(st + A_BYTES, cw, lane, zero2);
         // generic-proxy writes -> visible to the tensor core's operand reads.  The .shared::cta form is one FENCE.VIEW.ASYNC.S;
         // the unqualified fence also issues MEMBAR.ALL.GPU (ncu: 9 % of all stall samples, the converter warps 3x slower)
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          if (PAIR && rank != 0) mbar_arrive_cluster(cfull_leader + (uint32_t)c * 8u);
-          else mbar_arrive(&cfull[c]);
-          mbar_arrive(&empty_bar[s]);          // the raw stage may be refilled
+          if (PAIR && rank != 0) mbar_arrive_cluster(cfull_leader + (uint32_t)s * 8u);
+          else mbar_arrive(&cfull[s]);
         }
       }
     }
@@ -757,19 +760,17 @@ static int launch(const TcMaps& maps, const TcParams& p, int grid, cudaStream_t 
   return GB_OK;
 }
 
-// tile configurations: TF32 -- 128 x {64,128,256} single CTA, 256 x {128,256} pairs; bf16x3 -- the raw + converted rings
-// leave no room for a single-CTA 256-wide tile (48 KB per stage), so 128 x {64,128} single CTA, 256 x {128,256} pairs
+// tile configurations (both arithmetics): 128 x {64,128,256} single CTA, 256 x {128,256} pairs
 template <bool X3>
 static int dispatch_x(int BN, bool pair, int ta, int tb, const TcMaps& maps, const TcParams& p, int grid, cudaStream_t stream) {
   int rc = GB_OK;
   if (p.n_problems > 1) {   // grouped launches exist for weight gradients only (both operands MN-major)
-    if (!(ta && tb) || BN == 64 || (X3 && BN == 256 && !pair)) {
+    if (!(ta && tb) || BN == 64) {
       set_error("gemm: grouped launch needs trans_a = trans_b = 1 and 128/256-wide tiles");
       return GB_ERR_INVALID;
     }
     if (pair) rc = BN == 256 ? launch<256, 1, 1, 2, true, X3>(maps, p, grid, stream) : launch<128, 1, 1, 2, true, X3>(maps, p, grid, stream);
-    else if (BN == 256) { if constexpr (!X3) rc = launch<256, 1, 1, 1, true, false>(maps, p, grid, stream); }
-    else rc = launch<128, 1, 1, 1, true, X3>(maps, p, grid, stream);
+    else rc = BN == 256 ? launch<256, 1, 1, 1, true, X3>(maps, p, grid, stream) : launch<128, 1, 1, 1, true, X3>(maps, p, grid, stream);
     return rc;
   }
 #define GB_TC(BN_, TA_, TB_, C_) rc = launch<BN_, TA_, TB_, C_, false, X3>(maps, p, grid, stream)
@@ -784,8 +785,7 @@ static int dispatch_x(int BN, bool pair, int ta, int tb, const TcMaps& maps, con
     if (BN == 256) GB_TC4(256, 2);
     else GB_TC4(128, 2);
   } else if (BN == 256) {
-    if constexpr (!X3) GB_TC4(256, 1);
-    else { set_error("gemm: bf16x3 has no single-CTA 128 x 256 tile"); return GB_ERR_INVALID; }
+    GB_TC4(256, 1);
   } else if (BN == 128) {
     GB_TC4(128, 1);
   } else {
@@ -860,9 +860,8 @@ int gemm_tcgen05(const gb_gemm_args* a, cudaStream_t stream, bool* handled) {
     else if (N <= 64 || ((N + 127) / 128) * tiles_m < units / 2) BN = 64;
     else if (N % 256 == 0 && (N / 256) * tiles_m >= (x3 && pair ? units / 2 : units)) BN = 256;   // bf16x3 pairs: one wave of
     // 256-wide tiles on half the machine beats two waves of 128-wide ones (half the shared-memory traffic per FLOP)
-    if (x3 && !pair && BN == 256) BN = 128;   // no single-CTA 128 x 256 tile in the bf16x3 kernel (shared-memory budget)
     static const int forced = [] { const char* e = getenv("GRAPPA_B200_GEMM_BN"); return e ? atoi(e) : 0; }();   // tuning aid
-    if ((forced == 64 || forced == 128 || forced == 256) && (forced != 256 || (N % 256 == 0 && (pair || !x3)))) BN = forced;
+    if ((forced == 64 || forced == 128 || forced == 256) && (forced != 256 || N % 256 == 0)) BN = forced;
     if (pair && BN == 64) {
       if (forced_pair == 1) { BN = 128; break; }
       pair = false;   // too little work for 256-row tiles: single CTAs with 128 x 64 tiles
@@ -938,7 +937,7 @@ int gemm_tcgen05_grouped(const gb_gemm_args* list, int n, cudaStream_t stream, b
   if (!all128) return GB_OK;
   static const int forced_pair = [] { const char* e = getenv("GRAPPA_B200_GEMM_PAIR"); return e ? atoi(e) : -1; }();
   const bool pair = big_m && long_k && forced_pair != 0;
-  const int BN = (all256 && (pair || !x3)) ? 256 : 128;
+  const int BN = all256 ? 256 : 128;
   const int bm = pair ? 2 * TC_BM : TC_BM;
   // Grouped launches carry weight gradients, which run on a side stream NEXT TO the latency-critical backward chain: a
   // persistent kernel on all 148 SMs makes every small kernel of that chain wait for a free SM (14 us gaps per GNN block in

@@ -39,7 +39,7 @@ def test_config1_training_batch_forward_matches_oracle():
     assert g.num_nodes("n1") == 32 * 52 and g.nodes["n1"].data["xyz"].shape == (1664, 50, 3)
     h, params, en = _oracle_forward(model, g, cfg)
     model = model.cuda()
-    for prec, tol, tol_k4 in (("fp32", 1e-5, 1e-5), ("tf32", 1e-3, 5e-3)):
+    for prec, tol in (("fp32", 1e-5), (ops.BENCH_PRECISION, 1e-4)):
         ops.set_matmul_precision(prec)
         try:
             with torch.no_grad():
@@ -47,18 +47,18 @@ def test_config1_training_batch_forward_matches_oracle():
             assert rel_err(gd.nodes["g"].data["energy"].cpu().numpy(), en["energy"].detach().numpy()) < tol
             assert rel_err(gd.nodes["n1"].data["gradient"].cpu().numpy(), en["gradient"].detach().numpy()) < tol
             for l in LEVELS:
-                lim = tol_k4 if l in ("n4", "n4_improper") else tol
-                assert rel_err(gd.nodes[l].data["k"].cpu().numpy(), params[l]["k"].detach().numpy()) < lim, (prec, l)
+                assert rel_err(gd.nodes[l].data["k"].cpu().numpy(), params[l]["k"].detach().numpy()) < tol, (prec, l)
         finally:
             ops.set_matmul_precision("fp32")
 
 
 # Tolerances of the full-size checks per GEMM arithmetic (north_star: 1e-5 outputs / 1e-4 gradients in fp32; 1e-3 outputs
-# where reduced-precision tensor-core GEMMs are used).  'bench' = the arithmetic bench.py runs and prints in `dtype`.
+# where reduced-precision tensor-core GEMMs are used).  'bench' = the arithmetic bench.py runs and prints in `dtype`
+# (bf16x3 split operands): it is held to 1e-4 on outputs AND gradients, ten times tighter than north_star requires.
 FULL_SIZE_TOL = {
     # precision: (outputs k / eq / energy / forces, loss, gradient norms, sampled gradient entries)
     "fp32": (2e-5, 1e-5, 1e-3, 1e-4),
-    "bench": (1e-3, 1e-3, 2e-3, 1e-3),
+    "bench": (1e-4, 1e-4, 2e-3, 1e-4),        # measured on B200: outputs <= 5e-5, sampled gradient entries <= 2e-5
 }
 
 
@@ -126,15 +126,19 @@ def test_config2_protein_1502_atoms_parametrisation_matches_oracle():
     import grappa_oracle as orc2
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
     h, params = orc2.model_forward(sd, g, cfg)
-    ops.set_matmul_precision("fp32")
     model = model.cuda()
-    with torch.no_grad():
-        gd = model(g.to("cuda"))
-    assert rel_err(gd.nodes["n1"].data["h"].cpu().numpy(), h.detach().numpy()) < 1e-5
-    for l in LEVELS:
-        assert rel_err(gd.nodes[l].data["k"].cpu().numpy(), params[l]["k"].detach().numpy()) < 1e-5, l
-        if l in ("n2", "n3"):
-            assert rel_err(gd.nodes[l].data["eq"].cpu().numpy(), params[l]["eq"].detach().numpy()) < 1e-5, l
+    for prec, tol in (("fp32", 1e-5), (ops.BENCH_PRECISION, 1e-4)):       # FFMA parity path and the arithmetic bench.py times
+        ops.set_matmul_precision(prec)
+        try:
+            with torch.no_grad():
+                gd = model(g.to("cuda"))
+        finally:
+            ops.set_matmul_precision("fp32")
+        assert rel_err(gd.nodes["n1"].data["h"].cpu().numpy(), h.detach().numpy()) < tol, prec
+        for l in LEVELS:
+            assert rel_err(gd.nodes[l].data["k"].cpu().numpy(), params[l]["k"].detach().numpy()) < tol, (prec, l)
+            if l in ("n2", "n3"):
+                assert rel_err(gd.nodes[l].data["eq"].cpu().numpy(), params[l]["eq"].detach().numpy()) < tol, (prec, l)
     # params are written to the graph with the reference's shapes
     assert gd.nodes["n2"].data["k"].shape == (1501,) and gd.nodes["n4"].data["k"].shape == (3741, 3)
     assert gd.nodes["n4_improper"].data["k"].shape == (900, 3)

@@ -20,32 +20,26 @@ def _model(cfg, seed):
     return m.cuda()
 
 
-def _check_forward(g, z, tol, tol_h=None):
+def _check_forward(g, z, tol):
+    """Every output tensor of the path against the reference fixture at ONE tolerance (max |a - b| / max |b| per tensor) --
+    no per-tensor carve-outs: h, all k / eq (the gated torsion amplitudes included), energy, gradient."""
     errs = {"h": rel_err(g.nodes["n1"].data["h"].detach().cpu().numpy(), z["out.h"])}
     for l in LEVELS:
-        k_out, k_ref = g.nodes[l].data["k"].detach().cpu().numpy(), z[f"out.{l}.k"]
-        if tol_h and l in ("n4", "n4_improper"):
-            # HardCutoff (reference network_utils.py:144-145) zeroes |k| <= 1e-4: an amplitude that sits on the
-            # threshold may flip under reduced-precision GEMMs; such elements may differ by the threshold itself.
-            flipped = (k_out == 0) != (k_ref == 0)
-            assert np.all(np.abs(k_out - k_ref)[flipped] <= 1.1e-4), "cutoff flip larger than the cutoff"
-            k_out = np.where(flipped, k_ref, k_out)
-        errs[f"{l}.k"] = rel_err(k_out, k_ref)
+        errs[f"{l}.k"] = rel_err(g.nodes[l].data["k"].detach().cpu().numpy(), z[f"out.{l}.k"])
         if l in ("n2", "n3"):
             errs[f"{l}.eq"] = rel_err(g.nodes[l].data["eq"].detach().cpu().numpy(), z[f"out.{l}.eq"])
     errs["energy"] = rel_err(g.nodes["g"].data["energy"].detach().cpu().numpy(), z["out.g.energy"])
     errs["gradient"] = rel_err(g.nodes["n1"].data["gradient"].detach().cpu().numpy(), z["out.n1.gradient"])
-    def lim(k):
-        if k == "h" and tol_h:
-            return tol_h
-        if tol_h and k in ("n4.k", "n4_improper.k"):
-            # TF32 path: gated torsion amplitudes are the most sensitive output (a product of two head outputs, no
-            # mean shift); measured 2.4e-3 .. 3.5e-3 depending on rounding details -> documented in DESIGN.md
-            return 5 * tol
-        return tol
-    bad = {k: v for k, v in errs.items() if v > lim(k)}
-    assert not bad, f"relative errors above tolerance: {bad} (all: {errs})"
+    bad = {k: v for k, v in errs.items() if v > tol}
+    assert not bad, f"relative errors above tolerance {tol}: {bad} (all: {errs})"
     return errs
+
+
+# Tolerance of the tensor-core arithmetic bench.py runs (ops.BENCH_PRECISION = bf16x3): north_star allows 1e-3 where
+# reduced-precision GEMMs are used; the split-operand GEMMs reach 1e-4 on every output and on the gradients, so that is
+# what is asserted.  (The raw TF32 mode misses 1e-3 on the gated torsion amplitudes -- profiles/r2_error_budget.md -- and is
+# no longer a model-level mode under test; its GEMM kernel is still unit-tested in tests/test_ops_gpu.py.)
+TENSOR_TOL = 1e-4
 
 
 def test_grappa12_dipeptide_matches_reference_fp32():
@@ -71,47 +65,47 @@ def test_grappa12_dipeptide_matches_reference_fp32():
         assert g.nodes[l].data["x"].shape == z[f"out.{l}.x"].shape
 
 
-def test_grappa12_dipeptide_matches_reference_tf32_tensor_cores():
-    """Same fixture through the tcgen05 TF32 GEMMs: 1e-3 relative (north_star tolerance for reduced-precision GEMMs)."""
+def test_grappa12_dipeptide_matches_reference_tensor_cores():
+    """Same fixture through the tcgen05 GEMMs at the arithmetic bench.py measures (bf16x3 split operands)."""
     import grappa_oracle as orc
     from grappa_b200 import ops
     from grappa_b200.energy import Energy
     z = load_golden("dipeptide_grappa12.npz")
-    ops.set_matmul_precision("tf32")
+    ops.set_matmul_precision(ops.BENCH_PRECISION)
     try:
         model = _model(orc.grappa_1_2_model_config(), seed=3).eval()
         g = graph_from_fixture(z).to("cuda")
         with torch.no_grad():
             g = torch.nn.Sequential(model, Energy())(g)
-        errs = _check_forward(g, z, 1e-3, tol_h=2e-3)
-        print("tf32 relative errors:", errs)
+        errs = _check_forward(g, z, TENSOR_TOL)
+        print(ops.BENCH_PRECISION, "relative errors:", errs)
     finally:
         ops.set_matmul_precision("fp32")
 
 
-def test_small_model_gradients_tf32_tensor_cores():
+def test_small_model_gradients_tensor_cores():
     import grappa_oracle as orc
     from grappa_b200 import ops
     from grappa_b200.energy import Energy
     from grappa_b200.loss import MolwiseLoss
     z = load_golden("mixed_batch_small_model.npz")
-    ops.set_matmul_precision("tf32")
+    ops.set_matmul_precision(ops.BENCH_PRECISION)
     try:
         model = _model(orc.small_model_config(), seed=7).eval()
         g = graph_from_fixture(z).to("cuda")
         g = torch.nn.Sequential(model, Energy(write_tuple_terms=False))(g)
-        _check_forward(g, z, 1e-3, tol_h=2e-3)
+        _check_forward(g, z, TENSOR_TOL)
         loss = MolwiseLoss(gradient_weight=0.8, energy_weight=1.0, param_weight=1e-3, proper_regularisation=1e-3,
                            improper_regularisation=1e-3)(g)
-        assert abs(loss.item() - float(z["out.loss"])) < 2e-3 * abs(float(z["out.loss"]))
+        assert abs(loss.item() - float(z["out.loss"])) < TENSOR_TOL * abs(float(z["out.loss"]))
         loss.backward()
         named = dict(model.named_parameters())
         worst = 0.0
         for k in z.files:
             if k.startswith("grad."):
                 worst = max(worst, rel_err(named[k[5:]].grad.cpu().numpy(), z[k]))
-        print("tf32 worst picked-gradient error", worst)
-        assert worst < 1e-2
+        print(ops.BENCH_PRECISION, "worst picked-gradient error", worst)
+        assert worst < 2 * TENSOR_TOL
     finally:
         ops.set_matmul_precision("fp32")
 
