@@ -148,8 +148,8 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 // Two fp32 values (one 64-bit register) -> packed bf16 pair of the leading parts and packed bf16 pair of the remainders.
 //   hi = rn_bf16(a) by Veltkamp's splitting in PACKED fp32 arithmetic: c = a * (2^16 + 1); hi = c - (c - a) keeps the
 //        leading 8 significant bits of a, rounded to nearest (identical to cvt.rn.bf16.f32 on every finite input tested);
-//   lo = a - hi is exact in fp32; its leading 8 bits (truncated: lo has no preferred sign relative to a) go to the lo plane.
-// hi + lo carries 16 significant bits (|error| <= 2^-16 |a|, unbiased).  4 packed FP instructions + 2 PRMT per PAIR.
+//   lo = a - hi is exact in fp32; its leading 8 bits (rounded half-up on the bit pattern) go to the lo plane.
+// hi + lo carries 16 significant bits (|error| <= 2^-17 |a|, unbiased).  4 packed FP + 2 integer adds + 2 PRMT per PAIR.
 // History (ncu, profiles/r2_summary.md): cvt.rn.bf16x2.f32 (F2FP) runs on the XU pipe, ~7 cycles per warp instruction
 // per SM -- 84 % busy, converter 3x slower than the MMAs; integer rounding (IADD + LOP + FADD + IADD + PRMT per element)
 // left one converter warp per scheduler at 0.24 IPC with ~490 instructions per k-block.
@@ -162,7 +162,9 @@ __device__ __forceinline__ void split_pair2(F2 a, F2 z, uint32_t& hi, uint32_t& 
   const F2 h = c - (c - a);
   const F2 l = a - h;
   hi = __byte_perm((uint32_t)(h.v & 0xffffffffull), (uint32_t)(h.v >> 32), 0x7632);   // {h1[31:16], h0[31:16]}
-  lo = __byte_perm((uint32_t)(l.v & 0xffffffffull), (uint32_t)(l.v >> 32), 0x7632);
+  const unsigned long long lr = l.v + 0x0000800000008000ull;   // round the remainders half-up to bf16 (no carry between the halves
+                                                                // for finite values); truncation alone left 2^-16 relative error
+  lo = __byte_perm((uint32_t)(lr & 0xffffffffull), (uint32_t)(lr >> 32), 0x7632);
 }
 __device__ __forceinline__ void split8(const float (&v)[8], F2 z, uint4& hi, uint4& lo) {
   split_pair2(f2(v[0], v[1]), z, hi.x, lo.x);
@@ -171,7 +173,13 @@ __device__ __forceinline__ void split8(const float (&v)[8], F2 z, uint4& hi, uin
   split_pair2(f2(v[6], v[7]), z, hi.w, lo.w);
 }
 
-constexpr int TC_CONV_WARPS = 4;   // converter warps of the bf16x3 kernel (warps 10..13)
+// bf16x3 warp roles (448 threads): TMA warp, MMA warp, 4 epilogue warps (one per TMEM lane quarter, all BN columns each),
+// 8 converter warps in two groups of four: group g rewrites the stages of k-blocks g, g + 2, ..., so two stages are being
+// converted at any time (one group alone spent ~40 % of its time in the fence / barrier hand-off of each stage)
+constexpr int TC_CONV_WARPS = 4;    // converter warps per group (= warps that share one stage)
+constexpr int TC_CONV_GROUPS = 2;
+constexpr int TC_EPI_WARPS_X3 = 4;
+constexpr int TC_THREADS_X3 = 32 * (2 + TC_EPI_WARPS_X3 + TC_CONV_WARPS * TC_CONV_GROUPS);
 
 // One operand tile of one k-block, converted IN PLACE: fp32 (as TMA staged it) -> [32 bf16 hi | 32 bf16 lo] rows, K-major
 // SWIZZLE_128B (16-byte chunk j of row r lives at chunk j ^ (r & 7) of the row's 128 bytes).  The converted tile takes
@@ -316,11 +324,13 @@ struct TcCfg {
   static constexpr int B_BYTES = B_ROWS * TC_BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   // 144-168 KB of operand ring.  bf16x3 converts every stage in place (same bytes), so both arithmetics share the ring depth.
-  static constexpr int STAGES = CTAS == 2 ? (BN == 256 ? 5 : 7) : (BN == 256 ? 3 : (BN == 128 ? 5 : 7));
+  // (bf16x3 has four epilogue patches instead of eight: room for one more stage)
+  static constexpr int STAGES = (CTAS == 2 ? (BN == 256 ? 5 : 7) : (BN == 256 ? 3 : (BN == 128 ? 5 : 7))) + (X3 ? 1 : 0);
   static constexpr int CONV_STAGES = X3 ? STAGES : 0;   // one "converted" barrier per stage
-  static constexpr int THREADS = X3 ? TC_THREADS + 32 * TC_CONV_WARPS : TC_THREADS;
+  static constexpr int THREADS = X3 ? TC_THREADS_X3 : TC_THREADS;
+  static constexpr int EPI_WARPS = X3 ? TC_EPI_WARPS_X3 : 8;
   static constexpr int EPI_LD = 36;                     // floats per staged row (float4-aligned, conflict-free)
-  static constexpr int EPI_BYTES = 8 * 32 * EPI_LD * 4; // one 32x32 transpose patch per epilogue warp
+  static constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_LD * 4; // one 32x32 transpose patch per epilogue warp
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
   static_assert(RING_BYTES + EPI_BYTES + 1024 + 512 <= 232448, "shared memory budget");
   static constexpr int SMEM = RING_BYTES + EPI_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
@@ -330,7 +340,7 @@ struct TcCfg {
 // Two TMEM accumulator stages: the epilogue of item i overlaps the mainloop of item i+1.
 // GROUPED = false: exactly one problem, indexed statically (its fields stay immediate constant-bank operands).
 template <int BN, int TA, int TB, int CTAS, bool GROUPED, bool X3>
-__global__ void __launch_bounds__(X3 ? TC_THREADS + 32 * TC_CONV_WARPS : TC_THREADS, 1)
+__global__ void __launch_bounds__(X3 ? TC_THREADS_X3 : TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   using Cfg = TcCfg<BN, CTAS, X3>;
@@ -370,7 +380,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 8 * CTAS);   // one arrival per epilogue warp (of both CTAs of a pair, on the leader)
+      mbar_init(&acc_empty[s], Cfg::EPI_WARPS * CTAS);   // one arrival per epilogue warp (of both CTAs of a pair, on the leader)
     }
     if (X3) {
       for (int c = 0; c < CONV; ++c) mbar_init(&cfull[c], TC_CONV_WARPS * CTAS);
@@ -538,9 +548,10 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         __syncwarp();
       }
     }
-  } else if (X3 && warp >= TC_THREADS / 32) {
+  } else if (X3 && warp >= 2 + Cfg::EPI_WARPS) {
     // ===================== converter warps (bf16x3): fp32 stage -> [bf16 hi | bf16 lo] stage, in place =====================
-    const int cw = warp - TC_THREADS / 32;
+    const int cw = (warp - (2 + Cfg::EPI_WARPS)) % TC_CONV_WARPS;      // position inside the group
+    const int cgrp = (warp - (2 + Cfg::EPI_WARPS)) / TC_CONV_WARPS;    // group: k-blocks with it % TC_CONV_GROUPS == cgrp
     const uint32_t cfull_leader = PAIR ? mapa_rank(smem_u32(&cfull[0]), 0) : 0u;
     const F2 zero2 = f2(__int_as_float(p.n_items >> 30));   // 0.0f the compiler cannot fold (see split_pair2)
     uint32_t it = 0;
@@ -551,6 +562,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       const int kb0 = z * q.k_blocks_per_split;
       const int num_kb = min(total_kb, kb0 + q.k_blocks_per_split) - kb0;
       for (int i = 0; i < num_kb; ++i, ++it) {
+        if ((int)(it % TC_CONV_GROUPS) != cgrp) continue;
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&full_bar[s], ph);          // TMA bytes of this stage have landed
@@ -573,7 +585,8 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     // 4 consecutive columns of a row, so all global traffic of the fused epilogue is 128-byte coalesced.
     // Two warps share each TMEM lane quarter and split the tile's columns between them.
     const int q = warp & 3;                            // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;                  // which half of the tile's columns
+    constexpr int EPI_COLS = BN / (Cfg::EPI_WARPS / 4);   // columns of the tile this warp handles (TF32: half, bf16x3: all)
+    const int half = (warp - 2) >> 2;                  // which slice of the tile's columns
     float* patch = epi + (warp - 2) * (32 * Cfg::EPI_LD);
     const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
     const uint32_t acc_empty_remote = PAIR ? mapa_rank(smem_u32(&acc_empty[0]), 0) : 0u;   // leader's acc_empty[0]
@@ -587,13 +600,13 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       const int rest = local / pq.tiles_n;
       const int mb = rest % pq.tiles_m;
       const int z = rest / pq.tiles_m;
-      const int m0 = mb * (TC_BM * CTAS) + (int)rank * TC_BM + q * 32, n0 = nb * BN + half * (BN / 2);
+      const int m0 = mb * (TC_BM * CTAS) + (int)rank * TC_BM + q * 32, n0 = nb * BN + half * EPI_COLS;
       const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
-      const uint32_t t_addr = tmem_base + as * BN + half * (BN / 2) + ((uint32_t)(q * 32) << 16);
+      const uint32_t t_addr = tmem_base + as * BN + half * EPI_COLS + ((uint32_t)(q * 32) << 16);
       const bool side_inputs = !pq.partial && vec_ok && (pq.ep.residual != nullptr || pq.ep.mul_elu_out != nullptr);
       const int fmask = pq.ep.feature_mask();      // warp-uniform: selects one specialised row loop per tile
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN / 2; c0 += 32) {
+      for (int c0 = 0; c0 < EPI_COLS; c0 += 32) {
         const int col = n0 + c0 + sub_c;
         // Side inputs of this 32x32 patch (residual / saved activation) are requested BEFORE the accumulator is
         // touched: 8 independent 16-byte loads per lane are in flight while the MMAs finish, the TMEM read and the
@@ -618,7 +631,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         float v[32];
         tc_ld16(t_addr + (uint32_t)c0, v);
         tc_ld16(t_addr + (uint32_t)c0 + 16u, v + 16);
-        if (c0 + 32 >= BN / 2) {   // accumulator fully read: hand the TMEM stage back to the MMA warp
+        if (c0 + 32 >= EPI_COLS) {   // accumulator fully read: hand the TMEM stage back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
