@@ -383,7 +383,9 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       mbar_init(&acc_empty[s], Cfg::EPI_WARPS * CTAS);   // one arrival per epilogue warp (of both CTAs of a pair, on the leader)
     }
     if (X3) {
-      for (int c = 0; c < CONV; ++c) mbar_init(&cfull[c], TC_CONV_WARPS * CTAS);
+      // pair: the peer's converter warps arrive on the PEER's cfull; its otherwise idle MMA warp forwards ONE arrival
+      // per stage to the leader (a release at cluster scope costs ~600 cycles: kept off the converter warps)
+      for (int c = 0; c < CONV; ++c) mbar_init(&cfull[c], TC_CONV_WARPS + ((PAIR && rank == 0) ? 1 : 0));
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -472,6 +474,25 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)TA << 15) | ((uint32_t)TB << 16) |
                                ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((TC_BM * CTAS) >> 4) << 24);
     uint32_t it = 0, lt = 0;
+    if (X3 && PAIR && rank != 0) {
+      // forwarder: when this CTA's converter warps have rewritten a stage, tell the leader (whose MMAs read both CTAs'
+      // shared memory).  The converters' writes were fenced to the async proxy before their (CTA-scope) arrival; the
+      // acquire here + the cluster-scope release below carry them to the leader's MMA thread.
+      const uint32_t cfull_leader = mapa_rank(smem_u32(&cfull[0]), 0);
+      for (int item = first_item; item < n_items; item += item_stride) {
+        const TcProblem& q = p.pr[GROUPED ? find_problem(p, item) : 0];
+        const int z = (item - q.item_begin) / (q.tiles_n * q.tiles_m);
+        const int total_kb = (q.K + TC_BK - 1) / TC_BK;
+        const int kb0 = z * q.k_blocks_per_split;
+        const int num_kb = min(total_kb, kb0 + q.k_blocks_per_split) - kb0;
+        for (int i = 0; i < num_kb; ++i, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&cfull[s], (it / STAGES) & 1);
+          if (lane == 0) mbar_arrive_cluster(cfull_leader + (uint32_t)s * 8u);
+          __syncwarp();
+        }
+      }
+    }
     for (int item = first_item; item < n_items && rank == 0; item += item_stride, ++lt) {
       const TcProblem& q = p.pr[GROUPED ? find_problem(p, item) : 0];
       const int z = (item - q.item_begin) / (q.tiles_n * q.tiles_m);
@@ -552,7 +573,6 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     // ===================== converter warps (bf16x3): fp32 stage -> [bf16 hi | bf16 lo] stage, in place =====================
     const int cw = (warp - (2 + Cfg::EPI_WARPS)) % TC_CONV_WARPS;      // position inside the group
     const int cgrp = (warp - (2 + Cfg::EPI_WARPS)) / TC_CONV_WARPS;    // group: k-blocks with it % TC_CONV_GROUPS == cgrp
-    const uint32_t cfull_leader = PAIR ? mapa_rank(smem_u32(&cfull[0]), 0) : 0u;
     const F2 zero2 = f2(__int_as_float(p.n_items >> 30));   // 0.0f the compiler cannot fold (see split_pair2)
     uint32_t it = 0;
     for (int item = first_item; item < n_items; item += item_stride) {
@@ -573,10 +593,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         // the unqualified fence also issues MEMBAR.ALL.GPU (ncu: 9 % of all stall samples, the converter warps 3x slower)
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
-          if (PAIR && rank != 0) mbar_arrive_cluster(cfull_leader + (uint32_t)s * 8u);
-          else mbar_arrive(&cfull[s]);
-        }
+        if (lane == 0) mbar_arrive(&cfull[s]);
       }
     }
   } else {
