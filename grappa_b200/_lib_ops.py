@@ -46,6 +46,18 @@ class ColsumBatch(C.Structure):
     _fields_ = [("n", i32), ("pad_", i32), ("desc", ColsumDesc * COLSUM_MAX)]
 
 
+COLLATE_MAX_JOBS = 64
+
+
+class CollateJob(C.Structure):
+    _fields_ = [("src", vp), ("dst", vp), ("src_off", vp), ("dst_off", vp), ("add", vp), ("confs", vp), ("csel", vp),
+                ("row_words", i32), ("kind", i32), ("n_confs_out", i32), ("n_rows", i32)]
+
+
+class CollateArgs(C.Structure):
+    _fields_ = [("n_jobs", i32), ("B", i32), ("mol", vp), ("job", CollateJob * COLLATE_MAX_JOBS)]
+
+
 class Perms(C.Structure):
     _fields_ = [("n_perm", i32), ("perm", (i32 * 4) * 6)]
 
@@ -95,6 +107,8 @@ def declare(lib):
     lib.grappa_b200_gemm.argtypes = [P(GemmArgs), vp]
     lib.grappa_b200_neighbor_mean.argtypes = [vp, i32, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.grappa_b200_neighbor_mean.restype = C.c_int
+    lib.grappa_b200_collate.argtypes = [vp, i32, i64, vp]
+    lib.grappa_b200_collate.restype = C.c_int
     lib.grappa_b200_pad_rows.argtypes = [vp, i32, i32, i32, vp, i32, vp]
     lib.grappa_b200_pad_rows.restype = C.c_int
     lib.grappa_b200_gemm_can_fuse_colsum.argtypes = [P(GemmArgs)]

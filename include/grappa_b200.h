@@ -130,6 +130,40 @@ int64_t grappa_b200_energy_bwd_workspace(const gb_energy_args* a);
 int grappa_b200_energy_bwd(const gb_energy_bwd_args* a, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Device-side batch assembly from a dataset resident in HBM.  Replaces, per batch, the reference's host collate
+ * (data/GraphDataLoader.py:23-73), set_number_confs (utils/dgl_utils.py:132-171) and batch (utils/dgl_utils.py:11-60)
+ * and the host construction of the index tables.  A batch is `n_jobs` concatenations of per-molecule pieces; the
+ * argument block itself lives in DEVICE memory (it is part of the one small host->device upload a batch needs:
+ * molecule ids, batch offsets, conformation selection, job descriptors).
+ *   kind 0: rows of `row_words` 4-byte words copied verbatim          kind 1: int32 rows, non-negative entries + add[b]
+ *   kind 2: int64 rows (row_words = 2 * elements) + add[b]            kind 3: conformation field: output row =
+ *           n_confs_out x row_words words, conformation c taken from stored conformation csel[b, c]
+ *   kind 4: plain copy of n_rows * row_words words (src_off / dst_off unused)
+ * src_off [n_dataset_molecules + 1] (int64) = first row (kinds 0-2) or first WORD (kind 3) of every molecule in `src`;
+ * dst_off [B + 1] = first output row of every molecule of the batch; mol [B] = dataset molecule ids.
+ * ------------------------------------------------------------------------------------------- */
+#define GB_COLLATE_MAX_JOBS 64
+typedef struct {
+  const void* src;
+  void* dst;
+  const int64_t* src_off;
+  const int32_t* dst_off;
+  const int32_t* add;          /* [B] or NULL */
+  const int32_t* confs;        /* kind 3: [n_dataset_molecules] stored conformations */
+  const int32_t* csel;         /* kind 3: [B, n_confs_out] */
+  int32_t row_words, kind, n_confs_out, n_rows;
+} gb_collate_job;
+
+typedef struct {
+  int32_t n_jobs, B;
+  const int32_t* mol;
+  gb_collate_job job[GB_COLLATE_MAX_JOBS];
+} gb_collate_args;
+
+/* dev_args: DEVICE pointer to a gb_collate_args; max_words = largest job (sizes the grid) */
+int grappa_b200_collate(const gb_collate_args* dev_args, int32_t n_jobs, int64_t max_words, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Dense linear layer GEMM with fused epilogue.  Replaces every torch.nn.Linear on the path
  * (reference models/graph_attention.py:98-101,125-127,261,267-272; DGL DotGatConv.fc;
  * interaction_parameters.py:148-151; network_utils.py:31-32,105; perm_equiv_transformer.py:231-237)
