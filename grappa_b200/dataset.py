@@ -31,6 +31,7 @@ import numpy as np
 import torch
 
 from .graph import NTYPES, MolGraph
+from .pack import ENERGY_SCHED_GROUPS as ENERGY_GROUPS
 
 _CONF_FIELDS_G = ("energy",)        # substring match, as the reference does ('energy' in feat)
 _CONF_FIELDS_N1 = ("gradient",)
@@ -349,3 +350,266 @@ def batch_sampler(indices: Sequence[int], batch_size: int, rng: Optional[np.rand
         if len(b) < batch_size and drop_last:
             return
         yield b
+
+
+# --------------------------------------------------------------------------------------------------
+# device-resident dataset: batches assembled on the GPU
+# --------------------------------------------------------------------------------------------------
+class DeviceDataset:
+    """A `PackedDataset` resident in HBM whose batches are assembled ON THE DEVICE by one kernel launch.
+
+    Replaces, per batch, the reference's host-side collate (data/GraphDataLoader.py:23-73), `set_number_confs`
+    (utils/dgl_utils.py:132-171: conformation sub-sampling / padding) and `batch` (utils/dgl_utils.py:11-60: per-type
+    concatenation, `idxs += atom offset`) AND the host construction of `pack.PackedBatch`'s index tables: every one of
+    those tables (inverse incidence CSR, bonded-graph CSR, reverse-edge table, conflict-free schedule of the energy
+    kernel) is a concatenation of per-molecule tables shifted by a per-molecule offset, so they are computed ONCE per
+    molecule when the dataset is uploaded and merely gathered + shifted per batch (`grappa_b200_collate`).
+
+    Per batch the host does O(B) work: a few cumulative sums over the per-molecule counts, the conformation selection
+    (B x n_confs integers, same rules as the host collate) and the job descriptors -- one pinned buffer of a few KB, one
+    H2D copy, one kernel launch.  The result is the same batched graph (on the device) with its `PackedBatch`, field for
+    field and bit for bit what `PackedDataset.collate(...).to(device)` gives (tests/test_dataset_gpu.py).
+    """
+
+    _TABLES = ("idx", "inv_ptr", "inv_ent", "sched")      # per level
+
+    def __init__(self, ds: PackedDataset, device="cuda"):
+        from . import _lib
+        from .pack import LEVELS, TUPLE_LEN, PackedBatch
+        self.ds, self.device = ds, torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.GrappaB200Error("DeviceDataset needs a CUDA device (the host collate is PackedDataset.collate)")
+        A = ds._nd
+        n = ds.n
+        self.n = n
+        self.counts = {nt: np.diff(A[f"off.{nt}"]).astype(np.int64) for nt in NTYPES}
+        self.confs = A["confs"].astype(np.int64)
+        self.ecounts = np.diff(A["off.edges"]).astype(np.int64)
+        dev = self.device
+        up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        # ---- node fields and edges, as stored
+        self.field = {}          # (nt, k) -> (device tensor, row_words, kind, torch dtype, trailing shape)
+        self.off_dev = {nt: up(A[f"off.{nt}"].astype(np.int64)) for nt in NTYPES}
+        self.eoff_dev = up(A["off.edges"].astype(np.int64))
+        self.confs_dev = up(self.confs.astype(np.int32))
+        self.foff_dev = {}
+        for nt in NTYPES:
+            for k in ds.meta["fields"][nt]:
+                arr = A[f"data.{nt}.{k}"]
+                t = torch.from_numpy(np.ascontiguousarray(arr))
+                if (nt, k) in ds._conf_fields:
+                    tail = 3 if nt == "n1" else 1
+                    self.field[(nt, k)] = (t.to(dev), tail, 3, t.dtype, (3,) if nt == "n1" else ())
+                    self.foff_dev[(nt, k)] = up(A[f"foff.{nt}.{k}"].astype(np.int64))
+                else:
+                    trailing = tuple(arr.shape[1:])
+                    words = int(np.prod(trailing, dtype=np.int64)) * t.element_size() // 4
+                    if t.element_size() not in (4, 8):
+                        raise ValueError(f"field {nt}.{k}: element size {t.element_size()} is not supported on the device path")
+                    kind = 2 if (k == "idxs" and t.dtype == torch.int64) else (1 if k == "idxs" else 0)
+                    self.field[(nt, k)] = (t.to(dev), max(words, 1), kind, t.dtype, trailing)
+        self.esrc_dev, self.edst_dev = up(A["edges.src"].astype(np.int32)), up(A["edges.dst"].astype(np.int32))
+        # ---- per-molecule index tables, built once with the host code of pack.PackedBatch
+        tabs: Dict[str, list] = {}
+        self.rounds = {l: np.zeros(n, dtype=np.int64) for l in range(4)}
+        self.max_degree = np.zeros(n, dtype=np.int64)
+        for i in range(n):
+            p = PackedBatch(ds.molecule(i), device="cpu")
+            h = p.host
+            na = int(self.counts["n1"][i])
+            for l in range(4):
+                tabs.setdefault(f"idx{l}", []).append(h[f"idx{l}"].reshape(-1))
+                tabs.setdefault(f"inv_ptr{l}", []).append(h[f"inv_ptr{l}"][:na])
+                tabs.setdefault(f"inv_ent{l}", []).append(h[f"inv_ent{l}"].reshape(-1))
+                tabs.setdefault(f"sched{l}", []).append(h[f"sched{l}"].reshape(-1))
+                self.rounds[l][i] = h[f"sched{l}"].shape[0]
+            tabs.setdefault("indptr", []).append(h["indptr"][:na])
+            tabs.setdefault("esrc", []).append(h["esrc"])
+            tabs.setdefault("erev", []).append(h["erev"])
+            self.max_degree[i] = p.max_degree
+        self.table, self.table_off = {}, {}
+        for name, parts in tabs.items():
+            sizes = np.array([len(x) for x in parts], dtype=np.int64)
+            self.table[name] = up(np.concatenate(parts).astype(np.int32) if len(parts) else np.zeros(0, np.int32))
+            self.table_off[name] = np.concatenate(([0], np.cumsum(sizes)))
+        self._table_rows = {}      # name -> (row_words, per-molecule row offsets on the device)
+        for l, L in enumerate(TUPLE_LEN):
+            self._table_rows[f"idx{l}"] = (L, self.off_dev[LEVELS[l]])
+            self._table_rows[f"inv_ptr{l}"] = (1, self.off_dev["n1"])
+            self._table_rows[f"inv_ent{l}"] = (1, up(self.table_off[f"inv_ent{l}"]))
+            self._table_rows[f"sched{l}"] = (ENERGY_GROUPS, up(np.concatenate(([0], np.cumsum(self.rounds[l])))))
+        self._table_rows["indptr"] = (1, self.off_dev["n1"])
+        self._table_rows["esrc"] = (1, self.eoff_dev)
+        self._table_rows["erev"] = (1, self.eoff_dev)
+        self._names = None
+
+    def __len__(self):
+        return self.n
+
+    # ---------------------------------------------------------------------------------------------
+    def collate(self, indices: Sequence[int], conf_strategy: Union[str, int] = "mean",
+                rng: Optional[np.random.Generator] = None) -> MolGraph:
+        """Batched graph of the molecules `indices` on the device, with its PackedBatch attached (see class docstring)."""
+        import ctypes as C
+        from . import _lib
+        from ._lib_ops import COLLATE_MAX_JOBS, CollateArgs
+        from .pack import LEVELS, TUPLE_LEN, PackedBatch
+        ia = np.asarray([int(i) for i in indices], dtype=np.int64)
+        if len(ia) and (ia.min() < 0 or ia.max() >= self.n):
+            raise IndexError(f"molecule index out of range [0, {self.n})")
+        B = len(ia)
+        dev = self.device
+        cnt = {nt: self.counts[nt][ia] for nt in NTYPES}
+        off = {nt: np.concatenate(([0], np.cumsum(cnt[nt]))).astype(np.int32) for nt in NTYPES}
+        ecnt = self.ecounts[ia]
+        eoff = np.concatenate(([0], np.cumsum(ecnt))).astype(np.int32)
+        confs = self.confs[ia].tolist()
+        n_confs = batch_n_confs(confs, conf_strategy) if any(confs) else 0
+        csel = np.stack([conformation_indices(c, n_confs, rng) for c in confs]).astype(np.int32) if n_confs else np.zeros((B, 0), np.int32)
+        N = int(off["n1"][-1])
+        E = int(eoff[-1])
+        # ---- small per-batch tables computed on the host (O(B)): they travel in the upload buffer
+        small: Dict[str, np.ndarray] = {"mol": ia.astype(np.int32), "csel": csel.reshape(-1)}
+        for nt in NTYPES:
+            small[f"off.{nt}"] = off[nt]
+        small["eoff"] = eoff
+        roff = {}
+        for l, L in enumerate(TUPLE_LEN):
+            roff[l] = np.concatenate(([0], np.cumsum(self.rounds[l][ia]))).astype(np.int32)
+            small[f"round_off{l}"] = roff[l]
+            small[f"entoff{l}"] = (off[LEVELS[l]].astype(np.int64) * L).astype(np.int32)      # (tuple, slot) entry offsets
+            small[f"inv_end{l}"] = np.array([int(off[LEVELS[l]][-1]) * L], dtype=np.int32)
+        small["ind_end"] = np.array([E], dtype=np.int32)
+        if n_confs:
+            dummy = np.zeros((B, n_confs), dtype=np.float32)
+            for j, c in enumerate(confs):
+                dummy[j, min(c, n_confs):] = 1.0
+            small["is_dummy"] = dummy.view(np.int32).reshape(-1)
+            small["n_valid"] = (dummy == 0).sum(axis=1).astype(np.int32)
+        # ---- output buffers: one int32 pack buffer in PackedBatch's layout, one buffer for the graph fields
+        pack_sizes = {"atom_off": B + 1}
+        for l, L in enumerate(TUPLE_LEN):
+            T = int(off[LEVELS[l]][-1])
+            pack_sizes.update({f"idx{l}": T * L, f"tup_off{l}": B + 1, f"inv_ptr{l}": N + 1, f"inv_ent{l}": T * L})
+        for l in range(4):
+            pack_sizes.update({f"round_off{l}": B + 1, f"sched{l}": int(roff[l][-1]) * ENERGY_GROUPS})
+        pack_sizes.update({"indptr": N + 1, "esrc": E, "erev": E})
+        names = PackedBatch.TABLE_ORDER
+        p_off, total = {}, 0
+        for k in names:
+            p_off[k] = total
+            total += (pack_sizes[k] + 3) // 4 * 4
+        pack_flat = torch.zeros(total, dtype=torch.int32, device=dev)
+        # graph fields
+        f_off, f_total, f_meta = {}, 0, {}
+        for (nt, k), (src, words, kind, dtype, trailing) in self.field.items():
+            rows = int(off[nt][-1])
+            w = words * n_confs if kind == 3 else words
+            f_off[(nt, k)] = f_total
+            f_meta[(nt, k)] = (rows, w)
+            f_total += (rows * w + 3) // 4 * 4
+        f_off["src"], f_off["dst"] = f_total, f_total + (E + 3) // 4 * 4
+        f_total += 2 * ((E + 3) // 4 * 4)
+        field_flat = torch.empty(f_total, dtype=torch.int32, device=dev)
+        # ---- upload buffer: [small tables][CollateArgs]
+        s_off, s_total = {}, 0
+        for k, v in small.items():
+            s_off[k] = s_total
+            s_total += (v.size + 3) // 4 * 4
+        args_words = (C.sizeof(CollateArgs) + 3) // 4
+        s_total = (s_total + 1) // 2 * 2                       # 8-byte alignment of the argument block
+        up_host = torch.zeros(s_total + args_words, dtype=torch.int32).pin_memory()
+        up_np = up_host.numpy()
+        for k, v in small.items():
+            up_np[s_off[k]:s_off[k] + v.size] = v.reshape(-1)
+        up_dev = torch.empty_like(up_host, device=dev)
+        base = up_dev.data_ptr()
+        sp = lambda k: base + 4 * s_off[k]
+        a = CollateArgs()
+        a.B, a.mol = B, sp("mol")
+        jobs = []
+
+        def job(src, dst, src_off, dst_off, rows, words, kind, add=0, n_out=0, csel_p=0):
+            jobs.append((src, dst, src_off, dst_off, add, rows, words, kind, n_out, csel_p))
+        pp = lambda k: pack_flat.data_ptr() + 4 * p_off[k]
+        fp = lambda k: field_flat.data_ptr() + 4 * f_off[k]
+        # host-computed tables -> pack buffer (plain copies)
+        job(sp("off.n1"), pp("atom_off"), 0, 0, B + 1, 1, 4)
+        for l in range(4):
+            job(sp(f"off.{LEVELS[l]}"), pp(f"tup_off{l}"), 0, 0, B + 1, 1, 4)
+            job(sp(f"round_off{l}"), pp(f"round_off{l}"), 0, 0, B + 1, 1, 4)
+            job(sp(f"inv_end{l}"), pp(f"inv_ptr{l}") + 4 * N, 0, 0, 1, 1, 4)
+        job(sp("ind_end"), pp("indptr") + 4 * N, 0, 0, 1, 1, 4)
+        # per-molecule tables, shifted
+        for l, L in enumerate(TUPLE_LEN):
+            lvl = LEVELS[l]
+            T = int(off[lvl][-1])
+            nr = int(roff[l][-1])
+            job(self.table[f"idx{l}"].data_ptr(), pp(f"idx{l}"), self._table_rows[f"idx{l}"][1].data_ptr(), sp(f"off.{lvl}"), T, L, 1, sp("off.n1"))
+            job(self.table[f"inv_ptr{l}"].data_ptr(), pp(f"inv_ptr{l}"), self._table_rows[f"inv_ptr{l}"][1].data_ptr(), sp("off.n1"), N, 1, 1, sp(f"entoff{l}"))
+            # inverse entries: one row per (tuple, slot); their values are flat (tuple * L + slot) positions
+            job(self.table[f"inv_ent{l}"].data_ptr(), pp(f"inv_ent{l}"), self._table_rows[f"inv_ent{l}"][1].data_ptr(), sp(f"entoff{l}"), T * L, 1, 1, sp(f"entoff{l}"))
+            job(self.table[f"sched{l}"].data_ptr(), pp(f"sched{l}"), self._table_rows[f"sched{l}"][1].data_ptr(), sp(f"round_off{l}"), nr, ENERGY_GROUPS, 1, sp(f"off.{lvl}"))
+        job(self.table["indptr"].data_ptr(), pp("indptr"), self._table_rows["indptr"][1].data_ptr(), sp("off.n1"), N, 1, 1, sp("eoff"))
+        job(self.table["esrc"].data_ptr(), pp("esrc"), self._table_rows["esrc"][1].data_ptr(), sp("eoff"), E, 1, 1, sp("off.n1"))
+        job(self.table["erev"].data_ptr(), pp("erev"), self._table_rows["erev"][1].data_ptr(), sp("eoff"), E, 1, 1, sp("eoff"))
+        # graph edges and node fields
+        job(self.esrc_dev.data_ptr(), fp("src"), self.eoff_dev.data_ptr(), sp("eoff"), E, 1, 1, sp("off.n1"))
+        job(self.edst_dev.data_ptr(), fp("dst"), self.eoff_dev.data_ptr(), sp("eoff"), E, 1, 1, sp("off.n1"))
+        for (nt, k), (src, words, kind, dtype, trailing) in self.field.items():
+            rows = int(off[nt][-1])
+            if kind == 3:
+                job(src.data_ptr(), fp((nt, k)), self.foff_dev[(nt, k)].data_ptr(), sp(f"off.{nt}"), rows, words, 3, 0, n_confs, sp("csel"))
+            else:
+                job(src.data_ptr(), fp((nt, k)), self.off_dev[nt].data_ptr(), sp(f"off.{nt}"), rows, words, kind, sp("off.n1") if kind in (1, 2) else 0)
+        return self._finish(a, jobs, up_host, up_dev, s_total, pack_flat, p_off, pack_sizes, field_flat, f_off, f_meta, off, eoff,
+                            cnt, ia, n_confs, small, s_off, B, N, E, roff)
+
+    def _finish(self, a, jobs, up_host, up_dev, s_total, pack_flat, p_off, pack_sizes, field_flat, f_off, f_meta, off, eoff, cnt, ia,
+                n_confs, small, s_off, B, N, E, roff):
+        import ctypes as C
+        from . import _lib
+        from ._lib_ops import COLLATE_MAX_JOBS, CollateArgs
+        from .pack import LEVELS, TUPLE_LEN, PackedBatch
+        dev = self.device
+        # the inverse-entry job needs per-molecule OUTPUT offsets = tuple offsets * L: they are the `add.tupL` tables with the total appended
+        fixed = []
+        for (src, dst, src_off, dst_off, add, rows, words, kind, n_out, csel_p) in jobs:
+            fixed.append([src, dst, src_off, dst_off, add, rows, words, kind, n_out, csel_p])
+        if len(fixed) > COLLATE_MAX_JOBS:
+            raise _lib.GrappaB200Error(f"DeviceDataset.collate: {len(fixed)} jobs > {COLLATE_MAX_JOBS} (too many node fields)")
+        max_words = 1
+        a.n_jobs = len(fixed)
+        for i, (src, dst, src_off, dst_off, add, rows, words, kind, n_out, csel_p) in enumerate(fixed):
+            j = a.job[i]
+            j.src, j.dst, j.src_off, j.dst_off, j.add = src, dst, src_off or None, dst_off or None, add or None
+            j.confs = self.confs_dev.data_ptr() if kind == 3 else None
+            j.csel = csel_p or None
+            j.row_words, j.kind, j.n_confs_out, j.n_rows = words, kind, n_out, rows
+            max_words = max(max_words, rows * (words * n_out if kind == 3 else words))
+        raw = (C.c_int32 * ((C.sizeof(CollateArgs) + 3) // 4)).from_buffer_copy(bytes(a).ljust(((C.sizeof(CollateArgs) + 3) // 4) * 4, b"\0"))
+        up_host.numpy()[s_total:s_total + len(raw)] = np.frombuffer(raw, dtype=np.int32)
+        up_dev.copy_(up_host, non_blocking=True)
+        _lib.check(_lib.lib().grappa_b200_collate(up_dev.data_ptr() + 4 * s_total, a.n_jobs, max_words,
+                                                  torch.cuda.current_stream().cuda_stream), "collate")
+        # ---- views: graph
+        src = field_flat[f_off["src"]:f_off["src"] + E]
+        dst = field_flat[f_off["dst"]:f_off["dst"] + E]
+        g = MolGraph({nt: int(off[nt][-1]) for nt in NTYPES}, src, dst, {nt: torch.from_numpy(cnt[nt].copy()) for nt in NTYPES})
+        for (nt, k), (srct, words, kind, dtype, trailing) in self.field.items():
+            rows, w = f_meta[(nt, k)]
+            flat = field_flat[f_off[(nt, k)]:f_off[(nt, k)] + rows * w]
+            shape = (rows, n_confs) + trailing if kind == 3 else (rows,) + trailing
+            g.nodes[nt].data[k] = flat.view(dtype).view(shape)
+        if n_confs:
+            sv = lambda k, n_: up_dev[s_off[k]:s_off[k] + n_]
+            g.nodes["g"].data["is_dummy"] = sv("is_dummy", B * n_confs).view(torch.float32).view(B, n_confs)
+            g.nodes["g"].data["n_valid"] = sv("n_valid", B)
+        g._collate_keepalive = (up_host, up_dev)         # the pinned source of the asynchronous upload must outlive it
+        # ---- views: pack
+        meta = dict(n_atoms=N, n_mols=B, n_edges=E, n_tuples=[int(off[LEVELS[l]][-1]) for l in range(4)],
+                    max_atoms_per_mol=int(cnt["n1"].max()) if B else 0, max_degree=int(self.max_degree[ia].max()) if B else 0,
+                    max_tuples_per_mol=[int(cnt[LEVELS[l]].max()) if B else 0 for l in range(4)],
+                    max_rounds_per_mol=[int(self.rounds[l][ia].max()) if B else 0 for l in range(4)])
+        g._pack_cache = PackedBatch.from_device(pack_flat, p_off, pack_sizes, meta)
+        return g

@@ -730,18 +730,15 @@ class WriteTorsionParameters(_TupleWriter):
         return g
 
 
-# CUDA stream priorities of the (proper, angle, bond, improper) writer streams.  Off on one GPU (measured: 9.8 -> 10.5 ms
-# per step: serialising the writers costs more than it gains when there is nothing to overlap); training.Trainer turns them
-# on for data-parallel runs, where they let the small writers' gradient buckets be exchanged early.
-# GRAPPA_B200_WRITER_PRIO = 0 / 1 forces them off / on (tuning aid).
+# CUDA stream priorities of the (proper, angle, bond, improper) writer streams: OFF.  They were meant to finish the small
+# writers first so that their gradient buckets are exchanged early under data parallelism, but serialising the writers
+# costs more than the earlier exchange gains -- measured on B200: 1 GPU 9.8 -> 10.5 ms per step, 2 GPUs 8.74 -> 9.19 ms
+# (profiles/r2_summary.md).  GRAPPA_B200_WRITER_PRIO=1 turns them on (tuning aid).
 _WRITER_PRIORITIES = (0, -1, -2, -3) if os.environ.get("GRAPPA_B200_WRITER_PRIO") == "1" else None
 
 
 def set_writer_priorities(on: bool):
     global _WRITER_PRIORITIES
-    forced = os.environ.get("GRAPPA_B200_WRITER_PRIO")
-    if forced is not None:
-        on = forced == "1"
     _WRITER_PRIORITIES = (0, -1, -2, -3) if on else None
 
 
@@ -796,10 +793,7 @@ class WriteParameters(nn.Module):
         start = torch.cuda.Event()
         start.record(main)
         done = []
-        # Stream priorities, smallest writer first: all four writers issue the same ~70-kernel chain, so at equal priority
-        # they finish together however different their token counts are, and under data parallelism all four gradient
-        # buckets (54 % of the bytes) become ready at the same moment, right before the short GNN backward.  With the
-        # small writers scheduled first their buckets are exchanged while the large writers are still computing.
+        # Optional stream priorities, smallest writer first (off by default, see _WRITER_PRIORITIES above)
         prios = _WRITER_PRIORITIES if torch.is_grad_enabled() else None
         for w, st in zip(writers, T_.helper_streams(len(writers), "writer", prios)):
             st.wait_event(start)

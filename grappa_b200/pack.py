@@ -60,6 +60,33 @@ def _offsets(counts) -> np.ndarray:
 class PackedBatch:
     """Device-resident int32 index tables of one batch (see module docstring)."""
 
+    # order of the tables inside the flat buffer (each starts on a 16-byte boundary)
+    TABLE_ORDER = (("atom_off",) + tuple(f"{n}{l}" for l in range(4) for n in ("idx", "tup_off", "inv_ptr", "inv_ent"))
+                   + tuple(f"{n}{l}" for l in range(4) for n in ("round_off", "sched")) + ("indptr", "esrc", "erev"))
+
+    @classmethod
+    def from_device(cls, flat: torch.Tensor, offsets: Dict[str, int], sizes: Dict[str, int], meta: dict) -> "PackedBatch":
+        """A pack whose tables were assembled ON THE DEVICE (dataset.DeviceDataset.collate) in the flat layout above.
+        `meta`: n_atoms, n_mols, n_edges, n_tuples, max_atoms_per_mol, max_degree, max_tuples_per_mol, max_rounds_per_mol."""
+        p = cls.__new__(cls)
+        p.device = flat.device
+        for k, v in meta.items():
+            setattr(p, k, v)
+        p.sched_groups = ENERGY_SCHED_GROUPS
+        p.host = None
+        p._names = list(cls.TABLE_ORDER)
+        p._sizes = [int(sizes[k]) for k in p._names]
+        p._offsets = [int(offsets[k]) for k in p._names]
+        p._stage = None
+        p._flat = flat
+        p.bytes = flat.numel() * 4
+        shapes = {}
+        for l, L in enumerate(TUPLE_LEN):
+            shapes[f"idx{l}"] = (-1, L)
+            shapes[f"sched{l}"] = (-1, ENERGY_SCHED_GROUPS)
+        p._dev = {k: flat[o:o + s].view(shapes.get(k, (-1,))) for k, s, o in zip(p._names, p._sizes, p._offsets)}
+        return p
+
     def __init__(self, g, device=None):
         n_atoms = g.num_nodes("n1")
         dev = device if device is not None else g.nodes["n1"].data[next(iter(g.nodes["n1"].data))].device
@@ -125,6 +152,7 @@ class PackedBatch:
         self.max_degree = int(deg.max()) if n_atoms else 0
         self.host = host
         self._names = list(host.keys())
+        assert tuple(self._names) == self.TABLE_ORDER
         self._sizes = [host[k].size for k in self._names]
         # every table starts on a 16-byte boundary of the staging buffer (the energy kernel fetches a torsion's four atom
         # indices with one 16-byte load)
@@ -158,6 +186,14 @@ class PackedBatch:
         """Copy of the pack on another device (one H2D transfer of the staging buffer)."""
         import copy as _copy
         p = _copy.copy(self)
+        if self._stage is None:                 # assembled on the device: move the flat buffer itself
+            if torch.device(device) == self._flat.device:
+                return self
+            flat = self._flat.to(device)
+            return PackedBatch.from_device(flat, dict(zip(self._names, self._offsets)), dict(zip(self._names, self._sizes)),
+                                           dict(n_atoms=self.n_atoms, n_mols=self.n_mols, n_edges=self.n_edges, n_tuples=self.n_tuples,
+                                                max_atoms_per_mol=self.max_atoms_per_mol, max_degree=self.max_degree,
+                                                max_tuples_per_mol=self.max_tuples_per_mol, max_rounds_per_mol=self.max_rounds_per_mol))
         p._materialise(device)
         return p
 
@@ -171,7 +207,7 @@ class PackedBatch:
         """Overwrite the device tables in place with another pack of the same signature (one async H2D copy)."""
         if other.signature() != self.signature():
             raise ValueError("PackedBatch.copy_from: signatures differ")
-        src = other._stage if other._flat.device != self._flat.device else other._flat
+        src = other._stage if (other._flat.device != self._flat.device and other._stage is not None) else other._flat
         self._flat.copy_(src, non_blocking=True)
         self.host = other.host
 

@@ -129,7 +129,6 @@ class Trainer:
         self._next_bucket = 0
         if self.distributed:
             models.set_backward_hook(self._on_stage_backward)
-            models.set_writer_priorities(self.device.type == "cuda")
 
     # ---- learning rate / step count (device-resident) ------------------------------------------
     @property
