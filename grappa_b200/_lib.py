@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgrappa_b200.so")
+LIB_PATH = os.environ.get("GRAPPA_B200_LIB") or os.path.join(HERE, "libgrappa_b200.so")   # override: instrumented debug builds (tools/gemm_trace.py)
 
 
 class GrappaB200Error(RuntimeError):

@@ -39,6 +39,10 @@
 #include "gemm_epilogue.cuh"
 #include "mbar.cuh"
 
+#ifndef GB_X3_SPLIT
+#define GB_X3_SPLIT 1   // 0: Veltkamp split in packed fp32 + integer rounding of the remainder, 1: cvt.rn.bf16x2.f32 for both planes
+#endif
+
 namespace gb {
 
 constexpr int TC_BM = 128;
@@ -101,8 +105,13 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t cta_addr, uint32_t rank) 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
   return r;
 }
+// Arrival on a barrier of another CTA of the cluster.  The default form (what cutlass::arch::ClusterBarrier::arrive(cta_id)
+// issues) is ONE SYNCS.ARRIVE; spelling out .release.cluster makes ptxas emit MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in front
+// of it -- measured with clock64 stamps (tools/gemm_trace.py): ~1500 cycles per arrival, which serialised the bf16x3
+// pair pipeline at one k-block per 1600 cycles.  Data handed over with it is already fenced by its writers
+// (fence.proxy.async + CTA-scope barrier) or read out of tensor memory (tcgen05.wait::ld).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // data lands in THIS CTA's shared memory, the transaction bytes complete on the barrier at `mbar_cluster_addr`
 // (the leader CTA's full barrier): what cute::SM100_TMA_2SM_LOAD does
@@ -145,19 +154,31 @@ __device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t a_des
 // generic-proxy shared-memory writes (the converter's st.shared) -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// Two fp32 values (one 64-bit register) -> packed bf16 pair of the leading parts and packed bf16 pair of the remainders.
-//   hi = rn_bf16(a) by Veltkamp's splitting in PACKED fp32 arithmetic: c = a * (2^16 + 1); hi = c - (c - a) keeps the
-//        leading 8 significant bits of a, rounded to nearest (identical to cvt.rn.bf16.f32 on every finite input tested);
-//   lo = a - hi is exact in fp32; its leading 8 bits (rounded half-up on the bit pattern) go to the lo plane.
-// hi + lo carries 16 significant bits (|error| <= 2^-17 |a|, unbiased).  4 packed FP + 2 integer adds + 2 PRMT per PAIR.
-// History (ncu, profiles/r2_summary.md): cvt.rn.bf16x2.f32 (F2FP) runs on the XU pipe, ~7 cycles per warp instruction
-// per SM -- 84 % busy, converter 3x slower than the MMAs; integer rounding (IADD + LOP + FADD + IADD + PRMT per element)
-// left one converter warp per scheduler at 0.24 IPC with ~490 instructions per k-block.
-// `z` is a packed zero the compiler cannot see through: c must be ROUNDED before c - a is formed, but ptxas contracts a
-// packed multiply into the dependent add / sub even with explicit .rn (c - a became fma(a, 65537, -a) = 65536 a exactly,
-// the lo plane lost its meaning and results fell back to bf16 accuracy).  With c = fma(a, K, z) there is no bare multiply
-// left to contract.
+// Two fp32 values (one 64-bit register) -> packed bf16 pair of the leading parts and packed bf16 pair of the remainders:
+//   hi = rn_bf16(a);  lo = rn_bf16(a - hi)  (a - hi is exact in fp32), so hi + lo carries 16 significant bits
+//   (|error| <= 2^-17 |a|, unbiased).
+// GB_X3_SPLIT = 1 (default): cvt.rn.bf16x2.f32 (SASS F2FP.BF16.F32.PACK_AB) for both planes + shift / mask / one packed
+//   subtract -- 5 instructions per pair.
+// GB_X3_SPLIT = 0: Veltkamp's splitting in PACKED fp32 arithmetic (c = a * (2^16 + 1); hi = c - (c - a), identical to
+//   cvt.rn on every finite input tested) + integer half-up rounding of the remainder: 4 packed FP + 2 integer adds +
+//   2 PRMT per pair.  `z` is a packed zero the compiler cannot see through: c must be ROUNDED before c - a is formed,
+//   but ptxas contracts a packed multiply into the dependent add / sub even with explicit .rn (c - a became
+//   fma(a, 65537, -a) = 65536 a exactly and results fell back to bf16 accuracy); with c = fma(a, K, z) there is no bare
+//   multiply left to contract.
+// History (profiles/r2_summary.md): the first F2FP version looked XU-bound under ncu and was replaced by integer rounding
+// and then by the Veltkamp form -- all three were measured while the pipeline was serialised by a cluster-scope release
+// on the peer CTA's hand-off (see mbar_arrive_cluster), which hid the real ranking.  Measured once that was fixed
+// (tools/microbench/pipes.cu: F2FP issues at the same 1.9 warp instructions / clk / SM as PRMT / LOP3): training step
+// 7.17 ms with GB_X3_SPLIT = 0, 6.88 ms with 1.
 __device__ __forceinline__ void split_pair2(F2 a, F2 z, uint32_t& hi, uint32_t& lo) {
+#if GB_X3_SPLIT == 1
+  // cvt.rn.bf16x2.f32 (F2FP) for both planes: 2 F2FP + shift + mask + one packed subtract per pair
+  const float a0 = gb::lo(a), a1 = gb::hi(a);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(a1), "f"(a0));
+  const F2 l = a - f2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(gb::hi(l)), "f"(gb::lo(l)));
+  (void)z;
+#else
   const F2 c = fma2(a, f2(65537.0f), z);
   const F2 h = c - (c - a);
   const F2 l = a - h;
@@ -165,6 +186,7 @@ __device__ __forceinline__ void split_pair2(F2 a, F2 z, uint32_t& hi, uint32_t& 
   const unsigned long long lr = l.v + 0x0000800000008000ull;   // round the remainders half-up to bf16 (no carry between the halves
                                                                 // for finite values); truncation alone left 2^-16 relative error
   lo = __byte_perm((uint32_t)(lr & 0xffffffffull), (uint32_t)(lr >> 32), 0x7632);
+#endif
 }
 __device__ __forceinline__ void split8(const float (&v)[8], F2 z, uint4& hi, uint4& lo) {
   split_pair2(f2(v[0], v[1]), z, hi.x, lo.x);
@@ -173,12 +195,19 @@ __device__ __forceinline__ void split8(const float (&v)[8], F2 z, uint4& hi, uin
   split_pair2(f2(v[6], v[7]), z, hi.w, lo.w);
 }
 
-// bf16x3 warp roles (448 threads): TMA warp, MMA warp, 4 epilogue warps (one per TMEM lane quarter, all BN columns each),
-// 8 converter warps in two groups of four: group g rewrites the stages of k-blocks g, g + 2, ..., so two stages are being
-// converted at any time (one group alone spent ~40 % of its time in the fence / barrier hand-off of each stage)
-constexpr int TC_CONV_WARPS = 4;    // converter warps per group (= warps that share one stage)
-constexpr int TC_CONV_GROUPS = 2;
-constexpr int TC_EPI_WARPS_X3 = 4;
+// bf16x3 warp roles (512 threads, 128 registers): TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter, half of
+// the BN columns each -- with four the epilogue, 18-20 k cycles per 128 x 256 tile, was longer than the tile's mainloop),
+// 6 converter warps in three groups of two: group g rewrites the stages of k-blocks g, g + 3, ..., so three stages are
+// being converted at any time.  (18 warps = 8 + 8 cap the kernel at 96 registers: the epilogue spills and the step is
+// 0.8 ms slower; A/B builds: tools/gemm_trace.py build <name>.so -DGB_X3_CONV_WARPS=.. -DGB_X3_CONV_GROUPS=.. -DGB_X3_EPI_WARPS=..)
+#ifndef GB_X3_CONV_WARPS   // -D overrides: A/B builds through tools/gemm_trace.py
+#define GB_X3_CONV_WARPS 2
+#define GB_X3_CONV_GROUPS 3
+#define GB_X3_EPI_WARPS 8
+#endif
+constexpr int TC_CONV_WARPS = GB_X3_CONV_WARPS;    // converter warps per group (= warps that share one stage)
+constexpr int TC_CONV_GROUPS = GB_X3_CONV_GROUPS;
+constexpr int TC_EPI_WARPS_X3 = GB_X3_EPI_WARPS;
 constexpr int TC_THREADS_X3 = 32 * (2 + TC_EPI_WARPS_X3 + TC_CONV_WARPS * TC_CONV_GROUPS);
 
 // One operand tile of one k-block, converted IN PLACE: fp32 (as TMA staged it) -> [32 bf16 hi | 32 bf16 lo] rows, K-major
@@ -249,8 +278,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 
+// Epilogue transpose patch: 32 rows x 32 floats, the 16-byte chunk index XOR-ed with (row & 7).  Conflict-free for the
+// row-per-lane writes and the 8-lanes-per-row reads without padding: 4 KB per warp, so eight epilogue warps fit next to a
+// six-stage operand ring.
+__device__ __forceinline__ int patch_off(int row, int col) { return row * 32 + ((((col >> 2) ^ row) & 7) << 2); }
+
 // Rows sub_r, sub_r + 4, ... of one transposed 32 x 32 accumulator patch: bias, feature-specialised epilogue, 16-byte stores.
-template <int MASK, int EPI_LD>
+template <int MASK>
 __device__ __forceinline__ void epi_patch_rows(const Epilogue& ep, const float* __restrict__ patch, int sub_r, int sub_c, int m0,
                                                int M, int col, const float4* res4, const float4* elu4) {
   const float4 b4 = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -264,7 +298,7 @@ __device__ __forceinline__ void epi_patch_rows(const Epilogue& ep, const float* 
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     if (m0 + sub_r + 4 * i < M) {
-      float4 acc = *reinterpret_cast<const float4*>(patch + (sub_r + 4 * i) * EPI_LD + sub_c);
+      float4 acc = *reinterpret_cast<const float4*>(patch + patch_off(sub_r + 4 * i, sub_c));
       acc.x += b4.x; acc.y += b4.y; acc.z += b4.z; acc.w += b4.w;
       const float4 o = ep.template store4_masked<MASK>(acc, crow, arow, didx, sd, res4[i], elu4[i]);
       if (MASK & 32) { csum.x += o.x; csum.y += o.y; csum.z += o.z; csum.w += o.w; }
@@ -314,6 +348,17 @@ __device__ __forceinline__ int find_problem(const TcParams& p, int item) {
   return g;
 }
 
+#ifdef GB_GEMM_TRACE
+// Debug build only (tools/gemm_trace.py): per-CTA clock64() stamps of the pipeline events of the first 128 k-blocks / tiles.
+__device__ long long* g_gemm_trace = nullptr;
+#define GB_TRACE(ev, idx)                                                                                  \
+  do {                                                                                                     \
+    if (g_gemm_trace && (idx) < 128u) g_gemm_trace[((size_t)blockIdx.x * 128 + (idx)) * 8 + (ev)] = clock64(); \
+  } while (0)
+#else
+#define GB_TRACE(ev, idx)
+#endif
+
 // CTAS = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) computes a 256 x BN tile; each CTA stages its own 128 rows
 // of A but only HALF of the B tile, so a pair moves 32 KB per k-block and CTA where two independent 128 x 256 CTAs move
 // 48 KB for the same FLOPs -- the kernel is bound by exactly that L2 -> SM operand traffic (profiles/r1_summary.md).
@@ -324,12 +369,11 @@ struct TcCfg {
   static constexpr int B_BYTES = B_ROWS * TC_BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   // 144-168 KB of operand ring.  bf16x3 converts every stage in place (same bytes), so both arithmetics share the ring depth.
-  // (bf16x3 has four epilogue patches instead of eight: room for one more stage)
-  static constexpr int STAGES = (CTAS == 2 ? (BN == 256 ? 5 : 7) : (BN == 256 ? 3 : (BN == 128 ? 5 : 7))) + (X3 ? 1 : 0);
+  static constexpr int STAGES = CTAS == 2 ? (BN == 256 ? 6 : 8) : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int CONV_STAGES = X3 ? STAGES : 0;   // one "converted" barrier per stage
   static constexpr int THREADS = X3 ? TC_THREADS_X3 : TC_THREADS;
   static constexpr int EPI_WARPS = X3 ? TC_EPI_WARPS_X3 : 8;
-  static constexpr int EPI_LD = 36;                     // floats per staged row (float4-aligned, conflict-free)
+  static constexpr int EPI_LD = 32;                     // floats per staged row (16-byte chunks swizzled, see patch_off)
   static constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_LD * 4; // one 32x32 transpose patch per epilogue warp
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
   static_assert(RING_BYTES + EPI_BYTES + 1024 + 512 <= 232448, "shared memory budget");
@@ -383,9 +427,8 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       mbar_init(&acc_empty[s], Cfg::EPI_WARPS * CTAS);   // one arrival per epilogue warp (of both CTAs of a pair, on the leader)
     }
     if (X3) {
-      // pair: the peer's converter warps arrive on the PEER's cfull; its otherwise idle MMA warp forwards ONE arrival
-      // per stage to the leader (a release at cluster scope costs ~600 cycles: kept off the converter warps)
-      for (int c = 0; c < CONV; ++c) mbar_init(&cfull[c], TC_CONV_WARPS + ((PAIR && rank == 0) ? 1 : 0));
+      // pair: the converter warps of BOTH CTAs arrive on the leader's cfull (its MMAs read both shared memories)
+      for (int c = 0; c < CONV; ++c) mbar_init(&cfull[c], TC_CONV_WARPS * CTAS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -427,6 +470,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
+          GB_TRACE(0, it);
           uint8_t* sa = smem + s * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           const int k = (kb0 + i) * TC_BK;
@@ -474,25 +518,6 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)TA << 15) | ((uint32_t)TB << 16) |
                                ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((TC_BM * CTAS) >> 4) << 24);
     uint32_t it = 0, lt = 0;
-    if (X3 && PAIR && rank != 0) {
-      // forwarder: when this CTA's converter warps have rewritten a stage, tell the leader (whose MMAs read both CTAs'
-      // shared memory).  The converters' writes were fenced to the async proxy before their (CTA-scope) arrival; the
-      // acquire here + the cluster-scope release below carry them to the leader's MMA thread.
-      const uint32_t cfull_leader = mapa_rank(smem_u32(&cfull[0]), 0);
-      for (int item = first_item; item < n_items; item += item_stride) {
-        const TcProblem& q = p.pr[GROUPED ? find_problem(p, item) : 0];
-        const int z = (item - q.item_begin) / (q.tiles_n * q.tiles_m);
-        const int total_kb = (q.K + TC_BK - 1) / TC_BK;
-        const int kb0 = z * q.k_blocks_per_split;
-        const int num_kb = min(total_kb, kb0 + q.k_blocks_per_split) - kb0;
-        for (int i = 0; i < num_kb; ++i, ++it) {
-          const int s = it % STAGES;
-          mbar_wait(&cfull[s], (it / STAGES) & 1);
-          if (lane == 0) mbar_arrive_cluster(cfull_leader + (uint32_t)s * 8u);
-          __syncwarp();
-        }
-      }
-    }
     for (int item = first_item; item < n_items && rank == 0; item += item_stride, ++lt) {
       const TcProblem& q = p.pr[GROUPED ? find_problem(p, item) : 0];
       const int z = (item - q.item_begin) / (q.tiles_n * q.tiles_m);
@@ -513,6 +538,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           mbar_wait(&cfull[s], ph);
           tc_fence_after();
           if (elect_one()) {
+            GB_TRACE(3, it);
             const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
             const uint32_t sb = sa + A_BYTES;
 #pragma unroll
@@ -537,6 +563,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
               tc_commit(&empty_bar[s]);
               if (i == num_kb - 1) tc_commit(&acc_full[as]);
             }
+            GB_TRACE(4, it);
           }
           __syncwarp();
           continue;
@@ -546,6 +573,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         if (elect_one()) {
+          GB_TRACE(3, it);
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
           const uint32_t sb = sa + A_BYTES;
 #pragma unroll
@@ -574,6 +602,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const int cw = (warp - (2 + Cfg::EPI_WARPS)) % TC_CONV_WARPS;      // position inside the group
     const int cgrp = (warp - (2 + Cfg::EPI_WARPS)) / TC_CONV_WARPS;    // group: k-blocks with it % TC_CONV_GROUPS == cgrp
     const F2 zero2 = f2(__int_as_float(p.n_items >> 30));   // 0.0f the compiler cannot fold (see split_pair2)
+    const uint32_t cfull_leader = PAIR ? mapa_rank(smem_u32(&cfull[0]), 0) : 0u;
     uint32_t it = 0;
     for (int item = first_item; item < n_items; item += item_stride) {
       const TcProblem& q = p.pr[GROUPED ? find_problem(p, item) : 0];
@@ -586,6 +615,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&full_bar[s], ph);          // TMA bytes of this stage have landed
+        if (cw == 0 && lane == 0) GB_TRACE(1, it);
         uint8_t* st = smem + s * STAGE_BYTES;
         convert_tile<TC_BM, TA != 0>(st, cw, lane, zero2);
         convert_tile<B_ROWS, TB != 0>(st + A_BYTES, cw, lane, zero2);
@@ -593,7 +623,11 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         // the unqualified fence also issues MEMBAR.ALL.GPU (ncu: 9 % of all stall samples, the converter warps 3x slower)
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&cfull[s]);
+        if (lane == 0) {
+          if (PAIR && rank != 0) mbar_arrive_cluster(cfull_leader + (uint32_t)s * 8u);
+          else mbar_arrive(&cfull[s]);
+        }
+        if (cw == 0 && lane == 0) GB_TRACE(2, it);
       }
     }
   } else {
@@ -644,6 +678,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           if (X3) mbar_wait_backoff(&acc_full[as], aph);   // the converter warps share these schedulers: do not spin next to them
           else mbar_wait(&acc_full[as], aph);
           tc_fence_after();
+          if (warp == 2 && lane == 0) GB_TRACE(6, lt);
         }
         float v[32];
         tc_ld16(t_addr + (uint32_t)c0, v);
@@ -659,7 +694,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         if (n0 + c0 >= pq.N) continue;   // warp-uniform
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(patch + lane * Cfg::EPI_LD + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          *reinterpret_cast<float4*>(patch + patch_off(lane, 4 * j)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         __syncwarp();
         if (col < pq.N) {
           if (pq.partial) {
@@ -670,7 +705,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 if (m0 + sub_r + 4 * i < pq.M)
-                  *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(patch + (sub_r + 4 * i) * Cfg::EPI_LD + sub_c);
+                  *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(patch + patch_off(sub_r + 4 * i, sub_c));
                 dst += step;
               }
             } else {
@@ -678,7 +713,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
               for (int i = 0; i < 8; ++i) {
                 const int r = sub_r + 4 * i;
                 if (m0 + r >= pq.M) break;
-                const float4 acc = *reinterpret_cast<const float4*>(patch + r * Cfg::EPI_LD + sub_c);
+                const float4 acc = *reinterpret_cast<const float4*>(patch + patch_off(r, sub_c));
                 float* dst = dst0 + (size_t)r * pq.N;
                 const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
                 for (int e = 0; e < 4; ++e)
@@ -686,19 +721,19 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
               }
             }
           } else if (vec_ok) {
-            if (fmask == 0) epi_patch_rows<0, Cfg::EPI_LD>(pq.ep, patch, sub_r, sub_c, m0, pq.M, col, res4, elu4);
-            else if (fmask == 1) epi_patch_rows<1, Cfg::EPI_LD>(pq.ep, patch, sub_r, sub_c, m0, pq.M, col, res4, elu4);
-            else if (fmask == 12) epi_patch_rows<12, Cfg::EPI_LD>(pq.ep, patch, sub_r, sub_c, m0, pq.M, col, res4, elu4);
-            else if (fmask == 10) epi_patch_rows<10, Cfg::EPI_LD>(pq.ep, patch, sub_r, sub_c, m0, pq.M, col, res4, elu4);
-            else if (fmask == 42) epi_patch_rows<42, Cfg::EPI_LD>(pq.ep, patch, sub_r, sub_c, m0, pq.M, col, res4, elu4);
-            else if (fmask == 63) epi_patch_rows<63, Cfg::EPI_LD>(pq.ep, patch, sub_r, sub_c, m0, pq.M, col, res4, elu4);
-            else epi_patch_rows<31, Cfg::EPI_LD>(pq.ep, patch, sub_r, sub_c, m0, pq.M, col, res4, elu4);
+            if (fmask == 0) epi_patch_rows<0>(pq.ep, patch, sub_r, sub_c, m0, pq.M, col, res4, elu4);
+            else if (fmask == 1) epi_patch_rows<1>(pq.ep, patch, sub_r, sub_c, m0, pq.M, col, res4, elu4);
+            else if (fmask == 12) epi_patch_rows<12>(pq.ep, patch, sub_r, sub_c, m0, pq.M, col, res4, elu4);
+            else if (fmask == 10) epi_patch_rows<10>(pq.ep, patch, sub_r, sub_c, m0, pq.M, col, res4, elu4);
+            else if (fmask == 42) epi_patch_rows<42>(pq.ep, patch, sub_r, sub_c, m0, pq.M, col, res4, elu4);
+            else if (fmask == 63) epi_patch_rows<63>(pq.ep, patch, sub_r, sub_c, m0, pq.M, col, res4, elu4);
+            else epi_patch_rows<31>(pq.ep, patch, sub_r, sub_c, m0, pq.M, col, res4, elu4);
           } else {
 #pragma unroll 1
             for (int i = 0; i < 8; ++i) {
               const int r = sub_r + 4 * i;
               if (m0 + r >= pq.M) break;
-              const float4 acc = *reinterpret_cast<const float4*>(patch + r * Cfg::EPI_LD + sub_c);
+              const float4 acc = *reinterpret_cast<const float4*>(patch + patch_off(r, sub_c));
               const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
               for (int e = 0; e < 4; ++e)
                 if (col + e < pq.N) pq.ep.store(a4[e], m0 + r, col + e);
@@ -707,6 +742,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         }
         __syncwarp();
       }
+      if (warp == 2 && lane == 0) GB_TRACE(7, lt);
     }
   }
   tc_fence_before();
@@ -1043,3 +1079,9 @@ int gemm_tcgen05_grouped(const gb_gemm_args* list, int n, cudaStream_t stream, b
 }
 
 }  // namespace gb
+
+#ifdef GB_GEMM_TRACE
+extern "C" int grappa_b200_debug_set_gemm_trace(long long* buf) {
+  return cudaMemcpyToSymbol(gb::g_gemm_trace, &buf, sizeof(buf)) == cudaSuccess ? 0 : -1;
+}
+#endif
