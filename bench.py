@@ -450,8 +450,12 @@ def main():
     exec_equiv = sum(mma_factor.get(k, 0.0) * v for k, v in by_prec.items()) / tot_alg
     roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 + TMA)" if tensor_path else "sgemm_kernel (fp32 FFMA)",
                 "achieved": achieved_tf, "peak": peaks["tflops_burst"], "unit": "TFLOP/s",
-                "frac": achieved_tf / peaks["tflops_burst"], "traffic": None,
-                "traffic_source": "see profiles/ (ncu --set full of the step's largest token GEMM)",
+                "frac": achieved_tf / peaks["tflops_burst"],
+                "traffic": 67.4e6 if prec == "bf16x3" else None,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum = 33.6 + 33.7 MB for ONE launch of the step's largest "
+                                  "token GEMM (proper in_proj, 14848 x 1536 x 512, bf16x3; ncu --set full, profiles/r2_gemm_x3_ncu_raw.csv); "
+                                  "algorithmic bytes of that launch 124.7 MB (A 30.4 + B 3.1 + C 91.2): no operand is re-read from HBM, "
+                                  "most of C is still in the 126 MB L2 when the kernel ends",
                 "algorithmic_flops_by_arithmetic": {k: v for k, v in by_prec.items()},
                 "tensor_pipe_bf16_equivalent_frac": achieved_tf * exec_equiv / peaks["tflops_burst"],
                 "tensor_pipe_note": "frac counts ALGORITHMIC FLOPs (2*M*N*K); the tensor pipe executes 3 bf16 MMAs per bf16x3 "
@@ -507,7 +511,7 @@ def main():
         try:
             from grappa_b200 import graph as gbg
             from grappa_b200.training import shard_molecules
-            n_mols_total = 1000
+            n_mols_total = 1000 * world    # weak scaling like the training step: 1000 molecules per GPU
             mine = list(shard_molecules(n_mols_total, rank, world))      # molecule i -> rank i mod world, no communication
             rows = []
             for n_confs in (100, 1000):
@@ -551,9 +555,10 @@ def main():
                            "sweep": rows,
                            "roofline": {"bound": "hbm", "kernel": "energy_pairs_kernel (K13, two conformations per lane, f32x2)",
                                         "achieved": head["achieved_GBps_all_gpus"], "peak": world * peaks["hbm_gbs"], "unit": "GB/s",
-                                        "frac": head["frac_of_hbm_peak"], "traffic": None,
-                                        "traffic_source": "profiles/ (ncu --set full of this launch: dram bytes below the algorithmic "
-                                                          "bytes, part of the gradient still in L2 at kernel end)",
+                                        "frac": head["frac_of_hbm_peak"], "traffic": 94.2e6,
+                                        "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum = 71.0 + 23.2 MB per launch (1000 molecules "
+                                                          "x 100 conformations, lean; ncu --set full, profiles/r2_energy_pairs_ncu_raw.csv) against "
+                                                          "131.9 MB algorithmic: nothing is re-read, part of the gradient is still in L2 at kernel end",
                                         "bound_note": "instruction-issue / shared-memory bound, not HBM bound (SURVEY.md 8d: 22-55 flop/B "
                                                       "at the lean byte count, above the fp32 ridge); fp32-pipe utilisation from the ncu "
                                                       "capture in profiles/", "peak_source": peaks["source"]}}

@@ -59,7 +59,9 @@ _BACKWARD_HOOK = None
 def set_backward_hook(fn):
     """fn(tag) is called during backward when all gradients of a stage (('writer', module)), of one GNN
     block (('gnn_block', i)) or of the rest of the GNN (('gnn_rest', None)) are final -- used by
-    training.Trainer to start the bucketed gradient all-reduce while backward is still running."""
+    training.Trainer to start the bucketed gradient all-reduce while backward is still running.
+    Inside a writer, ('writer_part', (module, k, events)) fires when part k of `writer_parts(module)` is final once
+    `events` have completed (the backward chain itself does not wait for them)."""
     global _BACKWARD_HOOK
     _BACKWARD_HOOK = fn
 
@@ -475,6 +477,14 @@ class _TupleWriter(nn.Module):
     def _head_args(self, T: int) -> HeadOutArgs:
         raise NotImplementedError
 
+    def parts(self):
+        """Sub-modules whose gradients become final one after the other during this writer's backward pass (the
+        'writer_part' hook): symmetriser first, then the transformer layers from the last to the first.  Whatever else
+        the writer owns (projector, learnable statistics) is final at the ('writer', module) hook."""
+        m = self._model()
+        layers = list(m.grappa_transformer.transformer) if m.grappa_transformer is not None else []
+        return [m.symmetriser] + layers[::-1]
+
     def _stat_params(self):
         """learnable_statistics: the statistics parameters in the slot order of gb_head_out_args.stat, else None."""
         return None
@@ -499,6 +509,13 @@ class _TupleWriter(nn.Module):
         args = self._head_args(T)
         stat_params = self._stat_params()
 
+        n_layers = len(gt.transformer) if gt is not None else 0
+
+        def part_done(t: Tape, k: int):
+            # backward closures run in reverse order of their push: this one right after part k's backward ops
+            if _BACKWARD_HOOK is not None:
+                t.push(lambda: _fire(("writer_part", (self, k, t.flush_events()))))
+
         def run(t: Tape, ins, params):
             P = lambda p: params[index[id(p)]]
             h = ins[0]
@@ -507,8 +524,10 @@ class _TupleWriter(nn.Module):
                              out_ld=(E if E % 4 == 0 else (E + 3) // 4 * 4))
             x = T_.tuple_gather(t, proj, pack, self.level_id, pe, F, E)
             if gt is not None:
-                for layer in gt.transformer:
+                for li, layer in enumerate(gt.transformer):
+                    part_done(t, n_layers - li)          # parts in backward order: 0 = symmetriser, 1 = last layer, ...
                     x = layer.tape_forward(t, x, T, L, P)
+            part_done(t, 0)
             s = T_.perm_concat(t, x, sym._perms_c, T, L, E)
             for ff in sym.mlp:
                 s = ff.tape_forward(t, s, P)

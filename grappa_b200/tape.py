@@ -134,6 +134,25 @@ class Tape:
         with self.side_branch(*tensors):
             ops.gemm_grouped([(d, x, kw) for d, x, _, kw in batch])
 
+    def flush_events(self):
+        """Issue every deferred weight-gradient / column-sum kernel recorded so far and return CUDA events (current
+        stream, weight-gradient stream) after which the parameter gradients written so far are final -- WITHOUT making
+        the current stream wait for the weight-gradient branch (`join_side` does).  Used by the data-parallel trainer
+        to exchange a stage's gradients part by part while its backward pass is still running."""
+        self.flush_wgrads()
+        self.colsums.flush()
+        if not torch.cuda.is_available():
+            return ()
+        evs = []
+        ev = torch.cuda.Event()
+        ev.record()
+        evs.append(ev)
+        if self._side is not None and self._side_dirty:
+            ev2 = torch.cuda.Event()
+            ev2.record(self._side)
+            evs.append(ev2)
+        return tuple(evs)
+
     def join_side(self):
         """Fold the deferred column sums and make the current stream wait for the weight-gradient branch (before
         parameter gradients are consumed)."""

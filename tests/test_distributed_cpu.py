@@ -32,20 +32,37 @@ def _worker(rank, world, port, out):
     model = models.model_from_config(orc.small_model_config())
     tr = Trainer(model, None, None, device="cpu")
     assert tr.distributed and tr.world == world and tr.comm_stream is None
-    tr.fp.grad.fill_(float(rank + 1))
+    # gradients are garbage until the hook of their part fires: a part exchanged too early sums the garbage
+    tr.fp.grad.fill_(1000.0)
+    final = float(rank + 1)
+
+    def finish(spans):
+        for s, e in spans:
+            tr.fp.grad[s:e] = final
     # fire the hooks in the order the backward pass does
     w_ = model.parameter_writer
     # rank 1's batch has no propers: that writer never runs there, its (zero) bucket is only marked ready -- and the
     # hooks of the other writers fire in a different order than on rank 0.  The collectives must still pair up.
+    names = {id(mod): name for name, mod in tr.buckets}
     if rank == 1:
-        tr._ready.add("proper")
+        finish([tr._bucket_spans["proper"]])
+        tr._mark_unused("proper")
         fire = (w_.bond_writer, w_.improper_writer, w_.angle_writer)
     else:
         fire = (w_.improper_writer, w_.proper_writer, w_.angle_writer, w_.bond_writer)
     for mod in fire:
+        # a writer's gradients become final part by part (symmetriser, transformer layers, then the rest)
+        parts = tr._part_spans[names[id(mod)]]
+        for k in range(len(mod.parts())):
+            finish(parts[k])
+            tr._on_stage_backward(("writer_part", (mod, k, ())))
+        finish(parts[-1])
         tr._on_stage_backward(("writer", mod))
     for i in reversed(range(len(model.gnn.att_blocks))):
+        finish([tr._block_spans[i]])
         tr._on_stage_backward(("gnn_block", i))
+    (s0, e0), b0, b1 = tr._gnn_span, tr._block_spans[0][0], tr._block_spans[-1][1]
+    finish([(s0, b0), (b1, e0)])          # pre_dense / post_dense: the GNN span outside its blocks
     tr._on_stage_backward(("gnn_rest", None))
     ok = bool(torch.all(tr.fp.grad == float(sum(range(1, world + 1)))))
     shard = list(shard_molecules(10, rank, world))

@@ -84,6 +84,11 @@ print("avg concurrent kernels per 0.5 ms bucket:", [round(o / B, 2) for o in occ
 nccl = [e for e in step if "nccl" in e["name"].lower()]
 if nccl:
     print("NCCL kernels of the step (start us, duration us):", [(round(e["ts"] - t0), round(e["dur"])) for e in nccl])
+tail = [e for e in step if any(k in e["name"] for k in ("sumsq", "adam", "tick"))]
+print("optimizer tail (name, start us, duration us):", [(e["name"].split("(")[0][-24:], round(e["ts"] - t0), round(e["dur"])) for e in tail])
+other = [e for e in step if e not in tail and "nccl" not in e["name"].lower()]
+print("last compute kernel before the optimizer ends at", round(max(e["ts"] + e["dur"] for e in other) - t0), "us:",
+      max(other, key=lambda e: e["ts"] + e["dur"])["name"][:60])
 if world > 1:
     import torch.distributed as dist
     dist.barrier()
