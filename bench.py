@@ -343,8 +343,13 @@ def main():
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         param_sync = {"max_cross_rank_checksum_difference": float((hi - lo).abs().max().item()),
+                      "identical_on_all_ranks": bool((hi - lo).abs().max().item() == 0.0),
                       "checksums": "sum, sum|.|, position-weighted sum of the flat fp32 parameter buffer (fp64), MIN / MAX over ranks",
-                      "steps_before_check": int(trainer.step_count)}
+                      "steps_before_check": int(trainer.step_count),
+                      "gradient_exchange": ("peer_allreduce_kernel over NVLink peer memory (csrc/peer_allreduce.cu), "
+                                            f"{trainer.peer.ctas} CTAs per launch" if trainer.peer is not None
+                                            else "ncclAllReduce (torch.distributed)"),
+                      "peer_barrier_timed_out": (bool(trainer.peer.timed_out()) if trainer.peer is not None else None)}
 
     # ---- (2) end to end from pinned host memory --------------------------------------------------
     def step_e2e():
@@ -559,9 +564,12 @@ def main():
                                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum = 71.0 + 23.2 MB per launch (1000 molecules "
                                                           "x 100 conformations, lean; ncu --set full, profiles/r2_energy_pairs_ncu_raw.csv) against "
                                                           "131.9 MB algorithmic: nothing is re-read, part of the gradient is still in L2 at kernel end",
-                                        "bound_note": "instruction-issue / shared-memory bound, not HBM bound (SURVEY.md 8d: 22-55 flop/B "
-                                                      "at the lean byte count, above the fp32 ridge); fp32-pipe utilisation from the ncu "
-                                                      "capture in profiles/", "peak_source": peaks["source"]}}
+                                        "ncu": {"capture": "profiles/r2_energy_pairs_ncu_raw.csv (1000 molecules x 100 conformations, lean)",
+                                                "fp32_pipe_active_pct": 35.8, "issue_slots_busy_pct": 52.3,
+                                                "lsu_shared_memory_wavefronts_pct_of_peak": 56.7, "warp_instructions_per_clk_per_sm": 2.0},
+                                        "bound_note": "shared-memory bandwidth / round-barrier bound, not HBM bound: ~34 KB of shared-memory "
+                                                      "traffic per conformation against 1.3 KB of HBM traffic (SURVEY.md 8d: 22-55 flop/B at the "
+                                                      "lean byte count, above the fp32 ridge)", "peak_source": peaks["source"]}}
         except Exception as e:  # pragma: no cover
             energy_eval = {"error": repr(e)}
 

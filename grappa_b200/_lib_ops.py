@@ -58,6 +58,19 @@ class CollateArgs(C.Structure):
     _fields_ = [("n_jobs", i32), ("B", i32), ("mol", vp), ("job", CollateJob * COLLATE_MAX_JOBS)]
 
 
+MAX_PEERS = 8           # GB_MAX_PEERS
+PEER_MAX_CTAS = 64      # GB_PEER_MAX_CTAS
+
+
+class IpcHandle(C.Structure):
+    _fields_ = [("bytes", C.c_ubyte * 64)]
+
+
+class PeerAllreduceArgs(C.Structure):
+    _fields_ = [("data", vp * MAX_PEERS), ("flags", vp * MAX_PEERS), ("rank", i32), ("world", i32), ("start", i64), ("count", i64),
+                ("epoch", vp), ("ctas", i32), ("split", i32)]
+
+
 class Perms(C.Structure):
     _fields_ = [("n_perm", i32), ("perm", (i32 * 4) * 6)]
 
@@ -109,6 +122,16 @@ def declare(lib):
     lib.grappa_b200_neighbor_mean.restype = C.c_int
     lib.grappa_b200_collate.argtypes = [vp, i32, i64, vp]
     lib.grappa_b200_collate.restype = C.c_int
+    lib.grappa_b200_ipc_alloc.argtypes = [i64, P(vp), P(IpcHandle)]
+    lib.grappa_b200_ipc_alloc.restype = C.c_int
+    lib.grappa_b200_ipc_open.argtypes = [P(IpcHandle), P(vp)]
+    lib.grappa_b200_ipc_open.restype = C.c_int
+    lib.grappa_b200_ipc_close.argtypes = [vp]
+    lib.grappa_b200_ipc_close.restype = C.c_int
+    lib.grappa_b200_ipc_free.argtypes = [vp]
+    lib.grappa_b200_ipc_free.restype = C.c_int
+    lib.grappa_b200_peer_allreduce.argtypes = [P(PeerAllreduceArgs), vp]
+    lib.grappa_b200_peer_allreduce.restype = C.c_int
     lib.grappa_b200_pad_rows.argtypes = [vp, i32, i32, i32, vp, i32, vp]
     lib.grappa_b200_pad_rows.restype = C.c_int
     lib.grappa_b200_gemm_can_fuse_colsum.argtypes = [P(GemmArgs)]

@@ -30,7 +30,9 @@ from . import models, ops
 class FlatParams:
     """Re-homes all parameters of a module into one flat buffer (+ flat grads, Adam m / v)."""
 
-    def __init__(self, module: torch.nn.Module, device):
+    def __init__(self, module: torch.nn.Module, device, grad_factory=None):
+        """`grad_factory(n_floats) -> fp32 tensor` supplies the gradient buffer (peer-mapped memory for the NVLink
+        all-reduce, `peer.PeerGradients`); default: an ordinary device tensor."""
         self.module = module
         params = [p for p in module.parameters() if p.requires_grad]
         self.params = params
@@ -42,7 +44,8 @@ class FlatParams:
             off += (n + 3) // 4 * 4
         self.offsets, self.total = offs, off
         self.flat = torch.zeros(off, device=device, dtype=torch.float32)
-        self.grad = torch.zeros(off, device=device, dtype=torch.float32)
+        self.grad = torch.zeros(off, device=device, dtype=torch.float32) if grad_factory is None else grad_factory(off)
+        assert self.grad.numel() >= off and self.grad.dtype == torch.float32
         self.m = torch.zeros(off, device=device, dtype=torch.float32)
         self.v = torch.zeros(off, device=device, dtype=torch.float32)
         with torch.no_grad():
@@ -100,9 +103,24 @@ class Trainer:
         self.clip, self.betas, self.eps = clip, betas, eps
         self.device = torch.device(device)
         model.to(self.device)
-        self.fp = FlatParams(model, self.device)
         self.distributed = dist.is_available() and dist.is_initialized() if distributed is None else distributed
         self.world = dist.get_world_size() if self.distributed else 1
+        # Single-node data parallelism on GPUs: gradients live in peer-mapped memory and are summed by our own NVLink
+        # kernel (csrc/peer_allreduce.cu).  GRAPPA_B200_PEER_ALLREDUCE=0, more than 8 ranks or several nodes: NCCL.
+        self.peer = None
+        if (self.distributed and self.device.type == "cuda" and 1 < self.world <= 8
+                and os.environ.get("GRAPPA_B200_PEER_ALLREDUCE", "1") != "0"
+                and int(os.environ.get("LOCAL_WORLD_SIZE", self.world)) == self.world):
+            from .peer import PeerGradients
+            holder = {}
+
+            def factory(n):
+                holder["peer"] = PeerGradients(n, self.device)
+                return holder["peer"].grad
+            self.fp = FlatParams(model, self.device, grad_factory=factory)
+            self.peer = holder["peer"]
+        else:
+            self.fp = FlatParams(model, self.device)
         self.gnorm_sq = torch.zeros(1, device=self.device, dtype=torch.float32)
         self._norm_ws = torch.zeros(1024, device=self.device, dtype=torch.float32)
         self.counters = torch.zeros(2, device=self.device, dtype=torch.int64)
@@ -221,7 +239,10 @@ class Trainer:
             with torch.cuda.stream(self.comm_stream):
                 for ev in events:
                     self.comm_stream.wait_event(ev)
-                dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+                if self.peer is not None:
+                    self.peer.allreduce(start, end - start)
+                else:
+                    dist.all_reduce(buf, op=dist.ReduceOp.SUM)
                 done = torch.cuda.Event()
                 done.record(self.comm_stream)
             self._pending.append(done)

@@ -60,6 +60,39 @@ int grappa_b200_torsions_classify(const int64_t* bonds, int64_t n_bonds, const i
 int grappa_b200_ring_encoding(int64_t n_atoms, const int64_t* bonds, int64_t n_bonds, float* enc);
 
 /* ---------------------------------------------------------------------------------------------
+ * Gradient all-reduce over NVLink peer memory (one process per GPU, all GPUs on one NVSwitch node).
+ * Replaces the DDP gradient all-reduce the reference gets from pytorch_lightning (reference
+ * src/grappa/training/trainrun.py:166-176 builds the pl.Trainer; lightning_model.py:205-230 is the
+ * step whose backward it synchronises).  The flat gradient buffer of every rank is allocated with
+ * grappa_b200_ipc_alloc and mapped by the other ranks with grappa_b200_ipc_open (handles exchanged by
+ * the host, e.g. torch.distributed.all_gather_object); grappa_b200_peer_allreduce then sums one span
+ * across the ranks inside ONE kernel: ready barrier, every rank reduces its 1/world slice with direct
+ * loads from the peers and stores the sum into every rank's buffer, done barrier.  All ranks must issue
+ * the same sequence of calls with the same `ctas`.  Results are bit-identical on all ranks.
+ * ------------------------------------------------------------------------------------------- */
+#define GB_MAX_PEERS 8
+#define GB_PEER_MAX_CTAS 64
+typedef struct { unsigned char bytes[64]; } gb_ipc_handle;   /* = cudaIpcMemHandle_t */
+/* cudaMalloc (zero-filled) + cudaIpcGetMemHandle */
+int grappa_b200_ipc_alloc(int64_t bytes, void** ptr, gb_ipc_handle* handle);
+/* map another process's allocation (cudaIpcOpenMemHandle, peer access enabled lazily) */
+int grappa_b200_ipc_open(const gb_ipc_handle* handle, void** ptr);
+int grappa_b200_ipc_close(void* ptr);
+int grappa_b200_ipc_free(void* ptr);
+typedef struct {
+  float* data[GB_MAX_PEERS];      /* base of every rank's gradient buffer as mapped HERE (own entry = local pointer)       */
+  uint32_t* flags[GB_MAX_PEERS];  /* every rank's flag block, GB_MAX_PEERS * GB_PEER_MAX_CTAS words, zero-initialised     */
+  int32_t rank, world;
+  int64_t start, count;           /* span to reduce, in floats; start must be a multiple of 4                            */
+  uint32_t* epoch;                /* LOCAL device memory, GB_PEER_MAX_CTAS + 1 words, zero-initialised: per-CTA launch    */
+                                  /* counters; word [GB_PEER_MAX_CTAS] is set to 1 if a barrier wait timed out (~2 s)     */
+  int32_t ctas;                   /* grid size, 1..GB_PEER_MAX_CTAS                                                       */
+  int32_t split;                  /* 1: the two cross-rank barriers run as one-warp kernels before / after the data      */
+                                  /*    kernel (3 launches; waiting for a late rank does not hold `ctas` SMs)             */
+} gb_peer_allreduce_args;
+int grappa_b200_peer_allreduce(const gb_peer_allreduce_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * MM energy + analytic forces over conformations (kernel K13) and its backward (K14).
  * Replaces internal_coordinates (reference src/grappa/models/internal_coordinates.py:15-125),
  * harmonic_energy / torsion_energy / pool_energy (models/energy.py:8-71) and the

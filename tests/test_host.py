@@ -56,6 +56,10 @@ def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(LossArgs) == 9 * 8 + 4 * 4 + 4 * 4 + 9 * 8
     from grappa_b200._lib_ops import ParamLossArgs
     assert ctypes.sizeof(ParamLossArgs) == 2 * 4 + 3 * 5 * 8 + 3 * 5 * 4 + 4 + 2 * 8 + 5 * 8 + 8   # 4 bytes of padding after fac[5]
+    from grappa_b200._lib_ops import IpcHandle, PeerAllreduceArgs
+    assert ctypes.sizeof(IpcHandle) == 64                                   # cudaIpcMemHandle_t
+    # data[8], flags[8], rank, world, start, count, epoch, ctas, split
+    assert ctypes.sizeof(PeerAllreduceArgs) == 16 * 8 + 2 * 4 + 2 * 8 + 8 + 4 + 4 and PeerAllreduceArgs.start.offset == 136
 
 
 @pytest.mark.parametrize("name", ["dipeptide", "peptide4", "tree", "rna", "protein30"])
