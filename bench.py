@@ -7,14 +7,15 @@ Workload = BASELINE.json configs[1]: one training step on a batch of 32 syntheti
 (ACE-(ALA)4-NME, 52 atoms, 50 conformations each) per GPU: grappa-1.2 GNN + 4 writers + MM
 energy/forces + molecule-wise energy+force loss, backward, global-norm clip, Adam.  Dropout is ON
 (train mode), nothing is cached between steps.  N > 1: one process per GPU (torchrun), each rank its
-own batch (weak scaling), bucketed NCCL gradient all-reduce overlapped with backward.
+own batch (weak scaling), bucketed gradient all-reduce overlapped with backward -- our own kernel over NVLink peer
+memory (csrc/peer_allreduce.cu; GRAPPA_B200_PEER_ALLREDUCE=0 selects NCCL), captured into the step's CUDA graph.
 
 Printed JSON line (rank 0): metric = training molecules/s (whole job); `e2e` = same through the public
 API from pinned HOST buffers (H2D of the batch + D2H of the loss inside the timed region); `e2e_loader` =
 the same with a FRESH batch collated by dataset.PrefetchLoader every step; `roofline` for the dominant kernel
 family (GEMMs -> tensor pipe, burst peak: the family is replayed alone); `gather_kernels` = HBM fractions of the
 gather-bound kernels north_star names (edge attention, tuple gather, LayerNorm); `energy_eval` = the second half of
-BASELINE's metric (conformation energy+force evaluations/s of kernel K13 on configs[3]: 1k molecules x
+BASELINE's metric (conformation energy+force evaluations/s of kernel K13 on configs[3]: 1k molecules per GPU x
 {100, 1000} conformations, lean and full-contract outputs, molecules sharded over the ranks, HBM roofline);
 `cpu_baseline` = the reference's CPU path on the host cores, same workload.
 
