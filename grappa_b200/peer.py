@@ -28,6 +28,18 @@ class _DeviceArray:
         self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None}
 
 
+class PeerUnavailable(RuntimeError):
+    """Raised on ALL ranks alike when any rank could not set up the peer mappings (the caller falls back to NCCL)."""
+
+
+def _agree(ok: bool, device: torch.device, what: str):
+    """Collective: every rank learns whether every rank succeeded; raises PeerUnavailable everywhere if one did not."""
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:
+        raise PeerUnavailable(f"peer-memory setup failed on at least one rank ({what})")
+
+
 class PeerGradients:
     """Flat fp32 gradient buffer of `n_floats` (rounded up to 16 bytes) in IPC-shareable device memory + the peer mappings."""
 
@@ -41,15 +53,19 @@ class PeerGradients:
         self.ctas = int(os.environ.get("GRAPPA_B200_PEER_CTAS", ctas or 32))
         lib = _lib.lib()
         with torch.cuda.device(device):
+            # every step that can fail locally is followed by an agreement, so that either all ranks use the peer kernel or
+            # all of them fall back (a rank that silently left the protocol would hang the others in the first barrier)
             ptr, handle = C.c_void_p(), IpcHandle()
             nbytes = self.n * 4 + FLAG_WORDS * 4
-            _lib.check(lib.grappa_b200_ipc_alloc(nbytes, C.byref(ptr), C.byref(handle)), "ipc_alloc")
+            rc = lib.grappa_b200_ipc_alloc(nbytes, C.byref(ptr), C.byref(handle))
+            _agree(rc == 0, device, "cudaMalloc / cudaIpcGetMemHandle")
             self._base = ptr.value
             # handles travel as plain bytes through the process group (host plumbing only)
             mine = (self.rank, int(device.index if device.index is not None else torch.cuda.current_device()), bytes(handle.bytes))
             everyone = [None] * self.world
             dist.all_gather_object(everyone, mine)
             self._peer_ptrs = [None] * self.world
+            ok = True
             for r, _dev, hb in everyone:
                 if r == self.rank:
                     self._peer_ptrs[r] = self._base
@@ -57,8 +73,9 @@ class PeerGradients:
                 h = IpcHandle()
                 C.memmove(h.bytes, hb, 64)
                 p = C.c_void_p()
-                _lib.check(lib.grappa_b200_ipc_open(C.byref(h), C.byref(p)), f"ipc_open(rank {r})")
+                ok = ok and lib.grappa_b200_ipc_open(C.byref(h), C.byref(p)) == 0
                 self._peer_ptrs[r] = p.value
+            _agree(ok, device, "cudaIpcOpenMemHandle: " + _lib.lib().grappa_b200_last_error().decode("utf-8", "replace"))
             self.grad = torch.as_tensor(_DeviceArray(self._base, self.n), device=device)
             self.epoch = torch.zeros(PEER_MAX_CTAS + 1, dtype=torch.int32, device=device)
             torch.cuda.synchronize(device)

@@ -111,14 +111,19 @@ class Trainer:
         if (self.distributed and self.device.type == "cuda" and 1 < self.world <= 8
                 and os.environ.get("GRAPPA_B200_PEER_ALLREDUCE", "1") != "0"
                 and int(os.environ.get("LOCAL_WORLD_SIZE", self.world)) == self.world):
-            from .peer import PeerGradients
+            from .peer import PeerGradients, PeerUnavailable
             holder = {}
 
             def factory(n):
-                holder["peer"] = PeerGradients(n, self.device)
+                try:
+                    holder["peer"] = PeerGradients(n, self.device)
+                except PeerUnavailable as e:     # raised on all ranks alike: every rank falls back to NCCL
+                    import warnings
+                    warnings.warn(f"grappa_b200: {e}; gradients are exchanged with NCCL instead")
+                    return torch.zeros(n, device=self.device, dtype=torch.float32)
                 return holder["peer"].grad
             self.fp = FlatParams(model, self.device, grad_factory=factory)
-            self.peer = holder["peer"]
+            self.peer = holder.get("peer")
         else:
             self.fp = FlatParams(model, self.device)
         self.gnorm_sq = torch.zeros(1, device=self.device, dtype=torch.float32)
