@@ -368,7 +368,9 @@ struct TcCfg {
   static constexpr int B_ROWS = BN / CTAS;            // rows of the B tile this CTA stages
   static constexpr int B_BYTES = B_ROWS * TC_BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  // 144-168 KB of operand ring.  bf16x3 converts every stage in place (same bytes), so both arithmetics share the ring depth.
+  // 192 KB of operand ring next to 32 KB of epilogue patches.  bf16x3 converts every stage in place (same bytes), so both
+  // arithmetics share the ring depth (the TF32 kernel is bound by the latency of its operand stream: one more stage than in
+  // round 1 took the step from 5.94 to 5.86 ms).
   static constexpr int STAGES = CTAS == 2 ? (BN == 256 ? 6 : 8) : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int CONV_STAGES = X3 ? STAGES : 0;   // one "converted" barrier per stage
   static constexpr int THREADS = X3 ? TC_THREADS_X3 : TC_THREADS;
