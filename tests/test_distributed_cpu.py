@@ -84,3 +84,32 @@ def test_bucketed_allreduce_and_sharding_world2():
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in res), "a bucket was reduced twice or not at all"
     assert res[0][2] == [0, 2, 4, 6, 8] and res[1][2] == [1, 3, 5, 7, 9]
+
+
+def test_gradient_buckets_tile_the_flat_buffer_exactly_once():
+    """Every float of the flat gradient buffer belongs to exactly one exchanged span (writer parts, GNN blocks, the rest of
+    the GNN) -- for the released architecture and for the narrow one, with and without convolution blocks."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "oracle"))
+    import grappa_oracle as orc
+    from grappa_b200 import models
+    from grappa_b200.training import Trainer
+    for cfg in (orc.small_model_config(), dict(orc.small_model_config(), gnn_convolutions=1)):
+        torch.manual_seed(0)
+        model = models.model_from_config(cfg)
+        tr = Trainer(model, None, None, device="cpu", distributed=False)
+        spans = [sp for name in tr._part_spans for part in tr._part_spans[name] for sp in part]
+        spans += list(tr._block_spans)
+        s0, e0 = tr._gnn_span
+        if tr._block_spans:
+            spans += [(s0, tr._block_spans[0][0]), (tr._block_spans[-1][1], e0)]
+        else:
+            spans.append((s0, e0))
+        cover = torch.zeros(tr.fp.total, dtype=torch.int32)
+        for s, e in spans:
+            assert 0 <= s <= e <= tr.fp.total and s % 4 == 0       # 16-byte aligned starts (peer_allreduce_kernel)
+            cover[s:e] += 1
+        assert bool((cover == 1).all()), "a gradient span is exchanged twice or never"
+        order = tr._part_order()
+        assert sorted(order) == sorted((n, k) for n in tr._part_spans for k in range(len(tr._part_spans[n])))
