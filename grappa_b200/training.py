@@ -9,9 +9,10 @@ provides the equivalent plain loop, B200-first:
     modules' Parameters are views into it, so checkpoints / state_dict are unchanged
   * the backward kernels write weight gradients straight into the flat gradient buffer (no
     per-parameter accumulate kernels, no flatten / unflatten copies)
-  * one process per GPU; gradients are averaged with bucketed NCCL all-reduces on a side stream that
-    start as soon as a bucket's backward has finished (4 writer buckets first, then GNN blocks
-    last-to-first), overlapping communication with the remaining backward kernels
+  * one process per GPU; gradients are averaged with bucketed all-reduces on a side stream that start as
+    soon as a bucket's backward has finished (every writer in 5 parts, then the GNN blocks last-to-first),
+    overlapping communication with the remaining backward kernels.  Single node: our own kernel over
+    NVLink peer memory (`peer.PeerGradients`, csrc/peer_allreduce.cu); otherwise NCCL
   * global-norm clipping + Adam are two fused kernels over the flat buffers
 
 Each rank draws its own batch (weak scaling); the global loss is the mean of the rank losses.
@@ -81,7 +82,7 @@ class _Captured:
 class Trainer:
     """forward -> loss -> backward -> (bucketed all-reduce) -> clip + Adam, all on the GPU.
 
-    `use_cuda_graph=True` (default on CUDA): the whole step -- ~900 kernel launches, the NCCL bucket
+    `use_cuda_graph=True` (default on CUDA): the whole step -- ~550 kernel launches, the bucket
     all-reduces on the side stream, clip + Adam -- is captured once per batch *shape signature*
     (`PackedBatch.signature()` + conformation count) and replayed with a single launch.  The step count,
     the learning rate and the dropout RNG offset live in device memory so that replays stay correct:
