@@ -95,9 +95,14 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
+// Execution barrier over the CTAs of the cluster.  Relaxed arrival (what cute::cluster_arrive_relaxed + cluster_wait issue
+// after fence_barrier_init): the release / acquire forms put MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in front of the arrival,
+// ~1500 cycles at the start and at the end of every pair kernel.  What has to be visible across the pair at these two
+// points is published separately: the mbarrier initialisation by fence.mbarrier_init.release.cluster, and at the end of
+// the kernel nothing is exchanged -- the barrier only keeps shared / tensor memory alive until both CTAs are done.
 __device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
 }
 // shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
 __device__ __forceinline__ uint32_t mapa_rank(uint32_t cta_addr, uint32_t rank) {
